@@ -1,0 +1,164 @@
+"""ORACLE / TEST INFRASTRUCTURE -- not product code.
+
+ctypes front end of liboracle.so (rho_oracle.cpp, lusgs_oracle.cpp): the CPU
+restatement of the reference hot path.  Importable only from tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("rho_oracle.cpp", "lusgs_oracle.cpp")]
+    stale = (not os.path.exists(so)) or any(
+        os.path.getmtime(s) > os.path.getmtime(so) for s in srcs
+    )
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"],
+                              stdout=subprocess.DEVNULL)
+    return so
+
+
+class OmMesh(C.Structure):
+    _fields_ = [
+        ("dim", C.c_int32), ("ncells", C.c_int32), ("nfaces", C.c_int32), ("nint", C.c_int32),
+        ("c0", C.c_void_p), ("c1", C.c_void_p), ("S", C.c_void_p), ("dac", C.c_void_p),
+        ("fc", C.c_void_p), ("eta", C.c_void_p), ("flag", C.c_void_p), ("ftype", C.c_void_p),
+        ("cc", C.c_void_p), ("vol", C.c_void_p), ("cf_ptr", C.c_void_p), ("cf_idx", C.c_void_p),
+    ]
+
+
+class OmCfg(C.Structure):
+    _fields_ = [
+        ("order", C.c_int32), ("flux", C.c_int32), ("viscous", C.c_int32),
+        ("qf_copy_from", C.c_int32), ("nthreads", C.c_int32), ("pad_", C.c_int32),
+        ("gamma", C.c_double), ("delta", C.c_double), ("eor", C.c_double),
+        ("mu", C.c_double), ("kappa", C.c_double), ("cv", C.c_double),
+        ("inletQ", C.c_double * 5),
+    ]
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = build()
+        L = C.CDLL(so)
+        L.oracle_create.restype = C.c_void_p
+        L.oracle_create.argtypes = [C.POINTER(OmMesh), C.POINTER(OmCfg)]
+        L.oracle_destroy.argtypes = [C.c_void_p]
+        L.oracle_nthreads.argtypes = [C.c_void_p]
+        L.oracle_solve.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+        L.oracle_run.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+        L.oracle_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_riemann.argtypes = [C.c_int, C.c_int, C.POINTER(OmCfg), C.c_void_p,
+                                     C.c_void_p, C.c_int, C.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+# reference constants, R/include/CONST.h:38-48, 70-83
+GAMMA = 1.4
+CV = 715.8
+INI_T = 1 / 286.32
+
+
+def default_inlet(dim: int) -> np.ndarray:
+    """inletQ as the shipped macros build it (CONST.h:78-83): rho=1, u=0,
+    E = rho*(T*CV)."""
+    q = np.zeros(5)
+    q[0] = 1.0
+    q[dim + 1] = 1.0 * (INI_T * CV + 0.0)
+    return q
+
+
+def make_cfg(flat, order=2, flux="roe", viscous=0, qf_copy_from=None, nthreads=0,
+             inletQ=None, gamma=GAMMA, delta=0.125, eor=1e-10,
+             mu=1.7894e-05, kappa=0.0242, cv=CV) -> OmCfg:
+    c = OmCfg()
+    c.order = order
+    c.flux = {"roe": 0, "ausm": 1}[flux] if isinstance(flux, str) else int(flux)
+    c.viscous = viscous
+    c.qf_copy_from = flat["nint"] - 1 if qf_copy_from is None else qf_copy_from
+    c.nthreads = nthreads
+    c.gamma, c.delta, c.eor = gamma, delta, eor
+    c.mu, c.kappa, c.cv = mu, kappa, cv
+    iq = default_inlet(flat["dim"]) if inletQ is None else np.asarray(inletQ, dtype=np.float64)
+    for k in range(5):
+        c.inletQ[k] = float(iq[k]) if k < len(iq) else 0.0
+    return c
+
+
+class Oracle:
+    """One reference solver instance on a flat mesh (oracle/mesh_np.flatten)."""
+
+    def __init__(self, flat: dict, **cfg_kw):
+        self.flat = flat
+        self.dim = flat["dim"]
+        self.U = self.dim + 2
+        self._keep = {}
+        m = OmMesh()
+        m.dim, m.ncells, m.nfaces, m.nint = flat["dim"], flat["ncells"], flat["nfaces"], flat["nint"]
+        spec = dict(c0=np.int32, c1=np.int32, S=np.float64, dac=np.int8, fc=np.float64,
+                    eta=np.float64, flag=np.uint8, ftype=np.int32, cc=np.float64,
+                    vol=np.float64, cf_ptr=np.int32, cf_idx=np.int32)
+        for k, dt in spec.items():
+            a = np.ascontiguousarray(flat[k], dtype=dt)
+            self._keep[k] = a
+            setattr(m, k, a.ctypes.data)
+        self.mesh = m
+        self.cfg = make_cfg(flat, **cfg_kw)
+        self.h = lib().oracle_create(C.byref(self.mesh), C.byref(self.cfg))
+        if not self.h:
+            raise RuntimeError("oracle_create failed")
+
+    def close(self):
+        if self.h:
+            lib().oracle_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def nthreads(self) -> int:
+        return lib().oracle_nthreads(self.h)
+
+    def solve(self, dt: float, Qold: np.ndarray) -> np.ndarray:
+        Qold = np.ascontiguousarray(Qold, dtype=np.float64)
+        Qnew = np.empty_like(Qold)
+        lib().oracle_solve(self.h, dt, Qold.ctypes.data, Qnew.ctypes.data)
+        return Qnew
+
+    def run(self, dt: float, nsteps: int, Q: np.ndarray, residuals: bool = False):
+        Q = np.array(Q, dtype=np.float64, order="C", copy=True)
+        r = np.zeros((nsteps, self.U)) if residuals else None
+        lib().oracle_run(self.h, dt, nsteps, Q.ctypes.data, r.ctypes.data if residuals else None)
+        return (Q, r) if residuals else Q
+
+    def probe(self):
+        """(Qf [nf,U], G [nc,U,D], F [nf,D,U]) of the last solve()."""
+        f, n, U, D = self.flat["nfaces"], self.flat["ncells"], self.U, self.dim
+        Qf = np.empty((f, U)); G = np.empty((n, U, D)); F = np.empty((f, D, U))
+        lib().oracle_probe(self.h, Qf.ctypes.data, G.ctypes.data, F.ctypes.data)
+        return Qf, G, F
+
+
+def riemann(dim, flux, L, R, d, **cfg_kw) -> np.ndarray:
+    flat = dict(dim=dim, nint=1)
+    cfg = make_cfg(flat, flux=flux, **cfg_kw)
+    L = np.ascontiguousarray(L, dtype=np.float64); R = np.ascontiguousarray(R, dtype=np.float64)
+    out = np.empty(dim + 2)
+    lib().oracle_riemann(dim, cfg.flux, C.byref(cfg), L.ctypes.data, R.ctypes.data, d, out.ctypes.data)
+    return out
