@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""bench.py -- FP64 cell-updates/s of the rhoSolver hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU arm
+
+Workload (BASELINE.json configs[3], the one the metric is quoted on): synthetic
+unit-cube tet mesh, 203^3 hexes x 6 Kuhn tets = 50 192 562 cells, Roe flux,
+second order, explicit, all walls, SOD-type split at x = 0.5 plus a smooth
+perturbation on rho and p, DT = 1e-4.  A "step" is one RhoSolver::solve() +
+residual + new->old over the whole mesh.
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "mst-cfd_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+DT = 1e-4
+# algorithmic bytes per cell-update (every distinct datum once per pass)
+ALGO_BYTES = {
+    (3, 2): dict(step=600, gradient=248, flux_update=352),
+    (3, 1): dict(step=160, gradient=0, flux_update=160),
+    (2, 2): dict(step=370, gradient=152, flux_update=218),
+    (2, 1): dict(step=114, gradient=0, flux_update=114),
+}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def build_workload(args):
+    """Returns (flat mesh, Q0, description)."""
+    from mstgpu import host
+    t = time.time()
+    if args.workload == "box":
+        n = args.n
+        raw = host.box_tets_raw(n, n, n)
+        f = host.flatten_raw(raw)
+        x = f["cc"]
+        Q = np.zeros((f["ncells"], 5))
+        pert = 1e-2 * np.sin(2 * np.pi * x[:, 0]) * np.sin(2 * np.pi * x[:, 1]) * np.sin(2 * np.pi * x[:, 2])
+        right = x[:, 0] > 0.5
+        rho = np.where(right, 0.125, 1.0) + pert
+        p = np.where(right, 0.1, 1.0) + pert
+        Q[:, 0] = rho
+        Q[:, 4] = p / 0.4
+        desc = f"unit-cube {n}^3 hexes x 6 Kuhn tets, Roe, 2nd order, explicit, all walls"
+    elif args.workload == "step":
+        raw = host.forward_step_raw(args.n)
+        f = host.flatten_raw(raw)
+        u = 3.0 * np.sqrt(1.4)
+        Q = np.tile(np.array([1.0, u, 0.0, 1.0 / 0.4 + 0.5 * u * u]), (f["ncells"], 1))
+        desc = f"forward-facing step h=1/{args.n}, triangles"
+    else:
+        raise SystemExit("unknown workload")
+    log(f"[bench] mesh: {f['ncells']} cells, {f['nfaces']} faces in {time.time() - t:.1f}s")
+    return f, Q, desc
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (recipe line
+    of B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons, pw = [], [], set(), []
+        for ln in self.f.read().splitlines():
+            c = [t.strip() for t in ln.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2])); pw.append(float(c[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), power_w_max=float(max(pw)),
+                    samples=len(sm), reasons=sorted(reasons))
+
+
+def cpu_baseline(args, nsteps=3, n=None):
+    """Oracle (kind "port": the reference cannot be compiled without Eigen) on
+    the host cores, on a bounded sample of the same workload."""
+    from oracle import oracle
+    from mstgpu import host
+    n = n or args.cpu_n
+    a = argparse.Namespace(**vars(args)); a.n = n
+    f, Q, _ = build_workload(a)
+    o = oracle.Oracle(f, order=2, flux="roe", nthreads=0)
+    o.run(DT, 1, Q)  # warm-up (page faults of the work arrays)
+    t = time.perf_counter()
+    o.run(DT, nsteps, Q)
+    el = time.perf_counter() - t
+    return dict(value=f["ncells"] * nsteps / el, unit="cell-updates/s", cores=o.nthreads, kind="port",
+                sample=f"{args.workload} n={n}: {f['ncells']} cells x {nsteps} steps in {el:.2f}s "
+                       f"(oracle/rho_oracle.cpp, OpenMP, host has {os.cpu_count()} cpus)")
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    f_desc = None
+    from oracle import oracle
+    a = argparse.Namespace(**vars(args)); a.n = args.cpu_n
+    f, Q, desc = build_workload(a)
+    o = oracle.Oracle(f, order=2, flux="roe", nthreads=0)
+    for _ in range(args.warmup):
+        o.run(DT, 1, Q)
+    t = time.perf_counter()
+    o.run(DT, args.steps, Q)
+    el = time.perf_counter() - t
+    val = f["ncells"] * args.steps / el
+    sample = (f"{args.workload} n={args.cpu_n}: {f['ncells']} cells per step "
+              f"(bounded sample of the n={args.n} workload), {o.nthreads} threads of {os.cpu_count()} cpus")
+    out = dict(impl="reference", metric="cell_updates_per_sec", value=val, unit="cell-updates/s",
+               n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * el / args.steps,
+               higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
+               config=dict(workload=f"{args.workload}{args.n}: " + desc.replace(f"{args.cpu_n}^3", f"{args.n}^3"),
+                           flux="roe", order=2, dt=DT),
+               cpu_baseline=dict(value=val, unit="cell-updates/s", cores=o.nthreads, kind="port", sample=sample),
+               e2e=dict(value=val, unit="cell-updates/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+               gpu_launches=0)
+    print(json.dumps(out), flush=True)
+
+
+def run_ours(args, rank, world):
+    import torch
+    import mstgpu
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        raise SystemExit("multi-GPU path not built yet")
+
+    f, Q0, desc = build_workload(args)
+    nc, U, D = f["ncells"], f["dim"] + 2, f["dim"]
+    t = time.time()
+    ctx = mstgpu.Context(f, order=2, flux="roe", device=local)
+    log(f"[bench] context built in {time.time() - t:.1f}s, {ctx.device_bytes / 2**30:.2f} GiB on device")
+    ctx.set_state(Q0)
+    ctx.step(DT, args.warmup)
+    ctx.sync()
+    # ---- timed region: K steps, state resident in HBM -------------------------
+    ctx.enable_kernel_timing(True)
+    l0 = ctx.launch_count
+    clocks = ClockSampler(local)
+    clocks.start()
+    time.sleep(0.3)
+    torch.cuda.synchronize()
+    w0 = time.perf_counter()
+    ms = ctx.step_timed(DT, args.steps)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - w0
+    clk = clocks.stop()
+    launches = ctx.launch_count - l0
+    kt = {k: ctx.kernel_time(k) for k in ("gradient", "flux", "update")}
+    ctx.enable_kernel_timing(False)
+    res = ctx.residual()
+    value = nc * args.steps / (ms * 1e-3)
+    log(f"[bench] {args.steps} steps in {ms:.2f} ms (wall {wall * 1e3:.2f} ms), residual {res}")
+
+    # ---- roofline of the dominant kernel --------------------------------------
+    peak, peak_src = measured_peaks()
+    ab = ALGO_BYTES[(D, 2)]
+    per_kernel = {k: (v[0] / max(v[1], 1)) for k, v in kt.items()}
+    dom = max(per_kernel, key=per_kernel.get)
+    # V1 splits pass 2 of SURVEY.md 8(d) into flux + update; the algorithmic bytes
+    # of the pass are charged to the two kernels together.
+    pass2_ms = per_kernel["flux"] + per_kernel["update"]
+    achieved = ab["flux_update"] * nc / (pass2_ms * 1e-3) / 1e9
+    roof = dict(bound="hbm", kernel="flux+update (pass 2 of 8d)", achieved=achieved, peak=peak, unit="GB/s",
+                frac=achieved / peak, traffic=None, peak_source=peak_src,
+                algorithmic_bytes_per_cell=ab["flux_update"],
+                kernels_ms={k: round(v, 4) for k, v in per_kernel.items()}, dominant=dom,
+                step_frac=ab["step"] * value / 1e9 / peak)
+
+    # ---- e2e: reference-facing call sequence with HOST buffers -----------------
+    hin = torch.empty((nc, U), dtype=torch.float64, pin_memory=True)
+    hout = torch.empty((nc, U), dtype=torch.float64, pin_memory=True)
+    hin.numpy()[:] = Q0
+    r = np.zeros(U)
+    ne = max(2, min(args.steps, 5))
+    for it in range(1 + ne):
+        if it == 1:
+            torch.cuda.synchronize()
+            e0 = time.perf_counter()
+        ctx.set_state_ptr(hin.data_ptr())      # H2D of the step's input state
+        ctx.step(DT, 1)
+        ctx.get_state_ptr(hout.data_ptr())     # D2H of the new state (Time.cpp:66-67)
+        r = ctx.residual()                     # D2H of the residual (Time.cpp:69-76)
+        hin, hout = hout, hin                  # updateNewToOld on the host side
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - e0) / ne
+    e2e = dict(value=nc / e2e_s, unit="cell-updates/s", h2d_bytes_per_step=nc * U * 8,
+               d2h_bytes_per_step=nc * U * 8 + U * 8, ms_per_step=e2e_s * 1e3, steps=ne)
+
+    cpu = cpu_baseline(args) if (world == 1 and not args.no_cpu) else None
+
+    out = dict(metric="cell_updates_per_sec", value=value, unit="cell-updates/s", n_gpus=world,
+               steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True,
+               scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
+               config=dict(workload=f"{args.workload}{args.n}: {desc}", cells=nc, faces=f["nfaces"], flux="roe",
+                           order=2, dt=DT, l2="inputs larger than L2 (state + tables >> 126 MB)"
+                           if nc * U * 8 > 2 ** 28 else "inputs smaller than L2: flush not applied"),
+               clocks=clk, e2e=e2e, gpu_launches=launches, roofline=roof, cpu_baseline=cpu,
+               wall_ms_per_step=wall * 1e3 / args.steps, device_gib=ctx.device_bytes / 2 ** 30)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="box", choices=["box", "step"])
+    ap.add_argument("--n", type=int, default=203, help="hexes per side (box) or 1/h (step)")
+    ap.add_argument("--cpu-n", type=int, default=96, help="size of the bounded CPU sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_ours(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

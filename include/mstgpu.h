@@ -1,0 +1,163 @@
+/* mstgpu.h -- C ABI of the B200-native rhoSolver hot path.
+ *
+ * This is the drop-in boundary for MST-CFD's density-based solver
+ * (R = /root/reference/MST-CFD).  Host code -- the reference's own .msh
+ * reader, mesh classes and Time/Work driver -- stays as it is and reaches the
+ * GPU through these entry points only: plain pointers and sizes, no C++ or
+ * torch types.  What each entry point replaces:
+ *
+ *   mstgpu_create / mstgpu_destroy   RhoSolver::RhoSolver / ~RhoSolver
+ *                                    (R/rhoSolver/RhoSolver.cpp:3-31); the
+ *                                    reference rebuilds the solver every step
+ *                                    (R/time/Time.cpp:58), the context lives
+ *                                    outside it and is built once.
+ *   mstgpu_mesh                      what the kernels read through
+ *                                    Face::{getDirect,getCenter,getEta0,
+ *                                    getFlagLeftRight,getBeginItPNbCells}
+ *                                    (R/mesh/Face.cpp:94-133),
+ *                                    Cell::{getVolume,getCenter,
+ *                                    getBeginItDirectOfNbFaces,
+ *                                    getBeginItPNbFaces} (R/mesh/Cell.cpp:69-137)
+ *                                    and FacesInf::{getType,getStart,getEnd}
+ *                                    (R/mesh/FacesInf.cpp:24-32), flattened
+ *                                    once, in REFERENCE ORDER.
+ *   mstgpu_config                    the compile-time macros of
+ *                                    R/include/CONST.h as a runtime struct.
+ *   mstgpu_set_state                 AllData::getP1OldCellQs() contents
+ *                                    (R/data/AllData.cpp:3-27), host -> device.
+ *   mstgpu_step                      RhoSolver::setDT + solve + updateNewToOld
+ *                                    (RhoSolver.cpp:33-89, 513-517) repeated
+ *                                    nsteps times = Time::goNextTimeStep
+ *                                    (R/time/Time.cpp:54-81) without the host
+ *                                    round trip.
+ *   mstgpu_residual_linf             the residual loop of Time.cpp:69-76.
+ *   mstgpu_get_state                 RhoSolver::getNewValue (== old after
+ *                                    updateNewToOld), device -> host.
+ *   mstgpu_get_prev_state            RhoSolver::getOldValue as seen between
+ *                                    solve() and updateNewToOld().
+ *   mstgpu_debug_gradient            p1NewCellGradFlux   (RhoSolver.cpp:442-452)
+ *   mstgpu_debug_face_flux           sum_d S[d] * p1OldFaceConvectFlux.col(d)
+ *                                    per face (RhoSolver.cpp:53, 90-369)
+ *   mstgpu_lusgs_*                   SparseSolverNUM::solveILUSGS
+ *                                    (R/lusolver/SparseSolverNUM.cpp:144-212)
+ *                                    and SparseSolver<MT,VCT>::solveILU
+ *                                    (R/lusolver/SparseSolver.cpp:54-104).
+ *
+ * All state arrays are AoS [cell][DIMU] doubles in the reference's cell
+ * numbering, exactly the memory image of VCTDIMU[] (Eigen fixed vectors are
+ * plain doubles).  Return value: 0 = ok, negative = error (mstgpu_last_error
+ * gives the text).  There is no CPU fallback: every entry point fails when no
+ * CUDA device is usable.
+ */
+#ifndef MSTGPU_H
+#define MSTGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSTGPU_OK 0
+#define MSTGPU_ERR_ARG -1
+#define MSTGPU_ERR_CUDA -2
+#define MSTGPU_ERR_STATE -3
+#define MSTGPU_ERR_NCCL -4
+#define MSTGPU_ERR_NAN -5
+
+#define MSTGPU_FLUX_ROE 0  /* RHOSOLVER solverRoe  (R/rhoSolver/SolverRoe.cpp)  */
+#define MSTGPU_FLUX_AUSM 1 /* RHOSOLVER SolverAusm (R/rhoSolver/SolverAusm.cpp) */
+
+/* zone types handled by RhoSolver::updateFaceFlux (RhoSolver.cpp:98-229) */
+#define MSTGPU_BC_INTERIOR 2
+#define MSTGPU_BC_WALL 3
+#define MSTGPU_BC_OUTLET 5
+#define MSTGPU_BC_SYMMETRY 7
+#define MSTGPU_BC_INLET 10
+
+typedef struct mstgpu_ctx mstgpu_ctx;
+
+/* Flattened mesh, reference order.  D = dim, all arrays host memory. */
+typedef struct mstgpu_mesh {
+    int32_t dim;           /* DIM (2 or 3)                                          */
+    int32_t ncells;        /* MshBlock::getNumOfCells                                */
+    int32_t nfaces;        /* MshBlock::getNumOfFaces                                */
+    int32_t nint;          /* MshBlock::getNumOfIntFaces                             */
+    const int32_t* c0;     /* [nfaces] Face::getBeginItPNbCells()[0]->getId()        */
+    const int32_t* c1;     /* [nfaces] ...[1]->getId(), -1 on boundary faces         */
+    const double* S;       /* [nfaces*D] Face::getDirect() (area vector, as stored)  */
+    const int8_t* dac;     /* [nfaces] Face::getDirectAndCells() (+1 / -1)           */
+    const double* fc;      /* [nfaces*D] Face::getCenter()                           */
+    const double* eta;     /* [nfaces] Face::getEta0()                               */
+    const uint8_t* flag;   /* [nfaces*D] Face::getFlagLeftRight()                    */
+    const int32_t* ftype;  /* [nfaces] zone type of the face (FacesInf::getType)     */
+    const double* cc;      /* [ncells*D] Cell::getCenter()                           */
+    const double* vol;     /* [ncells] Cell::getVolume()                             */
+    const int32_t* cf_ptr; /* [ncells+1] CSR offsets of Cell::getBeginItPNbFaces()   */
+    const int32_t* cf_idx; /* face ids per cell, in the cell's own (file) order      */
+} mstgpu_mesh;
+
+typedef struct mstgpu_config {
+    int32_t order;        /* ACCURACY 1|2 (CONST.h:6)                                */
+    int32_t flux;         /* MSTGPU_FLUX_* (CONST.h:10)                              */
+    int32_t viscous;      /* FLAGVISCID (CONST.h:14)                                 */
+    int32_t qf_copy_from; /* first face with Qf = Q[c0]; reference: nint-1
+                             (the off-by-one of RhoSolver.cpp:438); <0 = nint-1     */
+    int32_t renumber;     /* 0 = keep reference order on the device, 1 = Morton      */
+    int32_t device;       /* CUDA ordinal, <0 = current device                       */
+    double gamma;         /* GAMMA (CONST.h:41)                                      */
+    double delta;         /* entropyError 0.125 (SolverRoe.cpp:115)                  */
+    double eor;           /* EOR 1e-10 (CONST.h:42)                                  */
+    double mu;            /* VISCIDMU (CONST.h:46)                                   */
+    double kappa;         /* TEMPK (CONST.h:48)                                      */
+    double cv;            /* CV (CONST.h:39)                                         */
+    double inletQ[5];     /* inlet state (RhoSolver.cpp:123,266)                     */
+} mstgpu_config;
+
+/* Fill `cfg` with the reference's shipped constants (CONST.h) for `dim`. */
+void mstgpu_default_config(mstgpu_config* cfg, int32_t dim);
+
+/* Build a solver context: renumber (Morton), lay the tables out in HBM,
+ * upload once.  The mesh arrays are not referenced after return. */
+int mstgpu_create(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_config* cfg);
+void mstgpu_destroy(mstgpu_ctx* ctx);
+
+/* Host <-> device state in reference cell order, AoS [ncells][DIMU]. */
+int mstgpu_set_state(mstgpu_ctx* ctx, const double* q_aos, int64_t ncells);
+int mstgpu_get_state(mstgpu_ctx* ctx, double* q_aos);
+int mstgpu_get_prev_state(mstgpu_ctx* ctx, double* q_aos);
+
+/* Advance nsteps explicit steps of size dt (state stays on the device). */
+int mstgpu_step(mstgpu_ctx* ctx, double dt, int32_t nsteps);
+/* Same, bracketed by CUDA events on the solver's own stream; *ms = elapsed. */
+int mstgpu_step_timed(mstgpu_ctx* ctx, double dt, int32_t nsteps, float* ms);
+/* L-inf relative change of the LAST step, DIMU doubles (Time.cpp:69-76). */
+int mstgpu_residual_linf(mstgpu_ctx* ctx, double* out_dimu);
+int mstgpu_sync(mstgpu_ctx* ctx);
+
+/* Stage probes of the last step, reference order.
+ * gradient: [ncells][DIMU][D]; face flux: [nfaces][DIMU] =
+ * sum_d (dac*S)[d] * F[:,d], i.e. the flux through the face oriented out of c0. */
+int mstgpu_debug_gradient(mstgpu_ctx* ctx, double* grad);
+int mstgpu_debug_face_flux(mstgpu_ctx* ctx, double* phi);
+
+/* Introspection for the bench: kernels launched so far by this context and
+ * per-kernel accumulated device time (ms) when timing is enabled. */
+int64_t mstgpu_launch_count(mstgpu_ctx* ctx);
+int mstgpu_enable_kernel_timing(mstgpu_ctx* ctx, int32_t on);
+/* names: "gradient", "flux", "update"; returns accumulated ms and launches */
+int mstgpu_kernel_time(mstgpu_ctx* ctx, const char* name, double* ms, int64_t* launches);
+int64_t mstgpu_device_bytes(mstgpu_ctx* ctx);
+
+/* Host-only: the renumbering mstgpu_create would apply (no CUDA call), for
+ * inspection and CPU tests.  cell_new2old [ncells], face_new2old [nfaces]. */
+int mstgpu_plan_permutation(const mstgpu_mesh* mesh, const mstgpu_config* cfg,
+                            int32_t* cell_new2old, int32_t* face_new2old);
+
+const char* mstgpu_last_error(mstgpu_ctx* ctx); /* ctx may be NULL (create errors) */
+const char* mstgpu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSTGPU_H */

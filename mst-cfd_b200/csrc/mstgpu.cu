@@ -1,0 +1,620 @@
+// mstgpu.cu -- C ABI (include/mstgpu.h) and the sm_100a kernels of the
+// rhoSolver hot path.  Reference path being replaced (R = /root/reference/MST-CFD):
+//   K1+K2  face interpolation + Green-Gauss gradient   R/rhoSolver/RhoSolver.cpp:430-452
+//   K3     reconstruction + Roe/AUSM+ face flux        RhoSolver.cpp:90-369, SolverRoe.cpp, SolverAusm.cpp
+//   K4+K5  cell gather + explicit Euler + residual     RhoSolver.cpp:45-68, R/time/Time.cpp:69-76
+//   K6     new -> old                                  RhoSolver.cpp:513-517 (pointer swap here)
+//
+// No CPU fallback exists in this file: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/mstgpu.h"
+#include "physics.cuh"
+#include "plan.h"
+
+using namespace mst;
+
+#define CK(call)                                                                       \
+    do {                                                                               \
+        cudaError_t e_ = (call);                                                       \
+        if (e_ != cudaSuccess) {                                                       \
+            set_error(ctx, std::string(#call) + ": " + cudaGetErrorString(e_));        \
+            return MSTGPU_ERR_CUDA;                                                    \
+        }                                                                              \
+    } while (0)
+
+namespace {
+thread_local std::string g_create_error;
+}
+
+struct KernelStat {
+    double ms = 0.0;
+    int64_t launches = 0;
+};
+
+struct mstgpu_ctx {
+    Plan plan;  // host copy of permutations (tables are freed after upload)
+    mstgpu_config cfg;
+    DevCfg dcfg;
+    int device = 0;
+    int D = 0, U = 0, nc = 0, nf = 0, nslot = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // device tables
+    double *Q[2] = {nullptr, nullptr}, *G = nullptr, *Phi = nullptr, *stage = nullptr;
+    double *Sd = nullptr, *dx0 = nullptr, *dx1 = nullptr, *eta = nullptr, *vol = nullptr;
+    int32_t *fc0 = nullptr, *fc1 = nullptr, *cf = nullptr, *cell_new2old = nullptr, *face_new2old = nullptr;
+    uint32_t* meta = nullptr;
+    unsigned long long* resid = nullptr;  // [U] bit patterns of non-negative doubles
+    int* nanflag = nullptr;
+    int cur = 0;          // Q[cur] = current ("old") state
+    bool has_state = false, stepped = false;
+    int64_t launches = 0, dev_bytes = 0;
+    bool ktiming = false;
+    std::map<std::string, KernelStat> kstat;
+    std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> pending;
+    std::vector<cudaEvent_t> evpool;
+    std::string err;
+};
+
+static void set_error(mstgpu_ctx* ctx, const std::string& s) {
+    if (ctx) ctx->err = s;
+    else g_create_error = s;
+}
+
+// ============================================================================
+// kernels (V1: one thread per cell / face, global-memory gathers)
+// ============================================================================
+namespace {
+
+template <int D>
+__global__ void __launch_bounds__(256) k_gradient(int nc, int nslot, const double* __restrict__ Q,
+                                                  const int32_t* __restrict__ cf,
+                                                  const int32_t* __restrict__ fc0,
+                                                  const int32_t* __restrict__ fc1,
+                                                  const double* __restrict__ eta,
+                                                  const double* __restrict__ Sd,
+                                                  const double* __restrict__ vol,
+                                                  double* __restrict__ G) {
+    constexpr int U = D + 2;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nc) return;
+    double qc[U];
+#pragma unroll
+    for (int k = 0; k < U; k++) qc[k] = Q[(size_t)c * U + k];
+    double t[U][D];
+#pragma unroll
+    for (int k = 0; k < U; k++)
+#pragma unroll
+        for (int d = 0; d < D; d++) t[k][d] = 0.0;
+    for (int j = 0; j < nslot; j++) {
+        const int v = cf[(size_t)j * nc + c];
+        if (v < 0) continue;
+        const int f = v >> 1;
+        const int side = v & 1;
+        const double e = eta[f];
+        const int nb = side ? fc0[f] : fc1[f];
+        double qf[U];
+        if (nb >= 0) {
+            // Qf = eta*Q[c0] + (1-eta)*Q[c1]   (RhoSolver.cpp:435)
+            const double e0 = side ? (1.0 - e) : e;  // weight of this cell
+            const double e1 = side ? e : (1.0 - e);  // weight of the neighbour
+#pragma unroll
+            for (int k = 0; k < U; k++) qf[k] = e0 * qc[k] + e1 * Q[(size_t)nb * U + k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < U; k++) qf[k] = qc[k];  // RhoSolver.cpp:439
+        }
+        const double sg = side ? -1.0 : 1.0;  // outward from this cell (MshBlock.cpp:307-318)
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            const double s = sg * Sd[(size_t)f * D + d];
+#pragma unroll
+            for (int k = 0; k < U; k++) t[k][d] += qf[k] * s;
+        }
+    }
+    const double v = vol[c];
+#pragma unroll
+    for (int k = 0; k < U; k++)
+#pragma unroll
+        for (int d = 0; d < D; d++) G[((size_t)c * U + k) * D + d] = t[k][d] / v;
+}
+
+template <int D, int ORDER>
+__global__ void __launch_bounds__(128) k_flux(int nf, DevCfg cfg, const double* __restrict__ Q,
+                                              const double* __restrict__ G,
+                                              const int32_t* __restrict__ fc0,
+                                              const int32_t* __restrict__ fc1,
+                                              const uint32_t* __restrict__ meta,
+                                              const double* __restrict__ Sd,
+                                              const double* __restrict__ dx0,
+                                              const double* __restrict__ dx1,
+                                              double* __restrict__ Phi) {
+    constexpr int U = D + 2;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nf) return;
+    const int a = fc0[f], b = fc1[f];
+    const uint32_t mt = meta[f];
+    const int type = mt & 0xff;
+    const uint32_t flags = mt >> 8;
+    double S[D];
+#pragma unroll
+    for (int d = 0; d < D; d++) S[d] = Sd[(size_t)f * D + d];
+    double qa[U], ra[U];
+#pragma unroll
+    for (int k = 0; k < U; k++) qa[k] = Q[(size_t)a * U + k];
+    if (ORDER == 2) {
+        double dx[D];
+#pragma unroll
+        for (int d = 0; d < D; d++) dx[d] = dx0[(size_t)f * D + d];
+#pragma unroll
+        for (int k = 0; k < U; k++) {
+            double s = 0.0;
+#pragma unroll
+            for (int d = 0; d < D; d++) s += G[((size_t)a * U + k) * D + d] * dx[d];
+            ra[k] = qa[k] + s;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < U; k++) ra[k] = qa[k];
+    }
+    double A[U], B[U], phi[U];
+    bool live = true;
+    if (b >= 0) {
+#pragma unroll
+        for (int k = 0; k < U; k++) A[k] = ra[k];
+        if (ORDER == 2) {
+            double dx[D];
+#pragma unroll
+            for (int d = 0; d < D; d++) dx[d] = dx1[(size_t)f * D + d];
+#pragma unroll
+            for (int k = 0; k < U; k++) {
+                double s = 0.0;
+#pragma unroll
+                for (int d = 0; d < D; d++) s += G[((size_t)b * U + k) * D + d] * dx[d];
+                B[k] = Q[(size_t)b * U + k] + s;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < U; k++) B[k] = Q[(size_t)b * U + k];
+        }
+    } else {
+        live = boundary_states<D>(type, qa, ra, S, cfg, A, B);
+    }
+    if (live) {
+        riemann_contract<D>(cfg.flux, A, B, flags, S, cfg, phi);
+    } else {
+#pragma unroll
+        for (int k = 0; k < U; k++) phi[k] = 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < U; k++) Phi[(size_t)f * U + k] = phi[k];
+}
+
+__device__ __forceinline__ double warp_max(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
+    return x;
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) k_update(int nc, int nslot, double dt,
+                                                const double* __restrict__ Qold,
+                                                const double* __restrict__ Phi,
+                                                const int32_t* __restrict__ cf,
+                                                const double* __restrict__ vol,
+                                                double* __restrict__ Qnew,
+                                                unsigned long long* __restrict__ resid,
+                                                int* __restrict__ nanflag) {
+    constexpr int U = D + 2;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    double r[U];
+#pragma unroll
+    for (int k = 0; k < U; k++) r[k] = 0.0;
+    bool bad = false;
+    if (c < nc) {
+        double acc[U];
+#pragma unroll
+        for (int k = 0; k < U; k++) acc[k] = 0.0;
+        for (int j = 0; j < nslot; j++) {
+            const int v = cf[(size_t)j * nc + c];
+            if (v < 0) continue;
+            const int f = v >> 1;
+            const double sg = (v & 1) ? -1.0 : 1.0;
+#pragma unroll
+            for (int k = 0; k < U; k++) acc[k] += sg * Phi[(size_t)f * U + k];
+        }
+        const double s = dt / vol[c];  // RhoSolver.cpp:64
+#pragma unroll
+        for (int k = 0; k < U; k++) {
+            const double qo = Qold[(size_t)c * U + k];
+            const double qn = qo - s * acc[k];
+            Qnew[(size_t)c * U + k] = qn;
+            // Time.cpp:72: signed denominator; NaN never wins, +inf can
+            const double x = fabs(qn - qo) / qo;
+            r[k] = (x > 0.0) ? x : 0.0;
+            bad |= (qn != qn);
+        }
+    }
+    __shared__ double sm[U][8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+        const double m = warp_max(r[k]);
+        if (lane == 0) sm[k][wid] = m;
+    }
+    const bool anybad = __syncthreads_or(bad);
+    if (threadIdx.x < U) {
+        double m = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) m = fmax(m, sm[threadIdx.x][w]);
+        if (m > 0.0) atomicMax(&resid[threadIdx.x], (unsigned long long)__double_as_longlong(m));
+    }
+    if (anybad && threadIdx.x == 0) atomicOr(nanflag, 1);
+}
+
+// state in reference order <-> device order
+__global__ void k_permute_in(int nc, int U, const double* __restrict__ src,
+                             const int32_t* __restrict__ new2old, double* __restrict__ dst) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)nc * U) return;
+    const int c = (int)(i / U), k = (int)(i % U);
+    dst[i] = src[(size_t)new2old[c] * U + k];
+}
+__global__ void k_permute_out(int n, int W, const double* __restrict__ src,
+                              const int32_t* __restrict__ new2old, double* __restrict__ dst) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)n * W) return;
+    const int c = (int)(i / W), k = (int)(i % W);
+    dst[(size_t)new2old[c] * W + k] = src[i];
+}
+
+}  // namespace
+
+// ============================================================================
+// host side
+// ============================================================================
+namespace {
+
+template <typename T>
+int upload(mstgpu_ctx* ctx, T** dptr, const std::vector<T>& h) {
+    const size_t bytes = h.size() * sizeof(T);
+    CK(cudaMalloc((void**)dptr, bytes ? bytes : 8));
+    ctx->dev_bytes += (int64_t)bytes;
+    if (bytes) CK(cudaMemcpyAsync(*dptr, h.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return MSTGPU_OK;
+}
+template <typename T>
+int dalloc(mstgpu_ctx* ctx, T** dptr, size_t n) {
+    CK(cudaMalloc((void**)dptr, n * sizeof(T)));
+    ctx->dev_bytes += (int64_t)(n * sizeof(T));
+    return MSTGPU_OK;
+}
+
+struct KTimer {
+    mstgpu_ctx* ctx;
+    const char* name;
+    cudaEvent_t a = nullptr, b = nullptr;
+    KTimer(mstgpu_ctx* c, const char* n) : ctx(c), name(n) {
+        ctx->launches++;
+        if (!ctx->ktiming) return;
+        auto get = [&]() {
+            cudaEvent_t e;
+            if (!ctx->evpool.empty()) { e = ctx->evpool.back(); ctx->evpool.pop_back(); }
+            else cudaEventCreate(&e);
+            return e;
+        };
+        a = get(); b = get();
+        cudaEventRecord(a, ctx->stream);
+    }
+    ~KTimer() {
+        if (!ctx->ktiming) { ctx->kstat[name].launches++; return; }
+        cudaEventRecord(b, ctx->stream);
+        ctx->pending.push_back({name, {a, b}});
+    }
+};
+
+void drain_timers(mstgpu_ctx* ctx) {
+    for (auto& p : ctx->pending) {
+        float ms = 0.f;
+        cudaEventSynchronize(p.second.second);
+        cudaEventElapsedTime(&ms, p.second.first, p.second.second);
+        auto& s = ctx->kstat[p.first];
+        s.ms += ms;
+        s.launches++;
+        ctx->evpool.push_back(p.second.first);
+        ctx->evpool.push_back(p.second.second);
+    }
+    ctx->pending.clear();
+}
+
+template <int D>
+int step_impl(mstgpu_ctx* ctx, double dt, int nsteps) {
+    const int nc = ctx->nc, nf = ctx->nf;
+    for (int s = 0; s < nsteps; s++) {
+        const double* Qo = ctx->Q[ctx->cur];
+        double* Qn = ctx->Q[ctx->cur ^ 1];
+        CK(cudaMemsetAsync(ctx->resid, 0, 8 * sizeof(unsigned long long), ctx->stream));
+        if (ctx->cfg.order == 2) {
+            KTimer t(ctx, "gradient");
+            k_gradient<D><<<(nc + 255) / 256, 256, 0, ctx->stream>>>(
+                nc, ctx->nslot, Qo, ctx->cf, ctx->fc0, ctx->fc1, ctx->eta, ctx->Sd, ctx->vol, ctx->G);
+        }
+        {
+            KTimer t(ctx, "flux");
+            if (ctx->cfg.order == 2)
+                k_flux<D, 2><<<(nf + 127) / 128, 128, 0, ctx->stream>>>(
+                    nf, ctx->dcfg, Qo, ctx->G, ctx->fc0, ctx->fc1, ctx->meta, ctx->Sd, ctx->dx0, ctx->dx1, ctx->Phi);
+            else
+                k_flux<D, 1><<<(nf + 127) / 128, 128, 0, ctx->stream>>>(
+                    nf, ctx->dcfg, Qo, ctx->G, ctx->fc0, ctx->fc1, ctx->meta, ctx->Sd, ctx->dx0, ctx->dx1, ctx->Phi);
+        }
+        {
+            KTimer t(ctx, "update");
+            k_update<D><<<(nc + 255) / 256, 256, 0, ctx->stream>>>(
+                nc, ctx->nslot, dt, Qo, ctx->Phi, ctx->cf, ctx->vol, Qn, ctx->resid, ctx->nanflag);
+        }
+        ctx->cur ^= 1;  // RhoSolver::updateNewToOld as a pointer swap
+    }
+    CK(cudaGetLastError());
+    ctx->stepped = nsteps > 0 || ctx->stepped;
+    return MSTGPU_OK;
+}
+
+int fetch_permuted(mstgpu_ctx* ctx, const double* dsrc, const int32_t* new2old, int n, int W, double* host) {
+    const size_t tot = (size_t)n * W;
+    k_permute_out<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(n, W, dsrc, new2old, ctx->stage);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(host, ctx->stage, tot * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MSTGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* mstgpu_version(void) { return "mstgpu 0.1 (sm_100a)"; }
+
+const char* mstgpu_last_error(mstgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+void mstgpu_default_config(mstgpu_config* cfg, int32_t dim) {
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->order = 2;
+    cfg->flux = MSTGPU_FLUX_ROE;
+    cfg->viscous = 0;
+    cfg->qf_copy_from = -1;
+    cfg->renumber = 1;
+    cfg->device = -1;
+    cfg->gamma = 1.4;
+    cfg->delta = 0.125;
+    cfg->eor = 1e-10;
+    cfg->mu = 1.7894e-05;
+    cfg->kappa = 0.0242;
+    cfg->cv = 715.8;
+    // CONST.h:70-83: rho = 1, u = v = w = 0, E = rho * (T*CV), T = 1/286.32
+    cfg->inletQ[0] = 1.0;
+    cfg->inletQ[dim + 1] = 1.0 * ((1 / 286.32) * 715.8 + 0.0);
+}
+
+int mstgpu_create(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_config* cfg) {
+    mstgpu_ctx* ctx = nullptr;
+    if (!out || !mesh || !cfg) { set_error(nullptr, "null argument"); return MSTGPU_ERR_ARG; }
+    *out = nullptr;
+    if (cfg->order != 1 && cfg->order != 2) { set_error(nullptr, "order must be 1 or 2"); return MSTGPU_ERR_ARG; }
+    if (cfg->flux != MSTGPU_FLUX_ROE && cfg->flux != MSTGPU_FLUX_AUSM) { set_error(nullptr, "unknown flux"); return MSTGPU_ERR_ARG; }
+    if (cfg->viscous != 0) { set_error(nullptr, "laminar viscous term not built yet"); return MSTGPU_ERR_ARG; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_error(nullptr, std::string("no CUDA device: ") + cudaGetErrorString(e));
+        return MSTGPU_ERR_CUDA;
+    }
+    ctx = new mstgpu_ctx;
+    ctx->cfg = *cfg;
+    std::string perr = build_plan(*mesh, *cfg, ctx->plan);
+    if (!perr.empty()) { set_error(nullptr, perr); delete ctx; return MSTGPU_ERR_ARG; }
+    Plan& p = ctx->plan;
+    ctx->D = p.D; ctx->U = p.U; ctx->nc = p.nc; ctx->nf = p.nf; ctx->nslot = p.nslot;
+    int rc = [&]() -> int {
+        if (cfg->device >= 0) { CK(cudaSetDevice(cfg->device)); ctx->device = cfg->device; }
+        else CK(cudaGetDevice(&ctx->device));
+        CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        CK(cudaEventCreate(&ctx->ev0));
+        CK(cudaEventCreate(&ctx->ev1));
+        int r;
+        if ((r = upload(ctx, &ctx->fc0, p.fc0))) return r;
+        if ((r = upload(ctx, &ctx->fc1, p.fc1))) return r;
+        if ((r = upload(ctx, &ctx->Sd, p.Sd))) return r;
+        if ((r = upload(ctx, &ctx->dx0, p.dx0))) return r;
+        if ((r = upload(ctx, &ctx->dx1, p.dx1))) return r;
+        if ((r = upload(ctx, &ctx->eta, p.eta))) return r;
+        if ((r = upload(ctx, &ctx->meta, p.meta))) return r;
+        if ((r = upload(ctx, &ctx->vol, p.vol))) return r;
+        if ((r = upload(ctx, &ctx->cf, p.cf))) return r;
+        if ((r = upload(ctx, &ctx->cell_new2old, p.cell_new2old))) return r;
+        if ((r = upload(ctx, &ctx->face_new2old, p.face_new2old))) return r;
+        const size_t nq = (size_t)p.nc * p.U;
+        if ((r = dalloc(ctx, &ctx->Q[0], nq))) return r;
+        if ((r = dalloc(ctx, &ctx->Q[1], nq))) return r;
+        if ((r = dalloc(ctx, &ctx->G, nq * p.D))) return r;
+        if ((r = dalloc(ctx, &ctx->Phi, (size_t)p.nf * p.U))) return r;
+        size_t nstage = std::max(nq * p.D, (size_t)p.nf * p.U);
+        if ((r = dalloc(ctx, &ctx->stage, nstage))) return r;
+        if ((r = dalloc(ctx, &ctx->resid, (size_t)8))) return r;
+        if ((r = dalloc(ctx, &ctx->nanflag, (size_t)1))) return r;
+        CK(cudaMemsetAsync(ctx->resid, 0, 8 * sizeof(unsigned long long), ctx->stream));
+        CK(cudaMemsetAsync(ctx->nanflag, 0, sizeof(int), ctx->stream));
+        CK(cudaMemsetAsync(ctx->G, 0, nq * p.D * sizeof(double), ctx->stream));
+        CK(cudaMemsetAsync(ctx->Phi, 0, (size_t)p.nf * p.U * sizeof(double), ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return MSTGPU_OK;
+    }();
+    if (rc != MSTGPU_OK) {
+        g_create_error = ctx->err;
+        mstgpu_destroy(ctx);
+        return rc;
+    }
+    // device config
+    DevCfg& d = ctx->dcfg;
+    d.gamma = cfg->gamma; d.gm1 = cfg->gamma - 1.0; d.delta = cfg->delta;
+    d.delta2 = cfg->delta * cfg->delta; d.inv2delta = 1.0 / (2.0 * cfg->delta); d.eor = cfg->eor;
+    d.astar_fac = 2.0 * (cfg->gamma - 1.0) / (cfg->gamma + 1.0);
+    d.mu = cfg->mu; d.lambda = -0.666667 * cfg->mu; d.kappa = cfg->kappa; d.cv = cfg->cv;
+    for (int k = 0; k < 5; k++) d.inletQ[k] = cfg->inletQ[k];
+    d.order = cfg->order; d.flux = cfg->flux; d.viscous = cfg->viscous; d.pad = 0;
+    // the big host tables are no longer needed
+    p.fc0 = {}; p.fc1 = {}; p.Sd = {}; p.dx0 = {}; p.dx1 = {}; p.eta = {}; p.meta = {}; p.vol = {}; p.cf = {};
+    *out = ctx;
+    return MSTGPU_OK;
+}
+
+void mstgpu_destroy(mstgpu_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    void* ptrs[] = {ctx->Q[0], ctx->Q[1], ctx->G, ctx->Phi, ctx->stage, ctx->Sd, ctx->dx0, ctx->dx1, ctx->eta,
+                    ctx->vol, ctx->fc0, ctx->fc1, ctx->cf, ctx->cell_new2old, ctx->face_new2old, ctx->meta,
+                    ctx->resid, ctx->nanflag};
+    for (void* q : ptrs)
+        if (q) cudaFree(q);
+    for (auto& pnd : ctx->pending) { cudaEventDestroy(pnd.second.first); cudaEventDestroy(pnd.second.second); }
+    for (auto e : ctx->evpool) cudaEventDestroy(e);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int mstgpu_set_state(mstgpu_ctx* ctx, const double* q, int64_t ncells) {
+    if (!ctx || !q) return MSTGPU_ERR_ARG;
+    if (ncells != ctx->nc) { set_error(ctx, "set_state: ncells mismatch"); return MSTGPU_ERR_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    const size_t tot = (size_t)ctx->nc * ctx->U;
+    CK(cudaMemcpyAsync(ctx->stage, q, tot * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    k_permute_in<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(ctx->nc, ctx->U, ctx->stage,
+                                                                         ctx->cell_new2old, ctx->Q[ctx->cur]);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    // prev state == current until the first step (Time.cpp:16-18 fills both)
+    CK(cudaMemcpyAsync(ctx->Q[ctx->cur ^ 1], ctx->Q[ctx->cur], tot * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->nanflag, 0, sizeof(int), ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->has_state = true;
+    return MSTGPU_OK;
+}
+
+int mstgpu_get_state(mstgpu_ctx* ctx, double* q) {
+    if (!ctx || !q) return MSTGPU_ERR_ARG;
+    if (!ctx->has_state) { set_error(ctx, "get_state before set_state"); return MSTGPU_ERR_STATE; }
+    CK(cudaSetDevice(ctx->device));
+    return fetch_permuted(ctx, ctx->Q[ctx->cur], ctx->cell_new2old, ctx->nc, ctx->U, q);
+}
+
+int mstgpu_get_prev_state(mstgpu_ctx* ctx, double* q) {
+    if (!ctx || !q) return MSTGPU_ERR_ARG;
+    if (!ctx->has_state) { set_error(ctx, "get_prev_state before set_state"); return MSTGPU_ERR_STATE; }
+    CK(cudaSetDevice(ctx->device));
+    return fetch_permuted(ctx, ctx->Q[ctx->cur ^ 1], ctx->cell_new2old, ctx->nc, ctx->U, q);
+}
+
+int mstgpu_step(mstgpu_ctx* ctx, double dt, int32_t nsteps) {
+    if (!ctx) return MSTGPU_ERR_ARG;
+    if (!ctx->has_state) { set_error(ctx, "step before set_state"); return MSTGPU_ERR_STATE; }
+    if (nsteps < 0) { set_error(ctx, "nsteps < 0"); return MSTGPU_ERR_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    int rc = (ctx->D == 2) ? step_impl<2>(ctx, dt, nsteps) : step_impl<3>(ctx, dt, nsteps);
+    if (ctx->ktiming) drain_timers(ctx);
+    return rc;
+}
+
+int mstgpu_step_timed(mstgpu_ctx* ctx, double dt, int32_t nsteps, float* ms) {
+    if (!ctx || !ms) return MSTGPU_ERR_ARG;
+    if (!ctx->has_state) { set_error(ctx, "step before set_state"); return MSTGPU_ERR_STATE; }
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    int rc = (ctx->D == 2) ? step_impl<2>(ctx, dt, nsteps) : step_impl<3>(ctx, dt, nsteps);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev1));
+    CK(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    if (ctx->ktiming) drain_timers(ctx);
+    return MSTGPU_OK;
+}
+
+int mstgpu_sync(mstgpu_ctx* ctx) {
+    if (!ctx) return MSTGPU_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MSTGPU_OK;
+}
+
+int mstgpu_residual_linf(mstgpu_ctx* ctx, double* out) {
+    if (!ctx || !out) return MSTGPU_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    unsigned long long bits[8];
+    int nan = 0;
+    CK(cudaMemcpyAsync(bits, ctx->resid, sizeof(bits), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&nan, ctx->nanflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < ctx->U; k++) std::memcpy(&out[k], &bits[k], 8);
+    if (nan) { set_error(ctx, "NaN in the state"); return MSTGPU_ERR_NAN; }
+    return MSTGPU_OK;
+}
+
+int mstgpu_debug_gradient(mstgpu_ctx* ctx, double* grad) {
+    if (!ctx || !grad) return MSTGPU_ERR_ARG;
+    if (ctx->cfg.order != 2 || !ctx->stepped) { set_error(ctx, "no gradient: order 1 or no step yet"); return MSTGPU_ERR_STATE; }
+    CK(cudaSetDevice(ctx->device));
+    return fetch_permuted(ctx, ctx->G, ctx->cell_new2old, ctx->nc, ctx->U * ctx->D, grad);
+}
+
+int mstgpu_debug_face_flux(mstgpu_ctx* ctx, double* phi) {
+    if (!ctx || !phi) return MSTGPU_ERR_ARG;
+    if (!ctx->stepped) { set_error(ctx, "no flux: no step yet"); return MSTGPU_ERR_STATE; }
+    CK(cudaSetDevice(ctx->device));
+    return fetch_permuted(ctx, ctx->Phi, ctx->face_new2old, ctx->nf, ctx->U, phi);
+}
+
+int64_t mstgpu_launch_count(mstgpu_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+int mstgpu_enable_kernel_timing(mstgpu_ctx* ctx, int32_t on) {
+    if (!ctx) return MSTGPU_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    drain_timers(ctx);
+    ctx->ktiming = on != 0;
+    ctx->kstat.clear();
+    return MSTGPU_OK;
+}
+
+int mstgpu_kernel_time(mstgpu_ctx* ctx, const char* name, double* ms, int64_t* launches) {
+    if (!ctx || !name) return MSTGPU_ERR_ARG;
+    auto it = ctx->kstat.find(name);
+    if (it == ctx->kstat.end()) { if (ms) *ms = 0; if (launches) *launches = 0; return MSTGPU_OK; }
+    if (ms) *ms = it->second.ms;
+    if (launches) *launches = it->second.launches;
+    return MSTGPU_OK;
+}
+
+int64_t mstgpu_device_bytes(mstgpu_ctx* ctx) { return ctx ? ctx->dev_bytes : -1; }
+
+int mstgpu_plan_permutation(const mstgpu_mesh* mesh, const mstgpu_config* cfg, int32_t* cell_new2old,
+                            int32_t* face_new2old) {
+    if (!mesh || !cfg) { set_error(nullptr, "null argument"); return MSTGPU_ERR_ARG; }
+    Plan p;
+    std::string perr = build_plan(*mesh, *cfg, p);
+    if (!perr.empty()) { set_error(nullptr, perr); return MSTGPU_ERR_ARG; }
+    if (cell_new2old) std::memcpy(cell_new2old, p.cell_new2old.data(), sizeof(int32_t) * p.nc);
+    if (face_new2old) std::memcpy(face_new2old, p.face_new2old.data(), sizeof(int32_t) * p.nf);
+    return MSTGPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,154 @@
+// plan.cpp -- see plan.h
+#include "plan.h"
+
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+namespace mst {
+
+namespace {
+
+inline uint64_t spread3(uint64_t x) {  // 21 bits -> every third bit
+    x &= 0x1fffffULL;
+    x = (x | x << 32) & 0x1f00000000ffffULL;
+    x = (x | x << 16) & 0x1f0000ff0000ffULL;
+    x = (x | x << 8) & 0x100f00f00f00f00fULL;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ULL;
+    x = (x | x << 2) & 0x1249249249249249ULL;
+    return x;
+}
+inline uint64_t spread2(uint64_t x) {  // 31 bits -> every second bit
+    x &= 0x7fffffffULL;
+    x = (x | x << 16) & 0x0000ffff0000ffffULL;
+    x = (x | x << 8) & 0x00ff00ff00ff00ffULL;
+    x = (x | x << 4) & 0x0f0f0f0f0f0f0f0fULL;
+    x = (x | x << 2) & 0x3333333333333333ULL;
+    x = (x | x << 1) & 0x5555555555555555ULL;
+    return x;
+}
+
+}  // namespace
+
+std::string build_plan(const mstgpu_mesh& m, const mstgpu_config& cfg, Plan& p) {
+    const int D = m.dim;
+    if (D != 2 && D != 3) return "dim must be 2 or 3";
+    if (m.ncells <= 0 || m.nfaces <= 0) return "empty mesh";
+    if (m.nint < 0 || m.nint > m.nfaces) return "nint out of range";
+    const int nc = m.ncells, nf = m.nfaces;
+    p.D = D; p.U = D + 2; p.nc = nc; p.nf = nf; p.nint = m.nint;
+
+    // ---- validate connectivity ------------------------------------------------
+    for (int f = 0; f < nf; f++) {
+        if (m.c0[f] < 0 || m.c0[f] >= nc) return "c0 out of range";
+        if (m.c1[f] >= nc) return "c1 out of range";
+        if (m.ftype[f] == MSTGPU_BC_INTERIOR && m.c1[f] < 0) return "interior face without c1";
+    }
+    int nslot = 0;
+    for (int c = 0; c < nc; c++) nslot = std::max(nslot, m.cf_ptr[c + 1] - m.cf_ptr[c]);
+    if (nslot <= 0 || nslot > 8) return "cells must have 1..8 faces";
+    p.nslot = nslot;
+
+    // ---- cell order: Morton curve through the cell centres ----------------------
+    p.cell_new2old.resize(nc);
+    std::iota(p.cell_new2old.begin(), p.cell_new2old.end(), 0);
+    if (cfg.renumber != 0) {
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        for (int c = 0; c < nc; c++)
+            for (int d = 0; d < D; d++) {
+                double x = m.cc[(size_t)c * D + d];
+                if (x == x) { lo[d] = std::min(lo[d], x); hi[d] = std::max(hi[d], x); }
+            }
+        const double bits = (D == 3) ? 2097151.0 : 2147483647.0;
+        double sc[3];
+        for (int d = 0; d < D; d++) sc[d] = (hi[d] > lo[d]) ? bits / (hi[d] - lo[d]) : 0.0;
+        std::vector<std::pair<uint64_t, int32_t>> key(nc);
+#pragma omp parallel for schedule(static)
+        for (int c = 0; c < nc; c++) {
+            uint64_t k = 0;
+            for (int d = 0; d < D; d++) {
+                double x = m.cc[(size_t)c * D + d];
+                double t = (x == x) ? (x - lo[d]) * sc[d] : 0.0;
+                uint64_t q = (uint64_t)std::min(std::max(t, 0.0), bits);
+                k |= (D == 3 ? spread3(q) : spread2(q)) << d;
+            }
+            key[c] = {k, c};
+        }
+        std::sort(key.begin(), key.end());
+        for (int i = 0; i < nc; i++) p.cell_new2old[i] = key[i].second;
+    }
+    p.cell_old2new.resize(nc);
+    for (int i = 0; i < nc; i++) p.cell_old2new[p.cell_new2old[i]] = i;
+
+    // ---- face order: interior by (lower new cell, higher new cell), then boundary
+    {
+        std::vector<std::pair<uint64_t, int32_t>> key(nf);
+#pragma omp parallel for schedule(static)
+        for (int f = 0; f < nf; f++) {
+            uint64_t a = (uint64_t)p.cell_old2new[m.c0[f]];
+            uint64_t k;
+            if (m.c1[f] >= 0 && m.ftype[f] == MSTGPU_BC_INTERIOR) {
+                uint64_t b = (uint64_t)p.cell_old2new[m.c1[f]];
+                k = (std::min(a, b) << 31) | std::max(a, b);
+            } else {
+                k = (1ULL << 62) | (a << 8) | (uint64_t)(m.ftype[f] & 0xff);
+            }
+            key[f] = {k, f};
+        }
+        if (cfg.renumber != 0) std::sort(key.begin(), key.end());
+        else std::stable_sort(key.begin(), key.end(),
+                              [](const auto& x, const auto& y) { return (x.first >> 62) < (y.first >> 62); });
+        p.face_new2old.resize(nf);
+        p.face_old2new.resize(nf);
+        for (int i = 0; i < nf; i++) {
+            p.face_new2old[i] = key[i].second;
+            p.face_old2new[key[i].second] = i;
+        }
+    }
+
+    // ---- per-face records -------------------------------------------------------
+    int qf_from = cfg.qf_copy_from < 0 ? m.nint - 1 : cfg.qf_copy_from;
+    p.fc0.resize(nf); p.fc1.resize(nf);
+    p.Sd.resize((size_t)nf * D); p.dx0.resize((size_t)nf * D); p.dx1.assign((size_t)nf * D, 0.0);
+    p.eta.resize(nf); p.meta.resize(nf);
+    int nint_new = 0;
+#pragma omp parallel for schedule(static) reduction(+ : nint_new)
+    for (int i = 0; i < nf; i++) {
+        const int f = p.face_new2old[i];
+        const int a = m.c0[f], b = m.c1[f];
+        const bool interior = (b >= 0 && m.ftype[f] == MSTGPU_BC_INTERIOR);
+        p.fc0[i] = p.cell_old2new[a];
+        p.fc1[i] = interior ? p.cell_old2new[b] : -1;
+        uint32_t fl = 0;
+        for (int d = 0; d < D; d++) {
+            p.Sd[(size_t)i * D + d] = (double)m.dac[f] * m.S[(size_t)f * D + d];
+            p.dx0[(size_t)i * D + d] = m.fc[(size_t)f * D + d] - m.cc[(size_t)a * D + d];
+            if (interior) p.dx1[(size_t)i * D + d] = m.fc[(size_t)f * D + d] - m.cc[(size_t)b * D + d];
+            if (m.flag[(size_t)f * D + d]) fl |= 1u << d;
+        }
+        // Qf = eta Q[c0] + (1-eta) Q[c1] below qf_from, Q[c0] from there on
+        // (RhoSolver.cpp:434-440, including the off-by-one at nint-1)
+        p.eta[i] = (f >= qf_from || !interior) ? 1.0 : m.eta[f];
+        p.meta[i] = (uint32_t)(m.ftype[f] & 0xff) | (fl << 8);
+        nint_new += interior ? 1 : 0;
+    }
+    (void)nint_new;
+
+    // ---- per-cell tables --------------------------------------------------------
+    p.vol.resize(nc);
+    p.cf.assign((size_t)nslot * nc, -1);
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < nc; i++) {
+        const int c = p.cell_new2old[i];
+        p.vol[i] = m.vol[c];
+        int j = 0;
+        for (int k = m.cf_ptr[c]; k < m.cf_ptr[c + 1]; k++, j++) {
+            const int f = m.cf_idx[k];
+            const int side = (m.c0[f] == c) ? 0 : 1;
+            p.cf[(size_t)j * nc + i] = 2 * p.face_old2new[f] + side;
+        }
+    }
+    return "";
+}
+
+}  // namespace mst

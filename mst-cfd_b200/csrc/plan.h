@@ -1,0 +1,47 @@
+// plan.h -- host-side layout plan: reference-order mesh tables -> renumbered,
+// device-ready tables.  Built once in mstgpu_create().
+//
+// Input is exactly what the reference's mesh getters expose (include/mstgpu.h,
+// mstgpu_mesh).  Output:
+//   * cells renumbered along a Morton (Z-order) curve through the cell centres,
+//     so that face neighbours are close in memory and any contiguous index
+//     range is a compact blob (tiles, partitions);
+//   * faces renumbered so that faces of consecutive cells are consecutive
+//     (interior faces first, sorted by their lower cell; boundary faces after);
+//   * per-cell face lists in ELL form, [slot][cell], keeping each cell's own
+//     face ORDER (the reference's file order, R/mesh/MshBlock.cpp:238-239,
+//     254-255) so the gather sums in the reference's sequence;
+//   * per-face records with everything the flux needs precomputed bit-for-bit
+//     as the reference would compute it at run time: Sd = dac*S (outward from
+//     c0, MshBlock.cpp:307-318), dx0 = fc - cc[c0], dx1 = fc - cc[c1]
+//     (RhoSolver.cpp:250), eta with the off-by-one of RhoSolver.cpp:438 folded
+//     in, zone type and left/right flags packed in one word.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/mstgpu.h"
+
+namespace mst {
+
+struct Plan {
+    int D = 0, U = 0;
+    int nc = 0, nf = 0, nint = 0, nslot = 0;
+    std::vector<int32_t> cell_new2old, cell_old2new;
+    std::vector<int32_t> face_new2old, face_old2new;
+    // faces (new order)
+    std::vector<int32_t> fc0, fc1;  // new cell ids, fc1 = -1 on boundary faces
+    std::vector<double> Sd;         // [nf*D]
+    std::vector<double> dx0, dx1;   // [nf*D]
+    std::vector<double> eta;        // [nf]   effective eta (1 where Qf = Q[c0])
+    std::vector<uint32_t> meta;     // [nf]   type | flags << 8
+    // cells (new order)
+    std::vector<double> vol;        // [nc]
+    std::vector<int32_t> cf;        // [nslot*nc] 2*face + side (side 1: cell is c1), -1 = pad
+};
+
+// returns empty string on success, error text otherwise
+std::string build_plan(const mstgpu_mesh& m, const mstgpu_config& cfg, Plan& p);
+
+}  // namespace mst

@@ -1,0 +1,271 @@
+"""mstgpu -- ctypes binding of the C ABI in include/mstgpu.h (libmstgpu.so).
+
+This is the thinnest possible host layer: the same calls a cgo/JNI/C++ host
+would make.  `GpuRhoSolver` mirrors the reference's seven-method solver
+interface (R/rhoSolver/RhoSolver.h:17-24) so tests read like the reference's
+call sequence in R/time/Time.cpp:54-81.
+
+There is no CPU fallback: importing works without a GPU (the library loads and
+its symbols resolve), but every compute entry point returns an error when no
+CUDA device is usable, and a missing libmstgpu.so raises at import.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+LIB_PATH = os.path.join(_ROOT, "libmstgpu.so")
+
+EXPORTS = [
+    "mstgpu_default_config", "mstgpu_create", "mstgpu_destroy", "mstgpu_set_state",
+    "mstgpu_get_state", "mstgpu_get_prev_state", "mstgpu_step", "mstgpu_step_timed",
+    "mstgpu_residual_linf", "mstgpu_sync", "mstgpu_debug_gradient", "mstgpu_debug_face_flux",
+    "mstgpu_launch_count", "mstgpu_enable_kernel_timing", "mstgpu_kernel_time",
+    "mstgpu_device_bytes", "mstgpu_plan_permutation", "mstgpu_last_error", "mstgpu_version",
+]
+
+
+class MstMesh(C.Structure):
+    _fields_ = [
+        ("dim", C.c_int32), ("ncells", C.c_int32), ("nfaces", C.c_int32), ("nint", C.c_int32),
+        ("c0", C.c_void_p), ("c1", C.c_void_p), ("S", C.c_void_p), ("dac", C.c_void_p),
+        ("fc", C.c_void_p), ("eta", C.c_void_p), ("flag", C.c_void_p), ("ftype", C.c_void_p),
+        ("cc", C.c_void_p), ("vol", C.c_void_p), ("cf_ptr", C.c_void_p), ("cf_idx", C.c_void_p),
+    ]
+
+
+class MstConfig(C.Structure):
+    _fields_ = [
+        ("order", C.c_int32), ("flux", C.c_int32), ("viscous", C.c_int32),
+        ("qf_copy_from", C.c_int32), ("renumber", C.c_int32), ("device", C.c_int32),
+        ("gamma", C.c_double), ("delta", C.c_double), ("eor", C.c_double),
+        ("mu", C.c_double), ("kappa", C.c_double), ("cv", C.c_double),
+        ("inletQ", C.c_double * 5),
+    ]
+
+
+class MstGpuError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load libmstgpu.so.  Raises if the CUDA extension has not been built --
+    the product path has no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MstGpuError(
+                f"{LIB_PATH} is missing: build it with `make -C mst-cfd_b200` "
+                "(or __graft_entry__.build()); there is no CPU fallback"
+            )
+        L = C.CDLL(LIB_PATH)
+        vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+        L.mstgpu_default_config.argtypes = [C.POINTER(MstConfig), i32]
+        L.mstgpu_default_config.restype = None
+        L.mstgpu_create.argtypes = [C.POINTER(vp), C.POINTER(MstMesh), C.POINTER(MstConfig)]
+        L.mstgpu_destroy.argtypes = [vp]
+        L.mstgpu_destroy.restype = None
+        L.mstgpu_set_state.argtypes = [vp, vp, i64]
+        L.mstgpu_get_state.argtypes = [vp, vp]
+        L.mstgpu_get_prev_state.argtypes = [vp, vp]
+        L.mstgpu_step.argtypes = [vp, dbl, i32]
+        L.mstgpu_step_timed.argtypes = [vp, dbl, i32, C.POINTER(C.c_float)]
+        L.mstgpu_residual_linf.argtypes = [vp, vp]
+        L.mstgpu_sync.argtypes = [vp]
+        L.mstgpu_debug_gradient.argtypes = [vp, vp]
+        L.mstgpu_debug_face_flux.argtypes = [vp, vp]
+        L.mstgpu_launch_count.argtypes = [vp]
+        L.mstgpu_launch_count.restype = i64
+        L.mstgpu_enable_kernel_timing.argtypes = [vp, i32]
+        L.mstgpu_kernel_time.argtypes = [vp, C.c_char_p, C.POINTER(dbl), C.POINTER(i64)]
+        L.mstgpu_device_bytes.argtypes = [vp]
+        L.mstgpu_device_bytes.restype = i64
+        L.mstgpu_plan_permutation.argtypes = [C.POINTER(MstMesh), C.POINTER(MstConfig), vp, vp]
+        L.mstgpu_last_error.argtypes = [vp]
+        L.mstgpu_last_error.restype = C.c_char_p
+        L.mstgpu_version.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+_MESH_SPEC = dict(c0=np.int32, c1=np.int32, S=np.float64, dac=np.int8, fc=np.float64,
+                  eta=np.float64, flag=np.uint8, ftype=np.int32, cc=np.float64,
+                  vol=np.float64, cf_ptr=np.int32, cf_idx=np.int32)
+
+
+def default_config(dim: int) -> MstConfig:
+    cfg = MstConfig()
+    lib().mstgpu_default_config(C.byref(cfg), dim)
+    return cfg
+
+
+def _mesh_struct(flat: dict):
+    m = MstMesh()
+    m.dim, m.ncells, m.nfaces, m.nint = int(flat["dim"]), int(flat["ncells"]), int(flat["nfaces"]), int(flat["nint"])
+    keep = {}
+    for k, dt in _MESH_SPEC.items():
+        a = np.ascontiguousarray(flat[k], dtype=dt)
+        keep[k] = a
+        setattr(m, k, a.ctypes.data)
+    return m, keep
+
+
+def plan_permutation(flat: dict, renumber: int = 1):
+    """(cell_new2old, face_new2old) that mstgpu_create would use; host only."""
+    m, keep = _mesh_struct(flat)
+    cfg = default_config(int(flat["dim"]))
+    cfg.renumber = renumber
+    c = np.empty(int(flat["ncells"]), dtype=np.int32)
+    f = np.empty(int(flat["nfaces"]), dtype=np.int32)
+    rc = lib().mstgpu_plan_permutation(C.byref(m), C.byref(cfg), c.ctypes.data, f.ctypes.data)
+    if rc != 0:
+        raise MstGpuError(f"plan_permutation failed ({rc}): {lib().mstgpu_last_error(None).decode()}")
+    return c, f
+
+
+class Context:
+    """Owns one mstgpu_ctx.  `flat` is the flattened reference-order mesh (the
+    dict produced by the host's mesh flattener)."""
+
+    def __init__(self, flat: dict, order=2, flux="roe", viscous=0, qf_copy_from=None,
+                 renumber=1, device=-1, inletQ=None, **consts):
+        L = lib()
+        self.dim = int(flat["dim"])
+        self.U = self.dim + 2
+        self.ncells = int(flat["ncells"])
+        self.nfaces = int(flat["nfaces"])
+        m, keep = _mesh_struct(flat)
+        cfg = default_config(self.dim)
+        cfg.order = order
+        cfg.flux = {"roe": 0, "ausm": 1}[flux] if isinstance(flux, str) else int(flux)
+        cfg.viscous = viscous
+        cfg.qf_copy_from = -1 if qf_copy_from is None else qf_copy_from
+        cfg.renumber = renumber
+        cfg.device = device
+        for k, v in consts.items():
+            setattr(cfg, k, v)
+        if inletQ is not None:
+            for k in range(5):
+                cfg.inletQ[k] = float(inletQ[k]) if k < len(inletQ) else 0.0
+        self.cfg = cfg
+        h = C.c_void_p()
+        rc = L.mstgpu_create(C.byref(h), C.byref(m), C.byref(cfg))
+        if rc != 0:
+            raise MstGpuError(f"mstgpu_create failed ({rc}): {L.mstgpu_last_error(None).decode()}")
+        self.h = h
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise MstGpuError(f"{what} failed ({rc}): {lib().mstgpu_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().mstgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_state(self, Q):
+        Q = np.ascontiguousarray(Q, dtype=np.float64)
+        assert Q.shape == (self.ncells, self.U)
+        self._check(lib().mstgpu_set_state(self.h, Q.ctypes.data, self.ncells), "set_state")
+
+    def set_state_ptr(self, ptr: int):
+        self._check(lib().mstgpu_set_state(self.h, ptr, self.ncells), "set_state")
+
+    def get_state(self, out=None):
+        out = np.empty((self.ncells, self.U)) if out is None else out
+        self._check(lib().mstgpu_get_state(self.h, out.ctypes.data), "get_state")
+        return out
+
+    def get_state_ptr(self, ptr: int):
+        self._check(lib().mstgpu_get_state(self.h, ptr), "get_state")
+
+    def get_prev_state(self):
+        out = np.empty((self.ncells, self.U))
+        self._check(lib().mstgpu_get_prev_state(self.h, out.ctypes.data), "get_prev_state")
+        return out
+
+    def step(self, dt: float, nsteps: int = 1):
+        self._check(lib().mstgpu_step(self.h, dt, nsteps), "step")
+
+    def step_timed(self, dt: float, nsteps: int = 1) -> float:
+        ms = C.c_float()
+        self._check(lib().mstgpu_step_timed(self.h, dt, nsteps, C.byref(ms)), "step_timed")
+        return float(ms.value)
+
+    def residual(self):
+        out = np.empty(self.U)
+        self._check(lib().mstgpu_residual_linf(self.h, out.ctypes.data), "residual_linf")
+        return out
+
+    def sync(self):
+        self._check(lib().mstgpu_sync(self.h), "sync")
+
+    def debug_gradient(self):
+        out = np.empty((self.ncells, self.U, self.dim))
+        self._check(lib().mstgpu_debug_gradient(self.h, out.ctypes.data), "debug_gradient")
+        return out
+
+    def debug_face_flux(self):
+        out = np.empty((self.nfaces, self.U))
+        self._check(lib().mstgpu_debug_face_flux(self.h, out.ctypes.data), "debug_face_flux")
+        return out
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().mstgpu_launch_count(self.h))
+
+    @property
+    def device_bytes(self) -> int:
+        return int(lib().mstgpu_device_bytes(self.h))
+
+    def enable_kernel_timing(self, on=True):
+        self._check(lib().mstgpu_enable_kernel_timing(self.h, 1 if on else 0), "enable_kernel_timing")
+
+    def kernel_time(self, name: str):
+        ms, n = C.c_double(), C.c_int64()
+        self._check(lib().mstgpu_kernel_time(self.h, name.encode(), C.byref(ms), C.byref(n)), "kernel_time")
+        return float(ms.value), int(n.value)
+
+
+class GpuRhoSolver:
+    """Python mirror of the reference's solver duck type
+    (R/rhoSolver/RhoSolver.h:17-24; PSolver has the same shape).  The reference
+    constructs the solver every step (R/time/Time.cpp:58); here the heavy
+    context is built once and handed in, the object itself is cheap."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        self.DT = None
+
+    def setDT(self, dt: float):  # RhoSolver.cpp:33-35
+        self.DT = float(dt)
+
+    def solve(self):  # RhoSolver.cpp:37-89 (+ pointer swap; see updateNewToOld)
+        if self.DT is None:
+            raise MstGpuError("solve() before setDT()")
+        self.ctx.step(self.DT, 1)
+
+    def getNewValue(self):  # RhoSolver.cpp:507-509
+        return self.ctx.get_state()
+
+    def getOldValue(self):  # RhoSolver.cpp:504-506 (as seen before updateNewToOld)
+        return self.ctx.get_prev_state()
+
+    def getOldNTimeValue(self):  # RhoSolver.cpp:510-512 (pseudo-time off: same as old)
+        return self.ctx.get_prev_state()
+
+    def updateNewToOld(self):  # RhoSolver.cpp:513-517: already a pointer swap on the device
+        return None

@@ -1,0 +1,88 @@
+"""CPU suite, part 2: the C-ABI boundary without a GPU -- the shared library
+loads, exports every symbol include/mstgpu.h declares, fails loudly when no
+CUDA device exists, and its host-side plan (renumbering) is a valid, locality-
+improving permutation."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, STEP_MESHES, have_gpu, load_flat, box_flat
+import mstgpu
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "mstgpu.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(mstgpu_[a-z_0-9]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = mstgpu.lib()
+    names = _declared_symbols()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/mstgpu.h but not exported"
+    assert set(mstgpu.EXPORTS) == set(names)
+
+
+def test_version_and_default_config():
+    assert b"sm_100a" in mstgpu.lib().mstgpu_version()
+    c = mstgpu.default_config(2)
+    # R/include/CONST.h:38-48, SolverRoe.cpp:115
+    assert (c.order, c.flux, c.viscous, c.renumber) == (2, 0, 0, 1)
+    assert (c.gamma, c.delta, c.eor, c.cv) == (1.4, 0.125, 1e-10, 715.8)
+    assert c.inletQ[0] == 1.0 and c.inletQ[1] == 0.0 and abs(c.inletQ[3] - 2.5) < 1e-12
+    c3 = mstgpu.default_config(3)
+    assert c3.inletQ[3] == 0.0 and abs(c3.inletQ[4] - 2.5) < 1e-12
+
+
+def test_struct_layout_matches_header():
+    # 4 int32 + 12 pointers; 6 int32 + 6 doubles + 5 doubles
+    assert C.sizeof(mstgpu.MstMesh) == 16 + 12 * 8
+    assert C.sizeof(mstgpu.MstConfig) == 24 + 11 * 8
+
+
+@pytest.mark.skipif(have_gpu(), reason="checks the no-GPU failure mode")
+def test_compute_fails_loudly_without_gpu():
+    f = load_flat("2d-stair-un-5-tri")
+    with pytest.raises(mstgpu.MstGpuError, match="CUDA"):
+        mstgpu.Context(f)
+
+
+def test_bad_arguments_are_rejected_before_touching_the_gpu():
+    f = dict(load_flat("2d-stair-un-5-tri"))
+    bad = dict(f); bad["dim"] = 4
+    with pytest.raises(mstgpu.MstGpuError):
+        mstgpu.plan_permutation(bad)
+    bad = dict(f); c0 = f["c0"].copy(); c0[3] = f["ncells"] + 5; bad["c0"] = c0
+    with pytest.raises(mstgpu.MstGpuError, match="c0 out of range"):
+        mstgpu.plan_permutation(bad)
+    with pytest.raises(mstgpu.MstGpuError):
+        mstgpu.Context(f, order=3)
+
+
+def _mean_neighbour_distance(f, perm):
+    inv = np.empty_like(perm); inv[perm] = np.arange(perm.size, dtype=perm.dtype)
+    i = f["c1"] >= 0
+    return np.abs(inv[f["c0"][i]].astype(np.int64) - inv[f["c1"][i]]).mean()
+
+
+@pytest.mark.parametrize("name", ["2d-shockwavepipe-2", "2d-stairW-1", "box"])
+def test_plan_is_a_locality_improving_permutation(name):
+    f = box_flat(12, 12, 12) if name == "box" else load_flat(name)
+    cp, fp = mstgpu.plan_permutation(f, 1)
+    assert np.array_equal(np.sort(cp), np.arange(f["ncells"]))
+    assert np.array_equal(np.sort(fp), np.arange(f["nfaces"]))
+    # interior faces stay in front of boundary faces
+    nint = int((f["c1"] >= 0).sum())
+    assert (f["c1"][fp[:nint]] >= 0).all() and (f["c1"][fp[nint:]] < 0).all()
+    ident = np.arange(f["ncells"], dtype=np.int32)
+    d_new, d_old = _mean_neighbour_distance(f, cp), _mean_neighbour_distance(f, ident)
+    if name != "box":
+        assert d_new < 0.5 * d_old, (d_new, d_old)
+    # renumber = 0 keeps the reference order
+    cp0, fp0 = mstgpu.plan_permutation(f, 0)
+    assert np.array_equal(cp0, ident)

@@ -1,0 +1,205 @@
+"""GPU suite: the CUDA path, called through the C ABI, against the CPU oracle on
+the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): relative L-inf on the conserved
+variables <= 1e-12 after one step and <= 1e-9 after 1000 steps in FP64, plus
+identical shock location on SOD.  "Relative" = per variable, against the
+characteristic scale defined in conftest.char_scales.
+"""
+import numpy as np
+import pytest
+
+from conftest import STEP_MESHES, load_flat, box_flat, rel_linf, char_scales
+from oracle import mesh_np, oracle
+import mstgpu
+
+pytestmark = pytest.mark.gpu
+
+TOL_1STEP = 1e-12
+TOL_1000 = 1e-9
+DT_SOD = 1.0 / 4e3
+
+
+def _run_pair(f, Q0, dt, nsteps, **kw):
+    o = oracle.Oracle(f, **kw)
+    Qo = o.run(dt, nsteps, Q0)
+    g = mstgpu.Context(f, **kw)
+    g.set_state(Q0)
+    g.step(dt, nsteps)
+    Qg = g.get_state()
+    return o, g, Qo, Qg
+
+
+@pytest.mark.parametrize("name", STEP_MESHES)
+@pytest.mark.parametrize("flux", ["roe", "ausm"])
+@pytest.mark.parametrize("order", [1, 2])
+def test_one_step_random_state(name, flux, order):
+    """Stress input of SURVEY.md 8d: |M| > 1 both signs -> entropy fix, AUSM
+    quirk branches, every boundary type of the mesh."""
+    f = load_flat(name)
+    Q0 = mesh_np.random_state(f)
+    o, g, Qo, Qg = _run_pair(f, Q0, 1e-4, 1, flux=flux, order=order)
+    assert rel_linf(Qg, Qo) <= TOL_1STEP
+    # stage probes: gradient and contracted face flux
+    Qf, G, F = o.probe()
+    phi_ref = np.einsum("fd,fdk->fk", f["dac"][:, None] * f["S"], F)
+    phi = g.debug_face_flux()
+    assert np.abs(phi - phi_ref).max() <= 1e-13 * np.abs(phi_ref).max()
+    if order == 2:
+        Gg = g.debug_gradient()
+        assert np.abs(Gg - G).max() <= 1e-13 * np.abs(G).max()
+    # residual (Time.cpp:69-76)
+    ro = np.zeros(4)
+    x = np.abs(Qo - Q0) / Q0
+    ro = np.nanmax(np.where(x > 0, x, 0), axis=0)
+    rg = g.residual()
+    assert np.allclose(rg, ro, rtol=1e-9, atol=0)
+
+
+@pytest.mark.parametrize("flux", ["roe", "ausm"])
+def test_one_step_as_shipped_flags(flux):
+    """The kernels take the flag table verbatim: parity holds under the
+    reference's as-shipped (inverted) convention too."""
+    f = load_flat("2d-stairW-1", "as_shipped")
+    Q0 = mesh_np.random_state(f, seed=7)
+    _, _, Qo, Qg = _run_pair(f, Q0, 1e-4, 1, flux=flux, order=2)
+    assert rel_linf(Qg, Qo) <= TOL_1STEP
+
+
+def test_off_by_one_and_its_correction():
+    f = load_flat("2d-stair-un-5-tri")
+    Q0 = mesh_np.random_state(f, seed=11)
+    for qf in (None, f["nint"]):
+        _, _, Qo, Qg = _run_pair(f, Q0, 1e-4, 1, order=2, qf_copy_from=qf)
+        assert rel_linf(Qg, Qo) <= TOL_1STEP
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_sod_1000_steps(order):
+    """BASELINE config 1: SOD tube, Roe, explicit, DT = 2.5e-4."""
+    f = load_flat("2d-shockwavepipe-2")
+    Q0 = mesh_np.sod_initial_state(f)
+    o = oracle.Oracle(f, order=order, flux="roe")
+    g = mstgpu.Context(f, order=order, flux="roe")
+    g.set_state(Q0)
+    Qo = Q0
+    for n in (1, 9, 390, 600):  # checkpoints at 1, 10, 400, 1000 steps
+        Qo = o.run(DT_SOD, n, Qo)
+        g.step(DT_SOD, n)
+        Qg = g.get_state()
+        err = rel_linf(Qg, Qo)
+        assert err <= (TOL_1STEP if n == 1 else TOL_1000), (n, err)
+    # identical shock location: same cell carries the steepest density drop
+    x = f["cc"][:, 0]
+    band = np.abs(f["cc"][:, 1] - f["cc"][:, 1].mean()) < 0.02
+    idx = np.nonzero(band)[0][np.argsort(x[band])]
+    jo = np.argmax(-np.diff(Qo[idx, 0]) * (x[idx][1:] > 0.6))
+    jg = np.argmax(-np.diff(Qg[idx, 0]) * (x[idx][1:] > 0.6))
+    assert jo == jg
+
+
+@pytest.mark.parametrize("flux", ["roe", "ausm"])
+def test_forward_step_ausm_and_roe_50_steps(flux):
+    """Inlet 10 / outlet 5 / wall 3 mesh with a Mach-3 inlet (BASELINE config 2
+    physics on the reference's own stair mesh)."""
+    f = load_flat("2d-stair-un-3-tri")
+    u = 3.0 * np.sqrt(1.4)
+    inlet = np.array([1.0, u, 0.0, 1.0 / 0.4 + 0.5 * u * u, 0.0])
+    Q0 = np.tile(inlet[:4], (f["ncells"], 1))
+    o = oracle.Oracle(f, order=1, flux=flux, inletQ=inlet)
+    g = mstgpu.Context(f, order=1, flux=flux, inletQ=inlet)
+    g.set_state(Q0)
+    Qo = o.run(2e-5, 50, Q0)
+    g.step(2e-5, 50)
+    assert np.isfinite(Qo).all()
+    assert rel_linf(g.get_state(), Qo) <= 1e-10
+
+
+@pytest.mark.parametrize("flux", ["roe", "ausm"])
+@pytest.mark.parametrize("order", [1, 2])
+def test_3d_tets_one_step_and_20_steps(flux, order):
+    """3-D extension (parity unpinned against the reference): GPU
+    vs oracle on a Kuhn-split box with all boundary types."""
+    f = box_flat(6, 5, 4, bc=(10, 5, 3, 7, 3, 3), l=(1.0, 0.8, 0.6))
+    Q0 = mesh_np.random_state(f, seed=3)
+    inlet = np.array([1.0, 0.4, 0.0, 0.0, 2.58])
+    o = oracle.Oracle(f, order=order, flux=flux, inletQ=inlet)
+    g = mstgpu.Context(f, order=order, flux=flux, inletQ=inlet)
+    g.set_state(Q0)
+    Q1 = o.run(1e-4, 1, Q0)
+    g.step(1e-4, 1)
+    assert rel_linf(g.get_state(), Q1) <= TOL_1STEP
+    Q20 = o.run(1e-4, 19, Q1)
+    g.step(1e-4, 19)
+    assert rel_linf(g.get_state(), Q20) <= 1e-10
+
+
+def test_renumbering_does_not_change_the_bits():
+    """Per-cell arithmetic is independent of the memory order: Morton-renumbered
+    and reference-ordered runs agree bit for bit; two runs are bit-identical
+    (no atomics on floating-point data)."""
+    f = load_flat("2d-stairW-1")
+    Q0 = mesh_np.random_state(f, seed=5)
+    outs = []
+    for ren in (1, 0, 1):
+        g = mstgpu.Context(f, order=2, flux="roe", renumber=ren)
+        g.set_state(Q0)
+        g.step(1e-4, 25)
+        outs.append(g.get_state())
+    assert np.array_equal(outs[0], outs[2])
+    assert np.array_equal(outs[0], outs[1])
+
+
+def test_state_roundtrip_and_solver_interface():
+    """set_state/get_state are exact; GpuRhoSolver mirrors the 7-method duck
+    type of R/rhoSolver/RhoSolver.h:17-24 in the order Time.cpp:58-80 uses it."""
+    f = load_flat("2d-stair-un-4-tri")
+    Q0 = mesh_np.random_state(f, seed=9)
+    ctx = mstgpu.Context(f, order=2, flux="roe")
+    ctx.set_state(Q0)
+    assert np.array_equal(ctx.get_state(), Q0)
+    s = mstgpu.GpuRhoSolver(ctx)
+    s.setDT(1e-4)
+    s.solve()
+    old, new = s.getOldValue(), s.getNewValue()
+    s.updateNewToOld()
+    assert np.array_equal(old, Q0)
+    Qo = oracle.Oracle(f, order=2, flux="roe").solve(1e-4, Q0)
+    assert rel_linf(new, Qo) <= TOL_1STEP
+    assert ctx.launch_count >= 3
+
+
+def test_api_errors():
+    f = load_flat("2d-stair-un-5-tri")
+    ctx = mstgpu.Context(f)
+    with pytest.raises(mstgpu.MstGpuError, match="before set_state"):
+        ctx.step(1e-4, 1)
+    rc = mstgpu.lib().mstgpu_set_state(ctx.h, np.zeros(8).ctypes.data, 2)
+    assert rc == -1
+    # a NaN state is reported, not hidden (failure detection)
+    Q = mesh_np.random_state(f); Q[17, 0] = np.nan
+    ctx.set_state(Q)
+    ctx.step(1e-4, 1)
+    with pytest.raises(mstgpu.MstGpuError, match="NaN"):
+        ctx.residual()
+
+
+def test_large_box_properties():
+    """Size-independent properties at a size the oracle does not need to run:
+    fluid at rest stays at rest, mass/energy are conserved in a closed box,
+    free-stream is preserved in the interior (1.3 M tets)."""
+    f = box_flat(60, 60, 60)
+    n = f["ncells"]
+    ctx = mstgpu.Context(f, order=2, flux="roe")
+    Q = np.zeros((n, 5)); Q[:, 0] = 1.0; Q[:, 4] = 2.5
+    ctx.set_state(Q); ctx.step(1e-4, 3)
+    assert np.abs(ctx.get_state() - Q).max() < 1e-12
+    x = f["cc"]
+    Q[:, 0] += 0.1 * np.sin(2 * np.pi * x[:, 0]) * np.sin(2 * np.pi * x[:, 1]) * np.sin(2 * np.pi * x[:, 2])
+    Q[x[:, 0] > 0.5, 4] *= 0.5
+    ctx.set_state(Q); ctx.step(1e-4, 10)
+    Qn = ctx.get_state()
+    V = f["vol"]
+    for k in (0, 4):
+        assert abs((V * Qn[:, k]).sum() - (V * Q[:, k]).sum()) < 1e-12 * (V * Q[:, k]).sum()
+    assert np.isfinite(Qn).all()
