@@ -60,13 +60,16 @@ def build_workload(args):
         f = host.flatten_raw(raw)
         x = f["cc"]
         Q = np.zeros((f["ncells"], 5))
-        pert = 1e-2 * np.sin(2 * np.pi * x[:, 0]) * np.sin(2 * np.pi * x[:, 1]) * np.sin(2 * np.pi * x[:, 2])
-        right = x[:, 0] > 0.5
-        rho = np.where(right, 0.125, 1.0) + pert
-        p = np.where(right, 0.1, 1.0) + pert
-        Q[:, 0] = rho
-        Q[:, 4] = p / 0.4
-        desc = f"unit-cube {n}^3 hexes x 6 Kuhn tets, Roe, 2nd order, explicit, all walls"
+        # Smooth acoustic initial state (every face carries a jump).  SURVEY.md 8d
+        # proposed a SOD split + perturbation; the reference scheme has no
+        # limiter and that state goes NaN within ~15 steps on Kuhn tets at any
+        # DT (measured, DESIGN.md "Measurement"), so the bench uses the smooth
+        # part only -- arithmetic per face is the same.
+        pert = 0.1 * np.sin(2 * np.pi * x[:, 0]) * np.sin(2 * np.pi * x[:, 1]) * np.sin(2 * np.pi * x[:, 2])
+        Q[:, 0] = 1.0 + pert
+        Q[:, 4] = (1.0 + pert) / 0.4
+        desc = (f"unit-cube {n}^3 hexes x 6 Kuhn tets, Roe, 2nd order, explicit, all walls, "
+                "smooth acoustic init rho=p=1+0.1*sin*sin*sin")
     elif args.workload == "step":
         raw = host.forward_step_raw(args.n)
         f = host.flatten_raw(raw)

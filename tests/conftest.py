@@ -66,11 +66,13 @@ def char_scales(Q, gamma=1.4):
     D = Q.shape[1] - 2
     rho = Q[:, 0]
     m2 = (Q[:, 1:1 + D] ** 2).sum(1)
-    p = np.maximum((Q[:, -1] - 0.5 * m2 / rho) * (gamma - 1), 0)
-    a = np.sqrt(gamma * p / rho)
+    # |.|: an unlimited 2nd-order step from a random state may leave p or rho
+    # negative in a few cells; the scale only needs the order of magnitude
+    p = np.abs((Q[:, -1] - 0.5 * m2 / rho) * (gamma - 1))
+    a = np.sqrt(gamma * p / np.abs(rho))
     s = np.empty(D + 2)
     s[0] = np.abs(rho).max()
-    s[1:1 + D] = (np.sqrt(m2) + rho * a).max()
+    s[1:1 + D] = (np.sqrt(m2) + np.abs(rho) * a).max()
     s[-1] = np.abs(Q[:, -1]).max()
     return s
 

@@ -44,10 +44,10 @@ def test_one_step_random_state(name, flux, order):
     Qf, G, F = o.probe()
     phi_ref = np.einsum("fd,fdk->fk", f["dac"][:, None] * f["S"], F)
     phi = g.debug_face_flux()
-    assert np.abs(phi - phi_ref).max() <= 1e-13 * np.abs(phi_ref).max()
+    assert np.abs(phi - phi_ref).max() <= TOL_1STEP * np.abs(phi_ref).max()
     if order == 2:
         Gg = g.debug_gradient()
-        assert np.abs(Gg - G).max() <= 1e-13 * np.abs(G).max()
+        assert np.abs(Gg - G).max() <= TOL_1STEP * np.abs(G).max()
     # residual (Time.cpp:69-76)
     ro = np.zeros(4)
     x = np.abs(Qo - Q0) / Q0
