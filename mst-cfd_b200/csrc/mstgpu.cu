@@ -17,6 +17,8 @@
 #include "../../include/mstgpu.h"
 #include "physics.cuh"
 #include "plan.h"
+#include "step_tiles.cuh"
+#include "tiles.h"
 
 using namespace mst;
 
@@ -51,6 +53,13 @@ struct mstgpu_ctx {
     double *Sd = nullptr, *dx0 = nullptr, *dx1 = nullptr, *eta = nullptr, *vol = nullptr;
     int32_t *fc0 = nullptr, *fc1 = nullptr, *cf = nullptr, *cell_new2old = nullptr, *face_new2old = nullptr;
     uint32_t* meta = nullptr;
+    // fused tile kernel
+    TileArrays ta{};
+    std::vector<void*> tile_allocs;
+    int ntiles = 0, tile_T = 0, tile_NT = 0;
+    size_t tile_smem = 0;
+    bool use_tiles = false;
+    bool probes_valid = false;  // G / Phi hold the stages of the last step
     unsigned long long* resid = nullptr;  // [U] bit patterns of non-negative doubles
     int* nanflag = nullptr;
     int cur = 0;          // Q[cur] = current ("old") state
@@ -333,9 +342,67 @@ void drain_timers(mstgpu_ctx* ctx) {
     ctx->pending.clear();
 }
 
+int ensure_stage_buffers(mstgpu_ctx* ctx) {
+    const size_t nq = (size_t)ctx->nc * ctx->U;
+    if (!ctx->G) {
+        int r;
+        if ((r = dalloc(ctx, &ctx->G, nq * ctx->D))) return r;
+        CK(cudaMemsetAsync(ctx->G, 0, nq * ctx->D * sizeof(double), ctx->stream));
+    }
+    if (!ctx->Phi) {
+        int r;
+        if ((r = dalloc(ctx, &ctx->Phi, (size_t)ctx->nf * ctx->U))) return r;
+        CK(cudaMemsetAsync(ctx->Phi, 0, (size_t)ctx->nf * ctx->U * sizeof(double), ctx->stream));
+    }
+    return MSTGPU_OK;
+}
+
+template <int D, int ORDER, int NT>
+int launch_tiles(mstgpu_ctx* ctx, double dt, const double* Qo, double* Qn) {
+    auto kern = k_step_tiles<D, ORDER, NT>;
+    static thread_local const void* configured = nullptr;
+    static thread_local size_t configured_smem = 0;
+    if (configured != (const void*)kern || configured_smem < ctx->tile_smem) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->tile_smem));
+        configured = (const void*)kern;
+        configured_smem = ctx->tile_smem;
+    }
+    kern<<<ctx->ntiles, NT, ctx->tile_smem, ctx->stream>>>(ctx->ta, ctx->dcfg, ctx->nslot, dt, Qo, Qn, ctx->resid,
+                                                           ctx->nanflag);
+    return MSTGPU_OK;
+}
+
+template <int D>
+int step_tiles_impl(mstgpu_ctx* ctx, double dt, int nsteps) {
+    for (int s = 0; s < nsteps; s++) {
+        const double* Qo = ctx->Q[ctx->cur];
+        double* Qn = ctx->Q[ctx->cur ^ 1];
+        CK(cudaMemsetAsync(ctx->resid, 0, 8 * sizeof(unsigned long long), ctx->stream));
+        {
+            KTimer t(ctx, "step_tiles");
+            int r;
+            const bool o2 = ctx->cfg.order == 2;
+            if (ctx->tile_NT == 128) r = o2 ? launch_tiles<D, 2, 128>(ctx, dt, Qo, Qn) : launch_tiles<D, 1, 128>(ctx, dt, Qo, Qn);
+            else r = o2 ? launch_tiles<D, 2, 256>(ctx, dt, Qo, Qn) : launch_tiles<D, 1, 256>(ctx, dt, Qo, Qn);
+            if (r) return r;
+        }
+        ctx->cur ^= 1;
+    }
+    CK(cudaGetLastError());
+    ctx->stepped = nsteps > 0 || ctx->stepped;
+    if (nsteps > 0) ctx->probes_valid = false;
+    return MSTGPU_OK;
+}
+
 template <int D>
 int step_impl(mstgpu_ctx* ctx, double dt, int nsteps) {
+    if (ctx->use_tiles) return step_tiles_impl<D>(ctx, dt, nsteps);
     const int nc = ctx->nc, nf = ctx->nf;
+    {
+        int r = ensure_stage_buffers(ctx);
+        if (r) return r;
+    }
+    if (nsteps > 0) ctx->probes_valid = true;
     for (int s = 0; s < nsteps; s++) {
         const double* Qo = ctx->Q[ctx->cur];
         double* Qn = ctx->Q[ctx->cur ^ 1];
@@ -366,6 +433,29 @@ int step_impl(mstgpu_ctx* ctx, double dt, int nsteps) {
     return MSTGPU_OK;
 }
 
+// Under the fused kernel the stages never reach HBM; recompute them from the
+// state the last step started from (Q[cur^1]) with the split kernels.
+template <int D>
+int recompute_stages(mstgpu_ctx* ctx) {
+    int r = ensure_stage_buffers(ctx);
+    if (r) return r;
+    const int nc = ctx->nc, nf = ctx->nf;
+    const double* Qo = ctx->Q[ctx->cur ^ 1];
+    if (ctx->cfg.order == 2)
+        k_gradient<D><<<(nc + 255) / 256, 256, 0, ctx->stream>>>(nc, ctx->nslot, Qo, ctx->cf, ctx->fc0, ctx->fc1, ctx->eta,
+                                                                 ctx->Sd, ctx->vol, ctx->G);
+    if (ctx->cfg.order == 2)
+        k_flux<D, 2><<<(nf + 127) / 128, 128, 0, ctx->stream>>>(nf, ctx->dcfg, Qo, ctx->G, ctx->fc0, ctx->fc1, ctx->meta,
+                                                                 ctx->Sd, ctx->dx0, ctx->dx1, ctx->Phi);
+    else
+        k_flux<D, 1><<<(nf + 127) / 128, 128, 0, ctx->stream>>>(nf, ctx->dcfg, Qo, ctx->G, ctx->fc0, ctx->fc1, ctx->meta,
+                                                                 ctx->Sd, ctx->dx0, ctx->dx1, ctx->Phi);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    ctx->probes_valid = true;
+    return MSTGPU_OK;
+}
+
 int fetch_permuted(mstgpu_ctx* ctx, const double* dsrc, const int32_t* new2old, int n, int W, double* host) {
     const size_t tot = (size_t)n * W;
     k_permute_out<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(n, W, dsrc, new2old, ctx->stage);
@@ -392,6 +482,9 @@ void mstgpu_default_config(mstgpu_config* cfg, int32_t dim) {
     cfg->qf_copy_from = -1;
     cfg->renumber = 1;
     cfg->device = -1;
+    cfg->kernel = 1;
+    cfg->tile_cells = 0;
+    cfg->block_threads = 0;
     cfg->gamma = 1.4;
     cfg->delta = 0.125;
     cfg->eor = 1e-10;
@@ -418,6 +511,7 @@ int mstgpu_create(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_config
     }
     ctx = new mstgpu_ctx;
     ctx->cfg = *cfg;
+    ctx->use_tiles = cfg->kernel != 0;
     std::string perr = build_plan(*mesh, *cfg, ctx->plan);
     if (!perr.empty()) { set_error(nullptr, perr); delete ctx; return MSTGPU_ERR_ARG; }
     Plan& p = ctx->plan;
@@ -441,18 +535,49 @@ int mstgpu_create(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_config
         if ((r = upload(ctx, &ctx->cell_new2old, p.cell_new2old))) return r;
         if ((r = upload(ctx, &ctx->face_new2old, p.face_new2old))) return r;
         const size_t nq = (size_t)p.nc * p.U;
-        if ((r = dalloc(ctx, &ctx->Q[0], nq))) return r;
-        if ((r = dalloc(ctx, &ctx->Q[1], nq))) return r;
-        if ((r = dalloc(ctx, &ctx->G, nq * p.D))) return r;
-        if ((r = dalloc(ctx, &ctx->Phi, (size_t)p.nf * p.U))) return r;
+        // + 2 rows: the fused kernel's bulk copies move an even number of rows
+        if ((r = dalloc(ctx, &ctx->Q[0], nq + 2 * p.U))) return r;
+        if ((r = dalloc(ctx, &ctx->Q[1], nq + 2 * p.U))) return r;
+        CK(cudaMemsetAsync(ctx->Q[0], 0, (nq + 2 * p.U) * sizeof(double), ctx->stream));
+        CK(cudaMemsetAsync(ctx->Q[1], 0, (nq + 2 * p.U) * sizeof(double), ctx->stream));
+        if (ctx->use_tiles) {
+            TilePack tp;
+            int T = cfg->tile_cells > 0 ? cfg->tile_cells : (p.D == 3 ? 128 : 256);
+            std::string terr = build_tiles(p, p.nc, T, cfg->order, tp);
+            if (!terr.empty()) { set_error(ctx, terr); return MSTGPU_ERR_ARG; }
+            int dev_smem = 0;
+            CK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+            if (tp.max_smem + 1024 > (size_t)dev_smem) { set_error(ctx, "tile needs more shared memory than the device has; lower tile_cells"); return MSTGPU_ERR_ARG; }
+            ctx->ntiles = tp.ntiles; ctx->tile_T = T; ctx->tile_smem = tp.max_smem;
+            ctx->tile_NT = cfg->block_threads == 128 ? 128 : (cfg->block_threads == 256 ? 256 : (T <= 128 ? 128 : 256));
+            TileDesc* ddesc; int32_t* dring; uint16_t* dslots; double *dcvol, *dfeta, *dfSd, *dfdx; uint32_t *dfab, *dfmeta;
+            if ((r = upload(ctx, &ddesc, tp.desc))) return r;
+            ctx->tile_allocs.push_back(ddesc);
+            if ((r = upload(ctx, &dring, tp.ring))) return r;
+            ctx->tile_allocs.push_back(dring);
+            if ((r = upload(ctx, &dslots, tp.slots))) return r;
+            ctx->tile_allocs.push_back(dslots);
+            if ((r = upload(ctx, &dcvol, tp.cvol))) return r;
+            ctx->tile_allocs.push_back(dcvol);
+            if ((r = upload(ctx, &dfab, tp.fab))) return r;
+            ctx->tile_allocs.push_back(dfab);
+            if ((r = upload(ctx, &dfeta, tp.feta))) return r;
+            ctx->tile_allocs.push_back(dfeta);
+            if ((r = upload(ctx, &dfSd, tp.fSd))) return r;
+            ctx->tile_allocs.push_back(dfSd);
+            if ((r = upload(ctx, &dfdx, tp.fdx))) return r;
+            ctx->tile_allocs.push_back(dfdx);
+            if ((r = upload(ctx, &dfmeta, tp.fmeta))) return r;
+            ctx->tile_allocs.push_back(dfmeta);
+            ctx->ta = TileArrays{ddesc, dring, dslots, dcvol, dfab, dfeta, dfSd, dfdx, dfmeta};
+            CK(cudaStreamSynchronize(ctx->stream));  // tp goes out of scope
+        }
         size_t nstage = std::max(nq * p.D, (size_t)p.nf * p.U);
         if ((r = dalloc(ctx, &ctx->stage, nstage))) return r;
         if ((r = dalloc(ctx, &ctx->resid, (size_t)8))) return r;
         if ((r = dalloc(ctx, &ctx->nanflag, (size_t)1))) return r;
         CK(cudaMemsetAsync(ctx->resid, 0, 8 * sizeof(unsigned long long), ctx->stream));
         CK(cudaMemsetAsync(ctx->nanflag, 0, sizeof(int), ctx->stream));
-        CK(cudaMemsetAsync(ctx->G, 0, nq * p.D * sizeof(double), ctx->stream));
-        CK(cudaMemsetAsync(ctx->Phi, 0, (size_t)p.nf * p.U * sizeof(double), ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         return MSTGPU_OK;
     }();
@@ -483,6 +608,8 @@ void mstgpu_destroy(mstgpu_ctx* ctx) {
                     ctx->vol, ctx->fc0, ctx->fc1, ctx->cf, ctx->cell_new2old, ctx->face_new2old, ctx->meta,
                     ctx->resid, ctx->nanflag};
     for (void* q : ptrs)
+        if (q) cudaFree(q);
+    for (void* q : ctx->tile_allocs)
         if (q) cudaFree(q);
     for (auto& pnd : ctx->pending) { cudaEventDestroy(pnd.second.first); cudaEventDestroy(pnd.second.second); }
     for (auto e : ctx->evpool) cudaEventDestroy(e);
@@ -573,6 +700,10 @@ int mstgpu_debug_gradient(mstgpu_ctx* ctx, double* grad) {
     if (!ctx || !grad) return MSTGPU_ERR_ARG;
     if (ctx->cfg.order != 2 || !ctx->stepped) { set_error(ctx, "no gradient: order 1 or no step yet"); return MSTGPU_ERR_STATE; }
     CK(cudaSetDevice(ctx->device));
+    if (!ctx->probes_valid) {
+        int r = (ctx->D == 2) ? recompute_stages<2>(ctx) : recompute_stages<3>(ctx);
+        if (r) return r;
+    }
     return fetch_permuted(ctx, ctx->G, ctx->cell_new2old, ctx->nc, ctx->U * ctx->D, grad);
 }
 
@@ -580,6 +711,10 @@ int mstgpu_debug_face_flux(mstgpu_ctx* ctx, double* phi) {
     if (!ctx || !phi) return MSTGPU_ERR_ARG;
     if (!ctx->stepped) { set_error(ctx, "no flux: no step yet"); return MSTGPU_ERR_STATE; }
     CK(cudaSetDevice(ctx->device));
+    if (!ctx->probes_valid) {
+        int r = (ctx->D == 2) ? recompute_stages<2>(ctx) : recompute_stages<3>(ctx);
+        if (r) return r;
+    }
     return fetch_permuted(ctx, ctx->Phi, ctx->face_new2old, ctx->nf, ctx->U, phi);
 }
 

@@ -45,6 +45,8 @@ class MstConfig(C.Structure):
         ("gamma", C.c_double), ("delta", C.c_double), ("eor", C.c_double),
         ("mu", C.c_double), ("kappa", C.c_double), ("cv", C.c_double),
         ("inletQ", C.c_double * 5),
+        ("kernel", C.c_int32), ("tile_cells", C.c_int32), ("block_threads", C.c_int32),
+        ("reserved_", C.c_int32),
     ]
 
 
@@ -135,7 +137,8 @@ class Context:
     dict produced by the host's mesh flattener)."""
 
     def __init__(self, flat: dict, order=2, flux="roe", viscous=0, qf_copy_from=None,
-                 renumber=1, device=-1, inletQ=None, **consts):
+                 renumber=1, device=-1, inletQ=None, kernel=None, tile_cells=0, block_threads=0,
+                 **consts):
         L = lib()
         self.dim = int(flat["dim"])
         self.U = self.dim + 2
@@ -149,6 +152,10 @@ class Context:
         cfg.qf_copy_from = -1 if qf_copy_from is None else qf_copy_from
         cfg.renumber = renumber
         cfg.device = device
+        if kernel is not None:
+            cfg.kernel = {"tiles": 1, "split": 0}[kernel] if isinstance(kernel, str) else int(kernel)
+        cfg.tile_cells = tile_cells
+        cfg.block_threads = block_threads
         for k, v in consts.items():
             setattr(cfg, k, v)
         if inletQ is not None:

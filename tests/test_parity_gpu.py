@@ -20,10 +20,13 @@ TOL_1000 = 1e-9
 DT_SOD = 1.0 / 4e3
 
 
-def _run_pair(f, Q0, dt, nsteps, **kw):
+KERNELS = ["tiles", "split"]  # fused tile kernel (default) and the three-kernel path
+
+
+def _run_pair(f, Q0, dt, nsteps, kernel="tiles", **kw):
     o = oracle.Oracle(f, **kw)
     Qo = o.run(dt, nsteps, Q0)
-    g = mstgpu.Context(f, **kw)
+    g = mstgpu.Context(f, kernel=kernel, **kw)
     g.set_state(Q0)
     g.step(dt, nsteps)
     Qg = g.get_state()
@@ -33,12 +36,13 @@ def _run_pair(f, Q0, dt, nsteps, **kw):
 @pytest.mark.parametrize("name", STEP_MESHES)
 @pytest.mark.parametrize("flux", ["roe", "ausm"])
 @pytest.mark.parametrize("order", [1, 2])
-def test_one_step_random_state(name, flux, order):
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_one_step_random_state(name, flux, order, kernel):
     """Stress input of SURVEY.md 8d: |M| > 1 both signs -> entropy fix, AUSM
     quirk branches, every boundary type of the mesh."""
     f = load_flat(name)
     Q0 = mesh_np.random_state(f)
-    o, g, Qo, Qg = _run_pair(f, Q0, 1e-4, 1, flux=flux, order=order)
+    o, g, Qo, Qg = _run_pair(f, Q0, 1e-4, 1, kernel=kernel, flux=flux, order=order)
     assert rel_linf(Qg, Qo) <= TOL_1STEP
     # stage probes: gradient and contracted face flux
     Qf, G, F = o.probe()
@@ -117,14 +121,15 @@ def test_forward_step_ausm_and_roe_50_steps(flux):
 
 @pytest.mark.parametrize("flux", ["roe", "ausm"])
 @pytest.mark.parametrize("order", [1, 2])
-def test_3d_tets_one_step_and_20_steps(flux, order):
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_3d_tets_one_step_and_20_steps(flux, order, kernel):
     """3-D extension (parity unpinned against the reference): GPU
     vs oracle on a Kuhn-split box with all boundary types."""
     f = box_flat(6, 5, 4, bc=(10, 5, 3, 7, 3, 3), l=(1.0, 0.8, 0.6))
     Q0 = mesh_np.random_state(f, seed=3)
     inlet = np.array([1.0, 0.4, 0.0, 0.0, 2.58])
     o = oracle.Oracle(f, order=order, flux=flux, inletQ=inlet)
-    g = mstgpu.Context(f, order=order, flux=flux, inletQ=inlet)
+    g = mstgpu.Context(f, order=order, flux=flux, inletQ=inlet, kernel=kernel)
     g.set_state(Q0)
     Q1 = o.run(1e-4, 1, Q0)
     g.step(1e-4, 1)
@@ -132,6 +137,45 @@ def test_3d_tets_one_step_and_20_steps(flux, order):
     Q20 = o.run(1e-4, 19, Q1)
     g.step(1e-4, 19)
     assert rel_linf(g.get_state(), Q20) <= 1e-10
+
+
+@pytest.mark.parametrize("tile_cells,block_threads", [(32, 128), (64, 256), (126, 128), (256, 256), (510, 256), (1024, 256)])
+@pytest.mark.parametrize("dim", [2, 3])
+def test_tile_shapes(tile_cells, block_threads, dim):
+    """Any tiling gives the oracle's answer: tiles smaller / larger than the
+    default, odd-sized last tile, one tile for the whole mesh (2-D case with
+    1024 on 3 103 cells has 4 tiles; the 3-D box of 720 cells fits in one)."""
+    if dim == 2:
+        f = load_flat("2d-stair-un-5-tri")
+        inlet = None
+    else:
+        f = box_flat(6, 5, 4, bc=(10, 5, 3, 7, 3, 3), l=(1.0, 0.8, 0.6))
+        inlet = np.array([1.0, 0.4, 0.0, 0.0, 2.58])
+    Q0 = mesh_np.random_state(f, seed=2)
+    for order in (1, 2):
+        o = oracle.Oracle(f, order=order, flux="roe", inletQ=inlet)
+        Qo = o.run(1e-4, 3, Q0)
+        g = mstgpu.Context(f, order=order, flux="roe", inletQ=inlet, kernel="tiles", tile_cells=tile_cells,
+                           block_threads=block_threads)
+        g.set_state(Q0)
+        g.step(1e-4, 3)
+        assert rel_linf(g.get_state(), Qo) <= 1e-11
+        ro = o.run(1e-4, 1, Qo)
+        g.step(1e-4, 1)
+        assert rel_linf(g.get_state(), ro) <= 1e-11
+
+
+def test_fused_and_split_kernels_agree():
+    f = load_flat("2d-stairW-1")
+    Q0 = mesh_np.random_state(f, seed=5)
+    outs = {}
+    for k in KERNELS:
+        g = mstgpu.Context(f, order=2, flux="roe", kernel=k)
+        g.set_state(Q0)
+        g.step(1e-4, 10)
+        outs[k] = (g.get_state(), g.residual())
+    assert rel_linf(outs["tiles"][0], outs["split"][0]) <= 1e-13
+    assert np.allclose(outs["tiles"][1], outs["split"][1], rtol=1e-10)
 
 
 def test_renumbering_does_not_change_the_bits():
