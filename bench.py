@@ -195,7 +195,8 @@ def run_ours(args, rank, world):
     f, Q0, desc = build_workload(args)
     nc, U, D = f["ncells"], f["dim"] + 2, f["dim"]
     t = time.time()
-    ctx = mstgpu.Context(f, order=2, flux="roe", device=local)
+    ctx = mstgpu.Context(f, order=2, flux="roe", device=local, kernel=args.kernel,
+                         tile_cells=args.tile_cells, block_threads=args.block_threads, renumber=args.renumber)
     log(f"[bench] context built in {time.time() - t:.1f}s, {ctx.device_bytes / 2**30:.2f} GiB on device")
     ctx.set_state(Q0)
     ctx.step(DT, args.warmup)
@@ -213,7 +214,8 @@ def run_ours(args, rank, world):
     wall = time.perf_counter() - w0
     clk = clocks.stop()
     launches = ctx.launch_count - l0
-    kt = {k: ctx.kernel_time(k) for k in ("gradient", "flux", "update")}
+    kt = {k: ctx.kernel_time(k) for k in ("gradient", "flux", "update", "step_tiles")}
+    kt = {k: v for k, v in kt.items() if v[1] > 0}
     ctx.enable_kernel_timing(False)
     res = ctx.residual()
     value = nc * args.steps / (ms * 1e-3)
@@ -224,13 +226,28 @@ def run_ours(args, rank, world):
     ab = ALGO_BYTES[(D, 2)]
     per_kernel = {k: (v[0] / max(v[1], 1)) for k, v in kt.items()}
     dom = max(per_kernel, key=per_kernel.get)
-    # V1 splits pass 2 of SURVEY.md 8(d) into flux + update; the algorithmic bytes
-    # of the pass are charged to the two kernels together.
-    pass2_ms = per_kernel["flux"] + per_kernel["update"]
-    achieved = ab["flux_update"] * nc / (pass2_ms * 1e-3) / 1e9
-    roof = dict(bound="hbm", kernel="flux+update (pass 2 of 8d)", achieved=achieved, peak=peak, unit="GB/s",
-                frac=achieved / peak, traffic=None, peak_source=peak_src,
-                algorithmic_bytes_per_cell=ab["flux_update"],
+    if "step_tiles" in per_kernel:
+        # fused kernel: one launch does both passes of SURVEY.md 8(d) -> the whole
+        # step's algorithmic bytes (600 B per tet cell-update) over its duration
+        achieved = ab["step"] * nc / (per_kernel["step_tiles"] * 1e-3) / 1e9
+        kname, abytes = "k_step_tiles (gradient+flux+update fused)", ab["step"]
+    else:
+        # split path: pass 2 of 8(d) is flux + update; its bytes are charged to the two together
+        pass2_ms = per_kernel["flux"] + per_kernel["update"]
+        achieved = ab["flux_update"] * nc / (pass2_ms * 1e-3) / 1e9
+        kname, abytes = "flux+update (pass 2 of 8d)", ab["flux_update"]
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel,
+        # from the committed ncu --set full capture, scaled per cell
+        tj = json.load(open(tp))
+        key = "step_tiles" if "step_tiles" in per_kernel else "flux_update"
+        if key in tj:
+            traffic = tj[key]["bytes_per_cell"] * nc
+    roof = dict(bound="hbm", kernel=kname, achieved=achieved, peak=peak, unit="GB/s",
+                frac=achieved / peak, traffic=traffic, peak_source=peak_src,
+                algorithmic_bytes_per_cell=abytes,
                 kernels_ms={k: round(v, 4) for k, v in per_kernel.items()}, dominant=dom,
                 step_frac=ab["step"] * value / 1e9 / peak)
 
@@ -260,7 +277,8 @@ def run_ours(args, rank, world):
                steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True,
                scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
                config=dict(workload=f"{args.workload}{args.n}: {desc}", cells=nc, faces=f["nfaces"], flux="roe",
-                           order=2, dt=DT, l2="inputs larger than L2 (state + tables >> 126 MB)"
+                           order=2, dt=DT, kernel=args.kernel, tile_cells=args.tile_cells, renumber=args.renumber,
+                           block_threads=args.block_threads, l2="inputs larger than L2 (state + tables >> 126 MB)"
                            if nc * U * 8 > 2 ** 28 else "inputs smaller than L2: flush not applied"),
                clocks=clk, e2e=e2e, gpu_launches=launches, roofline=roof, cpu_baseline=cpu,
                wall_ms_per_step=wall * 1e3 / args.steps, device_gib=ctx.device_bytes / 2 ** 30)
@@ -278,6 +296,10 @@ def main():
     ap.add_argument("--n", type=int, default=203, help="hexes per side (box) or 1/h (step)")
     ap.add_argument("--cpu-n", type=int, default=96, help="size of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--kernel", default="tiles", choices=["tiles", "split"])
+    ap.add_argument("--tile-cells", type=int, default=0)
+    ap.add_argument("--renumber", type=int, default=2, help="0 none, 1 Morton, 2 Hilbert")
+    ap.add_argument("--block-threads", type=int, default=0)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -103,7 +103,8 @@ typedef struct mstgpu_config {
     int32_t viscous;      /* FLAGVISCID (CONST.h:14)                                 */
     int32_t qf_copy_from; /* first face with Qf = Q[c0]; reference: nint-1
                              (the off-by-one of RhoSolver.cpp:438); <0 = nint-1     */
-    int32_t renumber;     /* 0 = keep reference order on the device, 1 = Morton      */
+    int32_t renumber;     /* device cell order: 0 = reference order, 1 = Morton,
+                             2 = Hilbert curve (default)                             */
     int32_t device;       /* CUDA ordinal, <0 = current device                       */
     double gamma;         /* GAMMA (CONST.h:41)                                      */
     double delta;         /* entropyError 0.125 (SolverRoe.cpp:115)                  */
@@ -157,6 +158,12 @@ int64_t mstgpu_device_bytes(mstgpu_ctx* ctx);
  * inspection and CPU tests.  cell_new2old [ncells], face_new2old [nfaces]. */
 int mstgpu_plan_permutation(const mstgpu_mesh* mesh, const mstgpu_config* cfg,
                             int32_t* cell_new2old, int32_t* face_new2old);
+
+/* Host-only: statistics of the tiling the fused kernel would use.
+ * out[0]=tiles out[1]=max smem bytes out[2]=mean smem bytes out[3]=sum ring1
+ * out[4]=sum ring2 out[5]=sum flux faces out[6]=sum local faces out[7]=packet bytes
+ * out[8..11]=smem histogram: tiles needing <=56K, <=75K, <=113K, more */
+int mstgpu_tile_stats(const mstgpu_mesh* mesh, const mstgpu_config* cfg, int64_t* out12);
 
 const char* mstgpu_last_error(mstgpu_ctx* ctx); /* ctx may be NULL (create errors) */
 const char* mstgpu_version(void);

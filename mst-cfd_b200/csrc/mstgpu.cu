@@ -58,6 +58,8 @@ struct mstgpu_ctx {
     std::vector<void*> tile_allocs;
     int ntiles = 0, tile_T = 0, tile_NT = 0;
     size_t tile_smem = 0;
+    struct TileClass { int first, count; size_t smem; };
+    std::vector<TileClass> tile_classes;  // tiles grouped by shared-memory need (CTAs per SM)
     bool use_tiles = false;
     bool probes_valid = false;  // G / Phi hold the stages of the last step
     unsigned long long* resid = nullptr;  // [U] bit patterns of non-negative doubles
@@ -367,8 +369,10 @@ int launch_tiles(mstgpu_ctx* ctx, double dt, const double* Qo, double* Qn) {
         configured = (const void*)kern;
         configured_smem = ctx->tile_smem;
     }
-    kern<<<ctx->ntiles, NT, ctx->tile_smem, ctx->stream>>>(ctx->ta, ctx->dcfg, ctx->nslot, dt, Qo, Qn, ctx->resid,
-                                                           ctx->nanflag);
+    for (const auto& tc : ctx->tile_classes)
+        kern<<<tc.count, NT, tc.smem, ctx->stream>>>(ctx->ta, tc.first, ctx->dcfg, ctx->nslot, dt, Qo, Qn, ctx->resid,
+                                                     ctx->nanflag);
+    ctx->launches += (int64_t)ctx->tile_classes.size() - 1;
     return MSTGPU_OK;
 }
 
@@ -470,6 +474,28 @@ int fetch_permuted(mstgpu_ctx* ctx, const double* dsrc, const int32_t* new2old, 
 
 extern "C" {
 
+int mstgpu_tile_stats(const mstgpu_mesh* mesh, const mstgpu_config* cfg, int64_t* out) {
+    if (!mesh || !cfg || !out) { set_error(nullptr, "null argument"); return MSTGPU_ERR_ARG; }
+    Plan p;
+    std::string perr = build_plan(*mesh, *cfg, p);
+    if (!perr.empty()) { set_error(nullptr, perr); return MSTGPU_ERR_ARG; }
+    TilePack tp;
+    int T = cfg->tile_cells > 0 ? cfg->tile_cells : (p.D == 3 ? 128 : 256);
+    perr = build_tiles(p, p.nc, T, cfg->order, tp);
+    if (!perr.empty()) { set_error(nullptr, perr); return MSTGPU_ERR_ARG; }
+    for (int i = 0; i < 12; i++) out[i] = 0;
+    out[0] = tp.ntiles; out[1] = (int64_t)tp.max_smem;
+    out[3] = tp.sum_r1; out[4] = tp.sum_r2; out[5] = tp.sum_FB; out[6] = tp.sum_FA; out[7] = (int64_t)tp.packets.size();
+    double sum = 0;
+    for (const TileDesc& d : tp.desc) {
+        const size_t b = tile_layout(p.D, cfg->order, p.nslot, d.n_own, d.n_r1, d.n_r2, d.nFB, d.nFA).total;
+        sum += (double)b;
+        out[8 + (b <= 56 * 1024 ? 0 : b <= 75 * 1024 ? 1 : b <= 113 * 1024 ? 2 : 3)]++;
+    }
+    out[2] = (int64_t)(sum / tp.ntiles);
+    return MSTGPU_OK;
+}
+
 const char* mstgpu_version(void) { return "mstgpu 0.1 (sm_100a)"; }
 
 const char* mstgpu_last_error(mstgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -480,7 +506,7 @@ void mstgpu_default_config(mstgpu_config* cfg, int32_t dim) {
     cfg->flux = MSTGPU_FLUX_ROE;
     cfg->viscous = 0;
     cfg->qf_copy_from = -1;
-    cfg->renumber = 1;
+    cfg->renumber = 2;
     cfg->device = -1;
     cfg->kernel = 1;
     cfg->tile_cells = 0;
@@ -549,27 +575,47 @@ int mstgpu_create(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_config
             CK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
             if (tp.max_smem + 1024 > (size_t)dev_smem) { set_error(ctx, "tile needs more shared memory than the device has; lower tile_cells"); return MSTGPU_ERR_ARG; }
             ctx->ntiles = tp.ntiles; ctx->tile_T = T; ctx->tile_smem = tp.max_smem;
-            ctx->tile_NT = cfg->block_threads == 128 ? 128 : (cfg->block_threads == 256 ? 256 : (T <= 128 ? 128 : 256));
-            TileDesc* ddesc; int32_t* dring; uint16_t* dslots; double *dcvol, *dfeta, *dfSd, *dfdx; uint32_t *dfab, *dfmeta;
+            {
+                // The dynamic shared memory of a launch is what its LARGEST tile needs, and
+                // it decides how many CTAs share an SM.  A few outlier tiles (ragged blobs)
+                // must not cost every tile a resident CTA: group the tiles by the CTAs/SM
+                // their size allows (4, 3, 2, 1) and launch each group with its own size.
+                const size_t lim[4] = {57000, 76500, 115000, (size_t)dev_smem};
+                std::vector<int> cls(tp.ntiles);
+                size_t cmax[4] = {0, 0, 0, 0};
+                int ccount[4] = {0, 0, 0, 0};
+                for (int t = 0; t < tp.ntiles; t++) {
+                    const TileDesc& d = tp.desc[t];
+                    const size_t b = tile_layout(p.D, cfg->order, p.nslot, d.n_own, d.n_r1, d.n_r2, d.nFB, d.nFA).total;
+                    int c = 0;
+                    while (c < 3 && b > lim[c]) c++;
+                    cls[t] = c; ccount[c]++; cmax[c] = std::max(cmax[c], b);
+                }
+                // merge a class that is too small to fill the machine into the next larger one
+                for (int c = 0; c < 3; c++)
+                    if (ccount[c] > 0 && ccount[c] < 2000 && (ccount[c + 1] > 0 || c == 2)) {
+                        if (c == 2 && ccount[3] == 0) continue;
+                        for (int t = 0; t < tp.ntiles; t++) if (cls[t] == c) cls[t] = c + 1;
+                        ccount[c + 1] += ccount[c]; cmax[c + 1] = std::max(cmax[c + 1], cmax[c]); ccount[c] = 0;
+                    }
+                std::vector<TileDesc> sorted;
+                sorted.reserve(tp.ntiles);
+                for (int c = 0; c < 4; c++) {
+                    if (!ccount[c]) continue;
+                    ctx->tile_classes.push_back({(int)sorted.size(), ccount[c], cmax[c]});
+                    for (int t = 0; t < tp.ntiles; t++) if (cls[t] == c) sorted.push_back(tp.desc[t]);
+                }
+                tp.desc.swap(sorted);
+            }
+            ctx->tile_NT = cfg->block_threads == 128 ? 128 : (cfg->block_threads == 256 ? 256 : (T <= 96 ? 128 : 256));
+            TileDesc* ddesc; int32_t* dring; unsigned char* dpk;
             if ((r = upload(ctx, &ddesc, tp.desc))) return r;
             ctx->tile_allocs.push_back(ddesc);
             if ((r = upload(ctx, &dring, tp.ring))) return r;
             ctx->tile_allocs.push_back(dring);
-            if ((r = upload(ctx, &dslots, tp.slots))) return r;
-            ctx->tile_allocs.push_back(dslots);
-            if ((r = upload(ctx, &dcvol, tp.cvol))) return r;
-            ctx->tile_allocs.push_back(dcvol);
-            if ((r = upload(ctx, &dfab, tp.fab))) return r;
-            ctx->tile_allocs.push_back(dfab);
-            if ((r = upload(ctx, &dfeta, tp.feta))) return r;
-            ctx->tile_allocs.push_back(dfeta);
-            if ((r = upload(ctx, &dfSd, tp.fSd))) return r;
-            ctx->tile_allocs.push_back(dfSd);
-            if ((r = upload(ctx, &dfdx, tp.fdx))) return r;
-            ctx->tile_allocs.push_back(dfdx);
-            if ((r = upload(ctx, &dfmeta, tp.fmeta))) return r;
-            ctx->tile_allocs.push_back(dfmeta);
-            ctx->ta = TileArrays{ddesc, dring, dslots, dcvol, dfab, dfeta, dfSd, dfdx, dfmeta};
+            if ((r = upload(ctx, &dpk, tp.packets))) return r;
+            ctx->tile_allocs.push_back(dpk);
+            ctx->ta = TileArrays{ddesc, dring, dpk};
             CK(cudaStreamSynchronize(ctx->stream));  // tp goes out of scope
         }
         size_t nstage = std::max(nq * p.D, (size_t)p.nf * p.U);

@@ -54,6 +54,19 @@ __device__ __forceinline__ void prim_of(const double (&q)[D + 2], const DevCfg& 
     for (int i = 0; i < D; i++) s.u[i] = q[i + 1] * s.r;
 }
 
+template <int D>
+__device__ __forceinline__ void prim_with_r(const double (&q)[D + 2], double r, const DevCfg& c, Prim<D>& s) {
+    constexpr int U = D + 2;
+    s.r = r;
+    double m2 = q[1] * q[1];
+#pragma unroll
+    for (int i = 1; i < D; i++) m2 += q[i + 1] * q[i + 1];
+    s.p = (q[U - 1] - 0.5 * m2 * s.r) * c.gm1;
+    s.ht = (q[U - 1] + s.p) * s.r;
+#pragma unroll
+    for (int i = 0; i < D; i++) s.u[i] = q[i + 1] * s.r;
+}
+
 // SolverRoe.cpp:114-123  (absolute delta, not scaled by a)
 __device__ __forceinline__ double entropy_fix(double x, const DevCfg& c) {
     return (x > c.delta) ? x : (x * x + c.delta2) * c.inv2delta;
@@ -65,24 +78,38 @@ __device__ __forceinline__ void roe_contract(const double (&A)[D + 2], const dou
                                              uint32_t flags, const double (&Sd)[D],
                                              const DevCfg& c, double (&phi)[D + 2]) {
     constexpr int U = D + 2;
+    // FP64 divisions and square roots are the expensive instructions here
+    // (~20 issue slots each), so the reciprocals are shared: 1/rhoA and 1/rhoB
+    // come from one division, 1/(1+w) and 1/g from another, 1/a from rsqrt, and
+    // 1/(rho+EOR) from a three-term series (relative error (EOR/rho)^3).
     Prim<D> a, b;
-    prim_of<D>(A, c, a);
-    prim_of<D>(B, c, b);
+    const double rab = 1.0 / (A[0] * B[0]);
+    prim_with_r<D>(A, B[0] * rab, c, a);
+    prim_with_r<D>(B, A[0] * rab, c, b);
     // Roe averages, SolverRoe.cpp:7-14 (symmetric under L<->R)
     const double w = sqrt(fabs(B[0] * a.r));
-    const double iw = 1.0 / (1.0 + w);
-    double uh[D];
-    double q2 = 0.0;
+    const double sw = 1.0 + w;
+    double un[D];
+    double qn2 = 0.0;
 #pragma unroll
     for (int i = 0; i < D; i++) {
-        uh[i] = (a.u[i] + w * b.u[i]) * iw;
-        q2 += uh[i] * uh[i];
+        un[i] = a.u[i] + w * b.u[i];
+        qn2 += un[i] * un[i];
     }
-    const double H = (a.ht + w * b.ht) * iw;
+    const double Hn = a.ht + w * b.ht;
+    const double gn = Hn * sw - 0.5 * qn2;  // = g (1+w)^2
+    const double z = 1.0 / (sw * gn);
+    const double iw = z * gn;            // 1/(1+w)
+    const double ig = sw * sw * sw * z;  // 1/g
+    double uh[D];
+#pragma unroll
+    for (int i = 0; i < D; i++) uh[i] = un[i] * iw;
+    const double q2 = qn2 * iw * iw;
+    const double H = Hn * iw;
     const double g = H - 0.5 * q2;
-    const double ah = sqrt(fabs(c.gm1 * g));
-    const double ig = 1.0 / g;
-    const double ia = 1.0 / ah;
+    const double ya = fabs(c.gm1 * g);
+    const double ia = rsqrt(ya);
+    const double ah = ya * ia;
     double dq[U];
 #pragma unroll
     for (int k = 0; k < U; k++) dq[k] = B[k] - A[k];
@@ -94,9 +121,11 @@ __device__ __forceinline__ void roe_contract(const double (&A)[D + 2], const dou
     double sh[D];  // shear strengths  dq[t+1] - u_t dq0
 #pragma unroll
     for (int i = 0; i < D; i++) sh[i] = dq[i + 1] - uh[i] * dq[0];
-    // (rho + EOR) denominators of the physical fluxes, SolverRoe.cpp:87-94
-    const double rea = 1.0 / (A[0] + c.eor);
-    const double reb = 1.0 / (B[0] + c.eor);
+    // (rho + EOR) denominators of the physical fluxes, SolverRoe.cpp:87-94:
+    // 1/(rho+e) = r (1 - t + t^2 - ...), t = e r
+    const double ta = c.eor * a.r, tb = c.eor * b.r;
+    const double rea = a.r * (1.0 - ta + ta * ta);
+    const double reb = b.r * (1.0 - tb + tb * tb);
 #pragma unroll
     for (int k = 0; k < U; k++) phi[k] = 0.0;
 #pragma unroll

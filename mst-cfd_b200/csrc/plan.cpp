@@ -28,6 +28,24 @@ inline uint64_t spread2(uint64_t x) {  // 31 bits -> every second bit
     return x;
 }
 
+// Hilbert index (Skilling, "Programming the Hilbert curve", 2004): axes ->
+// transposed index, in place.  b bits per axis, n axes.
+inline void axes_to_transpose(uint32_t* X, int b, int n) {
+    const uint32_t M = 1u << (b - 1);
+    for (uint32_t Q = M; Q > 1; Q >>= 1) {
+        const uint32_t P = Q - 1;
+        for (int i = 0; i < n; i++) {
+            if (X[i] & Q) X[0] ^= P;
+            else { const uint32_t t = (X[0] ^ X[i]) & P; X[0] ^= t; X[i] ^= t; }
+        }
+    }
+    for (int i = 1; i < n; i++) X[i] ^= X[i - 1];
+    uint32_t t = 0;
+    for (uint32_t Q = M; Q > 1; Q >>= 1)
+        if (X[n - 1] & Q) t ^= Q - 1;
+    for (int i = 0; i < n; i++) X[i] ^= t;
+}
+
 }  // namespace
 
 std::string build_plan(const mstgpu_mesh& m, const mstgpu_config& cfg, Plan& p) {
@@ -66,11 +84,18 @@ std::string build_plan(const mstgpu_mesh& m, const mstgpu_config& cfg, Plan& p) 
 #pragma omp parallel for schedule(static)
         for (int c = 0; c < nc; c++) {
             uint64_t k = 0;
+            uint32_t qq[3] = {0, 0, 0};
             for (int d = 0; d < D; d++) {
                 double x = m.cc[(size_t)c * D + d];
                 double t = (x == x) ? (x - lo[d]) * sc[d] : 0.0;
                 uint64_t q = (uint64_t)std::min(std::max(t, 0.0), bits);
-                k |= (D == 3 ? spread3(q) : spread2(q)) << d;
+                if (cfg.renumber == 2) qq[d] = (uint32_t)q;
+                else k |= (D == 3 ? spread3(q) : spread2(q)) << d;
+            }
+            if (cfg.renumber == 2) {
+                // Hilbert: consecutive cells are always neighbours -> any index range is one blob
+                axes_to_transpose(qq, D == 3 ? 21 : 31, D);
+                for (int d = 0; d < D; d++) k |= (D == 3 ? spread3(qq[d]) : spread2(qq[d])) << (D - 1 - d);
             }
             key[c] = {k, c};
         }

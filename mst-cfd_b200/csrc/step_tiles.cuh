@@ -11,9 +11,15 @@
 // tile and its rings in, Q of the tile out.  Neither the cell gradients
 // (120 B/cell) nor the face fluxes (2 x 40 B/cell) ever reach HBM.
 //
-// sm_100a specifics: the packet arrays and the owned block of Q are staged by
-// TMA bulk copies (cp.async.bulk -> SASS UBLKCP) completing on an mbarrier; the
-// new state leaves through a bulk store.  Ring cells are 40-byte row gathers.
+// Data flow inside a CTA (all in shared memory):
+//   phase 0  TMA bulk copy of the packet + of the owned block of Q (one
+//            mbarrier), 40-byte row gathers of the ring cells
+//   phase 1  thread per gradient cell (owned + ring 1): Green-Gauss gradient in
+//            registers, reconstructed state written per (face, side) -> Rec
+//   phase 2  thread per flux face: A/B from Rec (conflict-free SoA reads),
+//            boundary ghost, Roe / AUSM+ contracted with the area vector -> Phis
+//   phase 3  thread per owned cell: gather of its faces' Phis in the reference's
+//            face order, Euler update in place, residual; TMA bulk store of Q
 #pragma once
 #include <cstdint>
 
@@ -26,13 +32,7 @@ namespace mst {
 struct TileArrays {
     const TileDesc* desc;
     const int32_t* ring;
-    const uint16_t* slots;
-    const double* cvol;
-    const uint32_t* fab;
-    const double* feta;
-    const double* fSd;
-    const double* fdx;
-    const uint32_t* fmeta;
+    const unsigned char* packets;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -69,32 +69,41 @@ __device__ __forceinline__ void bulk_commit_wait_read() {
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ double warp_max_d(double x) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
-    return x;
+// max over the warp of NON-NEGATIVE doubles: their order is the order of their
+// bit patterns as unsigned integers, so two 32-bit REDUX do it (no shuffles)
+__device__ __forceinline__ double warp_max_nonneg(double x) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    const unsigned hi = (unsigned)(b >> 32), lo = (unsigned)b;
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    return __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
 }
 
 template <int D, int ORDER, int NT>
-__global__ void __launch_bounds__(NT) k_step_tiles(TileArrays ta, DevCfg cfg, int nslot, double dt,
+__global__ void __launch_bounds__(NT) k_step_tiles(TileArrays ta, int tile_base, DevCfg cfg, int nslot, double dt,
                                                    const double* __restrict__ Qold,
                                                    double* __restrict__ Qnew,
                                                    unsigned long long* __restrict__ resid,
                                                    int* __restrict__ nanflag) {
     constexpr int U = D + 2;
     extern __shared__ __align__(128) unsigned char smem[];
-    const TileDesc d = ta.desc[blockIdx.x];
+    const TileDesc d = ta.desc[tile_base + blockIdx.x];
     const int tid = threadIdx.x;
-    const int n_own = d.n_own, n_ring = d.n_r1 + d.n_r2, ncg = d.n_own + d.n_r1;
-    const int nFB = d.nFB, nFAp = (d.nFA + 3) & ~3, nFBp = (d.nFB + 3) & ~3, ncgp = (ncg + 7) & ~7;
-    const TileSmem L = tile_layout(D, ORDER, d.n_own, d.n_r1, d.n_r2, d.nFB, d.nFA);
-    double* Qs = reinterpret_cast<double*>(smem + L.Qs);
-    double* Gs = reinterpret_cast<double*>(smem + L.Gs);
-    double* Phis = reinterpret_cast<double*>(smem + L.Phis);
-    double* Qout = reinterpret_cast<double*>(smem + L.Qout);
+    const int n_own = d.n_own, n_ring = d.n_r1 + d.n_r2;
+    const int nFB = d.nFB;
+    const TileLayout L = tile_layout(D, ORDER, nslot, d.n_own, d.n_r1, d.n_r2, d.nFB, d.nFA);
+    const int nFXp = L.nFXp, nFBp = L.nFBp, ncgp = L.ncgp, ncg = L.ncg;
     const uint32_t* fab_s = reinterpret_cast<const uint32_t*>(smem + L.fab);
     const double* feta_s = reinterpret_cast<const double*>(smem + L.feta);
     const double* fSd_s = reinterpret_cast<const double*>(smem + L.fSd);
+    const uint16_t* slots_s = reinterpret_cast<const uint16_t*>(smem + L.slots);
+    const double* cvol_s = reinterpret_cast<const double*>(smem + L.cvol);
+    const double* fdx_s = reinterpret_cast<const double*>(smem + L.fdx);
+    const uint32_t* fmeta_s = reinterpret_cast<const uint32_t*>(smem + L.fmeta);
+    double* Qs = reinterpret_cast<double*>(smem + L.Qs);
+    double* Rec = reinterpret_cast<double*>(smem + L.Rec);    // [side][k][nFBp]
+    // [k][nFBp]; order 2: aliases the A side of Rec -- thread f overwrites only what it alone has read
+    double* Phis = reinterpret_cast<double*>(smem + L.Phis);
     const uint32_t bar = smem_u32(smem + L.mbar);
 
     // ---- phase 0: stage the tile ------------------------------------------------
@@ -102,28 +111,24 @@ __global__ void __launch_bounds__(NT) k_step_tiles(TileArrays ta, DevCfg cfg, in
     __syncthreads();
     if (tid == 0) {
         const uint32_t qbytes = (uint32_t)((n_own + 1) & ~1) * U * 8u;
-        uint32_t tx = qbytes;
-        if (ORDER == 2) tx += (uint32_t)nFAp * 4u + (uint32_t)nFAp * 8u + (uint32_t)D * nFAp * 8u;
-        mbar_expect_tx(bar, tx);
+        mbar_expect_tx(bar, qbytes + L.pk_bytes);
+        bulk_g2s(smem_u32(smem), ta.packets + d.pk_off, L.pk_bytes, bar);
         bulk_g2s(smem_u32(Qs), Qold + (size_t)d.cb * U, qbytes, bar);
-        if (ORDER == 2) {
-            bulk_g2s(smem_u32(fab_s), ta.fab + d.fa_off, (uint32_t)nFAp * 4u, bar);
-            bulk_g2s(smem_u32(feta_s), ta.feta + d.fa_off, (uint32_t)nFAp * 8u, bar);
-            bulk_g2s(smem_u32(fSd_s), ta.fSd + (size_t)D * d.fa_off, (uint32_t)D * nFAp * 8u, bar);
-        }
     }
-    // ring cells: row gathers (rows are contiguous, 8*U bytes)
-    for (int i = tid; i < n_ring * U; i += NT) {
-        const int r = i / U, k = i - r * U;
+    // ring cells: one thread per cell, U independent loads of a contiguous row
+    for (int r = tid; r < n_ring; r += NT) {
         const int g = ta.ring[d.ring_off + r];
-        Qs[(size_t)(n_own + r) * U + k] = Qold[(size_t)g * U + k];
+        double q[U];
+#pragma unroll
+        for (int k = 0; k < U; k++) q[k] = Qold[(size_t)g * U + k];
+#pragma unroll
+        for (int k = 0; k < U; k++) Qs[(n_own + r) * U + k] = q[k];
     }
     mbar_wait(bar, 0);
     __syncthreads();
 
-    // ---- phase 1: Green-Gauss gradients of owned + ring-1 cells --------------------
+    // ---- phase 1: Green-Gauss gradient + reconstruction at the cell's faces --------
     if (ORDER == 2) {
-        const uint16_t* slots = ta.slots + (size_t)nslot * d.cell_off;
         for (int lc = tid; lc < ncg; lc += NT) {
             double qc[U];
 #pragma unroll
@@ -134,7 +139,7 @@ __global__ void __launch_bounds__(NT) k_step_tiles(TileArrays ta, DevCfg cfg, in
 #pragma unroll
                 for (int dd = 0; dd < D; dd++) t[k][dd] = 0.0;
             for (int j = 0; j < nslot; j++) {
-                const uint32_t v = slots[(size_t)j * ncgp + lc];
+                const uint32_t v = slots_s[j * ncgp + lc];
                 if (v == 0xFFFFu) continue;
                 const int lf = v >> 1;
                 const int side = v & 1;
@@ -143,142 +148,143 @@ __global__ void __launch_bounds__(NT) k_step_tiles(TileArrays ta, DevCfg cfg, in
                 const double e = feta_s[lf];
                 double qf[U];
                 if (nb != 0xFFFFu) {
+                    // Qf = eta Q[c0] + (1-eta) Q[c1]   (RhoSolver.cpp:435)
                     const double e0 = side ? (1.0 - e) : e;
                     const double e1 = side ? e : (1.0 - e);
 #pragma unroll
                     for (int k = 0; k < U; k++) qf[k] = e0 * qc[k] + e1 * Qs[nb * U + k];
                 } else {
 #pragma unroll
-                    for (int k = 0; k < U; k++) qf[k] = qc[k];
+                    for (int k = 0; k < U; k++) qf[k] = qc[k];  // RhoSolver.cpp:439
                 }
                 const double sg = side ? -1.0 : 1.0;
 #pragma unroll
                 for (int dd = 0; dd < D; dd++) {
-                    const double s = sg * fSd_s[dd * nFAp + lf];
+                    const double s = sg * fSd_s[dd * nFXp + lf];
 #pragma unroll
                     for (int k = 0; k < U; k++) t[k][dd] += qf[k] * s;
                 }
             }
-            const double v = ta.cvol[d.cell_off + lc];
+            const double iv = 1.0 / cvol_s[lc];
 #pragma unroll
             for (int k = 0; k < U; k++)
 #pragma unroll
-                for (int dd = 0; dd < D; dd++) Gs[(lc * U + k) * D + dd] = t[k][dd] / v;
-        }
-        __syncthreads();
-    }
-
-    // ---- phase 2: reconstruction + flux on every face with an owned cell ----------
-    {
-        const double* dxg = ta.fdx + (size_t)2 * D * d.fb_off;
-        for (int f = tid; f < nFB; f += NT) {
-            const uint32_t ab = (ORDER == 2) ? fab_s[f] : ta.fab[d.fa_off + f];
-            const int la = ab & 0xFFFFu, lb = ab >> 16;
-            const uint32_t mt = ta.fmeta[d.fb_off + f];
-            const int type = mt & 0xff;
-            const uint32_t flags = mt >> 8;
-            double S[D];
-#pragma unroll
-            for (int dd = 0; dd < D; dd++)
-                S[dd] = (ORDER == 2) ? fSd_s[dd * nFAp + f] : ta.fSd[(size_t)D * d.fa_off + (size_t)dd * nFAp + f];
-            double qa[U], ra[U];
-#pragma unroll
-            for (int k = 0; k < U; k++) qa[k] = Qs[la * U + k];
-            if (ORDER == 2) {
+                for (int dd = 0; dd < D; dd++) t[k][dd] *= iv;
+            // reconstructed state at every flux face of this cell (RhoSolver.cpp:250)
+            for (int j = 0; j < nslot; j++) {
+                const uint32_t v = slots_s[j * ncgp + lc];
+                if (v == 0xFFFFu) continue;
+                const int lf = v >> 1;
+                if (lf >= nFB) continue;
+                const int side = v & 1;
                 double dx[D];
 #pragma unroll
-                for (int dd = 0; dd < D; dd++) dx[dd] = dxg[(size_t)dd * nFBp + f];
+                for (int dd = 0; dd < D; dd++) dx[dd] = fdx_s[(side * D + dd) * nFBp + lf];
 #pragma unroll
                 for (int k = 0; k < U; k++) {
                     double s = 0.0;
 #pragma unroll
-                    for (int dd = 0; dd < D; dd++) s += Gs[(la * U + k) * D + dd] * dx[dd];
-                    ra[k] = qa[k] + s;
+                    for (int dd = 0; dd < D; dd++) s += t[k][dd] * dx[dd];
+                    Rec[(side * U + k) * nFBp + lf] = qc[k] + s;
                 }
-            } else {
+                // boundary face: the B side carries the un-reconstructed cell value
+                if ((fab_s[lf] >> 16) == 0xFFFFu) {
 #pragma unroll
-                for (int k = 0; k < U; k++) ra[k] = qa[k];
-            }
-            double A[U], B[U], phi[U];
-            bool live = true;
-            if (lb != 0xFFFF) {
-#pragma unroll
-                for (int k = 0; k < U; k++) A[k] = ra[k];
-                if (ORDER == 2) {
-                    double dx[D];
-#pragma unroll
-                    for (int dd = 0; dd < D; dd++) dx[dd] = dxg[(size_t)(D + dd) * nFBp + f];
-#pragma unroll
-                    for (int k = 0; k < U; k++) {
-                        double s = 0.0;
-#pragma unroll
-                        for (int dd = 0; dd < D; dd++) s += Gs[(lb * U + k) * D + dd] * dx[dd];
-                        B[k] = Qs[lb * U + k] + s;
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < U; k++) B[k] = Qs[lb * U + k];
+                    for (int k = 0; k < U; k++) Rec[(U + k) * nFBp + lf] = qc[k];
                 }
-            } else {
-                live = boundary_states<D>(type, qa, ra, S, cfg, A, B);
             }
-            if (live) {
-                riemann_contract<D>(cfg.flux, A, B, flags, S, cfg, phi);
-            } else {
-#pragma unroll
-                for (int k = 0; k < U; k++) phi[k] = 0.0;
-            }
-#pragma unroll
-            for (int k = 0; k < U; k++) Phis[f * U + k] = phi[k];
         }
         __syncthreads();
     }
 
-    // ---- phase 3: gather, explicit Euler, residual ---------------------------------
+    // ---- phase 2: flux on every face with an owned cell ------------------------------
+    for (int f = tid; f < nFB; f += NT) {
+        const uint32_t ab = fab_s[f];
+        const int la = ab & 0xFFFFu, lb = ab >> 16;
+        const uint32_t mt = fmeta_s[f];
+        const int type = mt & 0xff;
+        const uint32_t flags = mt >> 8;
+        double S[D];
+#pragma unroll
+        for (int dd = 0; dd < D; dd++) S[dd] = fSd_s[dd * nFXp + f];
+        double A[U], B[U], phi[U];
+        bool live = true;
+        if (ORDER == 2) {
+#pragma unroll
+            for (int k = 0; k < U; k++) {
+                A[k] = Rec[k * nFBp + f];
+                B[k] = Rec[(U + k) * nFBp + f];
+            }
+            if (lb == 0xFFFF) {
+                double ra[U], qa[U];
+#pragma unroll
+                for (int k = 0; k < U; k++) { ra[k] = A[k]; qa[k] = B[k]; }
+                live = boundary_states<D>(type, qa, ra, S, cfg, A, B);
+            }
+        } else {
+            double qa[U];
+#pragma unroll
+            for (int k = 0; k < U; k++) qa[k] = Qs[la * U + k];
+            if (lb != 0xFFFF) {
+#pragma unroll
+                for (int k = 0; k < U; k++) { A[k] = qa[k]; B[k] = Qs[lb * U + k]; }
+            } else {
+                live = boundary_states<D>(type, qa, qa, S, cfg, A, B);
+            }
+        }
+        if (live) {
+            riemann_contract<D>(cfg.flux, A, B, flags, S, cfg, phi);
+        } else {
+#pragma unroll
+            for (int k = 0; k < U; k++) phi[k] = 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < U; k++) Phis[k * nFBp + f] = phi[k];
+    }
+    __syncthreads();
+
+    // ---- phase 3: gather, explicit Euler (in place in Qs), residual -------------------
     double r[U];
 #pragma unroll
     for (int k = 0; k < U; k++) r[k] = 0.0;
     bool bad = false;
-    {
-        const uint16_t* slots = ta.slots + (size_t)nslot * d.cell_off;
-        for (int lc = tid; lc < n_own; lc += NT) {
-            double acc[U];
+    for (int lc = tid; lc < n_own; lc += NT) {
+        double acc[U];
 #pragma unroll
-            for (int k = 0; k < U; k++) acc[k] = 0.0;
-            for (int j = 0; j < nslot; j++) {
-                const uint32_t v = slots[(size_t)j * ncgp + lc];
-                if (v == 0xFFFFu) continue;
-                const int lf = v >> 1;
-                const double sg = (v & 1) ? -1.0 : 1.0;
+        for (int k = 0; k < U; k++) acc[k] = 0.0;
+        for (int j = 0; j < nslot; j++) {
+            const uint32_t v = slots_s[j * ncgp + lc];
+            if (v == 0xFFFFu) continue;
+            const int lf = v >> 1;
+            const double sg = (v & 1) ? -1.0 : 1.0;
 #pragma unroll
-                for (int k = 0; k < U; k++) acc[k] += sg * Phis[lf * U + k];
-            }
-            const double s = dt / ta.cvol[d.cell_off + lc];
+            for (int k = 0; k < U; k++) acc[k] += sg * Phis[k * nFBp + lf];
+        }
+        const double s = dt / cvol_s[lc];  // RhoSolver.cpp:64
 #pragma unroll
-            for (int k = 0; k < U; k++) {
-                const double qo = Qs[lc * U + k];
-                const double qn = qo - s * acc[k];
-                Qout[lc * U + k] = qn;
-                const double x = fabs(qn - qo) / qo;  // Time.cpp:72
-                r[k] = fmax(r[k], (x > 0.0) ? x : 0.0);
-                bad |= (qn != qn);
-            }
+        for (int k = 0; k < U; k++) {
+            const double qo = Qs[lc * U + k];
+            const double qn = qo - s * acc[k];
+            Qs[lc * U + k] = qn;
+            const double x = fabs(qn - qo) / qo;  // Time.cpp:72
+            r[k] = fmax(r[k], (x > 0.0) ? x : 0.0);
+            bad |= (qn != qn);
         }
     }
     __shared__ double sm[U][NT / 32];
     const int lane = tid & 31, wid = tid >> 5;
 #pragma unroll
     for (int k = 0; k < U; k++) {
-        const double m = warp_max_d(r[k]);
+        const double m = warp_max_nonneg(r[k]);
         if (lane == 0) sm[k][wid] = m;
     }
-    fence_async_smem();  // Qout (generic-proxy writes) -> visible to the bulk store
+    fence_async_smem();  // generic-proxy writes of Qs -> visible to the bulk store
     const bool anybad = __syncthreads_or(bad);
     if (tid == 0) {
         const int even = n_own & ~1;
-        if (even) bulk_s2g(Qnew + (size_t)d.cb * U, smem_u32(Qout), (uint32_t)even * U * 8u);
+        if (even) bulk_s2g(Qnew + (size_t)d.cb * U, smem_u32(Qs), (uint32_t)even * U * 8u);
         if (n_own & 1)
-            for (int k = 0; k < U; k++) Qnew[(size_t)(d.cb + even) * U + k] = Qout[even * U + k];
+            for (int k = 0; k < U; k++) Qnew[(size_t)(d.cb + even) * U + k] = Qs[even * U + k];
         bulk_commit_wait_read();
     }
     if (tid >= 32 && tid < 32 + U) {

@@ -8,10 +8,6 @@
 
 namespace mst {
 
-size_t tile_smem_bytes(int D, int order, int n_own, int n_r1, int n_r2, int nFB, int nFA) {
-    return tile_layout(D, order, n_own, n_r1, n_r2, nFB, nFA).total;
-}
-
 namespace {
 
 // tiny open-addressing map int32 -> int32 with O(1) reset (generation stamps)
@@ -62,25 +58,18 @@ std::string build_tiles(const Plan& p, int n_update, int T, int order, TilePack&
     // pass 1: sizes; pass 2: fill.  The traversal is identical in both passes.
     for (int pass = 0; pass < 2; pass++) {
         if (pass == 1) {
-            int64_t ro = 0, co = 0, fa = 0, fb = 0;
+            int64_t ro = 0, po = 0;
             for (int t = 0; t < nt; t++) {
                 TileDesc& d = tp.desc[t];
-                d.ring_off = ro; d.cell_off = co; d.fa_off = fa; d.fb_off = fb;
+                const TileLayout L = tile_layout(D, order, nslot, d.n_own, d.n_r1, d.n_r2, d.nFB, d.nFA);
+                d.ring_off = ro; d.pk_off = po;
                 ro += up(d.n_r1 + d.n_r2, 4);
-                co += up(d.n_own + d.n_r1, 8);
-                fa += up(d.nFA, 4);
-                fb += up(d.nFB, 4);
-                tp.max_smem = std::max(tp.max_smem, tile_smem_bytes(D, order, d.n_own, d.n_r1, d.n_r2, d.nFB, d.nFA));
+                po += L.pk_bytes;
+                tp.max_smem = std::max(tp.max_smem, (size_t)L.total);
                 tp.sum_r1 += d.n_r1; tp.sum_r2 += d.n_r2; tp.sum_FB += d.nFB; tp.sum_FA += d.nFA;
             }
             tp.ring.assign(ro, 0);
-            tp.slots.assign((size_t)nslot * co, 0xFFFF);
-            tp.cvol.assign(co, 1.0);
-            tp.fab.assign(fa, 0xFFFFFFFFu);
-            tp.feta.assign(fa, 1.0);
-            tp.fSd.assign((size_t)D * fa, 0.0);
-            tp.fdx.assign((size_t)2 * D * fb, 0.0);
-            tp.fmeta.assign(fb, 0);
+            tp.packets.assign((size_t)po, 0);
         }
         std::string err;
 #pragma omp parallel
@@ -148,33 +137,45 @@ std::string build_tiles(const Plan& p, int n_update, int T, int order, TilePack&
                     continue;
                 }
                 // ---- fill ---------------------------------------------------------
-                const int ncg = n_own + n_r1, ncgp = up(ncg, 8), nFAp = up(nFA, 4), nFBp = up(nFB, 4);
+                const TileLayout L = tile_layout(D, order, nslot, n_own, n_r1, n_r2, nFB, nFA);
+                unsigned char* pk = tp.packets.data() + d.pk_off;
+                uint32_t* fab = reinterpret_cast<uint32_t*>(pk + L.fab);
+                double* feta = reinterpret_cast<double*>(pk + L.feta);
+                double* fSd = reinterpret_cast<double*>(pk + L.fSd);
+                uint16_t* slots = reinterpret_cast<uint16_t*>(pk + L.slots);
+                double* cvol = reinterpret_cast<double*>(pk + L.cvol);
+                double* fdx = reinterpret_cast<double*>(pk + L.fdx);
+                uint32_t* fmeta = reinterpret_cast<uint32_t*>(pk + L.fmeta);
                 for (size_t i = 0; i < s.ring.size(); i++) tp.ring[d.ring_off + i] = s.ring[i];
-                for (int lc = 0; lc < ncg; lc++) {
+                for (uint32_t i = 0; i < (uint32_t)nslot * L.ncgp; i++) slots[i] = 0xFFFF;
+                for (uint32_t i = 0; i < L.ncgp; i++) cvol[i] = 1.0;
+                for (uint32_t i = 0; i < L.nFXp; i++) fab[i] = 0xFFFFFFFFu;
+                for (int lc = 0; lc < (int)L.ncg; lc++) {
                     const int g = lc < n_own ? cb + lc : s.ring[lc - n_own];
-                    tp.cvol[d.cell_off + lc] = p.vol[g];
+                    cvol[lc] = p.vol[g];
                     for (int j = 0; j < nslot; j++) {
                         int f, side;
                         nb_of(g, j, f, side);
                         if (f < 0) continue;
                         const int lf = s.faces.find(f);
-                        tp.slots[(size_t)nslot * d.cell_off + (size_t)j * ncgp + lc] = (uint16_t)((lf << 1) | side);
+                        slots[(size_t)j * L.ncgp + lc] = (uint16_t)((lf << 1) | side);
                     }
                 }
-                for (int lf = 0; lf < nFA; lf++) {
+                const int nFX = order == 2 ? nFA : nFB;
+                for (int lf = 0; lf < nFX; lf++) {
                     const int f = s.flist[lf];
                     const int la = local_of(p.fc0[f]);
                     const int lb = p.fc1[f] >= 0 ? local_of(p.fc1[f]) : 0xFFFF;
-                    // a ring-2/outside cell can be absent only on faces no gradient cell uses from that side
-                    tp.fab[d.fa_off + lf] = (uint32_t)(la < 0 ? 0xFFFF : la) | ((uint32_t)(lb < 0 ? 0xFFFF : lb) << 16);
-                    tp.feta[d.fa_off + lf] = p.eta[f];
-                    for (int k = 0; k < D; k++) tp.fSd[(size_t)D * d.fa_off + (size_t)k * nFAp + lf] = p.Sd[(size_t)f * D + k];
+                    fab[lf] = (uint32_t)(la < 0 ? 0xFFFF : la) | ((uint32_t)(lb < 0 ? 0xFFFF : lb) << 16);
+                    if (order == 2) feta[lf] = p.eta[f];
+                    for (int k = 0; k < D; k++) fSd[(size_t)k * L.nFXp + lf] = p.Sd[(size_t)f * D + k];
                     if (lf < nFB) {
-                        tp.fmeta[d.fb_off + lf] = p.meta[f];
-                        for (int k = 0; k < D; k++) {
-                            tp.fdx[(size_t)2 * D * d.fb_off + (size_t)k * nFBp + lf] = p.dx0[(size_t)f * D + k];
-                            tp.fdx[(size_t)2 * D * d.fb_off + (size_t)(D + k) * nFBp + lf] = p.dx1[(size_t)f * D + k];
-                        }
+                        fmeta[lf] = p.meta[f];
+                        if (order == 2)
+                            for (int k = 0; k < D; k++) {
+                                fdx[(size_t)k * L.nFBp + lf] = p.dx0[(size_t)f * D + k];
+                                fdx[(size_t)(D + k) * L.nFBp + lf] = p.dx1[(size_t)f * D + k];
+                            }
                     }
                 }
             }

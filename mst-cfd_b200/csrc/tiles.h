@@ -13,8 +13,8 @@
 //   FG faces      remaining faces of ring-1 cells: geometry for their gradient
 //
 // Everything a tile needs is stored in ITS OWN contiguous packet (16-byte
-// aligned sub-arrays, 16-bit local indices), so the kernel stages it with a
-// handful of TMA bulk copies (cp.async.bulk) instead of scattered gathers.
+// aligned sub-arrays, 16-bit local indices, layout in tile_layout.h), so the
+// kernel stages it with ONE TMA bulk copy instead of scattered gathers.
 // Reference semantics are unchanged: per-cell face order, eta, Sd, dx0/dx1,
 // flags are the values of plan.h, merely regrouped.
 #pragma once
@@ -32,31 +32,19 @@ struct TileDesc {
     int32_t n_r1;   // ring-1 cells
     int32_t n_r2;   // ring-2 cells
     int32_t nFB;    // flux faces
-    int32_t nFA;    // all local faces (FB first), nFAp = round_up(nFA, 4) is the array stride
-    int64_t ring_off;  // into ring[]           (n_r1 + n_r2 entries, padded to 4)
-    int64_t cell_off;  // into cvol[] / slots[] (ncg = n_own + n_r1 entries, padded to 8)
-    int64_t fa_off;    // into fab[] / feta[] / fSd[] (nFAp entries)
-    int64_t fb_off;    // into fdx[] / fmeta[]  (nFBp = round_up(nFB, 4) entries)
+    int32_t nFA;    // all local faces (FB first)
+    int64_t ring_off;  // into ring[] (n_r1 + n_r2 entries, padded to 4)
+    int64_t pk_off;    // byte offset of the packet in packets[] (16-byte aligned)
 };
 
 struct TilePack {
     int T = 0, ntiles = 0, order = 2, D = 0, nslot = 0;
     std::vector<TileDesc> desc;
-    std::vector<int32_t> ring;    // device-order cell ids of ring cells
-    std::vector<uint16_t> slots;  // per tile [nslot][ncgp]: local face << 1 | side, 0xFFFF = pad
-    std::vector<double> cvol;     // per tile [ncgp]
-    std::vector<uint32_t> fab;    // per tile [nFAp]: la | lb << 16 (lb = 0xFFFF on boundary faces)
-    std::vector<double> feta;     // per tile [nFAp]
-    std::vector<double> fSd;      // per tile [D][nFAp]
-    std::vector<double> fdx;      // per tile [2][D][nFBp]   (dx0 then dx1)
-    std::vector<uint32_t> fmeta;  // per tile [nFBp]
-    size_t max_smem = 0;          // dynamic shared memory the largest tile needs
-    // totals, for reporting
+    std::vector<int32_t> ring;           // device-order cell ids of ring cells
+    std::vector<unsigned char> packets;  // concatenated packets, layout = tile_layout()
+    size_t max_smem = 0;                 // dynamic shared memory the largest tile needs
     int64_t sum_r1 = 0, sum_r2 = 0, sum_FB = 0, sum_FA = 0;
 };
-
-// shared-memory bytes one tile needs in k_step_tiles (must match the kernel's carve-up)
-size_t tile_smem_bytes(int D, int order, int n_own, int n_r1, int n_r2, int nFB, int nFA);
 
 // n_update: cells [0, n_update) are advanced (the rest are ghosts, read only)
 std::string build_tiles(const Plan& p, int n_update, int T, int order, TilePack& tp);

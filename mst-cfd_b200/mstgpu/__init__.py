@@ -25,7 +25,7 @@ EXPORTS = [
     "mstgpu_get_state", "mstgpu_get_prev_state", "mstgpu_step", "mstgpu_step_timed",
     "mstgpu_residual_linf", "mstgpu_sync", "mstgpu_debug_gradient", "mstgpu_debug_face_flux",
     "mstgpu_launch_count", "mstgpu_enable_kernel_timing", "mstgpu_kernel_time",
-    "mstgpu_device_bytes", "mstgpu_plan_permutation", "mstgpu_last_error", "mstgpu_version",
+    "mstgpu_device_bytes", "mstgpu_plan_permutation", "mstgpu_tile_stats", "mstgpu_last_error", "mstgpu_version",
 ]
 
 
@@ -90,6 +90,7 @@ def lib():
         L.mstgpu_device_bytes.argtypes = [vp]
         L.mstgpu_device_bytes.restype = i64
         L.mstgpu_plan_permutation.argtypes = [C.POINTER(MstMesh), C.POINTER(MstConfig), vp, vp]
+        L.mstgpu_tile_stats.argtypes = [C.POINTER(MstMesh), C.POINTER(MstConfig), vp]
         L.mstgpu_last_error.argtypes = [vp]
         L.mstgpu_last_error.restype = C.c_char_p
         L.mstgpu_version.restype = C.c_char_p
@@ -119,7 +120,7 @@ def _mesh_struct(flat: dict):
     return m, keep
 
 
-def plan_permutation(flat: dict, renumber: int = 1):
+def plan_permutation(flat: dict, renumber: int = 2):
     """(cell_new2old, face_new2old) that mstgpu_create would use; host only."""
     m, keep = _mesh_struct(flat)
     cfg = default_config(int(flat["dim"]))
@@ -132,12 +133,26 @@ def plan_permutation(flat: dict, renumber: int = 1):
     return c, f
 
 
+def tile_stats(flat: dict, order: int = 2, tile_cells: int = 0, renumber: int = 2) -> dict:
+    """Statistics of the fused kernel's tiling (host only)."""
+    m, keep = _mesh_struct(flat)
+    cfg = default_config(int(flat["dim"]))
+    cfg.order, cfg.tile_cells, cfg.renumber = order, tile_cells, renumber
+    out = np.zeros(12, dtype=np.int64)
+    rc = lib().mstgpu_tile_stats(C.byref(m), C.byref(cfg), out.ctypes.data)
+    if rc != 0:
+        raise MstGpuError(f"tile_stats failed ({rc}): {lib().mstgpu_last_error(None).decode()}")
+    keys = ("tiles", "max_smem", "mean_smem", "sum_ring1", "sum_ring2", "sum_flux_faces", "sum_local_faces",
+            "packet_bytes", "le56k", "le75k", "le113k", "more")
+    return dict(zip(keys, (int(x) for x in out)))
+
+
 class Context:
     """Owns one mstgpu_ctx.  `flat` is the flattened reference-order mesh (the
     dict produced by the host's mesh flattener)."""
 
     def __init__(self, flat: dict, order=2, flux="roe", viscous=0, qf_copy_from=None,
-                 renumber=1, device=-1, inletQ=None, kernel=None, tile_cells=0, block_threads=0,
+                 renumber=2, device=-1, inletQ=None, kernel=None, tile_cells=0, block_threads=0,
                  **consts):
         L = lib()
         self.dim = int(flat["dim"])

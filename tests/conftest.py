@@ -81,5 +81,7 @@ def rel_linf(Qa, Qb, gamma=1.4):
     """max_k max_c |Qa - Qb| / scale_k(Qb)"""
     fin = np.isfinite(Qb).all(axis=1)
     assert np.array_equal(np.isfinite(Qa).all(axis=1), fin), "finite masks differ"
+    if not fin.any():
+        return 0.0  # everything NaN on both sides (unlimited scheme on a random state)
     s = char_scales(Qb[fin], gamma)
     return float((np.abs(Qa[fin] - Qb[fin]) / s).max())

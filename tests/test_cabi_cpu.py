@@ -32,7 +32,7 @@ def test_version_and_default_config():
     assert b"sm_100a" in mstgpu.lib().mstgpu_version()
     c = mstgpu.default_config(2)
     # R/include/CONST.h:38-48, SolverRoe.cpp:115
-    assert (c.order, c.flux, c.viscous, c.renumber) == (2, 0, 0, 1)
+    assert (c.order, c.flux, c.viscous, c.renumber, c.kernel) == (2, 0, 0, 2, 1)
     assert (c.gamma, c.delta, c.eor, c.cv) == (1.4, 0.125, 1e-10, 715.8)
     assert c.inletQ[0] == 1.0 and c.inletQ[1] == 0.0 and abs(c.inletQ[3] - 2.5) < 1e-12
     c3 = mstgpu.default_config(3)
@@ -73,7 +73,9 @@ def _mean_neighbour_distance(f, perm):
 @pytest.mark.parametrize("name", ["2d-shockwavepipe-2", "2d-stairW-1", "box"])
 def test_plan_is_a_locality_improving_permutation(name):
     f = box_flat(12, 12, 12) if name == "box" else load_flat(name)
-    cp, fp = mstgpu.plan_permutation(f, 1)
+    cp, fp = mstgpu.plan_permutation(f, 2)
+    cm, _ = mstgpu.plan_permutation(f, 1)
+    assert np.array_equal(np.sort(cm), np.arange(f["ncells"]))
     assert np.array_equal(np.sort(cp), np.arange(f["ncells"]))
     assert np.array_equal(np.sort(fp), np.arange(f["nfaces"]))
     # interior faces stay in front of boundary faces
@@ -86,3 +88,21 @@ def test_plan_is_a_locality_improving_permutation(name):
     # renumber = 0 keeps the reference order
     cp0, fp0 = mstgpu.plan_permutation(f, 0)
     assert np.array_equal(cp0, ident)
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_tiling_statistics(order):
+    """Host-side tiling of the fused kernel: every cell is owned by exactly one
+    tile; Hilbert ranges are more compact than Morton ranges on a mesh that is
+    not aligned with the octree; packets stay under the geometry budget."""
+    f = box_flat(23, 23, 23)
+    nc = f["ncells"]
+    sh = mstgpu.tile_stats(f, order=order, tile_cells=96, renumber=2)
+    sm = mstgpu.tile_stats(f, order=order, tile_cells=96, renumber=1)
+    assert sh["tiles"] == -(-nc // 96)
+    assert sh["sum_flux_faces"] >= f["nfaces"]            # every face is a flux face of some tile
+    assert sh["sum_flux_faces"] < 1.5 * f["nfaces"]       # ... with bounded duplication
+    assert sh["sum_ring1"] <= sm["sum_ring1"]
+    assert sh["max_smem"] < 227 * 1024
+    if order == 2:
+        assert sh["packet_bytes"] / nc < 400

@@ -48,16 +48,22 @@ def test_one_step_random_state(name, flux, order, kernel):
     Qf, G, F = o.probe()
     phi_ref = np.einsum("fd,fdk->fk", f["dac"][:, None] * f["S"], F)
     phi = g.debug_face_flux()
-    assert np.abs(phi - phi_ref).max() <= TOL_1STEP * np.abs(phi_ref).max()
+    m = np.isfinite(phi_ref)  # unlimited 2nd order from a random state can produce NaN (sqrt of p < 0): same faces
+    assert np.array_equal(np.isfinite(phi), m)
+    assert np.abs(phi[m] - phi_ref[m]).max() <= TOL_1STEP * np.abs(phi_ref[m]).max()
     if order == 2:
         Gg = g.debug_gradient()
         assert np.abs(Gg - G).max() <= TOL_1STEP * np.abs(G).max()
     # residual (Time.cpp:69-76)
-    ro = np.zeros(4)
-    x = np.abs(Qo - Q0) / Q0
+    with np.errstate(invalid="ignore", divide="ignore"):
+        x = np.abs(Qo - Q0) / Q0
     ro = np.nanmax(np.where(x > 0, x, 0), axis=0)
-    rg = g.residual()
-    assert np.allclose(rg, ro, rtol=1e-9, atol=0)
+    if np.isfinite(Qo).all():
+        rg = g.residual()
+        assert np.allclose(rg, ro, rtol=1e-9, atol=0)
+    else:  # failure detection: a NaN state is reported through the C ABI
+        with pytest.raises(mstgpu.MstGpuError, match="NaN"):
+            g.residual()
 
 
 @pytest.mark.parametrize("flux", ["roe", "ausm"])
@@ -139,12 +145,17 @@ def test_3d_tets_one_step_and_20_steps(flux, order, kernel):
     assert rel_linf(g.get_state(), Q20) <= 1e-10
 
 
-@pytest.mark.parametrize("tile_cells,block_threads", [(32, 128), (64, 256), (126, 128), (256, 256), (510, 256), (1024, 256)])
+def test_oversized_tile_is_rejected():
+    f = box_flat(6, 5, 4)
+    with pytest.raises(mstgpu.MstGpuError, match="shared memory"):
+        mstgpu.Context(f, order=2, kernel="tiles", tile_cells=2048)
+
+
+@pytest.mark.parametrize("tile_cells,block_threads", [(32, 128), (64, 256), (126, 128), (256, 256), (384, 256)])
 @pytest.mark.parametrize("dim", [2, 3])
 def test_tile_shapes(tile_cells, block_threads, dim):
     """Any tiling gives the oracle's answer: tiles smaller / larger than the
-    default, odd-sized last tile, one tile for the whole mesh (2-D case with
-    1024 on 3 103 cells has 4 tiles; the 3-D box of 720 cells fits in one)."""
+    default, odd-sized last tile, a handful of tiles for the whole mesh."""
     if dim == 2:
         f = load_flat("2d-stair-un-5-tri")
         inlet = None
