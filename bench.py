@@ -190,13 +190,29 @@ def run_ours(args, rank, world):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        raise SystemExit("multi-GPU path not built yet")
 
     f, Q0, desc = build_workload(args)
-    nc, U, D = f["ncells"], f["dim"] + 2, f["dim"]
+    nc_total, U, D = f["ncells"], f["dim"] + 2, f["dim"]
     t = time.time()
-    ctx = mstgpu.Context(f, order=2, flux="roe", device=local, kernel=args.kernel,
-                         tile_cells=args.tile_cells, block_threads=args.block_threads, renumber=args.renumber)
+    if world > 1:
+        # one partition per GPU (equal ranges of the Hilbert curve), 2 ghost layers
+        part = mstgpu.Partition(f, world, rank, order=2)
+        log(f"[bench] rank {rank}: {part.n_owned} owned + {part.n_local - part.n_owned} ghost cells, "
+            f"{part.n_neighbors} neighbours, partition in {time.time() - t:.1f}s")
+        ctx = mstgpu.Context(part, order=2, flux="roe", device=local, kernel=args.kernel,
+                             tile_cells=args.tile_cells, block_threads=args.block_threads, renumber=args.renumber)
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.frombuffer(bytearray(mstgpu.comm_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(idt, 0)
+        ctx.comm_init(world, rank, idt.cpu().numpy().tobytes())
+        Q0 = np.ascontiguousarray(Q0[part.cell_ids[:part.n_owned]])
+        nc = part.n_owned
+        del f["cf_idx"]
+    else:
+        ctx = mstgpu.Context(f, order=2, flux="roe", device=local, kernel=args.kernel,
+                             tile_cells=args.tile_cells, block_threads=args.block_threads, renumber=args.renumber)
+        nc = nc_total
     log(f"[bench] context built in {time.time() - t:.1f}s, {ctx.device_bytes / 2**30:.2f} GiB on device")
     ctx.set_state(Q0)
     ctx.step(DT, args.warmup)
@@ -207,18 +223,26 @@ def run_ours(args, rank, world):
     clocks = ClockSampler(local)
     clocks.start()
     time.sleep(0.3)
+    if dist is not None:
+        dist.barrier()
     torch.cuda.synchronize()
     w0 = time.perf_counter()
     ms = ctx.step_timed(DT, args.steps)
     torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
     wall = time.perf_counter() - w0
     clk = clocks.stop()
+    if dist is not None:  # device time of the slowest rank
+        tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
     launches = ctx.launch_count - l0
-    kt = {k: ctx.kernel_time(k) for k in ("gradient", "flux", "update", "step_tiles")}
+    kt = {k: ctx.kernel_time(k) for k in ("gradient", "flux", "update", "step_tiles", "halo_pack")}
     kt = {k: v for k, v in kt.items() if v[1] > 0}
     ctx.enable_kernel_timing(False)
     res = ctx.residual()
-    value = nc * args.steps / (ms * 1e-3)
+    value = nc_total * args.steps / (ms * 1e-3)
     log(f"[bench] {args.steps} steps in {ms:.2f} ms (wall {wall * 1e3:.2f} ms), residual {res}")
 
     # ---- roofline of the dominant kernel --------------------------------------
@@ -267,8 +291,14 @@ def run_ours(args, rank, world):
         r = ctx.residual()                     # D2H of the residual (Time.cpp:69-76)
         hin, hout = hout, hin                  # updateNewToOld on the host side
     torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
     e2e_s = (time.perf_counter() - e0) / ne
-    e2e = dict(value=nc / e2e_s, unit="cell-updates/s", h2d_bytes_per_step=nc * U * 8,
+    if dist is not None:
+        te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = float(te.item())
+    e2e = dict(value=nc_total / e2e_s, unit="cell-updates/s", h2d_bytes_per_step=nc * U * 8,
                d2h_bytes_per_step=nc * U * 8 + U * 8, ms_per_step=e2e_s * 1e3, steps=ne)
 
     cpu = cpu_baseline(args) if (world == 1 and not args.no_cpu) else None
@@ -276,14 +306,19 @@ def run_ours(args, rank, world):
     out = dict(metric="cell_updates_per_sec", value=value, unit="cell-updates/s", n_gpus=world,
                steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True,
                scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
-               config=dict(workload=f"{args.workload}{args.n}: {desc}", cells=nc, faces=f["nfaces"], flux="roe",
+               config=dict(workload=f"{args.workload}{args.n}: {desc}", cells=nc_total, faces=f["nfaces"], flux="roe",
+                           parallelism=f"{world} partition(s), Hilbert ranges, 2 ghost layers, NCCL send/recv + allreduce(max)",
                            order=2, dt=DT, kernel=args.kernel, tile_cells=args.tile_cells, renumber=args.renumber,
                            block_threads=args.block_threads, l2="inputs larger than L2 (state + tables >> 126 MB)"
-                           if nc * U * 8 > 2 ** 28 else "inputs smaller than L2: flush not applied"),
+                           if nc_total * U * 8 > 2 ** 28 else "inputs smaller than L2: flush not applied"),
                clocks=clk, e2e=e2e, gpu_launches=launches, roofline=roof, cpu_baseline=cpu,
                wall_ms_per_step=wall * 1e3 / args.steps, device_gib=ctx.device_bytes / 2 ** 30)
     if rank == 0:
         print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.barrier()
+        ctx.close()
+        dist.destroy_process_group()
 
 
 def main():

@@ -154,6 +154,36 @@ int mstgpu_enable_kernel_timing(mstgpu_ctx* ctx, int32_t on);
 int mstgpu_kernel_time(mstgpu_ctx* ctx, const char* name, double* ms, int64_t* launches);
 int64_t mstgpu_device_bytes(mstgpu_ctx* ctx);
 
+/* ---- multi-GPU: one partition per GPU, ghost-cell halo exchange over NCCL --------
+ * The reference has no distributed path; these entry points are
+ * the build's own.  Every rank holds the global flat mesh (as the reference's
+ * host code does after reading the .msh), asks for its partition, creates a
+ * context on it and joins a communicator.  State moves in the partition's own
+ * cell order: owned cells by ascending global id (mstgpu_partition_cell_ids).
+ * Results are bit-identical to the single-GPU run for any partition count. */
+typedef struct mstgpu_part mstgpu_part;
+
+/* cell_part: [ncells] partition of every global cell, or NULL for equal ranges of
+ * the Hilbert curve.  Host only (no CUDA call). */
+int mstgpu_partition_create(mstgpu_part** out, const mstgpu_mesh* global_mesh, const mstgpu_config* cfg,
+                            int32_t nparts, int32_t rank, const int32_t* cell_part);
+void mstgpu_partition_destroy(mstgpu_part* part);
+/* local mesh: owned cells, then ghost cells grouped by owner rank */
+const mstgpu_mesh* mstgpu_partition_mesh(const mstgpu_part* part);
+int mstgpu_partition_sizes(const mstgpu_part* part, int32_t* n_owned, int32_t* n_local, int32_t* n_neighbors);
+const int32_t* mstgpu_partition_cell_ids(const mstgpu_part* part); /* [n_local] local -> global */
+int mstgpu_partition_neighbor(const mstgpu_part* part, int32_t i, int32_t* rank, int32_t* send_count,
+                              const int32_t** send_local, int32_t* recv_first, int32_t* recv_count);
+
+/* Context on a partition: set/get_state move the n_owned owned rows only. */
+int mstgpu_create_partitioned(mstgpu_ctx** out, const mstgpu_part* part, const mstgpu_config* cfg);
+/* NCCL bootstrap: rank 0 obtains an id, the host broadcasts the 128 bytes by its
+ * own means (MPI, torch.distributed, a file), every rank calls comm_init. */
+int mstgpu_comm_unique_id(char* out128);
+int mstgpu_comm_init(mstgpu_ctx* ctx, int32_t nranks, int32_t rank, const char* id128);
+/* With a communicator, mstgpu_step exchanges ghost states before every step and
+ * mstgpu_residual_linf is COLLECTIVE (max over ranks, ncclAllReduce). */
+
 /* Host-only: the renumbering mstgpu_create would apply (no CUDA call), for
  * inspection and CPU tests.  cell_new2old [ncells], face_new2old [nfaces]. */
 int mstgpu_plan_permutation(const mstgpu_mesh* mesh, const mstgpu_config* cfg,

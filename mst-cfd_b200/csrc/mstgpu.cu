@@ -7,6 +7,8 @@
 //
 // No CPU fallback exists in this file: every entry point needs a CUDA device.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <cstdio>
 #include <cstring>
@@ -16,6 +18,7 @@
 
 #include "../../include/mstgpu.h"
 #include "physics.cuh"
+#include "partition.h"
 #include "plan.h"
 #include "step_tiles.cuh"
 #include "tiles.h"
@@ -33,6 +36,45 @@ using namespace mst;
 
 namespace {
 thread_local std::string g_create_error;
+
+// NCCL is bound at run time, on first use, not at link time: a host process
+// that also runs PyTorch already carries a libnccl.so.2 of its own (newer than
+// the system one), and two different NCCLs under one soname cannot coexist.
+// dlopen by soname returns whichever copy the process has loaded already.
+struct NcclApi {
+    void* h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string err;
+    bool load() {
+        if (h) return true;
+        h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) { err = std::string("cannot load libnccl: ") + dlerror(); return false; }
+#define MST_SYM(field, name)                                                   \
+    field = reinterpret_cast<decltype(field)>(dlsym(h, name));                 \
+    if (!field) { err = std::string("libnccl lacks ") + name; h = nullptr; return false; }
+        MST_SYM(GetUniqueId, "ncclGetUniqueId")
+        MST_SYM(CommInitRank, "ncclCommInitRank")
+        MST_SYM(CommDestroy, "ncclCommDestroy")
+        MST_SYM(GroupStart, "ncclGroupStart")
+        MST_SYM(GroupEnd, "ncclGroupEnd")
+        MST_SYM(Send, "ncclSend")
+        MST_SYM(Recv, "ncclRecv")
+        MST_SYM(AllReduce, "ncclAllReduce")
+        MST_SYM(GetErrorString, "ncclGetErrorString")
+#undef MST_SYM
+        return true;
+    }
+};
+NcclApi g_nccl;
 }
 
 struct KernelStat {
@@ -62,6 +104,16 @@ struct mstgpu_ctx {
     std::vector<TileClass> tile_classes;  // tiles grouped by shared-memory need (CTAs per SM)
     bool use_tiles = false;
     bool probes_valid = false;  // G / Phi hold the stages of the last step
+    // multi-GPU (partitioned context)
+    int n_owned = 0;  // cells advanced by this context (== nc when not partitioned)
+    bool partitioned = false;
+    struct HaloNb { int rank, send_off, send_count, recv_first, recv_count; };
+    std::vector<HaloNb> halo;
+    int32_t* send_idx = nullptr;  // device-order ids of the owned cells to send, all neighbours back to back
+    double* sendbuf = nullptr;
+    int send_total = 0;
+    ncclComm_t comm = nullptr;
+    int nranks = 1, rank = 0;
     unsigned long long* resid = nullptr;  // [U] bit patterns of non-negative doubles
     int* nanflag = nullptr;
     int cur = 0;          // Q[cur] = current ("old") state
@@ -215,7 +267,7 @@ __device__ __forceinline__ double warp_max(double x) {
 }
 
 template <int D>
-__global__ void __launch_bounds__(256) k_update(int nc, int nslot, double dt,
+__global__ void __launch_bounds__(256) k_update(int nc, int n_upd, int nslot, double dt,
                                                 const double* __restrict__ Qold,
                                                 const double* __restrict__ Phi,
                                                 const int32_t* __restrict__ cf,
@@ -229,7 +281,7 @@ __global__ void __launch_bounds__(256) k_update(int nc, int nslot, double dt,
 #pragma unroll
     for (int k = 0; k < U; k++) r[k] = 0.0;
     bool bad = false;
-    if (c < nc) {
+    if (c < n_upd) {
         double acc[U];
 #pragma unroll
         for (int k = 0; k < U; k++) acc[k] = 0.0;
@@ -267,6 +319,15 @@ __global__ void __launch_bounds__(256) k_update(int nc, int nslot, double dt,
         if (m > 0.0) atomicMax(&resid[threadIdx.x], (unsigned long long)__double_as_longlong(m));
     }
     if (anybad && threadIdx.x == 0) atomicOr(nanflag, 1);
+}
+
+// halo: gather the rows a neighbour needs into a contiguous send buffer
+__global__ void k_pack_rows(int n, int U, const int32_t* __restrict__ idx, const double* __restrict__ Q,
+                            double* __restrict__ buf) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * U) return;
+    const int r = i / U, k = i - r * U;
+    buf[i] = Q[(size_t)idx[r] * U + k];
 }
 
 // state in reference order <-> device order
@@ -376,9 +437,41 @@ int launch_tiles(mstgpu_ctx* ctx, double dt, const double* Qo, double* Qn) {
     return MSTGPU_OK;
 }
 
+#define NK(call)                                                                  \
+    do {                                                                          \
+        ncclResult_t r_ = (call);                                                 \
+        if (r_ != ncclSuccess) {                                                  \
+            set_error(ctx, std::string(#call) + ": " + g_nccl.GetErrorString(r_)); \
+            return MSTGPU_ERR_NCCL;                                               \
+        }                                                                         \
+    } while (0)
+
+// ghost rows of Q <- owners' rows.  One pack kernel, one grouped send/recv; the
+// receives land directly in the ghost block of Q (ghosts are ordered by owner).
+int halo_exchange(mstgpu_ctx* ctx, double* Q) {
+    if (!ctx->partitioned || ctx->halo.empty()) return MSTGPU_OK;
+    if (!ctx->comm) { set_error(ctx, "partitioned context without a communicator: call mstgpu_comm_init"); return MSTGPU_ERR_STATE; }
+    const int U = ctx->U;
+    if (ctx->send_total > 0) {
+        KTimer t(ctx, "halo_pack");
+        k_pack_rows<<<(ctx->send_total * U + 255) / 256, 256, 0, ctx->stream>>>(ctx->send_total, U, ctx->send_idx, Q, ctx->sendbuf);
+    }
+    NK(g_nccl.GroupStart());
+    for (const auto& h : ctx->halo) {
+        if (h.send_count) NK(g_nccl.Send(ctx->sendbuf + (size_t)h.send_off * U, (size_t)h.send_count * U, ncclDouble, h.rank, ctx->comm, ctx->stream));
+        if (h.recv_count) NK(g_nccl.Recv(Q + (size_t)h.recv_first * U, (size_t)h.recv_count * U, ncclDouble, h.rank, ctx->comm, ctx->stream));
+    }
+    NK(g_nccl.GroupEnd());
+    return MSTGPU_OK;
+}
+
 template <int D>
 int step_tiles_impl(mstgpu_ctx* ctx, double dt, int nsteps) {
     for (int s = 0; s < nsteps; s++) {
+        {
+            int r = halo_exchange(ctx, ctx->Q[ctx->cur]);
+            if (r) return r;
+        }
         const double* Qo = ctx->Q[ctx->cur];
         double* Qn = ctx->Q[ctx->cur ^ 1];
         CK(cudaMemsetAsync(ctx->resid, 0, 8 * sizeof(unsigned long long), ctx->stream));
@@ -408,6 +501,10 @@ int step_impl(mstgpu_ctx* ctx, double dt, int nsteps) {
     }
     if (nsteps > 0) ctx->probes_valid = true;
     for (int s = 0; s < nsteps; s++) {
+        {
+            int r = halo_exchange(ctx, ctx->Q[ctx->cur]);
+            if (r) return r;
+        }
         const double* Qo = ctx->Q[ctx->cur];
         double* Qn = ctx->Q[ctx->cur ^ 1];
         CK(cudaMemsetAsync(ctx->resid, 0, 8 * sizeof(unsigned long long), ctx->stream));
@@ -427,8 +524,8 @@ int step_impl(mstgpu_ctx* ctx, double dt, int nsteps) {
         }
         {
             KTimer t(ctx, "update");
-            k_update<D><<<(nc + 255) / 256, 256, 0, ctx->stream>>>(
-                nc, ctx->nslot, dt, Qo, ctx->Phi, ctx->cf, ctx->vol, Qn, ctx->resid, ctx->nanflag);
+            k_update<D><<<(ctx->n_owned + 255) / 256, 256, 0, ctx->stream>>>(
+                nc, ctx->n_owned, ctx->nslot, dt, Qo, ctx->Phi, ctx->cf, ctx->vol, Qn, ctx->resid, ctx->nanflag);
         }
         ctx->cur ^= 1;  // RhoSolver::updateNewToOld as a pointer swap
     }
@@ -522,7 +619,7 @@ void mstgpu_default_config(mstgpu_config* cfg, int32_t dim) {
     cfg->inletQ[dim + 1] = 1.0 * ((1 / 286.32) * 715.8 + 0.0);
 }
 
-int mstgpu_create(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_config* cfg) {
+static int create_impl(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_config* cfg, const Partition* part) {
     mstgpu_ctx* ctx = nullptr;
     if (!out || !mesh || !cfg) { set_error(nullptr, "null argument"); return MSTGPU_ERR_ARG; }
     *out = nullptr;
@@ -538,10 +635,14 @@ int mstgpu_create(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_config
     ctx = new mstgpu_ctx;
     ctx->cfg = *cfg;
     ctx->use_tiles = cfg->kernel != 0;
-    std::string perr = build_plan(*mesh, *cfg, ctx->plan);
+    mstgpu_config pcfg = *cfg;
+    if (part) pcfg.qf_copy_from = 0x7fffffff;  // already folded into the partition's eta table
+    std::string perr = build_plan(*mesh, pcfg, ctx->plan, part ? part->n_owned : -1);
     if (!perr.empty()) { set_error(nullptr, perr); delete ctx; return MSTGPU_ERR_ARG; }
     Plan& p = ctx->plan;
     ctx->D = p.D; ctx->U = p.U; ctx->nc = p.nc; ctx->nf = p.nf; ctx->nslot = p.nslot;
+    ctx->n_owned = part ? part->n_owned : p.nc;
+    ctx->partitioned = part != nullptr;
     int rc = [&]() -> int {
         if (cfg->device >= 0) { CK(cudaSetDevice(cfg->device)); ctx->device = cfg->device; }
         else CK(cudaGetDevice(&ctx->device));
@@ -569,7 +670,7 @@ int mstgpu_create(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_config
         if (ctx->use_tiles) {
             TilePack tp;
             int T = cfg->tile_cells > 0 ? cfg->tile_cells : (p.D == 3 ? 128 : 256);
-            std::string terr = build_tiles(p, p.nc, T, cfg->order, tp);
+            std::string terr = build_tiles(p, ctx->n_owned, T, cfg->order, tp);
             if (!terr.empty()) { set_error(ctx, terr); return MSTGPU_ERR_ARG; }
             int dev_smem = 0;
             CK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
@@ -620,6 +721,17 @@ int mstgpu_create(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_config
         }
         size_t nstage = std::max(nq * p.D, (size_t)p.nf * p.U);
         if ((r = dalloc(ctx, &ctx->stage, nstage))) return r;
+        if (part) {
+            std::vector<int32_t> sidx;
+            for (const Neighbor& nb : part->nbrs) {
+                mstgpu_ctx::HaloNb h{nb.rank, (int)sidx.size(), (int)nb.send_local.size(), nb.recv_first, nb.recv_count};
+                for (int32_t l : nb.send_local) sidx.push_back(p.cell_old2new[l]);
+                ctx->halo.push_back(h);
+            }
+            ctx->send_total = (int)sidx.size();
+            if ((r = upload(ctx, &ctx->send_idx, sidx))) return r;
+            if ((r = dalloc(ctx, &ctx->sendbuf, (size_t)std::max(1, ctx->send_total) * p.U))) return r;
+        }
         if ((r = dalloc(ctx, &ctx->resid, (size_t)8))) return r;
         if ((r = dalloc(ctx, &ctx->nanflag, (size_t)1))) return r;
         CK(cudaMemsetAsync(ctx->resid, 0, 8 * sizeof(unsigned long long), ctx->stream));
@@ -646,10 +758,17 @@ int mstgpu_create(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_config
     return MSTGPU_OK;
 }
 
+int mstgpu_create(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_config* cfg) {
+    return create_impl(out, mesh, cfg, nullptr);
+}
+
 void mstgpu_destroy(mstgpu_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm && g_nccl.h) g_nccl.CommDestroy(ctx->comm);
+    if (ctx->send_idx) cudaFree(ctx->send_idx);
+    if (ctx->sendbuf) cudaFree(ctx->sendbuf);
     void* ptrs[] = {ctx->Q[0], ctx->Q[1], ctx->G, ctx->Phi, ctx->stage, ctx->Sd, ctx->dx0, ctx->dx1, ctx->eta,
                     ctx->vol, ctx->fc0, ctx->fc1, ctx->cf, ctx->cell_new2old, ctx->face_new2old, ctx->meta,
                     ctx->resid, ctx->nanflag};
@@ -667,16 +786,16 @@ void mstgpu_destroy(mstgpu_ctx* ctx) {
 
 int mstgpu_set_state(mstgpu_ctx* ctx, const double* q, int64_t ncells) {
     if (!ctx || !q) return MSTGPU_ERR_ARG;
-    if (ncells != ctx->nc) { set_error(ctx, "set_state: ncells mismatch"); return MSTGPU_ERR_ARG; }
+    if (ncells != ctx->n_owned) { set_error(ctx, "set_state: ncells mismatch"); return MSTGPU_ERR_ARG; }
     CK(cudaSetDevice(ctx->device));
-    const size_t tot = (size_t)ctx->nc * ctx->U;
+    const size_t tot = (size_t)ctx->n_owned * ctx->U;
     CK(cudaMemcpyAsync(ctx->stage, q, tot * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    k_permute_in<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(ctx->nc, ctx->U, ctx->stage,
+    k_permute_in<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(ctx->n_owned, ctx->U, ctx->stage,
                                                                          ctx->cell_new2old, ctx->Q[ctx->cur]);
     ctx->launches++;
     CK(cudaGetLastError());
     // prev state == current until the first step (Time.cpp:16-18 fills both)
-    CK(cudaMemcpyAsync(ctx->Q[ctx->cur ^ 1], ctx->Q[ctx->cur], tot * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->Q[ctx->cur ^ 1], ctx->Q[ctx->cur], (size_t)ctx->nc * ctx->U * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->nanflag, 0, sizeof(int), ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->has_state = true;
@@ -687,14 +806,14 @@ int mstgpu_get_state(mstgpu_ctx* ctx, double* q) {
     if (!ctx || !q) return MSTGPU_ERR_ARG;
     if (!ctx->has_state) { set_error(ctx, "get_state before set_state"); return MSTGPU_ERR_STATE; }
     CK(cudaSetDevice(ctx->device));
-    return fetch_permuted(ctx, ctx->Q[ctx->cur], ctx->cell_new2old, ctx->nc, ctx->U, q);
+    return fetch_permuted(ctx, ctx->Q[ctx->cur], ctx->cell_new2old, ctx->n_owned, ctx->U, q);
 }
 
 int mstgpu_get_prev_state(mstgpu_ctx* ctx, double* q) {
     if (!ctx || !q) return MSTGPU_ERR_ARG;
     if (!ctx->has_state) { set_error(ctx, "get_prev_state before set_state"); return MSTGPU_ERR_STATE; }
     CK(cudaSetDevice(ctx->device));
-    return fetch_permuted(ctx, ctx->Q[ctx->cur ^ 1], ctx->cell_new2old, ctx->nc, ctx->U, q);
+    return fetch_permuted(ctx, ctx->Q[ctx->cur ^ 1], ctx->cell_new2old, ctx->n_owned, ctx->U, q);
 }
 
 int mstgpu_step(mstgpu_ctx* ctx, double dt, int32_t nsteps) {
@@ -734,6 +853,11 @@ int mstgpu_residual_linf(mstgpu_ctx* ctx, double* out) {
     CK(cudaSetDevice(ctx->device));
     unsigned long long bits[8];
     int nan = 0;
+    if (ctx->comm) {
+        // max of non-negative doubles == max of their bit patterns as unsigned integers
+        NK(g_nccl.AllReduce(ctx->resid, ctx->resid, 8, ncclUint64, ncclMax, ctx->comm, ctx->stream));
+        NK(g_nccl.AllReduce(ctx->nanflag, ctx->nanflag, 1, ncclInt32, ncclMax, ctx->comm, ctx->stream));
+    }
     CK(cudaMemcpyAsync(bits, ctx->resid, sizeof(bits), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(&nan, ctx->nanflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -786,6 +910,69 @@ int mstgpu_kernel_time(mstgpu_ctx* ctx, const char* name, double* ms, int64_t* l
 }
 
 int64_t mstgpu_device_bytes(mstgpu_ctx* ctx) { return ctx ? ctx->dev_bytes : -1; }
+
+struct mstgpu_part {
+    Partition p;
+};
+
+int mstgpu_partition_create(mstgpu_part** out, const mstgpu_mesh* g, const mstgpu_config* cfg, int32_t nparts,
+                            int32_t rank, const int32_t* cell_part) {
+    if (!out || !g || !cfg) { set_error(nullptr, "null argument"); return MSTGPU_ERR_ARG; }
+    *out = nullptr;
+    mstgpu_part* h = new mstgpu_part;
+    std::string e = build_partition(*g, *cfg, nparts, rank, cell_part, h->p);
+    if (!e.empty()) { set_error(nullptr, e); delete h; return MSTGPU_ERR_ARG; }
+    *out = h;
+    return MSTGPU_OK;
+}
+void mstgpu_partition_destroy(mstgpu_part* part) { delete part; }
+const mstgpu_mesh* mstgpu_partition_mesh(const mstgpu_part* part) { return part ? &part->p.mesh : nullptr; }
+int mstgpu_partition_sizes(const mstgpu_part* part, int32_t* n_owned, int32_t* n_local, int32_t* n_neighbors) {
+    if (!part) return MSTGPU_ERR_ARG;
+    if (n_owned) *n_owned = part->p.n_owned;
+    if (n_local) *n_local = part->p.n_local;
+    if (n_neighbors) *n_neighbors = (int32_t)part->p.nbrs.size();
+    return MSTGPU_OK;
+}
+const int32_t* mstgpu_partition_cell_ids(const mstgpu_part* part) { return part ? part->p.local2global.data() : nullptr; }
+int mstgpu_partition_neighbor(const mstgpu_part* part, int32_t i, int32_t* rank, int32_t* send_count,
+                              const int32_t** send_local, int32_t* recv_first, int32_t* recv_count) {
+    if (!part || i < 0 || i >= (int32_t)part->p.nbrs.size()) return MSTGPU_ERR_ARG;
+    const Neighbor& n = part->p.nbrs[i];
+    if (rank) *rank = n.rank;
+    if (send_count) *send_count = (int32_t)n.send_local.size();
+    if (send_local) *send_local = n.send_local.data();
+    if (recv_first) *recv_first = n.recv_first;
+    if (recv_count) *recv_count = n.recv_count;
+    return MSTGPU_OK;
+}
+
+int mstgpu_create_partitioned(mstgpu_ctx** out, const mstgpu_part* part, const mstgpu_config* cfg) {
+    if (!part) { set_error(nullptr, "null partition"); return MSTGPU_ERR_ARG; }
+    return create_impl(out, &part->p.mesh, cfg, &part->p);
+}
+
+int mstgpu_comm_unique_id(char* out128) {
+    mstgpu_ctx* ctx = nullptr;
+    if (!out128) return MSTGPU_ERR_ARG;
+    if (!g_nccl.load()) { set_error(nullptr, g_nccl.err); return MSTGPU_ERR_NCCL; }
+    ncclUniqueId id;
+    NK(g_nccl.GetUniqueId(&id));
+    static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+    std::memcpy(out128, &id, 128);
+    return MSTGPU_OK;
+}
+
+int mstgpu_comm_init(mstgpu_ctx* ctx, int32_t nranks, int32_t rank, const char* id128) {
+    if (!ctx || !id128) return MSTGPU_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (!g_nccl.load()) { set_error(ctx, g_nccl.err); return MSTGPU_ERR_NCCL; }
+    ncclUniqueId id;
+    std::memcpy(&id, id128, 128);
+    NK(g_nccl.CommInitRank(&ctx->comm, nranks, id, rank));
+    ctx->nranks = nranks; ctx->rank = rank;
+    return MSTGPU_OK;
+}
 
 int mstgpu_plan_permutation(const mstgpu_mesh* mesh, const mstgpu_config* cfg, int32_t* cell_new2old,
                             int32_t* face_new2old) {

@@ -48,7 +48,44 @@ inline void axes_to_transpose(uint32_t* X, int b, int n) {
 
 }  // namespace
 
-std::string build_plan(const mstgpu_mesh& m, const mstgpu_config& cfg, Plan& p) {
+void curve_order(const mstgpu_mesh& m, int renumber, int n, std::vector<int32_t>& new2old) {
+    const int D = m.dim;
+    new2old.resize(n);
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int c = 0; c < n; c++)
+        for (int d = 0; d < D; d++) {
+            double x = m.cc[(size_t)c * D + d];
+            if (x == x) { lo[d] = std::min(lo[d], x); hi[d] = std::max(hi[d], x); }
+        }
+    const double bits = (D == 3) ? 2097151.0 : 2147483647.0;
+    // one scale for all axes: the curve's cells stay cubes on a stretched domain
+    double ext = 0.0;
+    for (int d = 0; d < D; d++) ext = std::max(ext, hi[d] - lo[d]);
+    const double sc = ext > 0 ? bits / ext : 0.0;
+    std::vector<std::pair<uint64_t, int32_t>> key(n);
+#pragma omp parallel for schedule(static)
+    for (int c = 0; c < n; c++) {
+        uint64_t k = 0;
+        uint32_t qq[3] = {0, 0, 0};
+        for (int d = 0; d < D; d++) {
+            double x = m.cc[(size_t)c * D + d];
+            double t = (x == x) ? (x - lo[d]) * sc : 0.0;
+            uint64_t q = (uint64_t)std::min(std::max(t, 0.0), bits);
+            if (renumber == 2) qq[d] = (uint32_t)q;
+            else k |= (D == 3 ? spread3(q) : spread2(q)) << d;
+        }
+        if (renumber == 2) {
+            // Hilbert: consecutive cells are always neighbours -> any index range is one blob
+            axes_to_transpose(qq, D == 3 ? 21 : 31, D);
+            for (int d = 0; d < D; d++) k |= (D == 3 ? spread3(qq[d]) : spread2(qq[d])) << (D - 1 - d);
+        }
+        key[c] = {k, c};
+    }
+    std::sort(key.begin(), key.end());
+    for (int i = 0; i < n; i++) new2old[i] = key[i].second;
+}
+
+std::string build_plan(const mstgpu_mesh& m, const mstgpu_config& cfg, Plan& p, int n_owned) {
     const int D = m.dim;
     if (D != 2 && D != 3) return "dim must be 2 or 3";
     if (m.ncells <= 0 || m.nfaces <= 0) return "empty mesh";
@@ -67,40 +104,13 @@ std::string build_plan(const mstgpu_mesh& m, const mstgpu_config& cfg, Plan& p) 
     if (nslot <= 0 || nslot > 8) return "cells must have 1..8 faces";
     p.nslot = nslot;
 
-    // ---- cell order: Morton curve through the cell centres ----------------------
+    // ---- cell order: space-filling curve through the cell centres ------------------
     p.cell_new2old.resize(nc);
     std::iota(p.cell_new2old.begin(), p.cell_new2old.end(), 0);
     if (cfg.renumber != 0) {
-        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-        for (int c = 0; c < nc; c++)
-            for (int d = 0; d < D; d++) {
-                double x = m.cc[(size_t)c * D + d];
-                if (x == x) { lo[d] = std::min(lo[d], x); hi[d] = std::max(hi[d], x); }
-            }
-        const double bits = (D == 3) ? 2097151.0 : 2147483647.0;
-        double sc[3];
-        for (int d = 0; d < D; d++) sc[d] = (hi[d] > lo[d]) ? bits / (hi[d] - lo[d]) : 0.0;
-        std::vector<std::pair<uint64_t, int32_t>> key(nc);
-#pragma omp parallel for schedule(static)
-        for (int c = 0; c < nc; c++) {
-            uint64_t k = 0;
-            uint32_t qq[3] = {0, 0, 0};
-            for (int d = 0; d < D; d++) {
-                double x = m.cc[(size_t)c * D + d];
-                double t = (x == x) ? (x - lo[d]) * sc[d] : 0.0;
-                uint64_t q = (uint64_t)std::min(std::max(t, 0.0), bits);
-                if (cfg.renumber == 2) qq[d] = (uint32_t)q;
-                else k |= (D == 3 ? spread3(q) : spread2(q)) << d;
-            }
-            if (cfg.renumber == 2) {
-                // Hilbert: consecutive cells are always neighbours -> any index range is one blob
-                axes_to_transpose(qq, D == 3 ? 21 : 31, D);
-                for (int d = 0; d < D; d++) k |= (D == 3 ? spread3(qq[d]) : spread2(qq[d])) << (D - 1 - d);
-            }
-            key[c] = {k, c};
-        }
-        std::sort(key.begin(), key.end());
-        for (int i = 0; i < nc; i++) p.cell_new2old[i] = key[i].second;
+        std::vector<int32_t> ord;
+        curve_order(m, cfg.renumber, n_owned >= 0 ? n_owned : nc, ord);
+        std::copy(ord.begin(), ord.end(), p.cell_new2old.begin());
     }
     p.cell_old2new.resize(nc);
     for (int i = 0; i < nc; i++) p.cell_old2new[p.cell_new2old[i]] = i;

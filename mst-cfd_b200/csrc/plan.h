@@ -41,7 +41,12 @@ struct Plan {
     std::vector<int32_t> cf;        // [nslot*nc] 2*face + side (side 1: cell is c1), -1 = pad
 };
 
-// returns empty string on success, error text otherwise
-std::string build_plan(const mstgpu_mesh& m, const mstgpu_config& cfg, Plan& p);
+// returns empty string on success, error text otherwise.
+// n_owned >= 0: only cells [0, n_owned) are renumbered (among themselves); the
+// rest (ghost cells of a partition) keep their position behind them.
+std::string build_plan(const mstgpu_mesh& m, const mstgpu_config& cfg, Plan& p, int n_owned = -1);
+
+// space-filling-curve order of the first n cells (renumber: 1 Morton, 2 Hilbert)
+void curve_order(const mstgpu_mesh& m, int renumber, int n, std::vector<int32_t>& new2old);
 
 }  // namespace mst

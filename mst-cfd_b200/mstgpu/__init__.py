@@ -25,7 +25,10 @@ EXPORTS = [
     "mstgpu_get_state", "mstgpu_get_prev_state", "mstgpu_step", "mstgpu_step_timed",
     "mstgpu_residual_linf", "mstgpu_sync", "mstgpu_debug_gradient", "mstgpu_debug_face_flux",
     "mstgpu_launch_count", "mstgpu_enable_kernel_timing", "mstgpu_kernel_time",
-    "mstgpu_device_bytes", "mstgpu_plan_permutation", "mstgpu_tile_stats", "mstgpu_last_error", "mstgpu_version",
+    "mstgpu_device_bytes", "mstgpu_plan_permutation", "mstgpu_tile_stats",
+    "mstgpu_partition_create", "mstgpu_partition_destroy", "mstgpu_partition_mesh", "mstgpu_partition_sizes",
+    "mstgpu_partition_cell_ids", "mstgpu_partition_neighbor", "mstgpu_create_partitioned",
+    "mstgpu_comm_unique_id", "mstgpu_comm_init", "mstgpu_last_error", "mstgpu_version",
 ]
 
 
@@ -91,6 +94,19 @@ def lib():
         L.mstgpu_device_bytes.restype = i64
         L.mstgpu_plan_permutation.argtypes = [C.POINTER(MstMesh), C.POINTER(MstConfig), vp, vp]
         L.mstgpu_tile_stats.argtypes = [C.POINTER(MstMesh), C.POINTER(MstConfig), vp]
+        L.mstgpu_partition_create.argtypes = [C.POINTER(vp), C.POINTER(MstMesh), C.POINTER(MstConfig), i32, i32, vp]
+        L.mstgpu_partition_destroy.argtypes = [vp]
+        L.mstgpu_partition_destroy.restype = None
+        L.mstgpu_partition_mesh.argtypes = [vp]
+        L.mstgpu_partition_mesh.restype = C.POINTER(MstMesh)
+        L.mstgpu_partition_sizes.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+        L.mstgpu_partition_cell_ids.argtypes = [vp]
+        L.mstgpu_partition_cell_ids.restype = C.POINTER(i32)
+        L.mstgpu_partition_neighbor.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(C.POINTER(i32)),
+                                                C.POINTER(i32), C.POINTER(i32)]
+        L.mstgpu_create_partitioned.argtypes = [C.POINTER(vp), vp, C.POINTER(MstConfig)]
+        L.mstgpu_comm_unique_id.argtypes = [vp]
+        L.mstgpu_comm_init.argtypes = [vp, i32, i32, vp]
         L.mstgpu_last_error.argtypes = [vp]
         L.mstgpu_last_error.restype = C.c_char_p
         L.mstgpu_version.restype = C.c_char_p
@@ -147,14 +163,115 @@ def tile_stats(flat: dict, order: int = 2, tile_cells: int = 0, renumber: int = 
     return dict(zip(keys, (int(x) for x in out)))
 
 
+def make_config(dim, order=2, flux="roe", viscous=0, qf_copy_from=None, renumber=2, device=-1, inletQ=None,
+                kernel=None, tile_cells=0, block_threads=0, **consts) -> MstConfig:
+    cfg = default_config(dim)
+    cfg.order = order
+    cfg.flux = {"roe": 0, "ausm": 1}[flux] if isinstance(flux, str) else int(flux)
+    cfg.viscous = viscous
+    cfg.qf_copy_from = -1 if qf_copy_from is None else qf_copy_from
+    cfg.renumber = renumber
+    cfg.device = device
+    if kernel is not None:
+        cfg.kernel = {"tiles": 1, "split": 0}[kernel] if isinstance(kernel, str) else int(kernel)
+    cfg.tile_cells = tile_cells
+    cfg.block_threads = block_threads
+    for k, v in consts.items():
+        setattr(cfg, k, v)
+    if inletQ is not None:
+        for k in range(5):
+            cfg.inletQ[k] = float(inletQ[k]) if k < len(inletQ) else 0.0
+    return cfg
+
+
+class Partition:
+    """One rank's piece of a global flat mesh (host only): local mesh tables,
+    local->global cell ids, neighbour send / receive lists."""
+
+    def __init__(self, flat: dict, nparts: int, rank: int, cell_part=None, **cfg_kw):
+        L = lib()
+        m, keep = _mesh_struct(flat)
+        self.cfg = make_config(int(flat["dim"]), **cfg_kw)
+        cp = None if cell_part is None else np.ascontiguousarray(cell_part, dtype=np.int32)
+        h = C.c_void_p()
+        rc = L.mstgpu_partition_create(C.byref(h), C.byref(m), C.byref(self.cfg), nparts, rank,
+                                       None if cp is None else cp.ctypes.data)
+        if rc != 0:
+            raise MstGpuError(f"partition_create failed ({rc}): {L.mstgpu_last_error(None).decode()}")
+        self.h = h
+        self.dim = int(flat["dim"])
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        L.mstgpu_partition_sizes(h, C.byref(a), C.byref(b), C.byref(c))
+        self.n_owned, self.n_local, self.n_neighbors = a.value, b.value, c.value
+        self.cell_ids = np.ctypeslib.as_array(L.mstgpu_partition_cell_ids(h), shape=(self.n_local,)).copy()
+        self.neighbors = []
+        for i in range(self.n_neighbors):
+            r, sc, rf, rcnt = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+            sp = C.POINTER(C.c_int32)()
+            L.mstgpu_partition_neighbor(h, i, C.byref(r), C.byref(sc), C.byref(sp), C.byref(rf), C.byref(rcnt))
+            send = np.ctypeslib.as_array(sp, shape=(sc.value,)).copy() if sc.value else np.zeros(0, np.int32)
+            self.neighbors.append(dict(rank=r.value, send_local=send, recv_first=rf.value, recv_count=rcnt.value))
+
+    def local_flat(self) -> dict:
+        """The local mesh as a flat-mesh dict (copies), e.g. to run the oracle on it."""
+        m = lib().mstgpu_partition_mesh(self.h).contents
+        D, nc, nf = m.dim, m.ncells, m.nfaces
+
+        def arr(ptr, dt, shape):
+            n = int(np.prod(shape))
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(n,)).reshape(shape).copy()
+
+        cf_ptr = arr(m.cf_ptr, np.int32, (nc + 1,))
+        return dict(dim=D, ncells=nc, nfaces=nf, nint=m.nint, c0=arr(m.c0, np.int32, (nf,)), c1=arr(m.c1, np.int32, (nf,)),
+                    S=arr(m.S, np.float64, (nf, D)), dac=arr(m.dac, np.int8, (nf,)), fc=arr(m.fc, np.float64, (nf, D)),
+                    eta=arr(m.eta, np.float64, (nf,)), flag=arr(m.flag, np.uint8, (nf, D)),
+                    ftype=arr(m.ftype, np.int32, (nf,)), cc=arr(m.cc, np.float64, (nc, D)),
+                    vol=arr(m.vol, np.float64, (nc,)), cf_ptr=cf_ptr, cf_idx=arr(m.cf_idx, np.int32, (int(cf_ptr[-1]),)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().mstgpu_partition_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    rc = lib().mstgpu_comm_unique_id(buf)
+    if rc != 0:
+        raise MstGpuError(f"comm_unique_id failed ({rc}): {lib().mstgpu_last_error(None).decode()}")
+    return buf.raw
+
+
 class Context:
     """Owns one mstgpu_ctx.  `flat` is the flattened reference-order mesh (the
     dict produced by the host's mesh flattener)."""
 
-    def __init__(self, flat: dict, order=2, flux="roe", viscous=0, qf_copy_from=None,
+    def __init__(self, flat, order=2, flux="roe", viscous=0, qf_copy_from=None,
                  renumber=2, device=-1, inletQ=None, kernel=None, tile_cells=0, block_threads=0,
                  **consts):
         L = lib()
+        if isinstance(flat, Partition):
+            # one rank of a multi-GPU run: context on the partition's local mesh
+            part = flat
+            self.dim, self.U = part.dim, part.dim + 2
+            self.ncells = part.n_owned
+            self.nfaces = int(L.mstgpu_partition_mesh(part.h).contents.nfaces)
+            cfg = make_config(self.dim, order=order, flux=flux, viscous=viscous, qf_copy_from=qf_copy_from,
+                              renumber=renumber, device=device, inletQ=inletQ, kernel=kernel,
+                              tile_cells=tile_cells, block_threads=block_threads, **consts)
+            self.cfg = cfg
+            h = C.c_void_p()
+            rc = L.mstgpu_create_partitioned(C.byref(h), part.h, C.byref(cfg))
+            if rc != 0:
+                raise MstGpuError(f"mstgpu_create_partitioned failed ({rc}): {L.mstgpu_last_error(None).decode()}")
+            self.h = h
+            return
         self.dim = int(flat["dim"])
         self.U = self.dim + 2
         self.ncells = int(flat["ncells"])
@@ -197,6 +314,9 @@ class Context:
             self.close()
         except Exception:
             pass
+
+    def comm_init(self, nranks: int, rank: int, unique_id: bytes):
+        self._check(lib().mstgpu_comm_init(self.h, nranks, rank, unique_id), "comm_init")
 
     def set_state(self, Q):
         Q = np.ascontiguousarray(Q, dtype=np.float64)
