@@ -21,6 +21,12 @@ import tempfile
 import threading
 import time
 
+# torchrun pins OMP_NUM_THREADS=1; the host-side mesh / plan / partition builders
+# are OpenMP code, so give every rank its share of the cores before libgomp loads
+_world = int(os.environ.get("WORLD_SIZE", "1"))
+if os.environ.get("OMP_NUM_THREADS", "1") == "1":
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // _world))
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, "mst-cfd_b200")):
     if p not in sys.path:
@@ -322,13 +328,16 @@ def run_ours(args, rank, world):
 
 
 def main():
+    # stdout carries exactly one JSON line: keep NCCL's version banner off it
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="box", choices=["box", "step"])
-    ap.add_argument("--n", type=int, default=203, help="hexes per side (box) or 1/h (step)")
+    ap.add_argument("--size", "--n", dest="n", type=int, default=203, help="hexes per side (box) or 1/h (step)")
     ap.add_argument("--cpu-n", type=int, default=96, help="size of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--kernel", default="tiles", choices=["tiles", "split"])
