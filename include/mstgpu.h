@@ -184,6 +184,32 @@ int mstgpu_comm_init(mstgpu_ctx* ctx, int32_t nranks, int32_t rank, const char* 
 /* With a communicator, mstgpu_step exchanges ghost states before every step and
  * mstgpu_residual_linf is COLLECTIVE (max over ranks, ncclAllReduce). */
 
+/* ---- LU-SGS sweeps of the reference's lusolver ------------------------------------
+ * Replaces SparseSolverNUM::{setELE,addELE,setD,setRHSb,solveILUSGS,getPNewX}
+ * (R/lusolver/SparseSolverNUM.h:13-35) for block = 1 and
+ * SparseSolver<MT,VCT>::{setD,setL,setU,setRHSb,solveILU,getItBeginX}
+ * (R/lusolver/SparseSolver.h:13-22) for block = DIMU (4 or 5).  The matrix is
+ * handed over as CSR by row (columns ascending; blocks row-major, block x
+ * block doubles per entry): the entries a host would pass one by one to
+ * setELE / setD / setL / setU.  The sweeps run level by level and reproduce the
+ * reference's sequential result on the matrix ordering given;
+ * mstgpu_lusgs_color_order returns a colour ordering (few levels) for hosts that
+ * want to permute their system first. */
+typedef struct mstgpu_lusgs mstgpu_lusgs;
+int mstgpu_lusgs_create(mstgpu_lusgs** out, int32_t n, int32_t block, const int32_t* rowptr, const int32_t* col,
+                        int32_t device);
+void mstgpu_lusgs_destroy(mstgpu_lusgs* h);
+/* x: in = start vector (the constructors' pOldX), out = solution.  max_iter = LU_INTERVAL
+ * (CONST.h:58).  early_exit != 0 applies the scalar version's stop test
+ * 1e-20 < res < 1e-7 (SparseSolverNUM.cpp:205).  res_hist: [max_iter] or NULL. */
+int mstgpu_lusgs_solve(mstgpu_lusgs* h, const double* val, const double* b, double* x, int32_t max_iter,
+                       int32_t early_exit, double* res_hist, int32_t* iters_done);
+int mstgpu_lusgs_levels(mstgpu_lusgs* h, int32_t* forward_levels, int32_t* backward_levels);
+/* host only: greedy colouring of the symmetrised pattern; rows sorted by colour */
+int mstgpu_lusgs_color_order(int32_t n, const int32_t* rowptr, const int32_t* col, int32_t* perm_new2old,
+                             int32_t* ncolors);
+const char* mstgpu_lusgs_last_error(void);
+
 /* Host-only: the renumbering mstgpu_create would apply (no CUDA call), for
  * inspection and CPU tests.  cell_new2old [ncells], face_new2old [nfaces]. */
 int mstgpu_plan_permutation(const mstgpu_mesh* mesh, const mstgpu_config* cfg,

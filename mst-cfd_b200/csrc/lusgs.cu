@@ -1,0 +1,391 @@
+// lusgs.cu -- LU-SGS sweeps of the reference's lusolver on the GPU (C ABI in
+// include/mstgpu.h, mstgpu_lusgs_*).  Reference (R = /root/reference/MST-CFD):
+//   scalar  SparseSolverNUM::solveILUSGS    R/lusolver/SparseSolverNUM.cpp:144-212
+//   block   SparseSolver<MT,VCT>::solveILU  R/lusolver/SparseSolver.cpp:54-104
+//
+// The reference sweeps are strictly sequential (forward i = 0..n-1, backward
+// i = n-1..0, column-stored scatter).  Here the same recurrences run LEVEL BY
+// LEVEL: row r of the forward sweep only needs the final values of the rows
+// c < r it is coupled to, so all rows whose dependencies are complete form one
+// level and are processed by one launch.  Each row subtracts its terms in the
+// reference's order (ascending column forward, descending backward), so the
+// result equals the sequential sweep on the SAME matrix ordering -- no
+// reordering is imposed.  The number of levels is what the ordering makes it:
+// a colour-ordered matrix (mstgpu_lusgs_color_order) has one level per colour,
+// a lexicographic one a level per wavefront.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mstgpu.h"
+
+namespace {
+thread_local std::string g_lusgs_error;
+}
+
+struct mstgpu_lusgs {
+    int n = 0, B = 1, device = 0;
+    cudaStream_t stream = nullptr;
+    int nnz = 0, nL = 0, nU = 0;
+    // strictly-lower / strictly-upper CSR by row; pos = index of the entry in the caller's val array
+    int *Lptr = nullptr, *Lcol = nullptr, *Lpos = nullptr, *Uptr = nullptr, *Ucol = nullptr, *Upos = nullptr;
+    int *Dptr = nullptr, *Dpos = nullptr;  // diagonal entries per row (summed)
+    std::vector<int> fptr, bptr;           // level pointers (host)
+    int *frows = nullptr, *brows = nullptr;
+    double *val = nullptr, *D = nullptr, *Dinv = nullptr, *LD = nullptr, *UD = nullptr;
+    double *b = nullptr, *x = nullptr, *rhs = nullptr, *rhs1 = nullptr, *ux = nullptr;
+    unsigned long long* res = nullptr;
+    std::string err;
+};
+
+#define LCK(call)                                                                \
+    do {                                                                         \
+        cudaError_t e_ = (call);                                                 \
+        if (e_ != cudaSuccess) {                                                 \
+            g_lusgs_error = std::string(#call) + ": " + cudaGetErrorString(e_);  \
+            if (h) h->err = g_lusgs_error;                                       \
+            return MSTGPU_ERR_CUDA;                                              \
+        }                                                                        \
+    } while (0)
+
+namespace {
+
+template <int B>
+__device__ __forceinline__ void d_matvec(const double* m, const double* v, double* out) {
+#pragma unroll
+    for (int i = 0; i < B; i++) {
+        double s = m[i * B] * v[0];
+#pragma unroll
+        for (int k = 1; k < B; k++) s += m[i * B + k] * v[k];
+        out[i] = s;
+    }
+}
+
+template <int B>
+__device__ void d_inverse(const double* m, double* inv) {
+    if (B == 1) { inv[0] = 1.0 / m[0]; return; }
+    double w[B][2 * B];
+    for (int i = 0; i < B; i++)
+        for (int j = 0; j < B; j++) { w[i][j] = m[i * B + j]; w[i][B + j] = (i == j) ? 1.0 : 0.0; }
+    for (int c = 0; c < B; c++) {
+        int p = c;
+        for (int r = c + 1; r < B; r++) if (fabs(w[r][c]) > fabs(w[p][c])) p = r;
+        if (p != c) for (int j = 0; j < 2 * B; j++) { double t = w[c][j]; w[c][j] = w[p][j]; w[p][j] = t; }
+        const double ip = 1.0 / w[c][c];
+        for (int j = 0; j < 2 * B; j++) w[c][j] *= ip;
+        for (int r = 0; r < B; r++) {
+            if (r == c) continue;
+            const double f = w[r][c];
+            if (f == 0.0) continue;
+            for (int j = 0; j < 2 * B; j++) w[r][j] -= f * w[c][j];
+        }
+    }
+    for (int i = 0; i < B; i++) for (int j = 0; j < B; j++) inv[i * B + j] = w[i][B + j];
+}
+
+// D = sum of the row's diagonal entries (addD), Dinv = D^-1
+template <int B>
+__global__ void k_diag(int n, const int* Dptr, const int* Dpos, const double* val, double* D, double* Dinv) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    double d[B * B];
+    for (int q = 0; q < B * B; q++) d[q] = 0.0;
+    for (int k = Dptr[r]; k < Dptr[r + 1]; k++)
+        for (int q = 0; q < B * B; q++) d[q] += val[(size_t)Dpos[k] * B * B + q];
+    double di[B * B];
+    d_inverse<B>(d, di);
+    for (int q = 0; q < B * B; q++) { D[(size_t)r * B * B + q] = d[q]; Dinv[(size_t)r * B * B + q] = di[q]; }
+}
+
+// XD[e] = X[e] * Dinv[col[e]]   (the reference's (L * D^-1) factor, SparseSolver.cpp:86,96)
+template <int B>
+__global__ void k_scale(int ne, const int* col, const int* pos, const double* val, const double* D, const double* Dinv,
+                        double* XD) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ne) return;
+    const double* a = val + (size_t)pos[e] * B * B;
+    if (B == 1) { XD[e] = a[0] * (1. / D[col[e]]); return; }  // SparseSolverNUM.cpp:181: L * (1./D)
+    const double* di = Dinv + (size_t)col[e] * B * B;
+    for (int i = 0; i < B; i++)
+        for (int j = 0; j < B; j++) {
+            double s = a[i * B] * di[j];
+            for (int k = 1; k < B; k++) s += a[i * B + k] * di[k * B + j];
+            XD[(size_t)e * B * B + i * B + j] = s;
+        }
+}
+
+// ux[r] = D^-1 (sum_{c>r} U[r,c] x[c])     (SparseSolverNUM.cpp:158-166)
+template <int B>
+__global__ void k_ux(int n, const int* Uptr, const int* Ucol, const int* Upos, const double* val, const double* D,
+                     const double* Dinv, const double* x, double* ux) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    double acc[B], t[B];
+    for (int q = 0; q < B; q++) acc[q] = 0.0;
+    for (int k = Uptr[r]; k < Uptr[r + 1]; k++) {
+        d_matvec<B>(val + (size_t)Upos[k] * B * B, x + (size_t)Ucol[k] * B, t);
+        for (int q = 0; q < B; q++) acc[q] += t[q];
+    }
+    if (B == 1) { ux[r] = acc[0] / D[r]; return; }
+    d_matvec<B>(Dinv + (size_t)r * B * B, acc, t);
+    for (int q = 0; q < B; q++) ux[(size_t)r * B + q] = t[q];
+}
+
+// rhs[r] = b[r] + sum_{c<r} L[r,c] ux[c]   (SparseSolverNUM.cpp:167-175)
+template <int B>
+__global__ void k_rhs(int n, const int* Lptr, const int* Lcol, const int* Lpos, const double* val, const double* b,
+                      const double* ux, double* rhs) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    double acc[B], t[B];
+    for (int q = 0; q < B; q++) acc[q] = 0.0;
+    for (int k = Lptr[r]; k < Lptr[r + 1]; k++) {
+        d_matvec<B>(val + (size_t)Lpos[k] * B * B, ux + (size_t)Lcol[k] * B, t);
+        for (int q = 0; q < B; q++) acc[q] += t[q];
+    }
+    for (int q = 0; q < B; q++) rhs[(size_t)r * B + q] = b[(size_t)r * B + q] + acc[q];
+}
+
+// one level of a triangular sweep: v[r] -= sum_k XD[k] v[col[k]], k ascending (forward) or descending (backward)
+template <int B, bool FWD>
+__global__ void k_sweep_level(int nrows, const int* rows, const int* ptr, const int* col, const double* XD, double* v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrows) return;
+    const int r = rows[i];
+    double acc[B], t[B];
+    for (int q = 0; q < B; q++) acc[q] = v[(size_t)r * B + q];
+    const int k0 = ptr[r], k1 = ptr[r + 1];
+    for (int kk = 0; kk < k1 - k0; kk++) {
+        const int k = FWD ? k0 + kk : k1 - 1 - kk;
+        d_matvec<B>(XD + (size_t)k * B * B, v + (size_t)col[k] * B, t);
+        for (int q = 0; q < B; q++) acc[q] -= t[q];
+    }
+    for (int q = 0; q < B; q++) v[(size_t)r * B + q] = acc[q];
+}
+
+// X1 = D^-1 rhs; rhs1 = D X1   (SparseSolverNUM.cpp:184-187)
+template <int B>
+__global__ void k_mid(int n, const double* D, const double* Dinv, const double* rhs, double* rhs1) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    double x1[B], t[B];
+    if (B == 1) { x1[0] = (1. / D[r]) * rhs[r]; rhs1[r] = D[r] * x1[0]; return; }
+    d_matvec<B>(Dinv + (size_t)r * B * B, rhs + (size_t)r * B, x1);
+    d_matvec<B>(D + (size_t)r * B * B, x1, t);
+    for (int q = 0; q < B; q++) rhs1[(size_t)r * B + q] = t[q];
+}
+
+// xnew = D^-1 rhs1; residual (scalar only); x = xnew   (SparseSolverNUM.cpp:194-203)
+template <int B>
+__global__ void k_fin(int n, const double* D, const double* Dinv, const double* rhs1, double* x, unsigned long long* res) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    double rr = 0.0;
+    if (r < n) {
+        if (B == 1) {
+            const double xn = (1. / D[r]) * rhs1[r];
+            const double q = fabs(x[r] - xn) / x[r];
+            rr = (q > 0.0) ? q : 0.0;
+            x[r] = xn;
+        } else {
+            double t[B];
+            d_matvec<B>(Dinv + (size_t)r * B * B, rhs1 + (size_t)r * B, t);
+            for (int q = 0; q < B; q++) x[(size_t)r * B + q] = t[q];
+        }
+    }
+    if (B == 1) {
+        for (int o = 16; o > 0; o >>= 1) rr = fmax(rr, __shfl_xor_sync(0xffffffffu, rr, o));
+        if ((threadIdx.x & 31) == 0 && rr > 0.0) atomicMax(res, (unsigned long long)__double_as_longlong(rr));
+    }
+}
+
+template <typename T>
+int up(mstgpu_lusgs* h, T** d, const std::vector<T>& v) {
+    LCK(cudaMalloc((void**)d, std::max<size_t>(1, v.size()) * sizeof(T)));
+    if (!v.empty()) LCK(cudaMemcpy(*d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+template <int B>
+int solve_impl(mstgpu_lusgs* h, const double* val, const double* b, double* x, int max_iter, int early_exit,
+               double* res_hist, int32_t* iters_done) {
+    const int n = h->n, BB = B * B, T = 128;
+    cudaStream_t s = h->stream;
+    LCK(cudaMemcpyAsync(h->val, val, (size_t)h->nnz * BB * 8, cudaMemcpyHostToDevice, s));
+    LCK(cudaMemcpyAsync(h->b, b, (size_t)n * B * 8, cudaMemcpyHostToDevice, s));
+    LCK(cudaMemcpyAsync(h->x, x, (size_t)n * B * 8, cudaMemcpyHostToDevice, s));
+    k_diag<B><<<(n + T - 1) / T, T, 0, s>>>(n, h->Dptr, h->Dpos, h->val, h->D, h->Dinv);
+    if (h->nL) k_scale<B><<<(h->nL + T - 1) / T, T, 0, s>>>(h->nL, h->Lcol, h->Lpos, h->val, h->D, h->Dinv, h->LD);
+    if (h->nU) k_scale<B><<<(h->nU + T - 1) / T, T, 0, s>>>(h->nU, h->Ucol, h->Upos, h->val, h->D, h->Dinv, h->UD);
+    int it = 0;
+    for (; it < max_iter; it++) {
+        LCK(cudaMemsetAsync(h->res, 0, 8, s));
+        k_ux<B><<<(n + T - 1) / T, T, 0, s>>>(n, h->Uptr, h->Ucol, h->Upos, h->val, h->D, h->Dinv, h->x, h->ux);
+        k_rhs<B><<<(n + T - 1) / T, T, 0, s>>>(n, h->Lptr, h->Lcol, h->Lpos, h->val, h->b, h->ux, h->rhs);
+        for (size_t l = 1; l + 1 < h->fptr.size(); l++) {  // level 0 has no dependencies: nothing to subtract
+            const int cnt = h->fptr[l + 1] - h->fptr[l];
+            k_sweep_level<B, true><<<(cnt + T - 1) / T, T, 0, s>>>(cnt, h->frows + h->fptr[l], h->Lptr, h->Lcol, h->LD, h->rhs);
+        }
+        k_mid<B><<<(n + T - 1) / T, T, 0, s>>>(n, h->D, h->Dinv, h->rhs, h->rhs1);
+        for (size_t l = 1; l + 1 < h->bptr.size(); l++) {
+            const int cnt = h->bptr[l + 1] - h->bptr[l];
+            k_sweep_level<B, false><<<(cnt + T - 1) / T, T, 0, s>>>(cnt, h->brows + h->bptr[l], h->Uptr, h->Ucol, h->UD, h->rhs1);
+        }
+        k_fin<B><<<(n + T - 1) / T, T, 0, s>>>(n, h->D, h->Dinv, h->rhs1, h->x, h->res);
+        if (B == 1 && (res_hist || early_exit)) {
+            unsigned long long bits = 0;
+            LCK(cudaMemcpyAsync(&bits, h->res, 8, cudaMemcpyDeviceToHost, s));
+            LCK(cudaStreamSynchronize(s));
+            double r;
+            std::memcpy(&r, &bits, 8);
+            if (res_hist) res_hist[it] = r;
+            if (early_exit && r > 1e-10 * 1e-10 && r < 1e-7) { it++; break; }  // SparseSolverNUM.cpp:205
+        }
+    }
+    LCK(cudaGetLastError());
+    LCK(cudaMemcpyAsync(x, h->x, (size_t)n * B * 8, cudaMemcpyDeviceToHost, s));
+    LCK(cudaStreamSynchronize(s));
+    if (iters_done) *iters_done = it;
+    return MSTGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* mstgpu_lusgs_last_error(void) { return g_lusgs_error.c_str(); }
+
+int mstgpu_lusgs_color_order(int32_t n, const int32_t* rowptr, const int32_t* col, int32_t* perm_new2old,
+                             int32_t* ncolors) {
+    if (n <= 0 || !rowptr || !col || !perm_new2old) { g_lusgs_error = "bad argument"; return MSTGPU_ERR_ARG; }
+    // greedy first-fit colouring in the given order on the symmetrised pattern
+    std::vector<std::vector<int>> adj(n);
+    for (int r = 0; r < n; r++)
+        for (int k = rowptr[r]; k < rowptr[r + 1]; k++) {
+            const int c = col[k];
+            if (c < 0 || c >= n) { g_lusgs_error = "column out of range"; return MSTGPU_ERR_ARG; }
+            if (c != r) { adj[r].push_back(c); adj[c].push_back(r); }
+        }
+    std::vector<int> color(n, -1), used;
+    int nc = 0;
+    for (int r = 0; r < n; r++) {
+        used.assign(nc + 1, 0);
+        for (int c : adj[r]) if (color[c] >= 0) used[color[c]] = 1;
+        int k = 0;
+        while (k < nc && used[k]) k++;
+        color[r] = k;
+        nc = std::max(nc, k + 1);
+    }
+    std::vector<int> order(n);
+    for (int i = 0; i < n; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return color[a] < color[b]; });
+    for (int i = 0; i < n; i++) perm_new2old[i] = order[i];
+    if (ncolors) *ncolors = nc;
+    return MSTGPU_OK;
+}
+
+int mstgpu_lusgs_create(mstgpu_lusgs** out, int32_t n, int32_t block, const int32_t* rowptr, const int32_t* col,
+                        int32_t device) {
+    mstgpu_lusgs* h = nullptr;
+    if (!out || n <= 0 || !rowptr || !col) { g_lusgs_error = "bad argument"; return MSTGPU_ERR_ARG; }
+    *out = nullptr;
+    if (block != 1 && block != 4 && block != 5) { g_lusgs_error = "block size must be 1, 4 or 5"; return MSTGPU_ERR_ARG; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_lusgs_error = "no CUDA device"; return MSTGPU_ERR_CUDA; }
+    std::vector<int> Lptr(n + 1, 0), Uptr(n + 1, 0), Dptr(n + 1, 0), Lcol, Lpos, Ucol, Upos, Dpos;
+    for (int r = 0; r < n; r++) {
+        for (int k = rowptr[r]; k < rowptr[r + 1]; k++) {
+            const int c = col[k];
+            if (c < 0 || c >= n) { g_lusgs_error = "column out of range"; return MSTGPU_ERR_ARG; }
+            if (k > rowptr[r] && col[k - 1] > c) { g_lusgs_error = "columns must be ascending within a row"; return MSTGPU_ERR_ARG; }
+            if (c == r) Dpos.push_back(k);
+            else if (c < r) { Lcol.push_back(c); Lpos.push_back(k); }
+            else { Ucol.push_back(c); Upos.push_back(k); }
+        }
+        Lptr[r + 1] = (int)Lcol.size(); Uptr[r + 1] = (int)Ucol.size(); Dptr[r + 1] = (int)Dpos.size();
+        if (Dptr[r + 1] == Dptr[r]) { g_lusgs_error = "row without a diagonal entry"; return MSTGPU_ERR_ARG; }
+    }
+    // dependency levels
+    std::vector<int> lf(n, 0), lb(n, 0);
+    int nlf = 0, nlb = 0;
+    for (int r = 0; r < n; r++) {
+        int l = 0;
+        for (int k = Lptr[r]; k < Lptr[r + 1]; k++) l = std::max(l, lf[Lcol[k]] + 1);
+        lf[r] = l; nlf = std::max(nlf, l + 1);
+    }
+    for (int r = n - 1; r >= 0; r--) {
+        int l = 0;
+        for (int k = Uptr[r]; k < Uptr[r + 1]; k++) l = std::max(l, lb[Ucol[k]] + 1);
+        lb[r] = l; nlb = std::max(nlb, l + 1);
+    }
+    auto bucket = [&](const std::vector<int>& lev, int nl, std::vector<int>& ptr, std::vector<int>& rows) {
+        ptr.assign(nl + 1, 0);
+        for (int r = 0; r < n; r++) ptr[lev[r] + 1]++;
+        for (int l = 0; l < nl; l++) ptr[l + 1] += ptr[l];
+        rows.resize(n);
+        std::vector<int> pos(ptr.begin(), ptr.end() - 1);
+        for (int r = 0; r < n; r++) rows[pos[lev[r]]++] = r;
+    };
+    h = new mstgpu_lusgs;
+    h->n = n; h->B = block; h->nnz = rowptr[n]; h->nL = (int)Lcol.size(); h->nU = (int)Ucol.size();
+    std::vector<int> frows, brows;
+    bucket(lf, nlf, h->fptr, frows);
+    bucket(lb, nlb, h->bptr, brows);
+    int rc = [&]() -> int {
+        if (device >= 0) LCK(cudaSetDevice(device));
+        LCK(cudaGetDevice(&h->device));
+        LCK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        int r;
+        if ((r = up(h, &h->Lptr, Lptr)) || (r = up(h, &h->Lcol, Lcol)) || (r = up(h, &h->Lpos, Lpos))) return r;
+        if ((r = up(h, &h->Uptr, Uptr)) || (r = up(h, &h->Ucol, Ucol)) || (r = up(h, &h->Upos, Upos))) return r;
+        if ((r = up(h, &h->Dptr, Dptr)) || (r = up(h, &h->Dpos, Dpos))) return r;
+        if ((r = up(h, &h->frows, frows)) || (r = up(h, &h->brows, brows))) return r;
+        const size_t BB = (size_t)block * block;
+        LCK(cudaMalloc((void**)&h->val, std::max<size_t>(1, h->nnz) * BB * 8));
+        LCK(cudaMalloc((void**)&h->D, n * BB * 8));
+        LCK(cudaMalloc((void**)&h->Dinv, n * BB * 8));
+        LCK(cudaMalloc((void**)&h->LD, std::max<size_t>(1, h->nL) * BB * 8));
+        LCK(cudaMalloc((void**)&h->UD, std::max<size_t>(1, h->nU) * BB * 8));
+        for (double** p : {&h->b, &h->x, &h->rhs, &h->rhs1, &h->ux}) LCK(cudaMalloc((void**)p, (size_t)n * block * 8));
+        LCK(cudaMalloc((void**)&h->res, 8));
+        return 0;
+    }();
+    if (rc) { mstgpu_lusgs_destroy(h); return rc; }
+    *out = h;
+    return MSTGPU_OK;
+}
+
+void mstgpu_lusgs_destroy(mstgpu_lusgs* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void* p : {(void*)h->Lptr, (void*)h->Lcol, (void*)h->Lpos, (void*)h->Uptr, (void*)h->Ucol, (void*)h->Upos,
+                    (void*)h->Dptr, (void*)h->Dpos, (void*)h->frows, (void*)h->brows, (void*)h->val, (void*)h->D,
+                    (void*)h->Dinv, (void*)h->LD, (void*)h->UD, (void*)h->b, (void*)h->x, (void*)h->rhs, (void*)h->rhs1,
+                    (void*)h->ux, (void*)h->res})
+        if (p) cudaFree(p);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int mstgpu_lusgs_levels(mstgpu_lusgs* h, int32_t* fwd, int32_t* bwd) {
+    if (!h) return MSTGPU_ERR_ARG;
+    if (fwd) *fwd = (int32_t)h->fptr.size() - 1;
+    if (bwd) *bwd = (int32_t)h->bptr.size() - 1;
+    return MSTGPU_OK;
+}
+
+int mstgpu_lusgs_solve(mstgpu_lusgs* h, const double* val, const double* b, double* x, int32_t max_iter,
+                       int32_t early_exit, double* res_hist, int32_t* iters_done) {
+    if (!h || !val || !b || !x || max_iter < 0) { g_lusgs_error = "bad argument"; return MSTGPU_ERR_ARG; }
+    LCK(cudaSetDevice(h->device));
+    switch (h->B) {
+        case 1: return solve_impl<1>(h, val, b, x, max_iter, early_exit, res_hist, iters_done);
+        case 4: return solve_impl<4>(h, val, b, x, max_iter, early_exit, res_hist, iters_done);
+        default: return solve_impl<5>(h, val, b, x, max_iter, early_exit, res_hist, iters_done);
+    }
+}
+
+}  // extern "C"

@@ -28,7 +28,9 @@ EXPORTS = [
     "mstgpu_device_bytes", "mstgpu_plan_permutation", "mstgpu_tile_stats",
     "mstgpu_partition_create", "mstgpu_partition_destroy", "mstgpu_partition_mesh", "mstgpu_partition_sizes",
     "mstgpu_partition_cell_ids", "mstgpu_partition_neighbor", "mstgpu_create_partitioned",
-    "mstgpu_comm_unique_id", "mstgpu_comm_init", "mstgpu_last_error", "mstgpu_version",
+    "mstgpu_comm_unique_id", "mstgpu_comm_init", "mstgpu_lusgs_create", "mstgpu_lusgs_destroy",
+    "mstgpu_lusgs_solve", "mstgpu_lusgs_levels", "mstgpu_lusgs_color_order", "mstgpu_lusgs_last_error",
+    "mstgpu_last_error", "mstgpu_version",
 ]
 
 
@@ -107,6 +109,13 @@ def lib():
         L.mstgpu_create_partitioned.argtypes = [C.POINTER(vp), vp, C.POINTER(MstConfig)]
         L.mstgpu_comm_unique_id.argtypes = [vp]
         L.mstgpu_comm_init.argtypes = [vp, i32, i32, vp]
+        L.mstgpu_lusgs_create.argtypes = [C.POINTER(vp), i32, i32, vp, vp, i32]
+        L.mstgpu_lusgs_destroy.argtypes = [vp]
+        L.mstgpu_lusgs_destroy.restype = None
+        L.mstgpu_lusgs_solve.argtypes = [vp, vp, vp, vp, i32, i32, vp, C.POINTER(i32)]
+        L.mstgpu_lusgs_levels.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
+        L.mstgpu_lusgs_color_order.argtypes = [i32, vp, vp, vp, C.POINTER(i32)]
+        L.mstgpu_lusgs_last_error.restype = C.c_char_p
         L.mstgpu_last_error.argtypes = [vp]
         L.mstgpu_last_error.restype = C.c_char_p
         L.mstgpu_version.restype = C.c_char_p
@@ -411,3 +420,59 @@ class GpuRhoSolver:
 
     def updateNewToOld(self):  # RhoSolver.cpp:513-517: already a pointer swap on the device
         return None
+
+
+def lusgs_color_order(rowptr, col):
+    """(perm_new2old, ncolors): greedy colour ordering of a CSR pattern (host only)."""
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int32); col = np.ascontiguousarray(col, dtype=np.int32)
+    n = rowptr.shape[0] - 1
+    perm = np.empty(n, dtype=np.int32)
+    nc = C.c_int32()
+    rc = lib().mstgpu_lusgs_color_order(n, rowptr.ctypes.data, col.ctypes.data, perm.ctypes.data, C.byref(nc))
+    if rc != 0:
+        raise MstGpuError(f"lusgs_color_order failed ({rc}): {lib().mstgpu_lusgs_last_error().decode()}")
+    return perm, nc.value
+
+
+class LuSgs:
+    """GPU LU-SGS solver for one sparsity pattern (mirror of the reference's
+    SparseSolverNUM for block = 1 and SparseSolver<MT,VCT> for block = DIMU)."""
+
+    def __init__(self, rowptr, col, block=1, device=-1):
+        self.rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
+        self.col = np.ascontiguousarray(col, dtype=np.int32)
+        self.n, self.block = self.rowptr.shape[0] - 1, block
+        h = C.c_void_p()
+        rc = lib().mstgpu_lusgs_create(C.byref(h), self.n, block, self.rowptr.ctypes.data, self.col.ctypes.data, device)
+        if rc != 0:
+            raise MstGpuError(f"lusgs_create failed ({rc}): {lib().mstgpu_lusgs_last_error().decode()}")
+        self.h = h
+
+    def levels(self):
+        a, b = C.c_int32(), C.c_int32()
+        lib().mstgpu_lusgs_levels(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def solve(self, val, b, x0, max_iter=5, early_exit=False):
+        B = self.block
+        val = np.ascontiguousarray(val, dtype=np.float64); b = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.array(x0, dtype=np.float64, order="C", copy=True)
+        assert val.size == self.col.shape[0] * B * B and b.size == self.n * B and x.size == self.n * B
+        hist = np.zeros(max_iter)
+        it = C.c_int32()
+        rc = lib().mstgpu_lusgs_solve(self.h, val.ctypes.data, b.ctypes.data, x.ctypes.data, max_iter,
+                                      1 if early_exit else 0, hist.ctypes.data, C.byref(it))
+        if rc != 0:
+            raise MstGpuError(f"lusgs_solve failed ({rc}): {lib().mstgpu_lusgs_last_error().decode()}")
+        return x, hist[:it.value], it.value
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().mstgpu_lusgs_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

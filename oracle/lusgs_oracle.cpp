@@ -1,2 +1,186 @@
 // ORACLE / TEST INFRASTRUCTURE -- NOT PRODUCT CODE.
-// (LU-SGS restatement is added with the sweep kernel; see rho_oracle.cpp header.)
+//
+// CPU restatement of the reference's LU-SGS sweeps (R = /root/reference/MST-CFD):
+//   scalar  SparseSolverNUM::solveILUSGS   R/lusolver/SparseSolverNUM.cpp:144-212
+//           (setELE/addELE column storage  R/lusolver/SparseSolverNUM.cpp:101-140)
+//   block   SparseSolver<MT,VCT>::solveILU R/lusolver/SparseSolver.cpp:54-104
+//
+// Like the reference, L and U are stored BY COLUMN (`columnL[c]` holds the
+// entries of column c in the order setELE was called) and every loop scatters.
+// The input here is CSR by row; entries are fed to the column lists in CSR
+// order (row ascending, position ascending), which fixes the call order.
+// Duplicate off-diagonal entries stay separate terms, as addELE leaves them
+// (SparseSolverNUM.cpp:128-140).
+//
+// Pinned against the reference's own SparseSolverNUM / SparseSolver compiled in
+// oracle/refbuild (tests/golden/ref_lusgs_*.npz).
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+namespace {
+
+template <int B>
+struct Blk {
+    double a[B * B];  // row-major
+};
+
+template <int B>
+static void inv_block(const double* m, double* inv) {
+    if (B == 1) { inv[0] = 1.0 / m[0]; return; }
+    if (B == 4) {  // cofactor inverse, as the Eigen stand-in / Eigen's fixed 4x4 path
+        double a00 = m[0], a01 = m[1], a02 = m[2], a03 = m[3], a10 = m[4], a11 = m[5], a12 = m[6], a13 = m[7];
+        double a20 = m[8], a21 = m[9], a22 = m[10], a23 = m[11], a30 = m[12], a31 = m[13], a32 = m[14], a33 = m[15];
+        double b00 = a00 * a11 - a01 * a10, b01 = a00 * a12 - a02 * a10, b02 = a00 * a13 - a03 * a10;
+        double b03 = a01 * a12 - a02 * a11, b04 = a01 * a13 - a03 * a11, b05 = a02 * a13 - a03 * a12;
+        double b06 = a20 * a31 - a21 * a30, b07 = a20 * a32 - a22 * a30, b08 = a20 * a33 - a23 * a30;
+        double b09 = a21 * a32 - a22 * a31, b10 = a21 * a33 - a23 * a31, b11 = a22 * a33 - a23 * a32;
+        double det = b00 * b11 - b01 * b10 + b02 * b09 + b03 * b08 - b04 * b07 + b05 * b06;
+        double id = 1.0 / det;
+        inv[0] = (a11 * b11 - a12 * b10 + a13 * b09) * id;   inv[1] = (-a01 * b11 + a02 * b10 - a03 * b09) * id;
+        inv[2] = (a31 * b05 - a32 * b04 + a33 * b03) * id;   inv[3] = (-a21 * b05 + a22 * b04 - a23 * b03) * id;
+        inv[4] = (-a10 * b11 + a12 * b08 - a13 * b07) * id;  inv[5] = (a00 * b11 - a02 * b08 + a03 * b07) * id;
+        inv[6] = (-a30 * b05 + a32 * b02 - a33 * b01) * id;  inv[7] = (a20 * b05 - a22 * b02 + a23 * b01) * id;
+        inv[8] = (a10 * b10 - a11 * b08 + a13 * b06) * id;   inv[9] = (-a00 * b10 + a01 * b08 - a03 * b06) * id;
+        inv[10] = (a30 * b04 - a31 * b02 + a33 * b00) * id;  inv[11] = (-a20 * b04 + a21 * b02 - a23 * b00) * id;
+        inv[12] = (-a10 * b09 + a11 * b07 - a12 * b06) * id; inv[13] = (a00 * b09 - a01 * b07 + a02 * b06) * id;
+        inv[14] = (-a30 * b03 + a31 * b01 - a32 * b00) * id; inv[15] = (a20 * b03 - a21 * b01 + a22 * b00) * id;
+        return;
+    }
+    double w[B][2 * B];
+    for (int i = 0; i < B; i++)
+        for (int j = 0; j < B; j++) { w[i][j] = m[i * B + j]; w[i][B + j] = (i == j) ? 1.0 : 0.0; }
+    for (int c = 0; c < B; c++) {
+        int p = c;
+        for (int r = c + 1; r < B; r++) if (std::fabs(w[r][c]) > std::fabs(w[p][c])) p = r;
+        if (p != c) for (int j = 0; j < 2 * B; j++) { double t = w[c][j]; w[c][j] = w[p][j]; w[p][j] = t; }
+        double ip = 1.0 / w[c][c];
+        for (int j = 0; j < 2 * B; j++) w[c][j] *= ip;
+        for (int r = 0; r < B; r++) {
+            if (r == c) continue;
+            double f = w[r][c];
+            if (f == 0.0) continue;
+            for (int j = 0; j < 2 * B; j++) w[r][j] -= f * w[c][j];
+        }
+    }
+    for (int i = 0; i < B; i++) for (int j = 0; j < B; j++) inv[i * B + j] = w[i][B + j];
+}
+
+template <int B>
+static inline void matvec(const double* m, const double* v, double* out) {  // out = m v, left-to-right sums
+    for (int i = 0; i < B; i++) {
+        double s = m[i * B] * v[0];
+        for (int k = 1; k < B; k++) s = s + m[i * B + k] * v[k];
+        out[i] = s;
+    }
+}
+template <int B>
+static inline void matmat(const double* a, const double* b, double* out) {
+    for (int i = 0; i < B; i++)
+        for (int j = 0; j < B; j++) {
+            double s = a[i * B] * b[j];
+            for (int k = 1; k < B; k++) s = s + a[i * B + k] * b[k * B + j];
+            out[i * B + j] = s;
+        }
+}
+
+template <int B>
+int lusgs(int n, const int32_t* rowptr, const int32_t* col, const double* val, const double* bvec, double* x,
+          int max_iter, int scalar_early_exit, double* res_hist, int32_t* iters_done) {
+    constexpr int BB = B * B;
+    // column storage, as setELE builds it
+    std::vector<std::vector<int>> idL(n), idU(n);
+    std::vector<std::vector<const double*>> vL(n), vU(n);
+    std::vector<const double*> D(n, nullptr);
+    std::vector<double> Dsum((size_t)n * BB, 0.0);
+    for (int r = 0; r < n; r++)
+        for (int k = rowptr[r]; k < rowptr[r + 1]; k++) {
+            const int c = col[k];
+            const double* v = val + (size_t)k * BB;
+            if (c == r) { for (int q = 0; q < BB; q++) Dsum[(size_t)r * BB + q] += v[q]; D[r] = &Dsum[(size_t)r * BB]; }  // addD
+            else if (r > c) { idL[c].push_back(r); vL[c].push_back(v); }
+            else { idU[c].push_back(r); vU[c].push_back(v); }
+        }
+    for (int r = 0; r < n; r++) if (!D[r]) return -1;
+    std::vector<double> RHS((size_t)n * B), RHS1((size_t)n * B), X1((size_t)n * B), Ux((size_t)n * B), LDUx((size_t)n * B);
+    int it = 0;
+    for (; it < max_iter; it++) {
+        for (size_t i = 0; i < (size_t)n * B; i++) { Ux[i] = 0.0; LDUx[i] = 0.0; }
+        double t[B], t2[B], Di[BB], M[BB];
+        for (int i = 0; i < n; i++)
+            for (size_t e = 0; e < idU[i].size(); e++) {
+                matvec<B>(vU[i][e], x + (size_t)i * B, t);
+                for (int q = 0; q < B; q++) Ux[(size_t)idU[i][e] * B + q] += t[q];
+            }
+        for (int i = 0; i < n; i++) {
+            if (B == 1) Ux[i] /= D[i][0];  // SparseSolverNUM.cpp:164-166
+            else { inv_block<B>(D[i], Di); matvec<B>(Di, &Ux[(size_t)i * B], t); for (int q = 0; q < B; q++) Ux[(size_t)i * B + q] = t[q]; }
+        }
+        for (int i = 0; i < n; i++)
+            for (size_t e = 0; e < idL[i].size(); e++) {
+                matvec<B>(vL[i][e], &Ux[(size_t)i * B], t);
+                for (int q = 0; q < B; q++) LDUx[(size_t)idL[i][e] * B + q] += t[q];
+            }
+        for (size_t i = 0; i < (size_t)n * B; i++) RHS[i] = bvec[i] + LDUx[i];
+        for (int i = 0; i < n; i++) {  // forward sweep
+            if (idL[i].empty()) continue;
+            inv_block<B>(D[i], Di);
+            for (size_t e = 0; e < idL[i].size(); e++) {
+                if (B == 1) { RHS[idL[i][e]] -= (vL[i][e][0]) * (1. / D[i][0]) * RHS[i]; continue; }
+                matmat<B>(vL[i][e], Di, M);  // (L * D^-1) * RHS, left to right
+                matvec<B>(M, &RHS[(size_t)i * B], t);
+                for (int q = 0; q < B; q++) RHS[(size_t)idL[i][e] * B + q] -= t[q];
+            }
+        }
+        for (int i = 0; i < n; i++) {
+            if (B == 1) { X1[i] = (1. / D[i][0]) * RHS[i]; RHS1[i] = D[i][0] * X1[i]; continue; }
+            inv_block<B>(D[i], Di);
+            matvec<B>(Di, &RHS[(size_t)i * B], t);
+            for (int q = 0; q < B; q++) X1[(size_t)i * B + q] = t[q];
+            matvec<B>(D[i], t, t2);
+            for (int q = 0; q < B; q++) RHS1[(size_t)i * B + q] = t2[q];
+        }
+        for (int i = n - 1; i != -1; i--) {  // backward sweep
+            if (idU[i].empty()) continue;
+            inv_block<B>(D[i], Di);
+            for (size_t e = 0; e < idU[i].size(); e++) {
+                if (B == 1) { RHS1[idU[i][e]] -= (vU[i][e][0]) * (1. / D[i][0]) * RHS1[i]; continue; }
+                matmat<B>(vU[i][e], Di, M);
+                matvec<B>(M, &RHS1[(size_t)i * B], t);
+                for (int q = 0; q < B; q++) RHS1[(size_t)idU[i][e] * B + q] -= t[q];
+            }
+        }
+        double res = 0.0;
+        for (int i = 0; i < n; i++) {
+            if (B == 1) {
+                const double xn = (1. / D[i][0]) * RHS1[i];
+                const double r = std::fabs(x[i] - xn) / x[i];  // signed denominator, SparseSolverNUM.cpp:196
+                if (res < r) res = r;
+                x[i] = xn;
+            } else {
+                inv_block<B>(D[i], Di);
+                matvec<B>(Di, &RHS1[(size_t)i * B], t);
+                for (int q = 0; q < B; q++) x[(size_t)i * B + q] = t[q];
+            }
+        }
+        if (res_hist) res_hist[it] = res;
+        // SparseSolverNUM.cpp:205: EOR*EOR < res < EOR2; the block version has no exit test
+        if (B == 1 && scalar_early_exit && res > 1e-10 * 1e-10 && res < 1e-7) { it++; break; }
+    }
+    if (iters_done) *iters_done = it;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int oracle_lusgs(int n, int bs, const int32_t* rowptr, const int32_t* col, const double* val,
+                            const double* b, double* x, int max_iter, int early_exit, double* res_hist,
+                            int32_t* iters_done) {
+    switch (bs) {
+        case 1: return lusgs<1>(n, rowptr, col, val, b, x, max_iter, early_exit, res_hist, iters_done);
+        case 4: return lusgs<4>(n, rowptr, col, val, b, x, max_iter, early_exit, res_hist, iters_done);
+        case 5: return lusgs<5>(n, rowptr, col, val, b, x, max_iter, early_exit, res_hist, iters_done);
+        default: return -2;
+    }
+}

@@ -61,6 +61,8 @@ def lib():
         L.oracle_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_riemann.argtypes = [C.c_int, C.c_int, C.POINTER(OmCfg), C.c_void_p,
                                      C.c_void_p, C.c_int, C.c_void_p]
+        L.oracle_lusgs.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int32)]
         _LIB = L
     return _LIB
 
@@ -162,3 +164,18 @@ def riemann(dim, flux, L, R, d, **cfg_kw) -> np.ndarray:
     out = np.empty(dim + 2)
     lib().oracle_riemann(dim, cfg.flux, C.byref(cfg), L.ctypes.data, R.ctypes.data, d, out.ctypes.data)
     return out
+
+
+def lusgs(rowptr, col, val, b, x0, block=1, max_iter=5, early_exit=False):
+    """Reference LU-SGS sweeps (lusgs_oracle.cpp).  Returns (x, residual history, iterations)."""
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int32); col = np.ascontiguousarray(col, dtype=np.int32)
+    val = np.ascontiguousarray(val, dtype=np.float64); b = np.ascontiguousarray(b, dtype=np.float64)
+    x = np.array(x0, dtype=np.float64, order="C", copy=True)
+    n = rowptr.shape[0] - 1
+    hist = np.zeros(max_iter)
+    it = C.c_int32()
+    rc = lib().oracle_lusgs(n, block, rowptr.ctypes.data, col.ctypes.data, val.ctypes.data, b.ctypes.data,
+                            x.ctypes.data, max_iter, 1 if early_exit else 0, hist.ctypes.data, C.byref(it))
+    if rc != 0:
+        raise RuntimeError(f"oracle_lusgs failed ({rc})")
+    return x, hist[:it.value], it.value
