@@ -113,7 +113,8 @@ typedef struct mstgpu_config {
     double kappa;         /* TEMPK (CONST.h:48)                                      */
     double cv;            /* CV (CONST.h:39)                                         */
     double inletQ[5];     /* inlet state (RhoSolver.cpp:123,266)                     */
-    int32_t kernel;       /* 1 = fused tile kernel (default), 0 = three-kernel path  */
+    int32_t kernel;       /* 1 = fused tile kernel (default), 0 = three-kernel path;
+                             viscous = 1 always runs the three-kernel path            */
     int32_t tile_cells;   /* cells per tile of the fused kernel, 0 = default         */
     int32_t block_threads;/* CTA size of the fused kernel (128|256), 0 = default     */
     int32_t reserved_;

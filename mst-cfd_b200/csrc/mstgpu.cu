@@ -91,7 +91,7 @@ struct mstgpu_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // device tables
-    double *Q[2] = {nullptr, nullptr}, *G = nullptr, *Phi = nullptr, *stage = nullptr;
+    double *Q[2] = {nullptr, nullptr}, *G = nullptr, *Gp = nullptr, *Phi = nullptr, *stage = nullptr;
     double *Sd = nullptr, *dx0 = nullptr, *dx1 = nullptr, *eta = nullptr, *vol = nullptr;
     int32_t *fc0 = nullptr, *fc1 = nullptr, *cf = nullptr, *cell_new2old = nullptr, *face_new2old = nullptr;
     uint32_t* meta = nullptr;
@@ -144,10 +144,16 @@ __global__ void __launch_bounds__(256) k_gradient(int nc, int nslot, const doubl
                                                   const double* __restrict__ eta,
                                                   const double* __restrict__ Sd,
                                                   const double* __restrict__ vol,
-                                                  double* __restrict__ G) {
+                                                  double* __restrict__ G, double* __restrict__ Gp, double cv) {
     constexpr int U = D + 2;
+    constexpr int P = D + 1;  // primitives differentiated for the viscous term: u_0..u_{D-1}, T
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nc) return;
+    double tp[P][D];
+#pragma unroll
+    for (int k = 0; k < P; k++)
+#pragma unroll
+        for (int d = 0; d < D; d++) tp[k][d] = 0.0;
     double qc[U];
 #pragma unroll
     for (int k = 0; k < U; k++) qc[k] = Q[(size_t)c * U + k];
@@ -181,8 +187,27 @@ __global__ void __launch_bounds__(256) k_gradient(int nc, int nslot, const doubl
 #pragma unroll
             for (int k = 0; k < U; k++) t[k][d] += qf[k] * s;
         }
+        if (Gp) {
+            // Green-Gauss gradient of the face primitives (laminar viscous extension)
+            double pr[P], m2 = 0.0;
+#pragma unroll
+            for (int i = 0; i < D; i++) { pr[i] = qf[i + 1] / qf[0]; m2 += qf[i + 1] * qf[i + 1]; }
+            pr[D] = (qf[U - 1] - 0.5 * m2 / qf[0]) / qf[0] / cv;  // FUNCTION.cpp:8-11
+#pragma unroll
+            for (int d = 0; d < D; d++) {
+                const double s = sg * Sd[(size_t)f * D + d];
+#pragma unroll
+                for (int k = 0; k < P; k++) tp[k][d] += pr[k] * s;
+            }
+        }
     }
     const double v = vol[c];
+    if (Gp) {
+#pragma unroll
+        for (int k = 0; k < P; k++)
+#pragma unroll
+            for (int d = 0; d < D; d++) Gp[((size_t)c * P + k) * D + d] = tp[k][d] / v;
+    }
 #pragma unroll
     for (int k = 0; k < U; k++)
 #pragma unroll
@@ -198,8 +223,10 @@ __global__ void __launch_bounds__(128) k_flux(int nf, DevCfg cfg, const double* 
                                               const double* __restrict__ Sd,
                                               const double* __restrict__ dx0,
                                               const double* __restrict__ dx1,
-                                              double* __restrict__ Phi) {
+                                              double* __restrict__ Phi, const double* __restrict__ Gp,
+                                              const double* __restrict__ eta) {
     constexpr int U = D + 2;
+    constexpr int P = D + 1;
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nf) return;
     const int a = fc0[f], b = fc1[f];
@@ -255,6 +282,50 @@ __global__ void __launch_bounds__(128) k_flux(int nf, DevCfg cfg, const double* 
     } else {
 #pragma unroll
         for (int k = 0; k < U; k++) phi[k] = 0.0;
+    }
+    if (Gp) {
+        // laminar viscous flux, corrected formulation (the reference's updateViscid,
+        // RhoSolver.cpp:371-429, cannot run): tau = mu (grad u + grad u^T) + lambda div(u) I,
+        // energy flux u.tau + k grad T, face values by the eta interpolation of the gradient pass
+        const double e = eta[f];
+        double qf[U], gf[P][D];
+        if (b >= 0) {
+#pragma unroll
+            for (int k = 0; k < U; k++) qf[k] = e * qa[k] + (1.0 - e) * Q[(size_t)b * U + k];
+#pragma unroll
+            for (int k = 0; k < P; k++)
+#pragma unroll
+                for (int d = 0; d < D; d++)
+                    gf[k][d] = e * Gp[((size_t)a * P + k) * D + d] + (1.0 - e) * Gp[((size_t)b * P + k) * D + d];
+        } else {
+#pragma unroll
+            for (int k = 0; k < U; k++) qf[k] = qa[k];
+#pragma unroll
+            for (int k = 0; k < P; k++)
+#pragma unroll
+                for (int d = 0; d < D; d++) gf[k][d] = Gp[((size_t)a * P + k) * D + d];
+        }
+        double uf[D], div = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; i++) { uf[i] = qf[i + 1] / qf[0]; div += gf[i][i]; }
+        double en = 0.0, fv[D];
+#pragma unroll
+        for (int i = 0; i < D; i++) fv[i] = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+            double w = 0.0;
+#pragma unroll
+            for (int i = 0; i < D; i++) {
+                double tij = cfg.mu * (gf[i][j] + gf[j][i]);
+                if (i == j) tij += cfg.lambda * div;
+                fv[i] += tij * S[j];
+                w += uf[i] * tij;
+            }
+            en += (w + cfg.kappa * gf[D][j]) * S[j];
+        }
+#pragma unroll
+        for (int i = 0; i < D; i++) phi[i + 1] -= fv[i];
+        phi[U - 1] -= en;
     }
 #pragma unroll
     for (int k = 0; k < U; k++) Phi[(size_t)f * U + k] = phi[k];
@@ -412,6 +483,10 @@ int ensure_stage_buffers(mstgpu_ctx* ctx) {
         if ((r = dalloc(ctx, &ctx->G, nq * ctx->D))) return r;
         CK(cudaMemsetAsync(ctx->G, 0, nq * ctx->D * sizeof(double), ctx->stream));
     }
+    if (ctx->cfg.viscous && !ctx->Gp) {
+        int r;
+        if ((r = dalloc(ctx, &ctx->Gp, (size_t)ctx->nc * (ctx->D + 1) * ctx->D))) return r;
+    }
     if (!ctx->Phi) {
         int r;
         if ((r = dalloc(ctx, &ctx->Phi, (size_t)ctx->nf * ctx->U))) return r;
@@ -508,19 +583,19 @@ int step_impl(mstgpu_ctx* ctx, double dt, int nsteps) {
         const double* Qo = ctx->Q[ctx->cur];
         double* Qn = ctx->Q[ctx->cur ^ 1];
         CK(cudaMemsetAsync(ctx->resid, 0, 8 * sizeof(unsigned long long), ctx->stream));
-        if (ctx->cfg.order == 2) {
+        if (ctx->cfg.order == 2 || ctx->cfg.viscous) {
             KTimer t(ctx, "gradient");
             k_gradient<D><<<(nc + 255) / 256, 256, 0, ctx->stream>>>(
-                nc, ctx->nslot, Qo, ctx->cf, ctx->fc0, ctx->fc1, ctx->eta, ctx->Sd, ctx->vol, ctx->G);
+                nc, ctx->nslot, Qo, ctx->cf, ctx->fc0, ctx->fc1, ctx->eta, ctx->Sd, ctx->vol, ctx->G, ctx->Gp, ctx->dcfg.cv);
         }
         {
             KTimer t(ctx, "flux");
             if (ctx->cfg.order == 2)
                 k_flux<D, 2><<<(nf + 127) / 128, 128, 0, ctx->stream>>>(
-                    nf, ctx->dcfg, Qo, ctx->G, ctx->fc0, ctx->fc1, ctx->meta, ctx->Sd, ctx->dx0, ctx->dx1, ctx->Phi);
+                    nf, ctx->dcfg, Qo, ctx->G, ctx->fc0, ctx->fc1, ctx->meta, ctx->Sd, ctx->dx0, ctx->dx1, ctx->Phi, ctx->Gp, ctx->eta);
             else
                 k_flux<D, 1><<<(nf + 127) / 128, 128, 0, ctx->stream>>>(
-                    nf, ctx->dcfg, Qo, ctx->G, ctx->fc0, ctx->fc1, ctx->meta, ctx->Sd, ctx->dx0, ctx->dx1, ctx->Phi);
+                    nf, ctx->dcfg, Qo, ctx->G, ctx->fc0, ctx->fc1, ctx->meta, ctx->Sd, ctx->dx0, ctx->dx1, ctx->Phi, ctx->Gp, ctx->eta);
         }
         {
             KTimer t(ctx, "update");
@@ -542,15 +617,15 @@ int recompute_stages(mstgpu_ctx* ctx) {
     if (r) return r;
     const int nc = ctx->nc, nf = ctx->nf;
     const double* Qo = ctx->Q[ctx->cur ^ 1];
-    if (ctx->cfg.order == 2)
+    if (ctx->cfg.order == 2 || ctx->cfg.viscous)
         k_gradient<D><<<(nc + 255) / 256, 256, 0, ctx->stream>>>(nc, ctx->nslot, Qo, ctx->cf, ctx->fc0, ctx->fc1, ctx->eta,
-                                                                 ctx->Sd, ctx->vol, ctx->G);
+                                                                 ctx->Sd, ctx->vol, ctx->G, ctx->Gp, ctx->dcfg.cv);
     if (ctx->cfg.order == 2)
         k_flux<D, 2><<<(nf + 127) / 128, 128, 0, ctx->stream>>>(nf, ctx->dcfg, Qo, ctx->G, ctx->fc0, ctx->fc1, ctx->meta,
-                                                                 ctx->Sd, ctx->dx0, ctx->dx1, ctx->Phi);
+                                                                 ctx->Sd, ctx->dx0, ctx->dx1, ctx->Phi, ctx->Gp, ctx->eta);
     else
         k_flux<D, 1><<<(nf + 127) / 128, 128, 0, ctx->stream>>>(nf, ctx->dcfg, Qo, ctx->G, ctx->fc0, ctx->fc1, ctx->meta,
-                                                                 ctx->Sd, ctx->dx0, ctx->dx1, ctx->Phi);
+                                                                 ctx->Sd, ctx->dx0, ctx->dx1, ctx->Phi, ctx->Gp, ctx->eta);
     ctx->launches += 2;
     CK(cudaGetLastError());
     ctx->probes_valid = true;
@@ -625,7 +700,7 @@ static int create_impl(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_c
     *out = nullptr;
     if (cfg->order != 1 && cfg->order != 2) { set_error(nullptr, "order must be 1 or 2"); return MSTGPU_ERR_ARG; }
     if (cfg->flux != MSTGPU_FLUX_ROE && cfg->flux != MSTGPU_FLUX_AUSM) { set_error(nullptr, "unknown flux"); return MSTGPU_ERR_ARG; }
-    if (cfg->viscous != 0) { set_error(nullptr, "laminar viscous term not built yet"); return MSTGPU_ERR_ARG; }
+    if (cfg->viscous != 0 && cfg->viscous != 1) { set_error(nullptr, "viscous must be 0 or 1"); return MSTGPU_ERR_ARG; }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -634,7 +709,8 @@ static int create_impl(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_c
     }
     ctx = new mstgpu_ctx;
     ctx->cfg = *cfg;
-    ctx->use_tiles = cfg->kernel != 0;
+    // the laminar viscous term lives in the split-kernel path (the fused tile kernel is inviscid)
+    ctx->use_tiles = cfg->kernel != 0 && cfg->viscous == 0;
     mstgpu_config pcfg = *cfg;
     if (part) pcfg.qf_copy_from = 0x7fffffff;  // already folded into the partition's eta table
     std::string perr = build_plan(*mesh, pcfg, ctx->plan, part ? part->n_owned : -1);
@@ -769,7 +845,7 @@ void mstgpu_destroy(mstgpu_ctx* ctx) {
     if (ctx->comm && g_nccl.h) g_nccl.CommDestroy(ctx->comm);
     if (ctx->send_idx) cudaFree(ctx->send_idx);
     if (ctx->sendbuf) cudaFree(ctx->sendbuf);
-    void* ptrs[] = {ctx->Q[0], ctx->Q[1], ctx->G, ctx->Phi, ctx->stage, ctx->Sd, ctx->dx0, ctx->dx1, ctx->eta,
+    void* ptrs[] = {ctx->Q[0], ctx->Q[1], ctx->G, ctx->Gp, ctx->Phi, ctx->stage, ctx->Sd, ctx->dx0, ctx->dx1, ctx->eta,
                     ctx->vol, ctx->fc0, ctx->fc1, ctx->cf, ctx->cell_new2old, ctx->face_new2old, ctx->meta,
                     ctx->resid, ctx->nanflag};
     for (void* q : ptrs)

@@ -510,7 +510,8 @@ struct Ctx {
             const double* ga = &Gp[(size_t)m.c0[f] * P * D];
             if (f < nint) {
                 const double* gb = &Gp[(size_t)m.c1[f] * P * D];
-                double e = m.eta[f];
+                // same effective weight as the face values Qf (qf_copy_from folded in)
+                double e = (f >= (cfg.qf_copy_from < 0 ? 0 : cfg.qf_copy_from)) ? 1.0 : m.eta[f];
                 for (int i = 0; i < P * D; i++) gf[i] = e * ga[i] + (1 - e) * gb[i];
             } else {
                 for (int i = 0; i < P * D; i++) gf[i] = ga[i];

@@ -258,3 +258,29 @@ def test_large_box_properties():
     for k in (0, 4):
         assert abs((V * Qn[:, k]).sum() - (V * Q[:, k]).sum()) < 1e-12 * (V * Q[:, k]).sum()
     assert np.isfinite(Qn).all()
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("order", [1, 2])
+def test_viscous_extension(dim, order):
+    """Laminar viscous term (documented extension): GPU
+    (split-kernel path) vs the oracle's corrected formulation; viscous wall =
+    negated momentum ghost (RhoSolver.cpp:301-305)."""
+    if dim == 2:
+        f = load_flat("2d-stairW-1"); inlet = None
+    else:
+        f = box_flat(6, 5, 4, bc=(10, 5, 3, 7, 3, 3), l=(1.0, 0.8, 0.6)); inlet = np.array([1.0, 0.4, 0.0, 0.0, 2.58])
+    Q0 = mesh_np.random_state(f, seed=6)
+    kw = dict(order=order, flux="roe", viscous=1, mu=0.01, kappa=0.5, inletQ=inlet)
+    o = oracle.Oracle(f, **kw)
+    g = mstgpu.Context(f, **kw)
+    g.set_state(Q0)
+    Q1 = o.run(1e-5, 1, Q0)
+    g.step(1e-5, 1)
+    assert rel_linf(g.get_state(), Q1) <= TOL_1STEP
+    # the term is active: the inviscid result differs
+    Qi = oracle.Oracle(f, order=order, flux="roe", viscous=0, inletQ=inlet).run(1e-5, 1, Q0)
+    assert rel_linf(Q1, Qi) > 1e-8
+    Q5 = o.run(1e-5, 4, Q1)
+    g.step(1e-5, 4)
+    assert rel_linf(g.get_state(), Q5) <= 1e-10
