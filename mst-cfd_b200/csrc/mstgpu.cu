@@ -495,30 +495,13 @@ int ensure_stage_buffers(mstgpu_ctx* ctx) {
     return MSTGPU_OK;
 }
 
-template <int D, int ORDER, int NT>
-int launch_tiles(mstgpu_ctx* ctx, double dt, const double* Qo, double* Qn) {
-    auto kern = k_step_tiles<D, ORDER, NT>;
-    static thread_local const void* configured = nullptr;
-    static thread_local size_t configured_smem = 0;
-    if (configured != (const void*)kern || configured_smem < ctx->tile_smem) {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->tile_smem));
-        configured = (const void*)kern;
-        configured_smem = ctx->tile_smem;
-    }
-    for (const auto& tc : ctx->tile_classes)
-        kern<<<tc.count, NT, tc.smem, ctx->stream>>>(ctx->ta, tc.first, ctx->dcfg, ctx->nslot, dt, Qo, Qn, ctx->resid,
-                                                     ctx->nanflag);
-    ctx->launches += (int64_t)ctx->tile_classes.size() - 1;
-    return MSTGPU_OK;
-}
-
-#define NK(call)                                                                  \
-    do {                                                                          \
-        ncclResult_t r_ = (call);                                                 \
-        if (r_ != ncclSuccess) {                                                  \
+#define NK(call)                                                                   \
+    do {                                                                           \
+        ncclResult_t r_ = (call);                                                  \
+        if (r_ != ncclSuccess) {                                                   \
             set_error(ctx, std::string(#call) + ": " + g_nccl.GetErrorString(r_)); \
-            return MSTGPU_ERR_NCCL;                                               \
-        }                                                                         \
+            return MSTGPU_ERR_NCCL;                                                \
+        }                                                                          \
     } while (0)
 
 // ghost rows of Q <- owners' rows.  One pack kernel, one grouped send/recv; the
@@ -540,6 +523,27 @@ int halo_exchange(mstgpu_ctx* ctx, double* Q) {
     return MSTGPU_OK;
 }
 
+template <int D, int ORDER, int NT, int NS>
+int launch_tiles(mstgpu_ctx* ctx, double dt, const double* Qo, double* Qn) {
+    auto kern = k_step_tiles<D, ORDER, NT, NS>;
+    static thread_local size_t configured_smem = 0;
+    if (configured_smem < ctx->tile_smem) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->tile_smem));
+        configured_smem = ctx->tile_smem;
+    }
+    for (const auto& tc : ctx->tile_classes)
+        kern<<<tc.count, NT, tc.smem, ctx->stream>>>(ctx->ta, tc.first, ctx->dcfg, dt, Qo, Qn, ctx->resid, ctx->nanflag);
+    ctx->launches += (int64_t)ctx->tile_classes.size() - 1;
+    return MSTGPU_OK;
+}
+
+template <int D, int NS>
+int launch_tiles_ns(mstgpu_ctx* ctx, double dt, const double* Qo, double* Qn) {
+    const bool o2 = ctx->cfg.order == 2;
+    if (ctx->tile_NT == 128) return o2 ? launch_tiles<D, 2, 128, NS>(ctx, dt, Qo, Qn) : launch_tiles<D, 1, 128, NS>(ctx, dt, Qo, Qn);
+    return o2 ? launch_tiles<D, 2, 256, NS>(ctx, dt, Qo, Qn) : launch_tiles<D, 1, 256, NS>(ctx, dt, Qo, Qn);
+}
+
 template <int D>
 int step_tiles_impl(mstgpu_ctx* ctx, double dt, int nsteps) {
     for (int s = 0; s < nsteps; s++) {
@@ -553,9 +557,13 @@ int step_tiles_impl(mstgpu_ctx* ctx, double dt, int nsteps) {
         {
             KTimer t(ctx, "step_tiles");
             int r;
-            const bool o2 = ctx->cfg.order == 2;
-            if (ctx->tile_NT == 128) r = o2 ? launch_tiles<D, 2, 128>(ctx, dt, Qo, Qn) : launch_tiles<D, 1, 128>(ctx, dt, Qo, Qn);
-            else r = o2 ? launch_tiles<D, 2, 256>(ctx, dt, Qo, Qn) : launch_tiles<D, 1, 256>(ctx, dt, Qo, Qn);
+            // stencil size = 1 + faces per cell: triangles 4, tets / quads 5, hexes 7
+            switch (ctx->nslot) {
+                case 3: r = launch_tiles_ns<D, 4>(ctx, dt, Qo, Qn); break;
+                case 4: r = launch_tiles_ns<D, 5>(ctx, dt, Qo, Qn); break;
+                case 6: r = launch_tiles_ns<D, 7>(ctx, dt, Qo, Qn); break;
+                default: set_error(ctx, "fused kernel supports cells with 3, 4 or 6 faces"); return MSTGPU_ERR_ARG;
+            }
             if (r) return r;
         }
         ctx->cur ^= 1;
@@ -652,7 +660,7 @@ int mstgpu_tile_stats(const mstgpu_mesh* mesh, const mstgpu_config* cfg, int64_t
     std::string perr = build_plan(*mesh, *cfg, p);
     if (!perr.empty()) { set_error(nullptr, perr); return MSTGPU_ERR_ARG; }
     TilePack tp;
-    int T = cfg->tile_cells > 0 ? cfg->tile_cells : (p.D == 3 ? 128 : 256);
+    int T = cfg->tile_cells > 0 ? cfg->tile_cells : 512;
     perr = build_tiles(p, p.nc, T, cfg->order, tp);
     if (!perr.empty()) { set_error(nullptr, perr); return MSTGPU_ERR_ARG; }
     for (int i = 0; i < 12; i++) out[i] = 0;
@@ -660,7 +668,7 @@ int mstgpu_tile_stats(const mstgpu_mesh* mesh, const mstgpu_config* cfg, int64_t
     out[3] = tp.sum_r1; out[4] = tp.sum_r2; out[5] = tp.sum_FB; out[6] = tp.sum_FA; out[7] = (int64_t)tp.packets.size();
     double sum = 0;
     for (const TileDesc& d : tp.desc) {
-        const size_t b = tile_layout(p.D, cfg->order, p.nslot, d.n_own, d.n_r1, d.n_r2, d.nFB, d.nFA).total;
+        const size_t b = tile_layout(p.D, cfg->order, p.nslot, d.n_own, d.n_r1, d.n_r2, d.nFB).total;
         sum += (double)b;
         out[8 + (b <= 56 * 1024 ? 0 : b <= 75 * 1024 ? 1 : b <= 113 * 1024 ? 2 : 3)]++;
     }
@@ -745,7 +753,7 @@ static int create_impl(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_c
         CK(cudaMemsetAsync(ctx->Q[1], 0, (nq + 2 * p.U) * sizeof(double), ctx->stream));
         if (ctx->use_tiles) {
             TilePack tp;
-            int T = cfg->tile_cells > 0 ? cfg->tile_cells : (p.D == 3 ? 128 : 256);
+            int T = cfg->tile_cells > 0 ? cfg->tile_cells : 512;
             std::string terr = build_tiles(p, ctx->n_owned, T, cfg->order, tp);
             if (!terr.empty()) { set_error(ctx, terr); return MSTGPU_ERR_ARG; }
             int dev_smem = 0;
@@ -763,7 +771,7 @@ static int create_impl(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_c
                 int ccount[4] = {0, 0, 0, 0};
                 for (int t = 0; t < tp.ntiles; t++) {
                     const TileDesc& d = tp.desc[t];
-                    const size_t b = tile_layout(p.D, cfg->order, p.nslot, d.n_own, d.n_r1, d.n_r2, d.nFB, d.nFA).total;
+                    const size_t b = tile_layout(p.D, cfg->order, p.nslot, d.n_own, d.n_r1, d.n_r2, d.nFB).total;
                     int c = 0;
                     while (c < 3 && b > lim[c]) c++;
                     cls[t] = c; ccount[c]++; cmax[c] = std::max(cmax[c], b);

@@ -11,13 +11,21 @@
 // tile and its rings in, Q of the tile out.  Neither the cell gradients
 // (120 B/cell) nor the face fluxes (2 x 40 B/cell) ever reach HBM.
 //
-// Data flow inside a CTA (all in shared memory):
-//   phase 0  TMA bulk copy of the packet + of the owned block of Q (one
-//            mbarrier), 40-byte row gathers of the ring cells
-//   phase 1  thread per gradient cell (owned + ring 1): Green-Gauss gradient in
-//            registers, reconstructed state written per (face, side) -> Rec
-//   phase 2  thread per flux face: A/B from Rec (conflict-free SoA reads),
-//            boundary ghost, Roe / AUSM+ contracted with the area vector -> Phis
+// The Green-Gauss gradient is never formed.  rec(c,f) = Q_c + G_c.(fc_f - cc_c) with
+// G_c = (1/V) sum_j Qf_j (x) Sout_j and Qf_j = eta Q[c0] + (1-eta) Q[c1] is LINEAR in
+// the states of c and its face neighbours, with weights that depend on geometry only:
+//     rec(c,f) = b0 Q_c + sum_j bj Q_nb(j).
+// The weights are computed once at upload (csrc/tiles.cpp), so the second-order
+// reconstruction of a face side is a (1 + faces-per-cell)-point weighted sum of
+// cell states -- no gradient phase, no gradient storage, one barrier less.
+//
+// Data flow inside a CTA:
+//   phase 0  TMA bulk copy of the owned block of Q (mbarrier) + 40-byte row
+//            gathers of the ring cells -> Qs (shared)
+//   phase 2  thread per flux face: weights / stencil ids / area vector / flags
+//            streamed from the tile packet (coalesced, read once), states
+//            gathered from Qs, boundary ghost, Roe / AUSM+ contracted with the
+//            area vector -> Phis (shared, SoA)
 //   phase 3  thread per owned cell: gather of its faces' Phis in the reference's
 //            face order, Euler update in place, residual; TMA bulk store of Q
 #pragma once
@@ -79,44 +87,41 @@ __device__ __forceinline__ double warp_max_nonneg(double x) {
     return __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
 }
 
-template <int D, int ORDER, int NT>
-__global__ void __launch_bounds__(NT) k_step_tiles(TileArrays ta, int tile_base, DevCfg cfg, int nslot, double dt,
+template <int D, int ORDER, int NT, int NS>
+__global__ void __launch_bounds__(NT) k_step_tiles(TileArrays ta, int tile_base, DevCfg cfg, double dt,
                                                    const double* __restrict__ Qold,
                                                    double* __restrict__ Qnew,
                                                    unsigned long long* __restrict__ resid,
                                                    int* __restrict__ nanflag) {
     constexpr int U = D + 2;
+    constexpr int nslot = NS - 1;
     extern __shared__ __align__(128) unsigned char smem[];
     const TileDesc d = ta.desc[tile_base + blockIdx.x];
     const int tid = threadIdx.x;
     const int n_own = d.n_own, n_ring = d.n_r1 + d.n_r2;
     const int nFB = d.nFB;
-    const TileLayout L = tile_layout(D, ORDER, nslot, d.n_own, d.n_r1, d.n_r2, d.nFB, d.nFA);
-    const int nFXp = L.nFXp, nFBp = L.nFBp, ncgp = L.ncgp, ncg = L.ncg;
-    const uint32_t* fab_s = reinterpret_cast<const uint32_t*>(smem + L.fab);
-    const double* feta_s = reinterpret_cast<const double*>(smem + L.feta);
-    const double* fSd_s = reinterpret_cast<const double*>(smem + L.fSd);
-    const uint16_t* slots_s = reinterpret_cast<const uint16_t*>(smem + L.slots);
-    const double* cvol_s = reinterpret_cast<const double*>(smem + L.cvol);
-    const double* fdx_s = reinterpret_cast<const double*>(smem + L.fdx);
-    const uint32_t* fmeta_s = reinterpret_cast<const uint32_t*>(smem + L.fmeta);
+    const TileLayout L = tile_layout(D, ORDER, nslot, d.n_own, d.n_r1, d.n_r2, d.nFB);
+    const int nFBp = L.nFBp, ncp = L.ncp;
+    const unsigned char* pk = ta.packets + d.pk_off;
+    const double* __restrict__ w_g = reinterpret_cast<const double*>(pk + L.w);
+    const uint32_t* __restrict__ idx_g = reinterpret_cast<const uint32_t*>(pk + L.idx);
+    const double* __restrict__ fSd_g = reinterpret_cast<const double*>(pk + L.fSd);
+    const uint32_t* __restrict__ fmeta_g = reinterpret_cast<const uint32_t*>(pk + L.fmeta);
+    const uint16_t* __restrict__ slots_g = reinterpret_cast<const uint16_t*>(pk + L.slots);
+    const double* __restrict__ cvol_g = reinterpret_cast<const double*>(pk + L.cvol);
     double* Qs = reinterpret_cast<double*>(smem + L.Qs);
-    double* Rec = reinterpret_cast<double*>(smem + L.Rec);    // [side][k][nFBp]
-    // [k][nFBp]; order 2: aliases the A side of Rec -- thread f overwrites only what it alone has read
-    double* Phis = reinterpret_cast<double*>(smem + L.Phis);
+    double* Phis = reinterpret_cast<double*>(smem + L.Phis);  // [k][nFBp]
     const uint32_t bar = smem_u32(smem + L.mbar);
 
-    // ---- phase 0: stage the tile ------------------------------------------------
+    // ---- phase 0: stage the states of the tile and its rings ------------------------
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
     if (tid == 0) {
         const uint32_t qbytes = (uint32_t)((n_own + 1) & ~1) * U * 8u;
-        mbar_expect_tx(bar, qbytes + L.pk_bytes);
-        bulk_g2s(smem_u32(smem), ta.packets + d.pk_off, L.pk_bytes, bar);
+        mbar_expect_tx(bar, qbytes);
         bulk_g2s(smem_u32(Qs), Qold + (size_t)d.cb * U, qbytes, bar);
     }
-    // ring cells: one thread per cell, U independent loads of a contiguous row
-    for (int r = tid; r < n_ring; r += NT) {
+    for (int r = tid; r < n_ring; r += NT) {  // one thread per ring cell, U independent loads of a contiguous row
         const int g = ta.ring[d.ring_off + r];
         double q[U];
 #pragma unroll
@@ -127,101 +132,56 @@ __global__ void __launch_bounds__(NT) k_step_tiles(TileArrays ta, int tile_base,
     mbar_wait(bar, 0);
     __syncthreads();
 
-    // ---- phase 1: Green-Gauss gradient + reconstruction at the cell's faces --------
-    if (ORDER == 2) {
-        for (int lc = tid; lc < ncg; lc += NT) {
-            double qc[U];
-#pragma unroll
-            for (int k = 0; k < U; k++) qc[k] = Qs[lc * U + k];
-            double t[U][D];
-#pragma unroll
-            for (int k = 0; k < U; k++)
-#pragma unroll
-                for (int dd = 0; dd < D; dd++) t[k][dd] = 0.0;
-            for (int j = 0; j < nslot; j++) {
-                const uint32_t v = slots_s[j * ncgp + lc];
-                if (v == 0xFFFFu) continue;
-                const int lf = v >> 1;
-                const int side = v & 1;
-                const uint32_t ab = fab_s[lf];
-                const uint32_t nb = side ? (ab & 0xFFFFu) : (ab >> 16);
-                const double e = feta_s[lf];
-                double qf[U];
-                if (nb != 0xFFFFu) {
-                    // Qf = eta Q[c0] + (1-eta) Q[c1]   (RhoSolver.cpp:435)
-                    const double e0 = side ? (1.0 - e) : e;
-                    const double e1 = side ? e : (1.0 - e);
-#pragma unroll
-                    for (int k = 0; k < U; k++) qf[k] = e0 * qc[k] + e1 * Qs[nb * U + k];
-                } else {
-#pragma unroll
-                    for (int k = 0; k < U; k++) qf[k] = qc[k];  // RhoSolver.cpp:439
-                }
-                const double sg = side ? -1.0 : 1.0;
-#pragma unroll
-                for (int dd = 0; dd < D; dd++) {
-                    const double s = sg * fSd_s[dd * nFXp + lf];
-#pragma unroll
-                    for (int k = 0; k < U; k++) t[k][dd] += qf[k] * s;
-                }
-            }
-            const double iv = 1.0 / cvol_s[lc];
-#pragma unroll
-            for (int k = 0; k < U; k++)
-#pragma unroll
-                for (int dd = 0; dd < D; dd++) t[k][dd] *= iv;
-            // reconstructed state at every flux face of this cell (RhoSolver.cpp:250)
-            for (int j = 0; j < nslot; j++) {
-                const uint32_t v = slots_s[j * ncgp + lc];
-                if (v == 0xFFFFu) continue;
-                const int lf = v >> 1;
-                if (lf >= nFB) continue;
-                const int side = v & 1;
-                double dx[D];
-#pragma unroll
-                for (int dd = 0; dd < D; dd++) dx[dd] = fdx_s[(side * D + dd) * nFBp + lf];
-#pragma unroll
-                for (int k = 0; k < U; k++) {
-                    double s = 0.0;
-#pragma unroll
-                    for (int dd = 0; dd < D; dd++) s += t[k][dd] * dx[dd];
-                    Rec[(side * U + k) * nFBp + lf] = qc[k] + s;
-                }
-                // boundary face: the B side carries the un-reconstructed cell value
-                if ((fab_s[lf] >> 16) == 0xFFFFu) {
-#pragma unroll
-                    for (int k = 0; k < U; k++) Rec[(U + k) * nFBp + lf] = qc[k];
-                }
-            }
-        }
-        __syncthreads();
-    }
-
-    // ---- phase 2: flux on every face with an owned cell ------------------------------
+    // ---- phase 2: reconstruction (fixed stencil) + flux on every face with an owned cell ----
     for (int f = tid; f < nFB; f += NT) {
-        const uint32_t ab = fab_s[f];
-        const int la = ab & 0xFFFFu, lb = ab >> 16;
-        const uint32_t mt = fmeta_s[f];
+        const uint32_t mt = fmeta_g[f];
         const int type = mt & 0xff;
         const uint32_t flags = mt >> 8;
         double S[D];
 #pragma unroll
-        for (int dd = 0; dd < D; dd++) S[dd] = fSd_s[dd * nFXp + f];
+        for (int dd = 0; dd < D; dd++) S[dd] = fSd_g[dd * nFBp + f];
         double A[U], B[U], phi[U];
         bool live = true;
         if (ORDER == 2) {
+            uint32_t id[NS];
+            double wa[NS], wb[NS];
+#pragma unroll
+            for (int m = 0; m < NS; m++) {
+                id[m] = idx_g[m * nFBp + f];
+                wa[m] = w_g[m * nFBp + f];
+                wb[m] = w_g[(NS + m) * nFBp + f];
+            }
+            const bool interior = (id[0] >> 16) != 0xFFFFu;
+            double qa[U];
 #pragma unroll
             for (int k = 0; k < U; k++) {
-                A[k] = Rec[k * nFBp + f];
-                B[k] = Rec[(U + k) * nFBp + f];
+                qa[k] = Qs[(id[0] & 0xFFFFu) * U + k];
+                A[k] = wa[0] * qa[k];
             }
-            if (lb == 0xFFFF) {
-                double ra[U], qa[U];
 #pragma unroll
-                for (int k = 0; k < U; k++) { ra[k] = A[k]; qa[k] = B[k]; }
+            for (int m = 1; m < NS; m++) {
+                const int c = id[m] & 0xFFFFu;
+#pragma unroll
+                for (int k = 0; k < U; k++) A[k] += wa[m] * Qs[c * U + k];
+            }
+            if (interior) {
+#pragma unroll
+                for (int k = 0; k < U; k++) B[k] = wb[0] * Qs[(id[0] >> 16) * U + k];
+#pragma unroll
+                for (int m = 1; m < NS; m++) {
+                    const int c = id[m] >> 16;
+#pragma unroll
+                    for (int k = 0; k < U; k++) B[k] += wb[m] * Qs[c * U + k];
+                }
+            } else {
+                double ra[U];
+#pragma unroll
+                for (int k = 0; k < U; k++) ra[k] = A[k];
                 live = boundary_states<D>(type, qa, ra, S, cfg, A, B);
             }
         } else {
+            const uint32_t ab = idx_g[f];
+            const int la = ab & 0xFFFFu, lb = ab >> 16;
             double qa[U];
 #pragma unroll
             for (int k = 0; k < U; k++) qa[k] = Qs[la * U + k];
@@ -252,15 +212,16 @@ __global__ void __launch_bounds__(NT) k_step_tiles(TileArrays ta, int tile_base,
         double acc[U];
 #pragma unroll
         for (int k = 0; k < U; k++) acc[k] = 0.0;
+#pragma unroll
         for (int j = 0; j < nslot; j++) {
-            const uint32_t v = slots_s[j * ncgp + lc];
+            const uint32_t v = slots_g[j * ncp + lc];
             if (v == 0xFFFFu) continue;
             const int lf = v >> 1;
             const double sg = (v & 1) ? -1.0 : 1.0;
 #pragma unroll
             for (int k = 0; k < U; k++) acc[k] += sg * Phis[k * nFBp + lf];
         }
-        const double s = dt / cvol_s[lc];  // RhoSolver.cpp:64
+        const double s = dt / cvol_g[lc];  // RhoSolver.cpp:64
 #pragma unroll
         for (int k = 0; k < U; k++) {
             const double qo = Qs[lc * U + k];

@@ -32,7 +32,7 @@ struct SmallMap {
 
 struct TileScratch {
     SmallMap cells{14}, faces{14};
-    std::vector<int32_t> ring, flist;   // ring cell ids; local face -> device face id
+    std::vector<int32_t> ring, flist;  // ring cell ids; local face -> device face id
 };
 
 inline int up(int x, int m) { return (x + m - 1) / m * m; }
@@ -40,7 +40,7 @@ inline int up(int x, int m) { return (x + m - 1) / m * m; }
 }  // namespace
 
 std::string build_tiles(const Plan& p, int n_update, int T, int order, TilePack& tp) {
-    const int D = p.D, nc = p.nc, nslot = p.nslot;
+    const int D = p.D, nc = p.nc, nslot = p.nslot, NS = nslot + 1;
     if (T < 32 || T > 2048 || (T & 1)) return "tile size must be even, 32..2048";
     if (n_update <= 0 || n_update > nc) return "n_update out of range";
     tp.T = T; tp.order = order; tp.D = D; tp.nslot = nslot;
@@ -55,13 +55,13 @@ std::string build_tiles(const Plan& p, int n_update, int T, int order, TilePack&
         return side ? p.fc0[f] : p.fc1[f];
     };
 
-    // pass 1: sizes; pass 2: fill.  The traversal is identical in both passes.
+    // pass 0: sizes; pass 1: fill.  The traversal is identical in both passes.
     for (int pass = 0; pass < 2; pass++) {
         if (pass == 1) {
             int64_t ro = 0, po = 0;
             for (int t = 0; t < nt; t++) {
                 TileDesc& d = tp.desc[t];
-                const TileLayout L = tile_layout(D, order, nslot, d.n_own, d.n_r1, d.n_r2, d.nFB, d.nFA);
+                const TileLayout L = tile_layout(D, order, nslot, d.n_own, d.n_r1, d.n_r2, d.nFB);
                 d.ring_off = ro; d.pk_off = po;
                 ro += up(d.n_r1 + d.n_r2, 4);
                 po += L.pk_bytes;
@@ -80,102 +80,134 @@ std::string build_tiles(const Plan& p, int n_update, int T, int order, TilePack&
                 TileDesc& d = tp.desc[t];
                 const int cb = t * T, ce = std::min(cb + T, n_update), n_own = ce - cb;
                 s.cells.reset(); s.faces.reset(); s.ring.clear(); s.flist.clear();
-                auto local_of = [&](int g) -> int { return (g >= cb && g < ce) ? g - cb : s.cells.find(g); };
+                auto owned = [&](int g) { return g >= cb && g < ce; };
+                auto local_of = [&](int g) -> int { return owned(g) ? g - cb : s.cells.find(g); };
                 int n_r1 = 0, n_r2 = 0;
+                // ring 1: face neighbours of owned cells
                 for (int c = cb; c < ce; c++)
                     for (int j = 0; j < nslot; j++) {
                         int f, side;
                         const int nb = nb_of(c, j, f, side);
-                        if (nb >= 0 && !(nb >= cb && nb < ce) && s.cells.find(nb) < 0) {
+                        if (nb >= 0 && !owned(nb) && s.cells.find(nb) < 0) {
                             s.cells.put(nb, n_own + n_r1++);
                             s.ring.push_back(nb);
                         }
                     }
+                // ring 2: face neighbours of ring-1 cells (their reconstruction stencil), order 2 only
                 if (order == 2)
                     for (int i = 0; i < n_r1; i++) {
                         const int r = s.ring[i];
                         for (int j = 0; j < nslot; j++) {
                             int f, side;
                             const int nb = nb_of(r, j, f, side);
-                            if (nb >= 0 && !(nb >= cb && nb < ce) && s.cells.find(nb) < 0) {
+                            if (nb >= 0 && !owned(nb) && s.cells.find(nb) < 0) {
                                 s.cells.put(nb, n_own + n_r1 + n_r2++);
                                 s.ring.push_back(nb);
                             }
                         }
                     }
-                // FB: faces of owned cells, each once
+                // flux faces: faces of owned cells, each once
                 for (int c = cb; c < ce; c++)
                     for (int j = 0; j < nslot; j++) {
                         int f, side;
                         const int nb = nb_of(c, j, f, side);
                         if (f < 0) continue;
-                        const bool nb_owned = nb >= cb && nb < ce;
-                        if (nb_owned && side == 1) continue;  // the c0-side cell lists it
+                        if (nb >= 0 && owned(nb) && side == 1) continue;  // the c0-side cell lists it
                         if (s.faces.find(f) >= 0) continue;
                         s.faces.put(f, (int)s.flist.size());
                         s.flist.push_back(f);
                     }
                 const int nFB = (int)s.flist.size();
-                if (order == 2)
-                    for (int i = 0; i < n_r1; i++) {
-                        const int r = s.ring[i];
-                        for (int j = 0; j < nslot; j++) {
-                            int f, side;
-                            nb_of(r, j, f, side);
-                            if (f < 0 || s.faces.find(f) >= 0) continue;
-                            s.faces.put(f, (int)s.flist.size());
-                            s.flist.push_back(f);
-                        }
-                    }
-                const int nFA = (int)s.flist.size();
                 if (pass == 0) {
-                    d.cb = cb; d.n_own = n_own; d.n_r1 = n_r1; d.n_r2 = n_r2; d.nFB = nFB; d.nFA = nFA;
-                    if (n_own + n_r1 + n_r2 >= 0xFFFF || nFA >= 0x7FFF || n_own + n_r1 + n_r2 > 6000 || nFA > 6000) {
+                    d.cb = cb; d.n_own = n_own; d.n_r1 = n_r1; d.n_r2 = n_r2; d.nFB = nFB; d.nFA = nFB;
+                    if (n_own + n_r1 + n_r2 >= 0xFFFF || nFB >= 0x7FFF || n_own + n_r1 + n_r2 > 12000 || nFB > 12000) {
 #pragma omp critical
                         err = "tile too large for 16-bit local indices";
                     }
                     continue;
                 }
                 // ---- fill ---------------------------------------------------------
-                const TileLayout L = tile_layout(D, order, nslot, n_own, n_r1, n_r2, nFB, nFA);
+                const TileLayout L = tile_layout(D, order, nslot, n_own, n_r1, n_r2, nFB);
                 unsigned char* pk = tp.packets.data() + d.pk_off;
-                uint32_t* fab = reinterpret_cast<uint32_t*>(pk + L.fab);
-                double* feta = reinterpret_cast<double*>(pk + L.feta);
+                double* w = reinterpret_cast<double*>(pk + L.w);
+                uint32_t* idx = reinterpret_cast<uint32_t*>(pk + L.idx);
                 double* fSd = reinterpret_cast<double*>(pk + L.fSd);
+                uint32_t* fmeta = reinterpret_cast<uint32_t*>(pk + L.fmeta);
                 uint16_t* slots = reinterpret_cast<uint16_t*>(pk + L.slots);
                 double* cvol = reinterpret_cast<double*>(pk + L.cvol);
-                double* fdx = reinterpret_cast<double*>(pk + L.fdx);
-                uint32_t* fmeta = reinterpret_cast<uint32_t*>(pk + L.fmeta);
+                const uint32_t nFBp = L.nFBp, ncp = L.ncp;
                 for (size_t i = 0; i < s.ring.size(); i++) tp.ring[d.ring_off + i] = s.ring[i];
-                for (uint32_t i = 0; i < (uint32_t)nslot * L.ncgp; i++) slots[i] = 0xFFFF;
-                for (uint32_t i = 0; i < L.ncgp; i++) cvol[i] = 1.0;
-                for (uint32_t i = 0; i < L.nFXp; i++) fab[i] = 0xFFFFFFFFu;
-                for (int lc = 0; lc < (int)L.ncg; lc++) {
-                    const int g = lc < n_own ? cb + lc : s.ring[lc - n_own];
+                for (uint32_t i = 0; i < (uint32_t)nslot * ncp; i++) slots[i] = 0xFFFF;
+                for (uint32_t i = 0; i < ncp; i++) cvol[i] = 1.0;
+                for (uint32_t i = 0; i < (order == 2 ? (uint32_t)NS : 1u) * nFBp; i++) idx[i] = 0;  // padded faces read cell 0
+                for (int lc = 0; lc < n_own; lc++) {
+                    const int g = cb + lc;
                     cvol[lc] = p.vol[g];
                     for (int j = 0; j < nslot; j++) {
                         int f, side;
                         nb_of(g, j, f, side);
                         if (f < 0) continue;
-                        const int lf = s.faces.find(f);
-                        slots[(size_t)j * L.ncgp + lc] = (uint16_t)((lf << 1) | side);
+                        slots[(size_t)j * ncp + lc] = (uint16_t)((s.faces.find(f) << 1) | side);
                     }
                 }
-                const int nFX = order == 2 ? nFA : nFB;
-                for (int lf = 0; lf < nFX; lf++) {
+                // Second-order reconstruction as a fixed stencil (RhoSolver.cpp:250, 434-452):
+                //   rec(c,f) = Q_c + G_c (fc_f - cc_c),  G_c = (1/V) sum_j Qf_j (x) Sout_j,
+                //   Qf_j = eta Q[c0] + (1-eta) Q[c1]  (Q_c on boundary faces)
+                // is linear in the states of c and its face neighbours:
+                //   rec = b0 Q_c + sum_j bj Q_nb(j),  sigma_j = Sout_j.(fc_f - cc_c)/V,
+                //   b0 = 1 + sum_j wself_j sigma_j,  bj = wnb_j sigma_j.
+                // The weights depend on geometry only and are computed here, once.
+                auto stencil = [&](int c, const double* dx, double* beta, int* cells) {
+                    const double V = p.vol[c];
+                    beta[0] = 1.0;
+                    cells[0] = local_of(c);
+                    for (int j = 0; j < nslot; j++) {
+                        beta[1 + j] = 0.0;
+                        cells[1 + j] = cells[0];
+                        int g, side;
+                        const int nb = nb_of(c, j, g, side);
+                        if (g < 0) continue;
+                        double dot = 0.0;
+                        for (int k = 0; k < D; k++) dot += p.Sd[(size_t)g * D + k] * dx[k];
+                        const double sigma = (side ? -dot : dot) / V;
+                        const double e = p.eta[g];
+                        if (nb >= 0) {
+                            beta[0] += (side ? (1.0 - e) : e) * sigma;
+                            beta[1 + j] = (side ? e : (1.0 - e)) * sigma;
+                            cells[1 + j] = local_of(nb);
+                        } else {
+                            beta[0] += sigma;
+                        }
+                    }
+                };
+                for (int lf = 0; lf < nFB; lf++) {
                     const int f = s.flist[lf];
-                    const int la = local_of(p.fc0[f]);
-                    const int lb = p.fc1[f] >= 0 ? local_of(p.fc1[f]) : 0xFFFF;
-                    fab[lf] = (uint32_t)(la < 0 ? 0xFFFF : la) | ((uint32_t)(lb < 0 ? 0xFFFF : lb) << 16);
-                    if (order == 2) feta[lf] = p.eta[f];
-                    for (int k = 0; k < D; k++) fSd[(size_t)k * L.nFXp + lf] = p.Sd[(size_t)f * D + k];
-                    if (lf < nFB) {
-                        fmeta[lf] = p.meta[f];
-                        if (order == 2)
-                            for (int k = 0; k < D; k++) {
-                                fdx[(size_t)k * L.nFBp + lf] = p.dx0[(size_t)f * D + k];
-                                fdx[(size_t)(D + k) * L.nFBp + lf] = p.dx1[(size_t)f * D + k];
-                            }
+                    const int a = p.fc0[f], b = p.fc1[f];
+                    fmeta[lf] = p.meta[f];
+                    for (int k = 0; k < D; k++) fSd[(size_t)k * nFBp + lf] = p.Sd[(size_t)f * D + k];
+                    if (order != 2) {
+                        const int la = local_of(a), lb = b >= 0 ? local_of(b) : 0xFFFF;
+                        idx[lf] = (uint32_t)la | ((uint32_t)lb << 16);
+                        continue;
+                    }
+                    double beta[9];
+                    int cells[9];
+                    stencil(a, &p.dx0[(size_t)f * D], beta, cells);
+                    for (int m = 0; m < NS; m++) {
+                        w[(size_t)m * nFBp + lf] = beta[m];
+                        idx[(size_t)m * nFBp + lf] = (uint32_t)cells[m];
+                    }
+                    if (b >= 0) {
+                        stencil(b, &p.dx1[(size_t)f * D], beta, cells);
+                        for (int m = 0; m < NS; m++) {
+                            w[(size_t)(NS + m) * nFBp + lf] = beta[m];
+                            idx[(size_t)m * nFBp + lf] |= (uint32_t)cells[m] << 16;
+                        }
+                    } else {
+                        for (int m = 0; m < NS; m++) {
+                            w[(size_t)(NS + m) * nFBp + lf] = 0.0;
+                            idx[(size_t)m * nFBp + lf] |= 0xFFFFu << 16;  // boundary marker on every stencil entry
+                        }
                     }
                 }
             }

@@ -146,7 +146,7 @@ def test_3d_tets_one_step_and_20_steps(flux, order, kernel):
 
 
 def test_oversized_tile_is_rejected():
-    f = box_flat(6, 5, 4)
+    f = box_flat(14, 14, 14)
     with pytest.raises(mstgpu.MstGpuError, match="shared memory"):
         mstgpu.Context(f, order=2, kernel="tiles", tile_cells=2048)
 
