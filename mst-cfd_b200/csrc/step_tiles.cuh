@@ -75,6 +75,10 @@ __device__ __forceinline__ void bulk_commit_wait_read() {
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
+// pull a byte range into L2 ahead of its use (TMA prefetch, no destination)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // max over the warp of NON-NEGATIVE doubles: their order is the order of their
@@ -107,8 +111,6 @@ __global__ void __launch_bounds__(NT) k_step_tiles(TileArrays ta, int tile_base,
     const uint32_t* __restrict__ idx_g = reinterpret_cast<const uint32_t*>(pk + L.idx);
     const double* __restrict__ fSd_g = reinterpret_cast<const double*>(pk + L.fSd);
     const uint32_t* __restrict__ fmeta_g = reinterpret_cast<const uint32_t*>(pk + L.fmeta);
-    const uint16_t* __restrict__ slots_g = reinterpret_cast<const uint16_t*>(pk + L.slots);
-    const double* __restrict__ cvol_g = reinterpret_cast<const double*>(pk + L.cvol);
     double* Qs = reinterpret_cast<double*>(smem + L.Qs);
     double* Phis = reinterpret_cast<double*>(smem + L.Phis);  // [k][nFBp]
     const uint32_t bar = smem_u32(smem + L.mbar);
@@ -118,8 +120,15 @@ __global__ void __launch_bounds__(NT) k_step_tiles(TileArrays ta, int tile_base,
     __syncthreads();
     if (tid == 0) {
         const uint32_t qbytes = (uint32_t)((n_own + 1) & ~1) * U * 8u;
-        mbar_expect_tx(bar, qbytes);
+        // slots + cvol are adjacent in the packet: one more bulk copy brings the phase-3
+        // operands into shared memory without holding registers across phase 2
+        const uint32_t cbytes = L.pk_bytes - L.slots;
+        mbar_expect_tx(bar, qbytes + cbytes);
         bulk_g2s(smem_u32(Qs), Qold + (size_t)d.cb * U, qbytes, bar);
+        bulk_g2s(smem_u32(smem + L.cells_s), pk + L.slots, cbytes, bar);
+        // the packet is streamed from HBM by phase 2 / 3: start moving it into L2 now,
+        // while the states are being staged
+        bulk_prefetch_l2(pk, L.pk_bytes);
     }
     for (int r = tid; r < n_ring; r += NT) {  // one thread per ring cell, U independent loads of a contiguous row
         const int g = ta.ring[d.ring_off + r];
@@ -208,26 +217,28 @@ __global__ void __launch_bounds__(NT) k_step_tiles(TileArrays ta, int tile_base,
 #pragma unroll
     for (int k = 0; k < U; k++) r[k] = 0.0;
     bool bad = false;
+    const uint16_t* slots_s = reinterpret_cast<const uint16_t*>(smem + L.cells_s);
+    const double* cvol_s = reinterpret_cast<const double*>(smem + L.cells_s + (L.cvol - L.slots));
     for (int lc = tid; lc < n_own; lc += NT) {
         double acc[U];
 #pragma unroll
         for (int k = 0; k < U; k++) acc[k] = 0.0;
 #pragma unroll
         for (int j = 0; j < nslot; j++) {
-            const uint32_t v = slots_g[j * ncp + lc];
+            const uint32_t v = slots_s[j * ncp + lc];
             if (v == 0xFFFFu) continue;
             const int lf = v >> 1;
             const double sg = (v & 1) ? -1.0 : 1.0;
 #pragma unroll
             for (int k = 0; k < U; k++) acc[k] += sg * Phis[k * nFBp + lf];
         }
-        const double s = dt / cvol_g[lc];  // RhoSolver.cpp:64
+        const double s = dt / cvol_s[lc];  // RhoSolver.cpp:64
 #pragma unroll
         for (int k = 0; k < U; k++) {
             const double qo = Qs[lc * U + k];
             const double qn = qo - s * acc[k];
             Qs[lc * U + k] = qn;
-            const double x = fabs(qn - qo) / qo;  // Time.cpp:72
+            const double x = fabs(qn - qo) * __drcp_rn(qo);  // Time.cpp:72 (|d|/q; reporting only, 1 ulp)
             r[k] = fmax(r[k], (x > 0.0) ? x : 0.0);
             bad |= (qn != qn);
         }

@@ -28,7 +28,7 @@ struct TileLayout {
     uint32_t cvol;   // f64 [ncp]
     uint32_t pk_bytes;
     // shared memory
-    uint32_t mbar, Qs, Phis, total;
+    uint32_t mbar, Qs, Phis, cells_s, total;  // cells_s: copy of the packet's slots + cvol block
     uint32_t nFBp, ncp;
 };
 
@@ -54,6 +54,7 @@ MST_HD TileLayout tile_layout(int D, int order, int nslot, int n_own, int n_r1, 
     L.mbar = s; s += 16;
     L.Qs = s; s += up16(((n_loc + 1u) & ~1u) * U * 8u);
     L.Phis = s; s += up16(U * L.nFBp * 8u);
+    L.cells_s = s; s += L.pk_bytes - L.slots;
     L.total = s;
     return L;
 }
