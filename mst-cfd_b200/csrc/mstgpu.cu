@@ -524,7 +524,7 @@ int halo_exchange(mstgpu_ctx* ctx, double* Q) {
 }
 
 template <int D, int ORDER, int NT, int NS>
-int launch_tiles(mstgpu_ctx* ctx, double dt, const double* Qo, double* Qn) {
+int launch_tiles(mstgpu_ctx* ctx, double dt, const double* Qo, double* Qn, int want_resid) {
     auto kern = k_step_tiles<D, ORDER, NT, NS>;
     static thread_local size_t configured_smem = 0;
     if (configured_smem < ctx->tile_smem) {
@@ -532,16 +532,16 @@ int launch_tiles(mstgpu_ctx* ctx, double dt, const double* Qo, double* Qn) {
         configured_smem = ctx->tile_smem;
     }
     for (const auto& tc : ctx->tile_classes)
-        kern<<<tc.count, NT, tc.smem, ctx->stream>>>(ctx->ta, tc.first, ctx->dcfg, dt, Qo, Qn, ctx->resid, ctx->nanflag);
+        kern<<<tc.count, NT, tc.smem, ctx->stream>>>(ctx->ta, tc.first, want_resid, ctx->dcfg, dt, Qo, Qn, ctx->resid, ctx->nanflag);
     ctx->launches += (int64_t)ctx->tile_classes.size() - 1;
     return MSTGPU_OK;
 }
 
 template <int D, int NS>
-int launch_tiles_ns(mstgpu_ctx* ctx, double dt, const double* Qo, double* Qn) {
+int launch_tiles_ns(mstgpu_ctx* ctx, double dt, const double* Qo, double* Qn, int wr) {
     const bool o2 = ctx->cfg.order == 2;
-    if (ctx->tile_NT == 128) return o2 ? launch_tiles<D, 2, 128, NS>(ctx, dt, Qo, Qn) : launch_tiles<D, 1, 128, NS>(ctx, dt, Qo, Qn);
-    return o2 ? launch_tiles<D, 2, 256, NS>(ctx, dt, Qo, Qn) : launch_tiles<D, 1, 256, NS>(ctx, dt, Qo, Qn);
+    if (ctx->tile_NT == 128) return o2 ? launch_tiles<D, 2, 128, NS>(ctx, dt, Qo, Qn, wr) : launch_tiles<D, 1, 128, NS>(ctx, dt, Qo, Qn, wr);
+    return o2 ? launch_tiles<D, 2, 256, NS>(ctx, dt, Qo, Qn, wr) : launch_tiles<D, 1, 256, NS>(ctx, dt, Qo, Qn, wr);
 }
 
 template <int D>
@@ -553,15 +553,17 @@ int step_tiles_impl(mstgpu_ctx* ctx, double dt, int nsteps) {
         }
         const double* Qo = ctx->Q[ctx->cur];
         double* Qn = ctx->Q[ctx->cur ^ 1];
-        CK(cudaMemsetAsync(ctx->resid, 0, 8 * sizeof(unsigned long long), ctx->stream));
+        // the residual of a step is observable only for the last step of the call
+        const int wr = (s == nsteps - 1) ? 1 : 0;
+        if (wr) CK(cudaMemsetAsync(ctx->resid, 0, 8 * sizeof(unsigned long long), ctx->stream));
         {
             KTimer t(ctx, "step_tiles");
             int r;
             // stencil size = 1 + faces per cell: triangles 4, tets / quads 5, hexes 7
             switch (ctx->nslot) {
-                case 3: r = launch_tiles_ns<D, 4>(ctx, dt, Qo, Qn); break;
-                case 4: r = launch_tiles_ns<D, 5>(ctx, dt, Qo, Qn); break;
-                case 6: r = launch_tiles_ns<D, 7>(ctx, dt, Qo, Qn); break;
+                case 3: r = launch_tiles_ns<D, 4>(ctx, dt, Qo, Qn, wr); break;
+                case 4: r = launch_tiles_ns<D, 5>(ctx, dt, Qo, Qn, wr); break;
+                case 6: r = launch_tiles_ns<D, 7>(ctx, dt, Qo, Qn, wr); break;
                 default: set_error(ctx, "fused kernel supports cells with 3, 4 or 6 faces"); return MSTGPU_ERR_ARG;
             }
             if (r) return r;

@@ -92,7 +92,7 @@ __device__ __forceinline__ double warp_max_nonneg(double x) {
 }
 
 template <int D, int ORDER, int NT, int NS>
-__global__ void __launch_bounds__(NT) k_step_tiles(TileArrays ta, int tile_base, DevCfg cfg, double dt,
+__global__ void __launch_bounds__(NT) k_step_tiles(TileArrays ta, int tile_base, int want_resid, DevCfg cfg, double dt,
                                                    const double* __restrict__ Qold,
                                                    double* __restrict__ Qnew,
                                                    unsigned long long* __restrict__ resid,
@@ -232,23 +232,27 @@ __global__ void __launch_bounds__(NT) k_step_tiles(TileArrays ta, int tile_base,
 #pragma unroll
             for (int k = 0; k < U; k++) acc[k] += sg * Phis[k * nFBp + lf];
         }
-        const double s = dt / cvol_s[lc];  // RhoSolver.cpp:64
+        const double s = dt * cvol_s[lc];  // DT / V (RhoSolver.cpp:64); the packet stores 1/V
 #pragma unroll
         for (int k = 0; k < U; k++) {
             const double qo = Qs[lc * U + k];
             const double qn = qo - s * acc[k];
             Qs[lc * U + k] = qn;
-            const double x = fabs(qn - qo) * __drcp_rn(qo);  // Time.cpp:72 (|d|/q; reporting only, 1 ulp)
-            r[k] = fmax(r[k], (x > 0.0) ? x : 0.0);
+            if (want_resid) {  // only the last step of a multi-step call can be observed (mstgpu_residual_linf)
+                const double x = fabs(qn - qo) * __drcp_rn(qo);  // Time.cpp:72 (|d|/q; reporting only, 1 ulp)
+                r[k] = fmax(r[k], (x > 0.0) ? x : 0.0);
+            }
             bad |= (qn != qn);
         }
     }
     __shared__ double sm[U][NT / 32];
     const int lane = tid & 31, wid = tid >> 5;
+    if (want_resid) {
 #pragma unroll
-    for (int k = 0; k < U; k++) {
-        const double m = warp_max_nonneg(r[k]);
-        if (lane == 0) sm[k][wid] = m;
+        for (int k = 0; k < U; k++) {
+            const double m = warp_max_nonneg(r[k]);
+            if (lane == 0) sm[k][wid] = m;
+        }
     }
     fence_async_smem();  // generic-proxy writes of Qs -> visible to the bulk store
     const bool anybad = __syncthreads_or(bad);
@@ -259,7 +263,7 @@ __global__ void __launch_bounds__(NT) k_step_tiles(TileArrays ta, int tile_base,
             for (int k = 0; k < U; k++) Qnew[(size_t)(d.cb + even) * U + k] = Qs[even * U + k];
         bulk_commit_wait_read();
     }
-    if (tid >= 32 && tid < 32 + U) {
+    if (want_resid && tid >= 32 && tid < 32 + U) {
         const int k = tid - 32;
         double m = 0.0;
         for (int w = 0; w < NT / 32; w++) m = fmax(m, sm[k][w]);

@@ -25,7 +25,7 @@ struct TileLayout {
     uint32_t fSd;    // f64 [D][nFBp]     area vector, outward from c0
     uint32_t fmeta;  // u32 [nFBp]        zone type | left/right flags << 8
     uint32_t slots;  // u16 [nslot][ncp]  per owned cell: local face << 1 | side, 0xFFFF = pad
-    uint32_t cvol;   // f64 [ncp]
+    uint32_t cvol;   // f64 [ncp]         1 / cell volume
     uint32_t pk_bytes;
     // shared memory
     uint32_t mbar, Qs, Phis, cells_s, total;  // cells_s: copy of the packet's slots + cvol block

@@ -142,7 +142,7 @@ std::string build_tiles(const Plan& p, int n_update, int T, int order, TilePack&
                 for (uint32_t i = 0; i < (order == 2 ? (uint32_t)NS : 1u) * nFBp; i++) idx[i] = 0;  // padded faces read cell 0
                 for (int lc = 0; lc < n_own; lc++) {
                     const int g = cb + lc;
-                    cvol[lc] = p.vol[g];
+                    cvol[lc] = 1.0 / p.vol[g];  // the kernel multiplies: DT * (1/V)
                     for (int j = 0; j < nslot; j++) {
                         int f, side;
                         nb_of(g, j, f, side);
