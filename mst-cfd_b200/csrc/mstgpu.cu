@@ -11,6 +11,7 @@
 #include <nccl.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -100,7 +101,7 @@ struct mstgpu_ctx {
     std::vector<void*> tile_allocs;
     int ntiles = 0, tile_T = 0, tile_NT = 0;
     size_t tile_smem = 0;
-    struct TileClass { int first, count; size_t smem; };
+    struct TileClass { int first, count; size_t smem; bool halo; };  // halo: a ring of the tile holds ghost cells
     std::vector<TileClass> tile_classes;  // tiles grouped by shared-memory need (CTAs per SM)
     bool use_tiles = false;
     bool probes_valid = false;  // G / Phi hold the stages of the last step
@@ -112,6 +113,8 @@ struct mstgpu_ctx {
     int32_t* send_idx = nullptr;  // device-order ids of the owned cells to send, all neighbours back to back
     double* sendbuf = nullptr;
     int send_total = 0;
+    cudaStream_t stream2 = nullptr;  // halo exchange, overlapped with the interior tiles
+    cudaEvent_t ev_halo = nullptr, ev_done = nullptr;
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
     unsigned long long* resid = nullptr;  // [U] bit patterns of non-negative doubles
@@ -506,67 +509,86 @@ int ensure_stage_buffers(mstgpu_ctx* ctx) {
 
 // ghost rows of Q <- owners' rows.  One pack kernel, one grouped send/recv; the
 // receives land directly in the ghost block of Q (ghosts are ordered by owner).
-int halo_exchange(mstgpu_ctx* ctx, double* Q) {
+int halo_exchange(mstgpu_ctx* ctx, double* Q, cudaStream_t st) {
     if (!ctx->partitioned || ctx->halo.empty()) return MSTGPU_OK;
     if (!ctx->comm) { set_error(ctx, "partitioned context without a communicator: call mstgpu_comm_init"); return MSTGPU_ERR_STATE; }
     const int U = ctx->U;
     if (ctx->send_total > 0) {
-        KTimer t(ctx, "halo_pack");
-        k_pack_rows<<<(ctx->send_total * U + 255) / 256, 256, 0, ctx->stream>>>(ctx->send_total, U, ctx->send_idx, Q, ctx->sendbuf);
+        ctx->launches++;
+        k_pack_rows<<<(ctx->send_total * U + 255) / 256, 256, 0, st>>>(ctx->send_total, U, ctx->send_idx, Q, ctx->sendbuf);
     }
     NK(g_nccl.GroupStart());
     for (const auto& h : ctx->halo) {
-        if (h.send_count) NK(g_nccl.Send(ctx->sendbuf + (size_t)h.send_off * U, (size_t)h.send_count * U, ncclDouble, h.rank, ctx->comm, ctx->stream));
-        if (h.recv_count) NK(g_nccl.Recv(Q + (size_t)h.recv_first * U, (size_t)h.recv_count * U, ncclDouble, h.rank, ctx->comm, ctx->stream));
+        if (h.send_count) NK(g_nccl.Send(ctx->sendbuf + (size_t)h.send_off * U, (size_t)h.send_count * U, ncclDouble, h.rank, ctx->comm, st));
+        if (h.recv_count) NK(g_nccl.Recv(Q + (size_t)h.recv_first * U, (size_t)h.recv_count * U, ncclDouble, h.rank, ctx->comm, st));
     }
     NK(g_nccl.GroupEnd());
     return MSTGPU_OK;
 }
 
 template <int D, int ORDER, int NT, int NS>
-int launch_tiles(mstgpu_ctx* ctx, double dt, const double* Qo, double* Qn, int want_resid) {
+int launch_tiles(mstgpu_ctx* ctx, double dt, const double* Qo, double* Qn, int want_resid, int which, cudaStream_t st) {
     auto kern = k_step_tiles<D, ORDER, NT, NS>;
     static thread_local size_t configured_smem = 0;
     if (configured_smem < ctx->tile_smem) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->tile_smem));
         configured_smem = ctx->tile_smem;
     }
-    for (const auto& tc : ctx->tile_classes)
-        kern<<<tc.count, NT, tc.smem, ctx->stream>>>(ctx->ta, tc.first, want_resid, ctx->dcfg, dt, Qo, Qn, ctx->resid, ctx->nanflag);
-    ctx->launches += (int64_t)ctx->tile_classes.size() - 1;
+    // which: 0 = tiles without ghost cells, 1 = tiles whose rings hold ghost cells, 2 = all
+    for (const auto& tc : ctx->tile_classes) {
+        if (which != 2 && (int)tc.halo != which) continue;
+        kern<<<tc.count, NT, tc.smem, st>>>(ctx->ta, tc.first, want_resid, ctx->dcfg, dt, Qo, Qn, ctx->resid, ctx->nanflag);
+        ctx->launches++;
+    }
     return MSTGPU_OK;
 }
 
 template <int D, int NS>
-int launch_tiles_ns(mstgpu_ctx* ctx, double dt, const double* Qo, double* Qn, int wr) {
+int launch_tiles_ns(mstgpu_ctx* ctx, double dt, const double* Qo, double* Qn, int wr, int which, cudaStream_t st) {
     const bool o2 = ctx->cfg.order == 2;
-    if (ctx->tile_NT == 128) return o2 ? launch_tiles<D, 2, 128, NS>(ctx, dt, Qo, Qn, wr) : launch_tiles<D, 1, 128, NS>(ctx, dt, Qo, Qn, wr);
-    return o2 ? launch_tiles<D, 2, 256, NS>(ctx, dt, Qo, Qn, wr) : launch_tiles<D, 1, 256, NS>(ctx, dt, Qo, Qn, wr);
+    if (ctx->tile_NT == 128) return o2 ? launch_tiles<D, 2, 128, NS>(ctx, dt, Qo, Qn, wr, which, st) : launch_tiles<D, 1, 128, NS>(ctx, dt, Qo, Qn, wr, which, st);
+    return o2 ? launch_tiles<D, 2, 256, NS>(ctx, dt, Qo, Qn, wr, which, st) : launch_tiles<D, 1, 256, NS>(ctx, dt, Qo, Qn, wr, which, st);
+}
+
+template <int D>
+int launch_tiles_any(mstgpu_ctx* ctx, double dt, const double* Qo, double* Qn, int wr, int which, cudaStream_t st) {
+    // stencil size = 1 + faces per cell: triangles 4, tets / quads 5, hexes 7
+    switch (ctx->nslot) {
+        case 3: return launch_tiles_ns<D, 4>(ctx, dt, Qo, Qn, wr, which, st);
+        case 4: return launch_tiles_ns<D, 5>(ctx, dt, Qo, Qn, wr, which, st);
+        case 6: return launch_tiles_ns<D, 7>(ctx, dt, Qo, Qn, wr, which, st);
+        default: set_error(ctx, "fused kernel supports cells with 3, 4 or 6 faces"); return MSTGPU_ERR_ARG;
+    }
 }
 
 template <int D>
 int step_tiles_impl(mstgpu_ctx* ctx, double dt, int nsteps) {
+    const bool overlap = ctx->partitioned && !ctx->halo.empty();
+    if (overlap && !ctx->comm) { set_error(ctx, "partitioned context without a communicator: call mstgpu_comm_init"); return MSTGPU_ERR_STATE; }
+    if (overlap && nsteps > 0) CK(cudaEventRecord(ctx->ev_done, ctx->stream));
     for (int s = 0; s < nsteps; s++) {
-        {
-            int r = halo_exchange(ctx, ctx->Q[ctx->cur]);
-            if (r) return r;
-        }
-        const double* Qo = ctx->Q[ctx->cur];
+        double* Qc = ctx->Q[ctx->cur];
         double* Qn = ctx->Q[ctx->cur ^ 1];
         // the residual of a step is observable only for the last step of the call
         const int wr = (s == nsteps - 1) ? 1 : 0;
         if (wr) CK(cudaMemsetAsync(ctx->resid, 0, 8 * sizeof(unsigned long long), ctx->stream));
-        {
-            KTimer t(ctx, "step_tiles");
-            int r;
-            // stencil size = 1 + faces per cell: triangles 4, tets / quads 5, hexes 7
-            switch (ctx->nslot) {
-                case 3: r = launch_tiles_ns<D, 4>(ctx, dt, Qo, Qn, wr); break;
-                case 4: r = launch_tiles_ns<D, 5>(ctx, dt, Qo, Qn, wr); break;
-                case 6: r = launch_tiles_ns<D, 7>(ctx, dt, Qo, Qn, wr); break;
-                default: set_error(ctx, "fused kernel supports cells with 3, 4 or 6 faces"); return MSTGPU_ERR_ARG;
-            }
-            if (r) return r;
+        KTimer t(ctx, "step_tiles");
+        ctx->launches--;  // the launches are counted one by one in launch_tiles
+        int r;
+        if (overlap) {
+            // comm stream: ghost rows <- owners, as soon as the previous step is complete;
+            // compute stream: tiles that touch no ghost cell meanwhile, the others after
+            // (the halo tiles follow the exchange on the comm stream, so they fill the SMs
+            // the interior launch leaves idle in its tail instead of waiting behind it)
+            CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_done, 0));
+            if ((r = halo_exchange(ctx, Qc, ctx->stream2))) return r;
+            if ((r = launch_tiles_any<D>(ctx, dt, Qc, Qn, wr, 1, ctx->stream2))) return r;
+            CK(cudaEventRecord(ctx->ev_halo, ctx->stream2));
+            if ((r = launch_tiles_any<D>(ctx, dt, Qc, Qn, wr, 0, ctx->stream))) return r;
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_halo, 0));
+            CK(cudaEventRecord(ctx->ev_done, ctx->stream));
+        } else {
+            if ((r = launch_tiles_any<D>(ctx, dt, Qc, Qn, wr, 2, ctx->stream))) return r;
         }
         ctx->cur ^= 1;
     }
@@ -587,7 +609,7 @@ int step_impl(mstgpu_ctx* ctx, double dt, int nsteps) {
     if (nsteps > 0) ctx->probes_valid = true;
     for (int s = 0; s < nsteps; s++) {
         {
-            int r = halo_exchange(ctx, ctx->Q[ctx->cur]);
+            int r = halo_exchange(ctx, ctx->Q[ctx->cur], ctx->stream);
             if (r) return r;
         }
         const double* Qo = ctx->Q[ctx->cur];
@@ -733,6 +755,15 @@ static int create_impl(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_c
         if (cfg->device >= 0) { CK(cudaSetDevice(cfg->device)); ctx->device = cfg->device; }
         else CK(cudaGetDevice(&ctx->device));
         CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        {
+            // comm stream at the highest priority: when the exchange completes, the tiles that
+            // were waiting for it are dispatched ahead of the interior launch's remaining CTAs
+            int lo = 0, hi = 0;
+            CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CK(cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, hi));
+        }
+        CK(cudaEventCreateWithFlags(&ctx->ev_halo, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming));
         CK(cudaEventCreate(&ctx->ev0));
         CK(cudaEventCreate(&ctx->ev1));
         int r;
@@ -769,30 +800,37 @@ static int create_impl(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_c
                 // their size allows (4, 3, 2, 1) and launch each group with its own size.
                 const size_t lim[4] = {57000, 76500, 115000, (size_t)dev_smem};
                 std::vector<int> cls(tp.ntiles);
-                size_t cmax[4] = {0, 0, 0, 0};
-                int ccount[4] = {0, 0, 0, 0};
+                size_t cmax[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                int ccount[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                 for (int t = 0; t < tp.ntiles; t++) {
                     const TileDesc& d = tp.desc[t];
                     const size_t b = tile_layout(p.D, cfg->order, p.nslot, d.n_own, d.n_r1, d.n_r2, d.nFB).total;
                     int c = 0;
                     while (c < 3 && b > lim[c]) c++;
+                    // tiles whose rings reach into the ghost cells wait for the halo exchange
+                    bool halo = false;
+                    for (int i = 0; i < d.n_r1 + d.n_r2 && !halo; i++) halo = tp.ring[d.ring_off + i] >= ctx->n_owned;
+                    c += halo ? 4 : 0;
                     cls[t] = c; ccount[c]++; cmax[c] = std::max(cmax[c], b);
                 }
                 // merge a class that is too small to fill the machine into the next larger one
-                for (int c = 0; c < 3; c++)
-                    if (ccount[c] > 0 && ccount[c] < 2000 && (ccount[c + 1] > 0 || c == 2)) {
-                        if (c == 2 && ccount[3] == 0) continue;
-                        for (int t = 0; t < tp.ntiles; t++) if (cls[t] == c) cls[t] = c + 1;
-                        ccount[c + 1] += ccount[c]; cmax[c + 1] = std::max(cmax[c + 1], cmax[c]); ccount[c] = 0;
-                    }
+                for (int g = 0; g < 8; g += 4)
+                    for (int c = g; c < g + 3; c++)
+                        if (ccount[c] > 0 && ccount[c] < 64 && ccount[c + 1] > 0) {  // only a handful: not worth a launch
+                            for (int t = 0; t < tp.ntiles; t++) if (cls[t] == c) cls[t] = c + 1;
+                            ccount[c + 1] += ccount[c]; cmax[c + 1] = std::max(cmax[c + 1], cmax[c]); ccount[c] = 0;
+                        }
                 std::vector<TileDesc> sorted;
                 sorted.reserve(tp.ntiles);
-                for (int c = 0; c < 4; c++) {
+                for (int c = 0; c < 8; c++) {
                     if (!ccount[c]) continue;
-                    ctx->tile_classes.push_back({(int)sorted.size(), ccount[c], cmax[c]});
+                    ctx->tile_classes.push_back({(int)sorted.size(), ccount[c], cmax[c], c >= 4});
                     for (int t = 0; t < tp.ntiles; t++) if (cls[t] == c) sorted.push_back(tp.desc[t]);
                 }
                 tp.desc.swap(sorted);
+                if (getenv("MSTGPU_VERBOSE"))
+                    for (const auto& tc : ctx->tile_classes)
+                        fprintf(stderr, "[mstgpu] tile class: %d tiles, %zu B smem, %s\n", tc.count, tc.smem, tc.halo ? "halo" : "interior");
             }
             ctx->tile_NT = cfg->block_threads == 128 ? 128 : (cfg->block_threads == 256 ? 256 : (T <= 96 ? 128 : 256));
             TileDesc* ddesc; int32_t* dring; unsigned char* dpk;
@@ -866,6 +904,9 @@ void mstgpu_destroy(mstgpu_ctx* ctx) {
     for (auto e : ctx->evpool) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_halo) cudaEventDestroy(ctx->ev_halo);
+    if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
