@@ -199,13 +199,14 @@ def run_ours(args, rank, world):
 
     f, Q0, desc = build_workload(args)
     nc_total, U, D = f["ncells"], f["dim"] + 2, f["dim"]
+    inlet = list(Q0[0]) + [0.0] * (5 - U) if args.workload == "step" else None  # Mach-3 inlet state
     t = time.time()
     if world > 1:
         # one partition per GPU (equal ranges of the Hilbert curve), 2 ghost layers
         part = mstgpu.Partition(f, world, rank, order=2)
         log(f"[bench] rank {rank}: {part.n_owned} owned + {part.n_local - part.n_owned} ghost cells, "
             f"{part.n_neighbors} neighbours, partition in {time.time() - t:.1f}s")
-        ctx = mstgpu.Context(part, order=2, flux="roe", device=local, kernel=args.kernel,
+        ctx = mstgpu.Context(part, order=args.order, flux=args.flux, device=local, kernel=args.kernel, inletQ=inlet,
                              tile_cells=args.tile_cells, block_threads=args.block_threads, renumber=args.renumber)
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
@@ -216,12 +217,13 @@ def run_ours(args, rank, world):
         nc = part.n_owned
         del f["cf_idx"]
     else:
-        ctx = mstgpu.Context(f, order=2, flux="roe", device=local, kernel=args.kernel,
+        ctx = mstgpu.Context(f, order=args.order, flux=args.flux, device=local, kernel=args.kernel, inletQ=inlet,
                              tile_cells=args.tile_cells, block_threads=args.block_threads, renumber=args.renumber)
         nc = nc_total
     log(f"[bench] context built in {time.time() - t:.1f}s, {ctx.device_bytes / 2**30:.2f} GiB on device")
     ctx.set_state(Q0)
-    ctx.step(DT, args.warmup)
+    dt_run = DT if args.workload == "box" else 2e-5
+    ctx.step(dt_run, args.warmup)
     ctx.sync()
     # ---- timed region: K steps, state resident in HBM -------------------------
     ctx.enable_kernel_timing(True)
@@ -233,7 +235,7 @@ def run_ours(args, rank, world):
         dist.barrier()
     torch.cuda.synchronize()
     w0 = time.perf_counter()
-    ms = ctx.step_timed(DT, args.steps)
+    ms = ctx.step_timed(dt_run, args.steps)
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
@@ -253,7 +255,7 @@ def run_ours(args, rank, world):
 
     # ---- roofline of the dominant kernel --------------------------------------
     peak, peak_src = measured_peaks()
-    ab = ALGO_BYTES[(D, 2)]
+    ab = ALGO_BYTES[(D, args.order)]
     per_kernel = {k: (v[0] / max(v[1], 1)) for k, v in kt.items()}
     dom = max(per_kernel, key=per_kernel.get)
     if "step_tiles" in per_kernel:
@@ -292,7 +294,7 @@ def run_ours(args, rank, world):
             torch.cuda.synchronize()
             e0 = time.perf_counter()
         ctx.set_state_ptr(hin.data_ptr())      # H2D of the step's input state
-        ctx.step(DT, 1)
+        ctx.step(dt_run, 1)
         ctx.get_state_ptr(hout.data_ptr())     # D2H of the new state (Time.cpp:66-67)
         r = ctx.residual()                     # D2H of the residual (Time.cpp:69-76)
         hin, hout = hout, hin                  # updateNewToOld on the host side
@@ -312,9 +314,9 @@ def run_ours(args, rank, world):
     out = dict(metric="cell_updates_per_sec", value=value, unit="cell-updates/s", n_gpus=world,
                steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True,
                scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
-               config=dict(workload=f"{args.workload}{args.n}: {desc}", cells=nc_total, faces=f["nfaces"], flux="roe",
+               config=dict(workload=f"{args.workload}{args.n}: {desc}", cells=nc_total, faces=f["nfaces"], flux=args.flux,
                            parallelism=f"{world} partition(s), Hilbert ranges, 2 ghost layers, NCCL send/recv + allreduce(max)",
-                           order=2, dt=DT, kernel=args.kernel, tile_cells=args.tile_cells, renumber=args.renumber,
+                           order=args.order, dt=DT if args.workload == "box" else 2e-5, kernel=args.kernel, tile_cells=args.tile_cells, renumber=args.renumber,
                            block_threads=args.block_threads, l2="inputs larger than L2 (state + tables >> 126 MB)"
                            if nc_total * U * 8 > 2 ** 28 else "inputs smaller than L2: flush not applied"),
                clocks=clk, e2e=e2e, gpu_launches=launches, roofline=roof, cpu_baseline=cpu,
@@ -343,6 +345,8 @@ def main():
     ap.add_argument("--kernel", default="tiles", choices=["tiles", "split"])
     ap.add_argument("--tile-cells", type=int, default=0)
     ap.add_argument("--renumber", type=int, default=2, help="0 none, 1 Morton, 2 Hilbert")
+    ap.add_argument("--flux", default="roe", choices=["roe", "ausm"])
+    ap.add_argument("--order", type=int, default=2, choices=[1, 2])
     ap.add_argument("--block-threads", type=int, default=0)
     args = ap.parse_args()
     if args.warmup < 3:

@@ -152,35 +152,37 @@ __global__ void __launch_bounds__(NT) k_step_tiles(TileArrays ta, int tile_base,
         double A[U], B[U], phi[U];
         bool live = true;
         if (ORDER == 2) {
-            uint32_t id[NS];
+            uint32_t id[NS - 1];
             double wa[NS], wb[NS];
 #pragma unroll
             for (int m = 0; m < NS; m++) {
-                id[m] = idx_g[m * nFBp + f];
+                if (m < NS - 1) id[m] = idx_g[m * nFBp + f];
                 wa[m] = w_g[m * nFBp + f];
                 wb[m] = w_g[(NS + m) * nFBp + f];
             }
-            const bool interior = (id[0] >> 16) != 0xFFFFu;
-            double qa[U];
+            const int la = id[0] & 0xFFFFu, lb = id[0] >> 16;
+            const bool interior = lb != 0xFFFF;
+            // the two cells of the face serve both sides: own cell of one, first neighbour of the other
+            double qa[U], qb[U];
 #pragma unroll
             for (int k = 0; k < U; k++) {
-                qa[k] = Qs[(id[0] & 0xFFFFu) * U + k];
-                A[k] = wa[0] * qa[k];
+                qa[k] = Qs[la * U + k];
+                qb[k] = interior ? Qs[lb * U + k] : qa[k];
+                A[k] = wa[0] * qa[k] + wa[1] * qb[k];
+                B[k] = wb[0] * qb[k] + wb[1] * qa[k];
             }
 #pragma unroll
-            for (int m = 1; m < NS; m++) {
-                const int c = id[m] & 0xFFFFu;
+            for (int m = 2; m < NS; m++) {
+                const int ca = id[m - 1] & 0xFFFFu;
 #pragma unroll
-                for (int k = 0; k < U; k++) A[k] += wa[m] * Qs[c * U + k];
+                for (int k = 0; k < U; k++) A[k] += wa[m] * Qs[ca * U + k];
             }
             if (interior) {
 #pragma unroll
-                for (int k = 0; k < U; k++) B[k] = wb[0] * Qs[(id[0] >> 16) * U + k];
+                for (int m = 2; m < NS; m++) {
+                    const int cb = id[m - 1] >> 16;
 #pragma unroll
-                for (int m = 1; m < NS; m++) {
-                    const int c = id[m] >> 16;
-#pragma unroll
-                    for (int k = 0; k < U; k++) B[k] += wb[m] * Qs[c * U + k];
+                    for (int k = 0; k < U; k++) B[k] += wb[m] * Qs[cb * U + k];
                 }
             } else {
                 double ra[U];

@@ -21,7 +21,8 @@ namespace mst {
 struct TileLayout {
     // packet (global memory), byte offsets from the packet start
     uint32_t w;      // f64 [2*NS][nFBp]  reconstruction weights: side A (c0) then side B (c1)   (order 2)
-    uint32_t idx;    // u32 [NS][nFBp]    stencil cells, local ids: A | B << 16  (order 1: NS = 1: la | lb << 16)
+    uint32_t idx;    // u32 [NS-1][nFBp]  local cell ids, A | B << 16: row 0 = the face's own cells (la | lb),
+                     //                   row m-1 = stencil entry m >= 2 (entry 1 is the cell across the face)
     uint32_t fSd;    // f64 [D][nFBp]     area vector, outward from c0
     uint32_t fmeta;  // u32 [nFBp]        zone type | left/right flags << 8
     uint32_t slots;  // u16 [nslot][ncp]  per owned cell: local face << 1 | side, 0xFFFF = pad
@@ -44,7 +45,7 @@ MST_HD TileLayout tile_layout(int D, int order, int nslot, int n_own, int n_r1, 
     const uint32_t n_loc = (uint32_t)(n_own + n_r1 + n_r2);
     uint32_t o = 0;
     L.w = o; if (order == 2) o += up16(2u * NS * L.nFBp * 8u);
-    L.idx = o; o += up16(NS * L.nFBp * 4u);
+    L.idx = o; o += up16((NS > 1u ? NS - 1u : 1u) * L.nFBp * 4u);
     L.fSd = o; o += up16((uint32_t)D * L.nFBp * 8u);
     L.fmeta = o; o += up16(L.nFBp * 4u);
     L.slots = o; o += up16((uint32_t)nslot * L.ncp * 2u);

@@ -139,7 +139,7 @@ std::string build_tiles(const Plan& p, int n_update, int T, int order, TilePack&
                 for (size_t i = 0; i < s.ring.size(); i++) tp.ring[d.ring_off + i] = s.ring[i];
                 for (uint32_t i = 0; i < (uint32_t)nslot * ncp; i++) slots[i] = 0xFFFF;
                 for (uint32_t i = 0; i < ncp; i++) cvol[i] = 1.0;
-                for (uint32_t i = 0; i < (order == 2 ? (uint32_t)NS : 1u) * nFBp; i++) idx[i] = 0;  // padded faces read cell 0
+                for (uint32_t i = 0; i < (order == 2 ? (uint32_t)NS - 1u : 1u) * nFBp; i++) idx[i] = 0;  // padded faces read cell 0
                 for (int lc = 0; lc < n_own; lc++) {
                     const int g = cb + lc;
                     cvol[lc] = 1.0 / p.vol[g];  // the kernel multiplies: DT * (1/V)
@@ -157,7 +157,10 @@ std::string build_tiles(const Plan& p, int n_update, int T, int order, TilePack&
                 //   rec = b0 Q_c + sum_j bj Q_nb(j),  sigma_j = Sout_j.(fc_f - cc_c)/V,
                 //   b0 = 1 + sum_j wself_j sigma_j,  bj = wnb_j sigma_j.
                 // The weights depend on geometry only and are computed here, once.
-                auto stencil = [&](int c, const double* dx, double* beta, int* cells) {
+                // Slot 1 of a side's stencil is always the cell across the face itself (the other
+                // side's own cell), so the kernel loads the two cells of the face once for both sides.
+                auto stencil = [&](int c, int fself, const double* dx, double* beta, int* cells) {
+                    int jself = 0;
                     const double V = p.vol[c];
                     beta[0] = 1.0;
                     cells[0] = local_of(c);
@@ -167,6 +170,7 @@ std::string build_tiles(const Plan& p, int n_update, int T, int order, TilePack&
                         int g, side;
                         const int nb = nb_of(c, j, g, side);
                         if (g < 0) continue;
+                        if (g == fself) jself = j;
                         double dot = 0.0;
                         for (int k = 0; k < D; k++) dot += p.Sd[(size_t)g * D + k] * dx[k];
                         const double sigma = (side ? -dot : dot) / V;
@@ -179,6 +183,8 @@ std::string build_tiles(const Plan& p, int n_update, int T, int order, TilePack&
                             beta[0] += sigma;
                         }
                     }
+                    std::swap(beta[1], beta[1 + jself]);
+                    std::swap(cells[1], cells[1 + jself]);
                 };
                 for (int lf = 0; lf < nFB; lf++) {
                     const int f = s.flist[lf];
@@ -192,22 +198,19 @@ std::string build_tiles(const Plan& p, int n_update, int T, int order, TilePack&
                     }
                     double beta[9];
                     int cells[9];
-                    stencil(a, &p.dx0[(size_t)f * D], beta, cells);
-                    for (int m = 0; m < NS; m++) {
-                        w[(size_t)m * nFBp + lf] = beta[m];
-                        idx[(size_t)m * nFBp + lf] = (uint32_t)cells[m];
-                    }
+                    // idx rows: [0] = own cells (A | B << 16), [m-1] = stencil entry m >= 2; entry 1 is implicit
+                    stencil(a, f, &p.dx0[(size_t)f * D], beta, cells);
+                    for (int m = 0; m < NS; m++) w[(size_t)m * nFBp + lf] = beta[m];
+                    idx[lf] = (uint32_t)cells[0];
+                    for (int m = 2; m < NS; m++) idx[(size_t)(m - 1) * nFBp + lf] = (uint32_t)cells[m];
                     if (b >= 0) {
-                        stencil(b, &p.dx1[(size_t)f * D], beta, cells);
-                        for (int m = 0; m < NS; m++) {
-                            w[(size_t)(NS + m) * nFBp + lf] = beta[m];
-                            idx[(size_t)m * nFBp + lf] |= (uint32_t)cells[m] << 16;
-                        }
+                        stencil(b, f, &p.dx1[(size_t)f * D], beta, cells);
+                        for (int m = 0; m < NS; m++) w[(size_t)(NS + m) * nFBp + lf] = beta[m];
+                        idx[lf] |= (uint32_t)cells[0] << 16;
+                        for (int m = 2; m < NS; m++) idx[(size_t)(m - 1) * nFBp + lf] |= (uint32_t)cells[m] << 16;
                     } else {
-                        for (int m = 0; m < NS; m++) {
-                            w[(size_t)(NS + m) * nFBp + lf] = 0.0;
-                            idx[(size_t)m * nFBp + lf] |= 0xFFFFu << 16;  // boundary marker on every stencil entry
-                        }
+                        for (int m = 0; m < NS; m++) w[(size_t)(NS + m) * nFBp + lf] = 0.0;
+                        idx[lf] |= 0xFFFFu << 16;  // boundary marker
                     }
                 }
             }
