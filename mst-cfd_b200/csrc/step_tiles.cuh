@@ -91,8 +91,15 @@ __device__ __forceinline__ double warp_max_nonneg(double x) {
     return __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
 }
 
+// resident CTAs per SM the register allocation is sized for: 2 x 256 threads or 3 x 128 threads
+// (a cap of 80 registers for a third 256-thread CTA was measured slower: spills cost more than
+// the extra warps gain)
+#ifndef MST_TILE_MINB
+#define MST_TILE_MINB(NT) ((NT) >= 256 ? 2 : 3)
+#endif
+
 template <int D, int ORDER, int NT, int NS>
-__global__ void __launch_bounds__(NT) k_step_tiles(TileArrays ta, int tile_base, int want_resid, DevCfg cfg, double dt,
+__global__ void __launch_bounds__(NT, MST_TILE_MINB(NT)) k_step_tiles(TileArrays ta, int tile_base, int want_resid, DevCfg cfg, double dt,
                                                    const double* __restrict__ Qold,
                                                    double* __restrict__ Qnew,
                                                    unsigned long long* __restrict__ resid,
@@ -130,7 +137,10 @@ __global__ void __launch_bounds__(NT) k_step_tiles(TileArrays ta, int tile_base,
         // while the states are being staged
         bulk_prefetch_l2(pk, L.pk_bytes);
     }
-    for (int r = tid; r < n_ring; r += NT) {  // one thread per ring cell, U independent loads of a contiguous row
+    // ring cells: one thread per cell, U independent loads of a contiguous 8*U-byte row.
+    // (Batching several cells per thread -- ids first, then rows -- was measured: it helps the
+    // 128-thread variant but costs registers and was 1 % slower for the default 256-thread one.)
+    for (int r = tid; r < n_ring; r += NT) {
         const int g = ta.ring[d.ring_off + r];
         double q[U];
 #pragma unroll

@@ -18,7 +18,7 @@ import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-LIB_PATH = os.path.join(_ROOT, "libmstgpu.so")
+LIB_PATH = os.environ.get("MSTGPU_LIB", os.path.join(_ROOT, "libmstgpu.so"))  # override: A/B builds
 
 EXPORTS = [
     "mstgpu_default_config", "mstgpu_create", "mstgpu_destroy", "mstgpu_set_state",
