@@ -29,7 +29,8 @@ std::string build_partition(const mstgpu_mesh& g, const mstgpu_config& cfg, int 
         cell_part = own_part.data();
     }
     P.nparts = nparts; P.rank = rank; P.D = D;
-    P.layers = cfg.order == 2 ? 2 : 1;
+    // the viscous term needs the primitive gradient of layer-1 cells as well
+    P.layers = (cfg.order == 2 || cfg.viscous != 0) ? 2 : 1;
     const int L = P.layers;
 
     auto other = [&](int f, int c) -> int { return g.c0[f] == c ? g.c1[f] : g.c0[f]; };

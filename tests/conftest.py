@@ -85,3 +85,41 @@ def rel_linf(Qa, Qb, gamma=1.4):
         return 0.0  # everything NaN on both sides (unlimited scheme on a random state)
     s = char_scales(Qb[fin], gamma)
     return float((np.abs(Qa[fin] - Qb[fin]) / s).max())
+
+
+def hex_box_flat(nx, ny, nz, bc=(3, 3, 3, 3, 3, 3)):
+    """Structured hexahedral box (6 quad faces per cell) -> flat mesh.  Exercises
+    the 7-point reconstruction stencil of the fused kernel (3-D extension; the
+    reference's quad-face area vector has no 1/2, R/mesh/Face.cpp:30-35)."""
+    from mstgpu import host
+    nid = lambda i, j, k: (k * (ny + 1) + j) * (nx + 1) + i
+    cid = lambda i, j, k: (k * ny + j) * nx + i
+    I, J, K = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), np.arange(nz + 1), indexing="ij")
+    nodes = np.zeros(((nx + 1) * (ny + 1) * (nz + 1), 3))
+    nodes[nid(I, J, K).ravel()] = np.stack([I.ravel() / nx, J.ravel() / ny * 0.8, K.ravel() / nz * 0.6], axis=1)
+    inter, bnd = [], []
+    for ax in range(3):
+        n = [nx, ny, nz]
+        rng_ = [range(n[0] + (ax == 0)), range(n[1] + (ax == 1)), range(n[2] + (ax == 2))]
+        for i in rng_[0]:
+            for j in rng_[1]:
+                for k in rng_[2]:
+                    p = [i, j, k]
+                    a, b = (ax + 1) % 3, (ax + 2) % 3
+                    q = []
+                    for da, db in ((0, 0), (1, 0), (1, 1), (0, 1)):
+                        v = list(p); v[a] += da; v[b] += db
+                        q.append(nid(*v))
+                    lo = list(p); lo[ax] -= 1
+                    if p[ax] == 0:
+                        bnd.append((q, cid(*p), -1, bc[2 * ax]))
+                    elif p[ax] == n[ax]:
+                        bnd.append((q, cid(*lo), -1, bc[2 * ax + 1]))
+                    else:
+                        inter.append((q, cid(*lo), cid(*p), 2))
+    allf = inter + bnd
+    raw = dict(dim=3, ncells=nx * ny * nz, nodes=nodes,
+               face_nodes=np.array([f[0] for f in allf], dtype=np.int32),
+               c0=np.array([f[1] for f in allf], dtype=np.int32), c1=np.array([f[2] for f in allf], dtype=np.int32),
+               ftype=np.array([f[3] for f in allf], dtype=np.int32), nint=len(inter))
+    return host.flatten_raw(raw)

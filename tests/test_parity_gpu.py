@@ -327,3 +327,20 @@ def test_full_size_properties():
     assert abs((V * a[:, 0]).sum() - m0) < 1e-12 * m0 and abs((V * a[:, 4]).sum() - e0) < 1e-12 * e0
     ctx.set_state(Q); ctx.step(1e-4, 5)
     assert np.array_equal(ctx.get_state(), a)
+
+
+@pytest.mark.parametrize("order", [1, 2])
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_hexahedra_seven_point_stencil(order, kernel):
+    """Cells with 6 faces: NS = 7 instantiation of the fused kernel (extension)."""
+    from conftest import hex_box_flat
+    f = hex_box_flat(7, 6, 5, bc=(10, 5, 3, 7, 3, 3))
+    assert (np.diff(f["cf_ptr"]) == 6).all()
+    Q0 = mesh_np.random_state(f, seed=12)
+    inlet = np.array([1.0, 0.4, 0.0, 0.0, 2.58])
+    o = oracle.Oracle(f, order=order, flux="roe", inletQ=inlet)
+    g = mstgpu.Context(f, order=order, flux="roe", inletQ=inlet, kernel=kernel, tile_cells=64)
+    g.set_state(Q0)
+    Q1 = o.run(1e-4, 3, Q0)
+    g.step(1e-4, 3)
+    assert rel_linf(g.get_state(), Q1) <= 1e-11
