@@ -207,7 +207,7 @@ def run_ours(args, rank, world):
         log(f"[bench] rank {rank}: {part.n_owned} owned + {part.n_local - part.n_owned} ghost cells, "
             f"{part.n_neighbors} neighbours, partition in {time.time() - t:.1f}s")
         ctx = mstgpu.Context(part, order=args.order, flux=args.flux, device=local, kernel=args.kernel, inletQ=inlet,
-                             tile_cells=args.tile_cells, block_threads=args.block_threads, renumber=args.renumber)
+                             viscous=args.viscous, tile_cells=args.tile_cells, block_threads=args.block_threads, renumber=args.renumber)
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             idt = torch.frombuffer(bytearray(mstgpu.comm_unique_id()), dtype=torch.uint8).cuda()
@@ -218,7 +218,7 @@ def run_ours(args, rank, world):
         del f["cf_idx"]
     else:
         ctx = mstgpu.Context(f, order=args.order, flux=args.flux, device=local, kernel=args.kernel, inletQ=inlet,
-                             tile_cells=args.tile_cells, block_threads=args.block_threads, renumber=args.renumber)
+                             viscous=args.viscous, tile_cells=args.tile_cells, block_threads=args.block_threads, renumber=args.renumber)
         nc = nc_total
     log(f"[bench] context built in {time.time() - t:.1f}s, {ctx.device_bytes / 2**30:.2f} GiB on device")
     ctx.set_state(Q0)
@@ -258,6 +258,8 @@ def run_ours(args, rank, world):
     ab = ALGO_BYTES[(D, args.order)]
     per_kernel = {k: (v[0] / max(v[1], 1)) for k, v in kt.items()}
     dom = max(per_kernel, key=per_kernel.get)
+    if args.viscous:
+        ab = dict(ab, step=616, flux_update=368) if (D, args.order) == (3, 2) else ab  # + eta per face
     if "step_tiles" in per_kernel:
         # fused kernel: one launch does both passes of SURVEY.md 8(d) -> the whole
         # step's algorithmic bytes (600 B per tet cell-update) over its duration
@@ -316,7 +318,7 @@ def run_ours(args, rank, world):
                scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
                config=dict(workload=f"{args.workload}{args.n}: {desc}", cells=nc_total, faces=f["nfaces"], flux=args.flux,
                            parallelism=f"{world} partition(s), Hilbert ranges, 2 ghost layers, NCCL send/recv + allreduce(max)",
-                           order=args.order, dt=DT if args.workload == "box" else 2e-5, kernel=args.kernel, tile_cells=args.tile_cells, renumber=args.renumber,
+                           order=args.order, viscous=args.viscous, dt=DT if args.workload == "box" else 2e-5, kernel=args.kernel, tile_cells=args.tile_cells, renumber=args.renumber,
                            block_threads=args.block_threads, l2="inputs larger than L2 (state + tables >> 126 MB)"
                            if nc_total * U * 8 > 2 ** 28 else "inputs smaller than L2: flush not applied"),
                clocks=clk, e2e=e2e, gpu_launches=launches, roofline=roof, cpu_baseline=cpu,
@@ -347,6 +349,7 @@ def main():
     ap.add_argument("--renumber", type=int, default=2, help="0 none, 1 Morton, 2 Hilbert")
     ap.add_argument("--flux", default="roe", choices=["roe", "ausm"])
     ap.add_argument("--order", type=int, default=2, choices=[1, 2])
+    ap.add_argument("--viscous", type=int, default=0, choices=[0, 1], help="laminar viscous term (split-kernel path)")
     ap.add_argument("--block-threads", type=int, default=0)
     args = ap.parse_args()
     if args.warmup < 3:

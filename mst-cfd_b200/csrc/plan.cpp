@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <numeric>
+#include <parallel/algorithm>  // libstdc++ parallel mode: multi-threaded sort of the 50-100 M keys
 
 namespace mst {
 
@@ -81,7 +82,7 @@ void curve_order(const mstgpu_mesh& m, int renumber, int n, std::vector<int32_t>
         }
         key[c] = {k, c};
     }
-    std::sort(key.begin(), key.end());
+    __gnu_parallel::sort(key.begin(), key.end());
     for (int i = 0; i < n; i++) new2old[i] = key[i].second;
 }
 
@@ -130,7 +131,7 @@ std::string build_plan(const mstgpu_mesh& m, const mstgpu_config& cfg, Plan& p, 
             }
             key[f] = {k, f};
         }
-        if (cfg.renumber != 0) std::sort(key.begin(), key.end());
+        if (cfg.renumber != 0) __gnu_parallel::sort(key.begin(), key.end());
         else std::stable_sort(key.begin(), key.end(),
                               [](const auto& x, const auto& y) { return (x.first >> 62) < (y.first >> 62); });
         p.face_new2old.resize(nf);
