@@ -68,6 +68,12 @@ extern "C" {
 #define MSTGPU_FLUX_ROE 0  /* RHOSOLVER solverRoe  (R/rhoSolver/SolverRoe.cpp)  */
 #define MSTGPU_FLUX_AUSM 1 /* RHOSOLVER SolverAusm (R/rhoSolver/SolverAusm.cpp) */
 
+#define MSTGPU_GRAD_GREEN_GAUSS 0
+#define MSTGPU_GRAD_LSQ 1
+#define MSTGPU_LIMITER_NONE 0
+#define MSTGPU_LIMITER_BARTH_JESPERSEN 1
+#define MSTGPU_LIMITER_VENKATAKRISHNAN 2
+
 /* zone types handled by RhoSolver::updateFaceFlux (RhoSolver.cpp:98-229) */
 #define MSTGPU_BC_INTERIOR 2
 #define MSTGPU_BC_WALL 3
@@ -118,6 +124,15 @@ typedef struct mstgpu_config {
     int32_t tile_cells;   /* cells per tile of the fused kernel, 0 = default         */
     int32_t block_threads;/* CTA size of the fused kernel (128|256), 0 = default     */
     int32_t reserved_;
+    /* ---- build-defined extension: named by the project's north star, ABSENT from the
+     * reference (no limiter, Green-Gauss only, fixed DT: SURVEY.md fact 2, 8f.4).  The
+     * defaults (0, 0) are the reference's scheme.  Checked against the oracle's own
+     * restatement of the same formulas ("parity unpinned": there is no reference code). */
+    int32_t gradient;     /* MSTGPU_GRAD_*: 0 = Green-Gauss (RhoSolver.cpp:430-452),
+                             1 = inverse-distance weighted least squares               */
+    int32_t limiter;      /* MSTGPU_LIMITER_*: 0 = none, 1 = Barth-Jespersen,
+                             2 = Venkatakrishnan (on the conserved variables)          */
+    double limiter_k;     /* Venkatakrishnan K: eps^2 = (K h)^3, h = V^(1/D)            */
 } mstgpu_config;
 
 /* Fill `cfg` with the reference's shipped constants (CONST.h) for `dim`. */
@@ -137,6 +152,14 @@ int mstgpu_get_prev_state(mstgpu_ctx* ctx, double* q_aos);
 int mstgpu_step(mstgpu_ctx* ctx, double dt, int32_t nsteps);
 /* Same, bracketed by CUDA events on the solver's own stream; *ms = elapsed. */
 int mstgpu_step_timed(mstgpu_ctx* ctx, double dt, int32_t nsteps, float* ms);
+/* Extension (the reference's DT is the macro 1/STEP_TIME, R/time/Time.cpp:62):
+ * global CFL time step  dt = cfl * min_c V_c / sum_{f in c} (|u_c.S_f| + a_c |S_f|)
+ * of the current state.  With a communicator the minimum is taken over all ranks
+ * (ncclAllReduce(min)): COLLECTIVE. */
+int mstgpu_cfl_dt(mstgpu_ctx* ctx, double cfl, double* dt);
+/* nsteps steps, each at the CFL step of its own start state; dt never visits the
+ * host.  *time_advanced (optional) = sum of the steps taken.  Collective. */
+int mstgpu_step_cfl(mstgpu_ctx* ctx, double cfl, int32_t nsteps, double* time_advanced);
 /* L-inf relative change of the LAST step, DIMU doubles (Time.cpp:69-76). */
 int mstgpu_residual_linf(mstgpu_ctx* ctx, double* out_dimu);
 int mstgpu_sync(mstgpu_ctx* ctx);

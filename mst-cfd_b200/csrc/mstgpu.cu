@@ -117,6 +117,10 @@ struct mstgpu_ctx {
     cudaEvent_t ev_halo = nullptr, ev_done = nullptr;
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
+    // extension tables / CFL stepping (mstgpu_config.gradient / limiter, mstgpu_step_cfl)
+    double *lsq = nullptr, *eps2 = nullptr;
+    unsigned long long* dtmin = nullptr;  // bit pattern of the smallest cell time step
+    double* dt_dev = nullptr;             // [0] dt of the running step, [1] time advanced
     unsigned long long* resid = nullptr;  // [U] bit patterns of non-negative doubles
     int* nanflag = nullptr;
     int cur = 0;          // Q[cur] = current ("old") state
@@ -334,6 +338,185 @@ __global__ void __launch_bounds__(128) k_flux(int nf, DevCfg cfg, const double* 
     for (int k = 0; k < U; k++) Phi[(size_t)f * U + k] = phi[k];
 }
 
+// ---- extension kernels (absent from the reference; include/mstgpu.h, mstgpu_config) --------------
+
+// least-squares gradient with the fixed weights of plan.h: G_c = sum_j lsq[j][:][c] (Q_nb(j) - Q_c)
+template <int D>
+__global__ void __launch_bounds__(256) k_gradient_lsq(int nc, int nslot, const double* __restrict__ Q,
+                                                      const int32_t* __restrict__ cf,
+                                                      const int32_t* __restrict__ fc0,
+                                                      const int32_t* __restrict__ fc1,
+                                                      const double* __restrict__ lsq,
+                                                      double* __restrict__ G) {
+    constexpr int U = D + 2;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nc) return;
+    double qc[U], t[U][D];
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+        qc[k] = Q[(size_t)c * U + k];
+#pragma unroll
+        for (int d = 0; d < D; d++) t[k][d] = 0.0;
+    }
+    for (int j = 0; j < nslot; j++) {
+        const int v = cf[(size_t)j * nc + c];
+        if (v < 0) continue;
+        const int f = v >> 1;
+        const int nb = (v & 1) ? fc0[f] : fc1[f];
+        if (nb < 0) continue;
+        double g[D];
+#pragma unroll
+        for (int d = 0; d < D; d++) g[d] = lsq[((size_t)j * D + d) * nc + c];
+#pragma unroll
+        for (int k = 0; k < U; k++) {
+            const double dq = Q[(size_t)nb * U + k] - qc[k];
+#pragma unroll
+            for (int d = 0; d < D; d++) t[k][d] += g[d] * dq;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < U; k++)
+#pragma unroll
+        for (int d = 0; d < D; d++) G[((size_t)c * U + k) * D + d] = t[k][d];
+}
+
+// slope limiter value for one face of one cell (mode 1 Barth-Jespersen, 2 Venkatakrishnan)
+__device__ __forceinline__ double limiter_phi(int mode, double dl, double dmax, double dmin, double e2) {
+    if (mode == 1) {
+        if (dl > 0.0) return fmin(1.0, dmax / dl);
+        if (dl < 0.0) return fmin(1.0, dmin / dl);
+        return 1.0;
+    }
+    if (fabs(dl) < 1e-150) return 1.0;
+    const double dm = dl > 0.0 ? dmax : dmin;
+    const double num = (dm * dm + e2) * dl + 2.0 * dl * dl * dm;
+    const double den = dl * (dm * dm + 2.0 * dl * dl + dm * dl + e2);
+    return num / den;
+}
+
+// G[c][k][:] *= phi[c][k]: min / max over the cell and its face neighbours, slope tested at the
+// face centres of the cell
+template <int D>
+__global__ void __launch_bounds__(256) k_limit(int nc, int nslot, int mode, const double* __restrict__ Q,
+                                               const int32_t* __restrict__ cf,
+                                               const int32_t* __restrict__ fc0,
+                                               const int32_t* __restrict__ fc1,
+                                               const double* __restrict__ dx0,
+                                               const double* __restrict__ dx1,
+                                               const double* __restrict__ eps2,
+                                               double* __restrict__ G) {
+    constexpr int U = D + 2;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nc) return;
+    double qc[U], qmin[U], qmax[U], phi[U], g[U][D];
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+        qc[k] = qmin[k] = qmax[k] = Q[(size_t)c * U + k];
+        phi[k] = 1.0;
+#pragma unroll
+        for (int d = 0; d < D; d++) g[k][d] = G[((size_t)c * U + k) * D + d];
+    }
+    for (int j = 0; j < nslot; j++) {
+        const int v = cf[(size_t)j * nc + c];
+        if (v < 0) continue;
+        const int f = v >> 1;
+        const int nb = (v & 1) ? fc0[f] : fc1[f];
+        if (nb < 0) continue;
+#pragma unroll
+        for (int k = 0; k < U; k++) {
+            const double q = Q[(size_t)nb * U + k];
+            qmin[k] = fmin(qmin[k], q);
+            qmax[k] = fmax(qmax[k], q);
+        }
+    }
+    const double e2 = eps2 ? eps2[c] : 0.0;
+    for (int j = 0; j < nslot; j++) {
+        const int v = cf[(size_t)j * nc + c];
+        if (v < 0) continue;
+        const int f = v >> 1;
+        const double* dx = (v & 1) ? dx1 : dx0;
+        double r[D];
+#pragma unroll
+        for (int d = 0; d < D; d++) r[d] = dx[(size_t)f * D + d];
+#pragma unroll
+        for (int k = 0; k < U; k++) {
+            double dl = 0.0;
+#pragma unroll
+            for (int d = 0; d < D; d++) dl += g[k][d] * r[d];
+            phi[k] = fmin(phi[k], limiter_phi(mode, dl, qmax[k] - qc[k], qmin[k] - qc[k], e2));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < U; k++)
+#pragma unroll
+        for (int d = 0; d < D; d++) G[((size_t)c * U + k) * D + d] = g[k][d] * phi[k];
+}
+
+// min over the warp of POSITIVE doubles (their order is the order of their bit patterns)
+__device__ __forceinline__ unsigned long long warp_min_bits(unsigned long long b) {
+    const unsigned hi = (unsigned)(b >> 32), lo = (unsigned)b;
+    const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+    return ((unsigned long long)mh << 32) | ml;
+}
+
+// CFL step: dtmin = min_c V_c / sum_f (|u_c.S_f| + a_c |S_f|); bit pattern of a positive double
+template <int D>
+__global__ void __launch_bounds__(256) k_cfl(int n, int nc, int nslot, double gamma, const double* __restrict__ Q,
+                                             const int32_t* __restrict__ cf,
+                                             const double* __restrict__ Sd,
+                                             const double* __restrict__ vol,
+                                             unsigned long long* __restrict__ dtmin) {
+    constexpr int U = D + 2;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long bits = 0x7FF0000000000000ULL;  // +inf
+    if (c < n) {
+        double q[U];
+#pragma unroll
+        for (int k = 0; k < U; k++) q[k] = Q[(size_t)c * U + k];
+        const double r = 1.0 / q[0];
+        double m2 = 0.0;
+#pragma unroll
+        for (int d = 0; d < D; d++) m2 += q[d + 1] * q[d + 1];
+        const double p = (q[U - 1] - 0.5 * m2 * r) * (gamma - 1.0);
+        const double a = sqrt(gamma * p * r);
+        double lam = 0.0;
+        for (int j = 0; j < nslot; j++) {
+            const int v = cf[(size_t)j * nc + c];
+            if (v < 0) continue;
+            const int f = v >> 1;
+            double un = 0.0, s2 = 0.0;
+#pragma unroll
+            for (int d = 0; d < D; d++) {
+                const double s = Sd[(size_t)f * D + d];
+                un += q[d + 1] * r * s;
+                s2 += s * s;
+            }
+            lam += fabs(un) + a * sqrt(s2);
+        }
+        const double t = vol[c] / lam;
+        if (t > 0.0) bits = (unsigned long long)__double_as_longlong(t);  // NaN / non-positive never win
+    }
+    bits = warp_min_bits(bits);
+    __shared__ unsigned long long sm[8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) sm[wid] = bits;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long mbits = sm[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) mbits = min(mbits, sm[w]);
+        atomicMin(dtmin, mbits);
+    }
+}
+
+// dt = cfl * dtmin; time += dt; dtmin re-armed for the next step
+__global__ void k_cfl_finish(double cfl, unsigned long long* dtmin, double* dt, double* time_acc) {
+    const double t = cfl * __longlong_as_double((long long)*dtmin);
+    *dt = t;
+    *time_acc += t;
+    *dtmin = 0x7FF0000000000000ULL;
+}
+
 __device__ __forceinline__ double warp_max(double x) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
@@ -341,7 +524,8 @@ __device__ __forceinline__ double warp_max(double x) {
 }
 
 template <int D>
-__global__ void __launch_bounds__(256) k_update(int nc, int n_upd, int nslot, double dt,
+__global__ void __launch_bounds__(256) k_update(int nc, int n_upd, int nslot, double dt_val,
+                                                const double* __restrict__ dt_dev,
                                                 const double* __restrict__ Qold,
                                                 const double* __restrict__ Phi,
                                                 const int32_t* __restrict__ cf,
@@ -351,6 +535,7 @@ __global__ void __launch_bounds__(256) k_update(int nc, int n_upd, int nslot, do
                                                 int* __restrict__ nanflag) {
     constexpr int U = D + 2;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const double dt = dt_dev ? *dt_dev : dt_val;  // device-resident dt: CFL stepping (extension)
     double r[U];
 #pragma unroll
     for (int k = 0; k < U; k++) r[k] = 0.0;
@@ -526,9 +711,9 @@ int halo_exchange(mstgpu_ctx* ctx, double* Q, cudaStream_t st) {
     return MSTGPU_OK;
 }
 
-template <int D, int ORDER, int NT, int NS>
-int launch_tiles(mstgpu_ctx* ctx, double dt, const double* Qo, double* Qn, int want_resid, int which, cudaStream_t st) {
-    auto kern = k_step_tiles<D, ORDER, NT, NS>;
+template <int D, int ORDER, int NT, int NS, bool LIM>
+int launch_tiles_lim(mstgpu_ctx* ctx, double dt, const double* dtd, const double* Qo, double* Qn, int want_resid, int which, cudaStream_t st) {
+    auto kern = k_step_tiles<D, ORDER, NT, NS, LIM>;
     static thread_local size_t configured_smem = 0;
     if (configured_smem < ctx->tile_smem) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->tile_smem));
@@ -537,32 +722,51 @@ int launch_tiles(mstgpu_ctx* ctx, double dt, const double* Qo, double* Qn, int w
     // which: 0 = tiles without ghost cells, 1 = tiles whose rings hold ghost cells, 2 = all
     for (const auto& tc : ctx->tile_classes) {
         if (which != 2 && (int)tc.halo != which) continue;
-        kern<<<tc.count, NT, tc.smem, st>>>(ctx->ta, tc.first, want_resid, ctx->dcfg, dt, Qo, Qn, ctx->resid, ctx->nanflag);
+        kern<<<tc.count, NT, tc.smem, st>>>(ctx->ta, tc.first, want_resid, ctx->dcfg, dt, dtd, Qo, Qn, ctx->resid, ctx->nanflag);
         ctx->launches++;
     }
     return MSTGPU_OK;
 }
 
+template <int D, int ORDER, int NT, int NS>
+int launch_tiles(mstgpu_ctx* ctx, double dt, const double* dtd, const double* Qo, double* Qn, int wr, int which, cudaStream_t st) {
+    if (ORDER == 2 && ctx->cfg.limiter != 0) return launch_tiles_lim<D, 2, NT, NS, true>(ctx, dt, dtd, Qo, Qn, wr, which, st);
+    return launch_tiles_lim<D, ORDER, NT, NS, false>(ctx, dt, dtd, Qo, Qn, wr, which, st);
+}
+
 template <int D, int NS>
-int launch_tiles_ns(mstgpu_ctx* ctx, double dt, const double* Qo, double* Qn, int wr, int which, cudaStream_t st) {
+int launch_tiles_ns(mstgpu_ctx* ctx, double dt, const double* dtd, const double* Qo, double* Qn, int wr, int which, cudaStream_t st) {
     const bool o2 = ctx->cfg.order == 2;
-    if (ctx->tile_NT == 128) return o2 ? launch_tiles<D, 2, 128, NS>(ctx, dt, Qo, Qn, wr, which, st) : launch_tiles<D, 1, 128, NS>(ctx, dt, Qo, Qn, wr, which, st);
-    return o2 ? launch_tiles<D, 2, 256, NS>(ctx, dt, Qo, Qn, wr, which, st) : launch_tiles<D, 1, 256, NS>(ctx, dt, Qo, Qn, wr, which, st);
+    if (ctx->tile_NT == 128) return o2 ? launch_tiles<D, 2, 128, NS>(ctx, dt, dtd, Qo, Qn, wr, which, st) : launch_tiles<D, 1, 128, NS>(ctx, dt, dtd, Qo, Qn, wr, which, st);
+    return o2 ? launch_tiles<D, 2, 256, NS>(ctx, dt, dtd, Qo, Qn, wr, which, st) : launch_tiles<D, 1, 256, NS>(ctx, dt, dtd, Qo, Qn, wr, which, st);
 }
 
 template <int D>
-int launch_tiles_any(mstgpu_ctx* ctx, double dt, const double* Qo, double* Qn, int wr, int which, cudaStream_t st) {
+int launch_tiles_any(mstgpu_ctx* ctx, double dt, const double* dtd, const double* Qo, double* Qn, int wr, int which, cudaStream_t st) {
     // stencil size = 1 + faces per cell: triangles 4, tets / quads 5, hexes 7
     switch (ctx->nslot) {
-        case 3: return launch_tiles_ns<D, 4>(ctx, dt, Qo, Qn, wr, which, st);
-        case 4: return launch_tiles_ns<D, 5>(ctx, dt, Qo, Qn, wr, which, st);
-        case 6: return launch_tiles_ns<D, 7>(ctx, dt, Qo, Qn, wr, which, st);
+        case 3: return launch_tiles_ns<D, 4>(ctx, dt, dtd, Qo, Qn, wr, which, st);
+        case 4: return launch_tiles_ns<D, 5>(ctx, dt, dtd, Qo, Qn, wr, which, st);
+        case 6: return launch_tiles_ns<D, 7>(ctx, dt, dtd, Qo, Qn, wr, which, st);
         default: set_error(ctx, "fused kernel supports cells with 3, 4 or 6 faces"); return MSTGPU_ERR_ARG;
     }
 }
 
+// dt of the step about to run, computed on the device from Q (extension, mstgpu_step_cfl):
+// cell minimum -> [min over ranks] -> dt_dev[0] = cfl * min, dt_dev[1] += dt
 template <int D>
-int step_tiles_impl(mstgpu_ctx* ctx, double dt, int nsteps) {
+int cfl_on_device(mstgpu_ctx* ctx, double cfl, const double* Q) {
+    k_cfl<D><<<(ctx->n_owned + 255) / 256, 256, 0, ctx->stream>>>(ctx->n_owned, ctx->nc, ctx->nslot, ctx->dcfg.gamma, Q, ctx->cf,
+                                                                 ctx->Sd, ctx->vol, ctx->dtmin);
+    if (ctx->comm) NK(g_nccl.AllReduce(ctx->dtmin, ctx->dtmin, 1, ncclUint64, ncclMin, ctx->comm, ctx->stream));
+    k_cfl_finish<<<1, 1, 0, ctx->stream>>>(cfl, ctx->dtmin, ctx->dt_dev, ctx->dt_dev + 1);
+    ctx->launches += 2;
+    return MSTGPU_OK;
+}
+
+template <int D>
+int step_tiles_impl(mstgpu_ctx* ctx, double dt, int nsteps, double cfl) {
+    const double* dtd = cfl > 0.0 ? ctx->dt_dev : nullptr;
     const bool overlap = ctx->partitioned && !ctx->halo.empty();
     if (overlap && !ctx->comm) { set_error(ctx, "partitioned context without a communicator: call mstgpu_comm_init"); return MSTGPU_ERR_STATE; }
     if (overlap && nsteps > 0) CK(cudaEventRecord(ctx->ev_done, ctx->stream));
@@ -572,9 +776,13 @@ int step_tiles_impl(mstgpu_ctx* ctx, double dt, int nsteps) {
         // the residual of a step is observable only for the last step of the call
         const int wr = (s == nsteps - 1) ? 1 : 0;
         if (wr) CK(cudaMemsetAsync(ctx->resid, 0, 8 * sizeof(unsigned long long), ctx->stream));
+        int r;
+        if (cfl > 0.0) {
+            if ((r = cfl_on_device<D>(ctx, cfl, Qc))) return r;
+            if (overlap) CK(cudaEventRecord(ctx->ev_done, ctx->stream));  // the comm stream needs dt too
+        }
         KTimer t(ctx, "step_tiles");
         ctx->launches--;  // the launches are counted one by one in launch_tiles
-        int r;
         if (overlap) {
             // comm stream: ghost rows <- owners, as soon as the previous step is complete;
             // compute stream: tiles that touch no ghost cell meanwhile, the others after
@@ -582,13 +790,13 @@ int step_tiles_impl(mstgpu_ctx* ctx, double dt, int nsteps) {
             // the interior launch leaves idle in its tail instead of waiting behind it)
             CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_done, 0));
             if ((r = halo_exchange(ctx, Qc, ctx->stream2))) return r;
-            if ((r = launch_tiles_any<D>(ctx, dt, Qc, Qn, wr, 1, ctx->stream2))) return r;
+            if ((r = launch_tiles_any<D>(ctx, dt, dtd, Qc, Qn, wr, 1, ctx->stream2))) return r;
             CK(cudaEventRecord(ctx->ev_halo, ctx->stream2));
-            if ((r = launch_tiles_any<D>(ctx, dt, Qc, Qn, wr, 0, ctx->stream))) return r;
+            if ((r = launch_tiles_any<D>(ctx, dt, dtd, Qc, Qn, wr, 0, ctx->stream))) return r;
             CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_halo, 0));
             CK(cudaEventRecord(ctx->ev_done, ctx->stream));
         } else {
-            if ((r = launch_tiles_any<D>(ctx, dt, Qc, Qn, wr, 2, ctx->stream))) return r;
+            if ((r = launch_tiles_any<D>(ctx, dt, dtd, Qc, Qn, wr, 2, ctx->stream))) return r;
         }
         ctx->cur ^= 1;
     }
@@ -598,9 +806,31 @@ int step_tiles_impl(mstgpu_ctx* ctx, double dt, int nsteps) {
     return MSTGPU_OK;
 }
 
+// the gradient stage of the split path: Green-Gauss (the reference) or least squares, then the limiter
 template <int D>
-int step_impl(mstgpu_ctx* ctx, double dt, int nsteps) {
-    if (ctx->use_tiles) return step_tiles_impl<D>(ctx, dt, nsteps);
+void launch_gradient_stage(mstgpu_ctx* ctx, const double* Qo) {
+    const int nc = ctx->nc;
+    const bool lsq = ctx->cfg.gradient == MSTGPU_GRAD_LSQ && ctx->cfg.order == 2;
+    if ((ctx->cfg.order == 2 && !lsq) || ctx->cfg.viscous) {
+        KTimer t(ctx, "gradient");
+        k_gradient<D><<<(nc + 255) / 256, 256, 0, ctx->stream>>>(
+            nc, ctx->nslot, Qo, ctx->cf, ctx->fc0, ctx->fc1, ctx->eta, ctx->Sd, ctx->vol, ctx->G, ctx->Gp, ctx->dcfg.cv);
+    }
+    if (lsq) {
+        KTimer t(ctx, "gradient_lsq");
+        k_gradient_lsq<D><<<(nc + 255) / 256, 256, 0, ctx->stream>>>(nc, ctx->nslot, Qo, ctx->cf, ctx->fc0, ctx->fc1, ctx->lsq, ctx->G);
+    }
+    if (ctx->cfg.order == 2 && ctx->cfg.limiter != 0) {
+        KTimer t(ctx, "limiter");
+        k_limit<D><<<(nc + 255) / 256, 256, 0, ctx->stream>>>(nc, ctx->nslot, ctx->cfg.limiter, Qo, ctx->cf, ctx->fc0, ctx->fc1,
+                                                              ctx->dx0, ctx->dx1, ctx->eps2, ctx->G);
+    }
+}
+
+template <int D>
+int step_impl(mstgpu_ctx* ctx, double dt, int nsteps, double cfl = 0.0) {
+    if (ctx->use_tiles) return step_tiles_impl<D>(ctx, dt, nsteps, cfl);
+    const double* dtd = cfl > 0.0 ? ctx->dt_dev : nullptr;
     const int nc = ctx->nc, nf = ctx->nf;
     {
         int r = ensure_stage_buffers(ctx);
@@ -615,11 +845,11 @@ int step_impl(mstgpu_ctx* ctx, double dt, int nsteps) {
         const double* Qo = ctx->Q[ctx->cur];
         double* Qn = ctx->Q[ctx->cur ^ 1];
         CK(cudaMemsetAsync(ctx->resid, 0, 8 * sizeof(unsigned long long), ctx->stream));
-        if (ctx->cfg.order == 2 || ctx->cfg.viscous) {
-            KTimer t(ctx, "gradient");
-            k_gradient<D><<<(nc + 255) / 256, 256, 0, ctx->stream>>>(
-                nc, ctx->nslot, Qo, ctx->cf, ctx->fc0, ctx->fc1, ctx->eta, ctx->Sd, ctx->vol, ctx->G, ctx->Gp, ctx->dcfg.cv);
+        if (cfl > 0.0) {
+            int r = cfl_on_device<D>(ctx, cfl, Qo);
+            if (r) return r;
         }
+        launch_gradient_stage<D>(ctx, Qo);
         {
             KTimer t(ctx, "flux");
             if (ctx->cfg.order == 2)
@@ -632,7 +862,7 @@ int step_impl(mstgpu_ctx* ctx, double dt, int nsteps) {
         {
             KTimer t(ctx, "update");
             k_update<D><<<(ctx->n_owned + 255) / 256, 256, 0, ctx->stream>>>(
-                nc, ctx->n_owned, ctx->nslot, dt, Qo, ctx->Phi, ctx->cf, ctx->vol, Qn, ctx->resid, ctx->nanflag);
+                nc, ctx->n_owned, ctx->nslot, dt, dtd, Qo, ctx->Phi, ctx->cf, ctx->vol, Qn, ctx->resid, ctx->nanflag);
         }
         ctx->cur ^= 1;  // RhoSolver::updateNewToOld as a pointer swap
     }
@@ -649,16 +879,14 @@ int recompute_stages(mstgpu_ctx* ctx) {
     if (r) return r;
     const int nc = ctx->nc, nf = ctx->nf;
     const double* Qo = ctx->Q[ctx->cur ^ 1];
-    if (ctx->cfg.order == 2 || ctx->cfg.viscous)
-        k_gradient<D><<<(nc + 255) / 256, 256, 0, ctx->stream>>>(nc, ctx->nslot, Qo, ctx->cf, ctx->fc0, ctx->fc1, ctx->eta,
-                                                                 ctx->Sd, ctx->vol, ctx->G, ctx->Gp, ctx->dcfg.cv);
+    launch_gradient_stage<D>(ctx, Qo);
     if (ctx->cfg.order == 2)
         k_flux<D, 2><<<(nf + 127) / 128, 128, 0, ctx->stream>>>(nf, ctx->dcfg, Qo, ctx->G, ctx->fc0, ctx->fc1, ctx->meta,
                                                                  ctx->Sd, ctx->dx0, ctx->dx1, ctx->Phi, ctx->Gp, ctx->eta);
     else
         k_flux<D, 1><<<(nf + 127) / 128, 128, 0, ctx->stream>>>(nf, ctx->dcfg, Qo, ctx->G, ctx->fc0, ctx->fc1, ctx->meta,
                                                                  ctx->Sd, ctx->dx0, ctx->dx1, ctx->Phi, ctx->Gp, ctx->eta);
-    ctx->launches += 2;
+    ctx->launches += 1;
     CK(cudaGetLastError());
     ctx->probes_valid = true;
     return MSTGPU_OK;
@@ -676,6 +904,10 @@ int fetch_permuted(mstgpu_ctx* ctx, const double* dsrc, const int32_t* new2old, 
 
 }  // namespace
 
+// cells per tile: the largest tile that still lets two CTAs share an SM (228 KB of shared
+// memory); the limiter extension adds a [U][own + ring 1] table, so its tiles are smaller
+static int default_tile_cells(const mstgpu_config& cfg) { return (cfg.order == 2 && cfg.limiter != 0) ? 384 : 512; }
+
 extern "C" {
 
 int mstgpu_tile_stats(const mstgpu_mesh* mesh, const mstgpu_config* cfg, int64_t* out) {
@@ -684,15 +916,15 @@ int mstgpu_tile_stats(const mstgpu_mesh* mesh, const mstgpu_config* cfg, int64_t
     std::string perr = build_plan(*mesh, *cfg, p);
     if (!perr.empty()) { set_error(nullptr, perr); return MSTGPU_ERR_ARG; }
     TilePack tp;
-    int T = cfg->tile_cells > 0 ? cfg->tile_cells : 512;
-    perr = build_tiles(p, p.nc, T, cfg->order, tp);
+    int T = cfg->tile_cells > 0 ? cfg->tile_cells : default_tile_cells(*cfg);
+    perr = build_tiles(p, p.nc, T, cfg->order, tp, cfg->order == 2 ? cfg->limiter : 0);
     if (!perr.empty()) { set_error(nullptr, perr); return MSTGPU_ERR_ARG; }
     for (int i = 0; i < 12; i++) out[i] = 0;
     out[0] = tp.ntiles; out[1] = (int64_t)tp.max_smem;
     out[3] = tp.sum_r1; out[4] = tp.sum_r2; out[5] = tp.sum_FB; out[6] = tp.sum_FA; out[7] = (int64_t)tp.packets.size();
     double sum = 0;
     for (const TileDesc& d : tp.desc) {
-        const size_t b = tile_layout(p.D, cfg->order, p.nslot, d.n_own, d.n_r1, d.n_r2, d.nFB).total;
+        const size_t b = tile_layout(p.D, cfg->order, p.nslot, d.n_own, d.n_r1, d.n_r2, d.nFB, cfg->limiter).total;
         sum += (double)b;
         out[8 + (b <= 56 * 1024 ? 0 : b <= 75 * 1024 ? 1 : b <= 113 * 1024 ? 2 : 3)]++;
     }
@@ -721,6 +953,9 @@ void mstgpu_default_config(mstgpu_config* cfg, int32_t dim) {
     cfg->mu = 1.7894e-05;
     cfg->kappa = 0.0242;
     cfg->cv = 715.8;
+    cfg->gradient = MSTGPU_GRAD_GREEN_GAUSS;  // the reference's scheme: Green-Gauss, no limiter
+    cfg->limiter = MSTGPU_LIMITER_NONE;
+    cfg->limiter_k = 5.0;
     // CONST.h:70-83: rho = 1, u = v = w = 0, E = rho * (T*CV), T = 1/286.32
     cfg->inletQ[0] = 1.0;
     cfg->inletQ[dim + 1] = 1.0 * ((1 / 286.32) * 715.8 + 0.0);
@@ -733,6 +968,9 @@ static int create_impl(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_c
     if (cfg->order != 1 && cfg->order != 2) { set_error(nullptr, "order must be 1 or 2"); return MSTGPU_ERR_ARG; }
     if (cfg->flux != MSTGPU_FLUX_ROE && cfg->flux != MSTGPU_FLUX_AUSM) { set_error(nullptr, "unknown flux"); return MSTGPU_ERR_ARG; }
     if (cfg->viscous != 0 && cfg->viscous != 1) { set_error(nullptr, "viscous must be 0 or 1"); return MSTGPU_ERR_ARG; }
+    if (cfg->gradient != MSTGPU_GRAD_GREEN_GAUSS && cfg->gradient != MSTGPU_GRAD_LSQ) { set_error(nullptr, "unknown gradient"); return MSTGPU_ERR_ARG; }
+    if (cfg->limiter < 0 || cfg->limiter > MSTGPU_LIMITER_VENKATAKRISHNAN) { set_error(nullptr, "unknown limiter"); return MSTGPU_ERR_ARG; }
+    if (cfg->limiter == MSTGPU_LIMITER_VENKATAKRISHNAN && !(cfg->limiter_k >= 0.0)) { set_error(nullptr, "limiter_k must be >= 0"); return MSTGPU_ERR_ARG; }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -778,6 +1016,8 @@ static int create_impl(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_c
         if ((r = upload(ctx, &ctx->cf, p.cf))) return r;
         if ((r = upload(ctx, &ctx->cell_new2old, p.cell_new2old))) return r;
         if ((r = upload(ctx, &ctx->face_new2old, p.face_new2old))) return r;
+        if (!p.lsq.empty() && (r = upload(ctx, &ctx->lsq, p.lsq))) return r;
+        if (!p.eps2.empty() && (r = upload(ctx, &ctx->eps2, p.eps2))) return r;
         const size_t nq = (size_t)p.nc * p.U;
         // + 2 rows: the fused kernel's bulk copies move an even number of rows
         if ((r = dalloc(ctx, &ctx->Q[0], nq + 2 * p.U))) return r;
@@ -786,8 +1026,8 @@ static int create_impl(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_c
         CK(cudaMemsetAsync(ctx->Q[1], 0, (nq + 2 * p.U) * sizeof(double), ctx->stream));
         if (ctx->use_tiles) {
             TilePack tp;
-            int T = cfg->tile_cells > 0 ? cfg->tile_cells : 512;
-            std::string terr = build_tiles(p, ctx->n_owned, T, cfg->order, tp);
+            int T = cfg->tile_cells > 0 ? cfg->tile_cells : default_tile_cells(*cfg);
+            std::string terr = build_tiles(p, ctx->n_owned, T, cfg->order, tp, cfg->order == 2 ? cfg->limiter : 0);
             if (!terr.empty()) { set_error(ctx, terr); return MSTGPU_ERR_ARG; }
             int dev_smem = 0;
             CK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
@@ -804,7 +1044,7 @@ static int create_impl(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_c
                 int ccount[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                 for (int t = 0; t < tp.ntiles; t++) {
                     const TileDesc& d = tp.desc[t];
-                    const size_t b = tile_layout(p.D, cfg->order, p.nslot, d.n_own, d.n_r1, d.n_r2, d.nFB).total;
+                    const size_t b = tile_layout(p.D, cfg->order, p.nslot, d.n_own, d.n_r1, d.n_r2, d.nFB, cfg->limiter).total;
                     int c = 0;
                     while (c < 3 && b > lim[c]) c++;
                     // tiles whose rings reach into the ghost cells wait for the halo exchange
@@ -856,6 +1096,13 @@ static int create_impl(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_c
             if ((r = upload(ctx, &ctx->send_idx, sidx))) return r;
             if ((r = dalloc(ctx, &ctx->sendbuf, (size_t)std::max(1, ctx->send_total) * p.U))) return r;
         }
+        if ((r = dalloc(ctx, &ctx->dtmin, (size_t)1))) return r;
+        if ((r = dalloc(ctx, &ctx->dt_dev, (size_t)2))) return r;
+        {
+            const unsigned long long inf = 0x7FF0000000000000ULL;
+            CK(cudaMemcpyAsync(ctx->dtmin, &inf, sizeof(inf), cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemsetAsync(ctx->dt_dev, 0, 2 * sizeof(double), ctx->stream));
+        }
         if ((r = dalloc(ctx, &ctx->resid, (size_t)8))) return r;
         if ((r = dalloc(ctx, &ctx->nanflag, (size_t)1))) return r;
         CK(cudaMemsetAsync(ctx->resid, 0, 8 * sizeof(unsigned long long), ctx->stream));
@@ -875,9 +1122,10 @@ static int create_impl(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_c
     d.astar_fac = 2.0 * (cfg->gamma - 1.0) / (cfg->gamma + 1.0);
     d.mu = cfg->mu; d.lambda = -0.666667 * cfg->mu; d.kappa = cfg->kappa; d.cv = cfg->cv;
     for (int k = 0; k < 5; k++) d.inletQ[k] = cfg->inletQ[k];
-    d.order = cfg->order; d.flux = cfg->flux; d.viscous = cfg->viscous; d.pad = 0;
+    d.order = cfg->order; d.flux = cfg->flux; d.viscous = cfg->viscous; d.limiter = cfg->order == 2 ? cfg->limiter : 0;
     // the big host tables are no longer needed
     p.fc0 = {}; p.fc1 = {}; p.Sd = {}; p.dx0 = {}; p.dx1 = {}; p.eta = {}; p.meta = {}; p.vol = {}; p.cf = {};
+    p.lsq = {}; p.eps2 = {};
     *out = ctx;
     return MSTGPU_OK;
 }
@@ -895,7 +1143,7 @@ void mstgpu_destroy(mstgpu_ctx* ctx) {
     if (ctx->sendbuf) cudaFree(ctx->sendbuf);
     void* ptrs[] = {ctx->Q[0], ctx->Q[1], ctx->G, ctx->Gp, ctx->Phi, ctx->stage, ctx->Sd, ctx->dx0, ctx->dx1, ctx->eta,
                     ctx->vol, ctx->fc0, ctx->fc1, ctx->cf, ctx->cell_new2old, ctx->face_new2old, ctx->meta,
-                    ctx->resid, ctx->nanflag};
+                    ctx->resid, ctx->nanflag, ctx->lsq, ctx->eps2, ctx->dtmin, ctx->dt_dev};
     for (void* q : ptrs)
         if (q) cudaFree(q);
     for (void* q : ctx->tile_allocs)
@@ -965,6 +1213,39 @@ int mstgpu_step_timed(mstgpu_ctx* ctx, double dt, int32_t nsteps, float* ms) {
     CK(cudaEventSynchronize(ctx->ev1));
     CK(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
     if (ctx->ktiming) drain_timers(ctx);
+    return MSTGPU_OK;
+}
+
+int mstgpu_cfl_dt(mstgpu_ctx* ctx, double cfl, double* dt) {
+    if (!ctx || !dt) return MSTGPU_ERR_ARG;
+    if (!ctx->has_state) { set_error(ctx, "cfl_dt before set_state"); return MSTGPU_ERR_STATE; }
+    if (!(cfl > 0.0)) { set_error(ctx, "cfl must be > 0"); return MSTGPU_ERR_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    int rc = (ctx->D == 2) ? cfl_on_device<2>(ctx, cfl, ctx->Q[ctx->cur]) : cfl_on_device<3>(ctx, cfl, ctx->Q[ctx->cur]);
+    if (rc) return rc;
+    double h[2];
+    CK(cudaMemcpyAsync(h, ctx->dt_dev, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    // a query does not advance the clock of mstgpu_step_cfl
+    CK(cudaMemsetAsync(ctx->dt_dev + 1, 0, sizeof(double), ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *dt = h[0];
+    return MSTGPU_OK;
+}
+
+int mstgpu_step_cfl(mstgpu_ctx* ctx, double cfl, int32_t nsteps, double* time_advanced) {
+    if (!ctx) return MSTGPU_ERR_ARG;
+    if (!ctx->has_state) { set_error(ctx, "step before set_state"); return MSTGPU_ERR_STATE; }
+    if (nsteps < 0) { set_error(ctx, "nsteps < 0"); return MSTGPU_ERR_ARG; }
+    if (!(cfl > 0.0)) { set_error(ctx, "cfl must be > 0"); return MSTGPU_ERR_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemsetAsync(ctx->dt_dev + 1, 0, sizeof(double), ctx->stream));
+    int rc = (ctx->D == 2) ? step_impl<2>(ctx, 0.0, nsteps, cfl) : step_impl<3>(ctx, 0.0, nsteps, cfl);
+    if (ctx->ktiming) drain_timers(ctx);
+    if (rc) return rc;
+    if (time_advanced) {
+        CK(cudaMemcpyAsync(time_advanced, ctx->dt_dev + 1, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
     return MSTGPU_OK;
 }
 

@@ -30,7 +30,7 @@ struct DevCfg {
     double astar_fac;  // 2 (g-1)/(g+1)      SolverAusm.cpp:6
     double mu, lambda, kappa, cv;
     double inletQ[5];
-    int32_t order, flux, viscous, pad;
+    int32_t order, flux, viscous, limiter;  // limiter: extension (0 none, 1 Barth-Jespersen, 2 Venkatakrishnan)
 };
 
 template <int D>

@@ -184,6 +184,70 @@ std::string build_plan(const mstgpu_mesh& m, const mstgpu_config& cfg, Plan& p, 
             p.cf[(size_t)j * nc + i] = 2 * p.face_old2new[f] + side;
         }
     }
+
+    // ---- extension tables (absent from the reference; include/mstgpu.h, mstgpu_config) -------
+    if (cfg.limiter == MSTGPU_LIMITER_VENKATAKRISHNAN) {
+        const double k3 = cfg.limiter_k * cfg.limiter_k * cfg.limiter_k;
+        p.eps2.resize(nc);
+        for (int i = 0; i < nc; i++) p.eps2[i] = k3 * (D == 3 ? p.vol[i] : p.vol[i] * std::sqrt(p.vol[i]));
+    }
+    if (cfg.gradient == MSTGPU_GRAD_LSQ && cfg.order == 2) {
+        // Inverse-distance weighted least squares over the face neighbours,
+        //   min sum_j w_j^2 (Q_j - Q_c - G.d_j)^2,  d_j = cc_j - cc_c,  w_j = 1/|d_j|;
+        // a boundary face adds a mirror neighbour at d = 2 (fc - cc) with the cell's own state
+        // (it enters the normal matrix only).  G = sum_j [w_j^2 M^-1 d_j] (Q_j - Q_c): the bracket
+        // depends on geometry only and is computed here, once.
+        p.lsq.assign((size_t)nslot * D * nc, 0.0);
+#pragma omp parallel for schedule(static)
+        for (int i = 0; i < nc; i++) {
+            const int c = p.cell_new2old[i];
+            double M[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+            double dj[8][3], w2[8];
+            bool real[8];
+            int n = 0;
+            for (int k = m.cf_ptr[c]; k < m.cf_ptr[c + 1]; k++, n++) {
+                const int f = m.cf_idx[k];
+                const bool interior = (m.c1[f] >= 0 && m.ftype[f] == MSTGPU_BC_INTERIOR);
+                const int nb = interior ? (m.c0[f] == c ? m.c1[f] : m.c0[f]) : -1;
+                double d2 = 0.0;
+                for (int a = 0; a < D; a++) {
+                    dj[n][a] = nb >= 0 ? m.cc[(size_t)nb * D + a] - m.cc[(size_t)c * D + a]
+                                       : 2.0 * (m.fc[(size_t)f * D + a] - m.cc[(size_t)c * D + a]);
+                    d2 += dj[n][a] * dj[n][a];
+                }
+                w2[n] = 1.0 / d2;
+                real[n] = nb >= 0;
+                for (int a = 0; a < D; a++)
+                    for (int b = 0; b < D; b++) M[a][b] += w2[n] * dj[n][a] * dj[n][b];
+            }
+            double inv[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+            if (D == 2) {
+                const double det = M[0][0] * M[1][1] - M[0][1] * M[1][0];
+                inv[0][0] = M[1][1] / det; inv[0][1] = -M[0][1] / det;
+                inv[1][0] = -M[1][0] / det; inv[1][1] = M[0][0] / det;
+            } else {
+                const double c00 = M[1][1] * M[2][2] - M[1][2] * M[2][1];
+                const double c01 = M[1][2] * M[2][0] - M[1][0] * M[2][2];
+                const double c02 = M[1][0] * M[2][1] - M[1][1] * M[2][0];
+                const double det = M[0][0] * c00 + M[0][1] * c01 + M[0][2] * c02;
+                inv[0][0] = c00 / det; inv[1][0] = c01 / det; inv[2][0] = c02 / det;
+                inv[0][1] = (M[0][2] * M[2][1] - M[0][1] * M[2][2]) / det;
+                inv[1][1] = (M[0][0] * M[2][2] - M[0][2] * M[2][0]) / det;
+                inv[2][1] = (M[0][1] * M[2][0] - M[0][0] * M[2][1]) / det;
+                inv[0][2] = (M[0][1] * M[1][2] - M[0][2] * M[1][1]) / det;
+                inv[1][2] = (M[0][2] * M[1][0] - M[0][0] * M[1][2]) / det;
+                inv[2][2] = (M[0][0] * M[1][1] - M[0][1] * M[1][0]) / det;
+            }
+            for (int j = 0; j < n; j++) {
+                if (!real[j]) continue;
+                for (int a = 0; a < D; a++) {
+                    double g = 0.0;
+                    for (int b = 0; b < D; b++) g += inv[a][b] * dj[j][b];
+                    p.lsq[((size_t)j * D + a) * nc + i] = w2[j] * g;
+                }
+            }
+        }
+    }
     return "";
 }
 

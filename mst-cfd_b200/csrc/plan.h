@@ -39,6 +39,11 @@ struct Plan {
     // cells (new order)
     std::vector<double> vol;        // [nc]
     std::vector<int32_t> cf;        // [nslot*nc] 2*face + side (side 1: cell is c1), -1 = pad
+    // extension (cfg.gradient == MSTGPU_GRAD_LSQ): least-squares gradient as fixed weights,
+    //   G_c = sum_j lsq[j][:][c] * (Q_nb(j) - Q_c),   [nslot][D][nc]; zero on boundary / pad slots
+    std::vector<double> lsq;
+    // extension (cfg.limiter == Venkatakrishnan): eps^2 = K^3 h^3 per cell, [nc]
+    std::vector<double> eps2;
 };
 
 // returns empty string on success, error text otherwise.

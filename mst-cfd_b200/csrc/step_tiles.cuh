@@ -98,8 +98,24 @@ __device__ __forceinline__ double warp_max_nonneg(double x) {
 #define MST_TILE_MINB(NT) ((NT) >= 256 ? 2 : 3)
 #endif
 
-template <int D, int ORDER, int NT, int NS>
-__global__ void __launch_bounds__(NT, MST_TILE_MINB(NT)) k_step_tiles(TileArrays ta, int tile_base, int want_resid, DevCfg cfg, double dt,
+// slope limiter value at one face centre (extension; same formulas as k_limit of the split path
+// and oracle/rho_oracle.cpp limitGradient): mode 1 Barth-Jespersen, 2 Venkatakrishnan
+__device__ __forceinline__ double tile_limiter_phi(int mode, double dl, double dmax, double dmin, double e2) {
+    if (mode == 1) {
+        if (dl > 0.0) return fmin(1.0, dmax / dl);
+        if (dl < 0.0) return fmin(1.0, dmin / dl);
+        return 1.0;
+    }
+    if (fabs(dl) < 1e-150) return 1.0;
+    const double dm = dl > 0.0 ? dmax : dmin;
+    const double num = (dm * dm + e2) * dl + 2.0 * dl * dl * dm;
+    const double den = dl * (dm * dm + 2.0 * dl * dl + dm * dl + e2);
+    return num / den;
+}
+
+template <int D, int ORDER, int NT, int NS, bool LIM = false>
+__global__ void __launch_bounds__(NT, MST_TILE_MINB(NT)) k_step_tiles(TileArrays ta, int tile_base, int want_resid, DevCfg cfg, double dt_val,
+                                                   const double* __restrict__ dt_dev,
                                                    const double* __restrict__ Qold,
                                                    double* __restrict__ Qnew,
                                                    unsigned long long* __restrict__ resid,
@@ -111,7 +127,8 @@ __global__ void __launch_bounds__(NT, MST_TILE_MINB(NT)) k_step_tiles(TileArrays
     const int tid = threadIdx.x;
     const int n_own = d.n_own, n_ring = d.n_r1 + d.n_r2;
     const int nFB = d.nFB;
-    const TileLayout L = tile_layout(D, ORDER, nslot, d.n_own, d.n_r1, d.n_r2, d.nFB);
+    const TileLayout L = tile_layout(D, ORDER, nslot, d.n_own, d.n_r1, d.n_r2, d.nFB, LIM ? 1 : 0);
+    const double dt = dt_dev ? *dt_dev : dt_val;  // device-resident dt: CFL stepping (extension)
     const int nFBp = L.nFBp, ncp = L.ncp;
     const unsigned char* pk = ta.packets + d.pk_off;
     const double* __restrict__ w_g = reinterpret_cast<const double*>(pk + L.w);
@@ -150,6 +167,50 @@ __global__ void __launch_bounds__(NT, MST_TILE_MINB(NT)) k_step_tiles(TileArrays
     }
     mbar_wait(bar, 0);
     __syncthreads();
+
+    // ---- phase 1 (limiter extension only): limiter value of every cell whose reconstruction the
+    // tile evaluates (own + ring 1).  Thread per cell: min / max over the cell and its face
+    // neighbours, slope at each of its face centres as a fixed-weight sum over the same stencil.
+    double* philim = reinterpret_cast<double*>(smem + L.philim);  // [k][nCLp]
+    if (LIM) {
+        const int nCL = n_own + d.n_r1, nCLp = L.nCLp;
+        const double* __restrict__ lw_g = reinterpret_cast<const double*>(pk + L.lw);
+        const uint16_t* __restrict__ lid_g = reinterpret_cast<const uint16_t*>(pk + L.lid);
+        const double* __restrict__ le2_g = reinterpret_cast<const double*>(pk + L.le2);
+        for (int i = tid; i < nCL; i += NT) {
+            // the weights stay in registers, the variables go by one at a time (register budget)
+            double wj[NS - 1][NS];
+            int cid[NS];
+            cid[0] = i;
+#pragma unroll
+            for (int m = 1; m < NS; m++) cid[m] = lid_g[(m - 1) * nCLp + i];
+#pragma unroll
+            for (int j = 0; j < nslot; j++)
+#pragma unroll
+                for (int m = 0; m < NS; m++) wj[j][m] = lw_g[(j * NS + m) * nCLp + i];
+            const double e2 = le2_g[i];
+#pragma unroll
+            for (int k = 0; k < U; k++) {
+                double q[NS];
+#pragma unroll
+                for (int m = 0; m < NS; m++) q[m] = Qs[cid[m] * U + k];
+                double qmax = q[0], qmin = q[0];
+#pragma unroll
+                for (int m = 1; m < NS; m++) { qmax = fmax(qmax, q[m]); qmin = fmin(qmin, q[m]); }
+                const double dmax = qmax - q[0], dmin = qmin - q[0];
+                double ph = 1.0;
+#pragma unroll
+                for (int j = 0; j < nslot; j++) {
+                    double dl = wj[j][0] * q[0];
+#pragma unroll
+                    for (int m = 1; m < NS; m++) dl += wj[j][m] * q[m];
+                    ph = fmin(ph, tile_limiter_phi(cfg.limiter, dl, dmax, dmin, e2));
+                }
+                philim[k * nCLp + i] = ph;
+            }
+        }
+        __syncthreads();
+    }
 
     // ---- phase 2: reconstruction (fixed stencil) + flux on every face with an owned cell ----
     for (int f = tid; f < nFB; f += NT) {
@@ -194,7 +255,18 @@ __global__ void __launch_bounds__(NT, MST_TILE_MINB(NT)) k_step_tiles(TileArrays
 #pragma unroll
                     for (int k = 0; k < U; k++) B[k] += wb[m] * Qs[cb * U + k];
                 }
+                if (LIM) {
+#pragma unroll
+                    for (int k = 0; k < U; k++) {
+                        A[k] = qa[k] + philim[k * L.nCLp + la] * (A[k] - qa[k]);
+                        B[k] = qb[k] + philim[k * L.nCLp + lb] * (B[k] - qb[k]);
+                    }
+                }
             } else {
+                if (LIM) {
+#pragma unroll
+                    for (int k = 0; k < U; k++) A[k] = qa[k] + philim[k * L.nCLp + la] * (A[k] - qa[k]);
+                }
                 double ra[U];
 #pragma unroll
                 for (int k = 0; k < U; k++) ra[k] = A[k];

@@ -39,11 +39,12 @@ inline int up(int x, int m) { return (x + m - 1) / m * m; }
 
 }  // namespace
 
-std::string build_tiles(const Plan& p, int n_update, int T, int order, TilePack& tp) {
+std::string build_tiles(const Plan& p, int n_update, int T, int order, TilePack& tp, int limiter) {
     const int D = p.D, nc = p.nc, nslot = p.nslot, NS = nslot + 1;
     if (T < 32 || T > 2048 || (T & 1)) return "tile size must be even, 32..2048";
     if (n_update <= 0 || n_update > nc) return "n_update out of range";
-    tp.T = T; tp.order = order; tp.D = D; tp.nslot = nslot;
+    tp.T = T; tp.order = order; tp.D = D; tp.nslot = nslot; tp.limiter = limiter;
+    const bool lsq = !p.lsq.empty();
     tp.ntiles = (n_update + T - 1) / T;
     tp.desc.assign(tp.ntiles, TileDesc{});
     const int nt = tp.ntiles;
@@ -61,7 +62,7 @@ std::string build_tiles(const Plan& p, int n_update, int T, int order, TilePack&
             int64_t ro = 0, po = 0;
             for (int t = 0; t < nt; t++) {
                 TileDesc& d = tp.desc[t];
-                const TileLayout L = tile_layout(D, order, nslot, d.n_own, d.n_r1, d.n_r2, d.nFB);
+                const TileLayout L = tile_layout(D, order, nslot, d.n_own, d.n_r1, d.n_r2, d.nFB, limiter);
                 d.ring_off = ro; d.pk_off = po;
                 ro += up(d.n_r1 + d.n_r2, 4);
                 po += L.pk_bytes;
@@ -127,7 +128,7 @@ std::string build_tiles(const Plan& p, int n_update, int T, int order, TilePack&
                     continue;
                 }
                 // ---- fill ---------------------------------------------------------
-                const TileLayout L = tile_layout(D, order, nslot, n_own, n_r1, n_r2, nFB);
+                const TileLayout L = tile_layout(D, order, nslot, n_own, n_r1, n_r2, nFB, limiter);
                 unsigned char* pk = tp.packets.data() + d.pk_off;
                 double* w = reinterpret_cast<double*>(pk + L.w);
                 uint32_t* idx = reinterpret_cast<uint32_t*>(pk + L.idx);
@@ -159,10 +160,11 @@ std::string build_tiles(const Plan& p, int n_update, int T, int order, TilePack&
                 // The weights depend on geometry only and are computed here, once.
                 // Slot 1 of a side's stencil is always the cell across the face itself (the other
                 // side's own cell), so the kernel loads the two cells of the face once for both sides.
-                auto stencil = [&](int c, int fself, const double* dx, double* beta, int* cells) {
-                    int jself = 0;
+                // gradient of cell c projected on dx, as weights of the stencil (c, face neighbours in the
+                // cell's own face order): G_c.dx = (beta[0] - init0) Q_c + sum_j beta[1+j] Q_nb(j)
+                auto project = [&](int c, const double* dx, double init0, double* beta, int* cells) {
                     const double V = p.vol[c];
-                    beta[0] = 1.0;
+                    beta[0] = init0;
                     cells[0] = local_of(c);
                     for (int j = 0; j < nslot; j++) {
                         beta[1 + j] = 0.0;
@@ -170,7 +172,16 @@ std::string build_tiles(const Plan& p, int n_update, int T, int order, TilePack&
                         int g, side;
                         const int nb = nb_of(c, j, g, side);
                         if (g < 0) continue;
-                        if (g == fself) jself = j;
+                        if (nb >= 0) cells[1 + j] = local_of(nb);
+                        if (lsq) {
+                            // extension: least-squares gradient, G = sum_j lsq_j (Q_nb(j) - Q_c) (plan.h)
+                            if (nb < 0) continue;
+                            double b = 0.0;
+                            for (int k = 0; k < D; k++) b += p.lsq[((size_t)j * D + k) * nc + c] * dx[k];
+                            beta[1 + j] = b;
+                            beta[0] -= b;
+                            continue;
+                        }
                         double dot = 0.0;
                         for (int k = 0; k < D; k++) dot += p.Sd[(size_t)g * D + k] * dx[k];
                         const double sigma = (side ? -dot : dot) / V;
@@ -178,14 +189,49 @@ std::string build_tiles(const Plan& p, int n_update, int T, int order, TilePack&
                         if (nb >= 0) {
                             beta[0] += (side ? (1.0 - e) : e) * sigma;
                             beta[1 + j] = (side ? e : (1.0 - e)) * sigma;
-                            cells[1 + j] = local_of(nb);
                         } else {
                             beta[0] += sigma;
                         }
                     }
+                };
+                auto stencil = [&](int c, int fself, const double* dx, double* beta, int* cells) {
+                    project(c, dx, 1.0, beta, cells);
+                    int jself = 0;
+                    for (int j = 0; j < nslot; j++) {
+                        int g, side;
+                        nb_of(c, j, g, side);
+                        if (g == fself) jself = j;
+                    }
                     std::swap(beta[1], beta[1 + jself]);
                     std::swap(cells[1], cells[1 + jself]);
                 };
+                if (limiter != 0 && order == 2) {
+                    // limiter tables of the cells whose reconstruction the tile evaluates: own + ring 1
+                    double* lw = reinterpret_cast<double*>(pk + L.lw);
+                    uint16_t* lid = reinterpret_cast<uint16_t*>(pk + L.lid);
+                    double* le2 = reinterpret_cast<double*>(pk + L.le2);
+                    const uint32_t nCLp = L.nCLp;
+                    for (int i = 0; i < n_own + n_r1; i++) {
+                        const int c = i < n_own ? cb + i : s.ring[i - n_own];
+                        le2[i] = p.eps2.empty() ? 0.0 : p.eps2[c];
+                        for (int j = 0; j < nslot; j++) {
+                            double beta[9];
+                            int cells[9];
+                            int g, side;
+                            nb_of(c, j, g, side);
+                            if (g < 0) {
+                                for (int m = 0; m < NS; m++) lw[((size_t)j * NS + m) * nCLp + i] = 0.0;
+                                continue;
+                            }
+                            project(c, side ? &p.dx1[(size_t)g * D] : &p.dx0[(size_t)g * D], 0.0, beta, cells);
+                            for (int m = 0; m < NS; m++) lw[((size_t)j * NS + m) * nCLp + i] = beta[m];
+                            if (j == 0)
+                                for (int m = 0; m < nslot; m++) lid[(size_t)m * nCLp + i] = (uint16_t)cells[1 + m];
+                        }
+                    }
+                    for (uint32_t i = (uint32_t)(n_own + n_r1); i < nCLp; i++)
+                        for (int m = 0; m < nslot; m++) lid[(size_t)m * nCLp + i] = 0;
+                }
                 for (int lf = 0; lf < nFB; lf++) {
                     const int f = s.flist[lf];
                     const int a = p.fc0[f], b = p.fc1[f];

@@ -23,7 +23,7 @@ LIB_PATH = os.environ.get("MSTGPU_LIB", os.path.join(_ROOT, "libmstgpu.so"))  # 
 EXPORTS = [
     "mstgpu_default_config", "mstgpu_create", "mstgpu_destroy", "mstgpu_set_state",
     "mstgpu_get_state", "mstgpu_get_prev_state", "mstgpu_step", "mstgpu_step_timed",
-    "mstgpu_residual_linf", "mstgpu_sync", "mstgpu_debug_gradient", "mstgpu_debug_face_flux",
+    "mstgpu_residual_linf", "mstgpu_sync", "mstgpu_cfl_dt", "mstgpu_step_cfl", "mstgpu_debug_gradient", "mstgpu_debug_face_flux",
     "mstgpu_launch_count", "mstgpu_enable_kernel_timing", "mstgpu_kernel_time",
     "mstgpu_device_bytes", "mstgpu_plan_permutation", "mstgpu_tile_stats",
     "mstgpu_partition_create", "mstgpu_partition_destroy", "mstgpu_partition_mesh", "mstgpu_partition_sizes",
@@ -52,7 +52,12 @@ class MstConfig(C.Structure):
         ("inletQ", C.c_double * 5),
         ("kernel", C.c_int32), ("tile_cells", C.c_int32), ("block_threads", C.c_int32),
         ("reserved_", C.c_int32),
+        # extension (absent from the reference): gradient / limiter choice, include/mstgpu.h
+        ("gradient", C.c_int32), ("limiter", C.c_int32), ("limiter_k", C.c_double),
     ]
+
+GRADIENTS = {"gg": 0, "lsq": 1}
+LIMITERS = {"none": 0, "bj": 1, "venkat": 2}
 
 
 class MstGpuError(RuntimeError):
@@ -84,6 +89,8 @@ def lib():
         L.mstgpu_get_prev_state.argtypes = [vp, vp]
         L.mstgpu_step.argtypes = [vp, dbl, i32]
         L.mstgpu_step_timed.argtypes = [vp, dbl, i32, C.POINTER(C.c_float)]
+        L.mstgpu_cfl_dt.argtypes = [vp, dbl, C.POINTER(dbl)]
+        L.mstgpu_step_cfl.argtypes = [vp, dbl, i32, C.POINTER(dbl)]
         L.mstgpu_residual_linf.argtypes = [vp, vp]
         L.mstgpu_sync.argtypes = [vp]
         L.mstgpu_debug_gradient.argtypes = [vp, vp]
@@ -172,6 +179,17 @@ def tile_stats(flat: dict, order: int = 2, tile_cells: int = 0, renumber: int = 
     return dict(zip(keys, (int(x) for x in out)))
 
 
+def _apply_consts(cfg, consts):
+    for k, v in consts.items():
+        if k == "gradient" and isinstance(v, str):
+            v = GRADIENTS[v]
+        if k == "limiter" and isinstance(v, str):
+            v = LIMITERS[v]
+        if not hasattr(cfg, k):
+            raise MstGpuError(f"unknown config field {k!r}")
+        setattr(cfg, k, v)
+
+
 def make_config(dim, order=2, flux="roe", viscous=0, qf_copy_from=None, renumber=2, device=-1, inletQ=None,
                 kernel=None, tile_cells=0, block_threads=0, **consts) -> MstConfig:
     cfg = default_config(dim)
@@ -185,8 +203,7 @@ def make_config(dim, order=2, flux="roe", viscous=0, qf_copy_from=None, renumber
         cfg.kernel = {"tiles": 1, "split": 0}[kernel] if isinstance(kernel, str) else int(kernel)
     cfg.tile_cells = tile_cells
     cfg.block_threads = block_threads
-    for k, v in consts.items():
-        setattr(cfg, k, v)
+    _apply_consts(cfg, consts)
     if inletQ is not None:
         for k in range(5):
             cfg.inletQ[k] = float(inletQ[k]) if k < len(inletQ) else 0.0
@@ -297,8 +314,7 @@ class Context:
             cfg.kernel = {"tiles": 1, "split": 0}[kernel] if isinstance(kernel, str) else int(kernel)
         cfg.tile_cells = tile_cells
         cfg.block_threads = block_threads
-        for k, v in consts.items():
-            setattr(cfg, k, v)
+        _apply_consts(cfg, consts)
         if inletQ is not None:
             for k in range(5):
                 cfg.inletQ[k] = float(inletQ[k]) if k < len(inletQ) else 0.0
@@ -355,6 +371,18 @@ class Context:
         ms = C.c_float()
         self._check(lib().mstgpu_step_timed(self.h, dt, nsteps, C.byref(ms)), "step_timed")
         return float(ms.value)
+
+    def cfl_dt(self, cfl: float) -> float:
+        """Global CFL time step of the current state (extension; collective with a communicator)."""
+        dt = C.c_double()
+        self._check(lib().mstgpu_cfl_dt(self.h, cfl, C.byref(dt)), "cfl_dt")
+        return float(dt.value)
+
+    def step_cfl(self, cfl: float, nsteps: int = 1) -> float:
+        """nsteps steps, each at its own CFL step (dt stays on the device); returns the time advanced."""
+        t = C.c_double()
+        self._check(lib().mstgpu_step_cfl(self.h, cfl, nsteps, C.byref(t)), "step_cfl")
+        return float(t.value)
 
     def residual(self):
         out = np.empty(self.U)

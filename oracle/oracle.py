@@ -44,6 +44,7 @@ class OmCfg(C.Structure):
         ("gamma", C.c_double), ("delta", C.c_double), ("eor", C.c_double),
         ("mu", C.c_double), ("kappa", C.c_double), ("cv", C.c_double),
         ("inletQ", C.c_double * 5),
+        ("gradient", C.c_int32), ("limiter", C.c_int32), ("limiter_k", C.c_double),
     ]
 
 
@@ -58,6 +59,9 @@ def lib():
         L.oracle_nthreads.argtypes = [C.c_void_p]
         L.oracle_solve.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
         L.oracle_run.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+        L.oracle_cfl_dt.restype = C.c_double
+        L.oracle_cfl_dt.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
+        L.oracle_run_cfl.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
         L.oracle_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_riemann.argtypes = [C.c_int, C.c_int, C.POINTER(OmCfg), C.c_void_p,
                                      C.c_void_p, C.c_int, C.c_void_p]
@@ -73,6 +77,11 @@ CV = 715.8
 INI_T = 1 / 286.32
 
 
+# build-defined extension (absent from the reference): gradient / limiter choices
+GRADIENTS = {"gg": 0, "lsq": 1}
+LIMITERS = {"none": 0, "bj": 1, "venkat": 2}
+
+
 def default_inlet(dim: int) -> np.ndarray:
     """inletQ as the shipped macros build it (CONST.h:78-83): rho=1, u=0,
     E = rho*(T*CV)."""
@@ -84,7 +93,7 @@ def default_inlet(dim: int) -> np.ndarray:
 
 def make_cfg(flat, order=2, flux="roe", viscous=0, qf_copy_from=None, nthreads=0,
              inletQ=None, gamma=GAMMA, delta=0.125, eor=1e-10,
-             mu=1.7894e-05, kappa=0.0242, cv=CV) -> OmCfg:
+             mu=1.7894e-05, kappa=0.0242, cv=CV, gradient="gg", limiter="none", limiter_k=5.0) -> OmCfg:
     c = OmCfg()
     c.order = order
     c.flux = {"roe": 0, "ausm": 1}[flux] if isinstance(flux, str) else int(flux)
@@ -93,6 +102,9 @@ def make_cfg(flat, order=2, flux="roe", viscous=0, qf_copy_from=None, nthreads=0
     c.nthreads = nthreads
     c.gamma, c.delta, c.eor = gamma, delta, eor
     c.mu, c.kappa, c.cv = mu, kappa, cv
+    c.gradient = GRADIENTS[gradient] if isinstance(gradient, str) else int(gradient)
+    c.limiter = LIMITERS[limiter] if isinstance(limiter, str) else int(limiter)
+    c.limiter_k = limiter_k
     iq = default_inlet(flat["dim"]) if inletQ is None else np.asarray(inletQ, dtype=np.float64)
     for k in range(5):
         c.inletQ[k] = float(iq[k]) if k < len(iq) else 0.0
@@ -148,6 +160,17 @@ class Oracle:
         r = np.zeros((nsteps, self.U)) if residuals else None
         lib().oracle_run(self.h, dt, nsteps, Q.ctypes.data, r.ctypes.data if residuals else None)
         return (Q, r) if residuals else Q
+
+    def cfl_dt(self, cfl: float, Q: np.ndarray) -> float:
+        Q = np.ascontiguousarray(Q, dtype=np.float64)
+        return float(lib().oracle_cfl_dt(self.h, cfl, Q.ctypes.data))
+
+    def run_cfl(self, cfl: float, nsteps: int, Q: np.ndarray):
+        """nsteps steps at dt = CFL step of each start state; returns (Q, dts)."""
+        Q = np.array(Q, dtype=np.float64, order="C", copy=True)
+        dts = np.zeros(nsteps)
+        lib().oracle_run_cfl(self.h, cfl, nsteps, Q.ctypes.data, dts.ctypes.data)
+        return Q, dts
 
     def probe(self):
         """(Qf [nf,U], G [nc,U,D], F [nf,D,U]) of the last solve()."""

@@ -61,6 +61,10 @@ struct om_cfg {
     double eor;            // EOR 1e-10
     double mu, kappa, cv;  // VISCIDMU, TEMPK, CV (CONST.h:38-48)
     double inletQ[5];      // RhoSolver.cpp:123,266
+    // ---- build-defined EXTENSION (absent from the reference): "parity unpinned" ----
+    int32_t gradient;      // 0 Green-Gauss (the reference, RhoSolver.cpp:430-452), 1 weighted least squares
+    int32_t limiter;       // 0 none (the reference), 1 Barth-Jespersen, 2 Venkatakrishnan
+    double limiter_k;      // Venkatakrishnan K: eps^2 = (K h)^3, h = V^(1/D)
 };
 
 }  // extern "C"
@@ -380,6 +384,139 @@ struct Ctx {
         }
     }
 
+    // ---- EXTENSION (no reference code; the north star names it) -------------
+    // Inverse-distance weighted least-squares gradient over the face neighbours:
+    //   minimise sum_j w_j^2 (Q_j - Q_c - G.d_j)^2,  d_j = cc_j - cc_c,  w_j = 1/|d_j|.
+    // A boundary face contributes a mirror neighbour at d = 2 (fc - cc) carrying the cell's own
+    // state (zero normal gradient), which keeps the normal matrix regular in corner cells.
+    void lsqGradient(const double* Q) {
+        const int nc = m.ncells;
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+        for (int c = 0; c < nc; c++) {
+            double M[D][D], rhs[U][D];
+            for (int a = 0; a < D; a++) for (int b = 0; b < D; b++) M[a][b] = 0.0;
+            for (int k = 0; k < U; k++) for (int a = 0; a < D; a++) rhs[k][a] = 0.0;
+            for (int j = m.cf_ptr[c]; j < m.cf_ptr[c + 1]; j++) {
+                const int f = m.cf_idx[j];
+                const int nb = (m.c0[f] == c) ? m.c1[f] : m.c0[f];
+                double d[D], d2 = 0.0;
+                for (int a = 0; a < D; a++) {
+                    d[a] = (nb >= 0) ? m.cc[(size_t)nb * D + a] - m.cc[(size_t)c * D + a]
+                                     : 2.0 * (m.fc[(size_t)f * D + a] - m.cc[(size_t)c * D + a]);
+                    d2 += d[a] * d[a];
+                }
+                const double w2 = 1.0 / d2;
+                for (int a = 0; a < D; a++) for (int b = 0; b < D; b++) M[a][b] += w2 * d[a] * d[b];
+                if (nb >= 0)
+                    for (int k = 0; k < U; k++) {
+                        const double dq = Q[(size_t)nb * U + k] - Q[(size_t)c * U + k];
+                        for (int a = 0; a < D; a++) rhs[k][a] += w2 * d[a] * dq;
+                    }
+            }
+            // solve M g = rhs by Gaussian elimination with partial pivoting (M is SPD, tiny)
+            for (int k = 0; k < U; k++) {
+                double A[D][D + 1];
+                for (int a = 0; a < D; a++) { for (int b = 0; b < D; b++) A[a][b] = M[a][b]; A[a][D] = rhs[k][a]; }
+                for (int i = 0; i < D; i++) {
+                    int piv = i;
+                    for (int r = i + 1; r < D; r++) if (std::fabs(A[r][i]) > std::fabs(A[piv][i])) piv = r;
+                    if (piv != i) for (int b = 0; b <= D; b++) std::swap(A[i][b], A[piv][b]);
+                    for (int r = i + 1; r < D; r++) {
+                        const double fct = A[r][i] / A[i][i];
+                        for (int b = i; b <= D; b++) A[r][b] -= fct * A[i][b];
+                    }
+                }
+                double g[D];
+                for (int i = D - 1; i >= 0; i--) {
+                    double sum = A[i][D];
+                    for (int b = i + 1; b < D; b++) sum -= A[i][b] * g[b];
+                    g[i] = sum / A[i][i];
+                }
+                for (int a = 0; a < D; a++) G[((size_t)c * U + k) * D + a] = g[a];
+            }
+        }
+    }
+
+    // Slope limiter on the conserved variables, evaluated at the face centres of the cell;
+    // min / max over the cell and its face neighbours.  Scales G in place: G[k][:] *= phi[k].
+    //   1  Barth-Jespersen:   phi_j = min(1, dmax/D) (D > 0), min(1, dmin/D) (D < 0), 1 (D == 0)
+    //   2  Venkatakrishnan:   phi_j = [(Dm^2 + e2) D + 2 D^2 Dm] / [D (Dm^2 + 2 D^2 + Dm D + e2)],
+    //                         e2 = K^3 h^3, h^3 = V (3-D), V sqrt(V) (2-D); |D| < 1e-150 -> 1
+    // with D = G.(fc_j - cc), Dm = dmax if D > 0 else dmin.
+    void limitGradient(const double* Q) {
+        const int nc = m.ncells;
+        const double k3 = cfg.limiter_k * cfg.limiter_k * cfg.limiter_k;
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+        for (int c = 0; c < nc; c++) {
+            double qmin[U], qmax[U];
+            for (int k = 0; k < U; k++) qmin[k] = qmax[k] = Q[(size_t)c * U + k];
+            for (int j = m.cf_ptr[c]; j < m.cf_ptr[c + 1]; j++) {
+                const int f = m.cf_idx[j];
+                const int nb = (m.c0[f] == c) ? m.c1[f] : m.c0[f];
+                if (nb < 0) continue;
+                for (int k = 0; k < U; k++) {
+                    const double q = Q[(size_t)nb * U + k];
+                    if (q < qmin[k]) qmin[k] = q;
+                    if (q > qmax[k]) qmax[k] = q;
+                }
+            }
+            const double V = m.vol[c];
+            const double e2 = k3 * (D == 3 ? V : V * std::sqrt(V));
+            for (int k = 0; k < U; k++) {
+                const double qc = Q[(size_t)c * U + k];
+                const double dmax = qmax[k] - qc, dmin = qmin[k] - qc;
+                double* g = &G[((size_t)c * U + k) * D];
+                double phi = 1.0;
+                for (int j = m.cf_ptr[c]; j < m.cf_ptr[c + 1]; j++) {
+                    const int f = m.cf_idx[j];
+                    double dl = 0.0;
+                    for (int a = 0; a < D; a++) dl += g[a] * (m.fc[(size_t)f * D + a] - m.cc[(size_t)c * D + a]);
+                    double pj = 1.0;
+                    if (cfg.limiter == 1) {
+                        if (dl > 0.0) pj = std::fmin(1.0, dmax / dl);
+                        else if (dl < 0.0) pj = std::fmin(1.0, dmin / dl);
+                    } else {
+                        if (std::fabs(dl) >= 1e-150) {
+                            const double dm = dl > 0.0 ? dmax : dmin;
+                            const double num = (dm * dm + e2) * dl + 2.0 * dl * dl * dm;
+                            const double den = dl * (dm * dm + 2.0 * dl * dl + dm * dl + e2);
+                            pj = num / den;
+                        }
+                    }
+                    if (pj < phi) phi = pj;
+                }
+                for (int a = 0; a < D; a++) g[a] *= phi;
+            }
+        }
+    }
+
+    // Largest stable explicit step of the cell-centred scheme (EXTENSION: the reference's DT is
+    // fixed, Time.cpp:62):  dt = CFL * min_c V_c / sum_{f in c} (|u_c . S_f| + a_c |S_f|),
+    // a = sqrt(gamma p / rho); cells whose value is not a positive finite number are skipped.
+    double cflDt(const double* Q, double cfl) const {
+        const int nc = m.ncells;
+        double best = HUGE_VAL;
+#pragma omp parallel for num_threads(nthreads) schedule(static) reduction(min : best)
+        for (int c = 0; c < nc; c++) {
+            const double* q = Q + (size_t)c * U;
+            const double r = 1.0 / q[0];
+            double m2 = 0.0;
+            for (int a = 0; a < D; a++) m2 += q[a + 1] * q[a + 1];
+            const double p = (q[U - 1] - 0.5 * m2 * r) * (cfg.gamma - 1.0);
+            const double a = std::sqrt(cfg.gamma * p * r);
+            double lam = 0.0;
+            for (int j = m.cf_ptr[c]; j < m.cf_ptr[c + 1]; j++) {
+                const int f = m.cf_idx[j];
+                double un = 0.0, s2 = 0.0;
+                for (int b = 0; b < D; b++) { un += q[b + 1] * r * m.S[(size_t)f * D + b]; s2 += m.S[(size_t)f * D + b] * m.S[(size_t)f * D + b]; }
+                lam += std::fabs(un) + a * std::sqrt(s2);
+            }
+            const double t = m.vol[c] / lam;
+            if (t > 0.0 && t < best) best = t;  // NaN and non-positive values never win
+        }
+        return cfl * best;
+    }
+
     // Q[c] + G[c] * (fc - cc[c])   (RhoSolver.cpp:250)
     inline void rec(const double* Q, int c, int f, double* out) const {
         double dx[D];
@@ -574,7 +711,11 @@ struct Ctx {
 
     // RhoSolver.cpp:37-68
     void solve(double dt, const double* Qold, double* Qnew) {
-        if (cfg.order == 2) updateGradFlux(Qold);
+        if (cfg.order == 2) {
+            updateGradFlux(Qold);                    // the reference's gradient (also fills Qf)
+            if (cfg.gradient == 1) lsqGradient(Qold);  // EXTENSION: replaces G
+            if (cfg.limiter != 0) limitGradient(Qold); // EXTENSION: scales G
+        }
         if (cfg.flux == 0) updateFaceFlux<Roe<D>>(Qold);
         else updateFaceFlux<Ausm<D>>(Qold);
         const int nc = m.ncells;
@@ -673,6 +814,27 @@ int oracle_run(void* hv, double dt, int nsteps, double* Q, double* resid) {
             else ((Ctx<3>*)h->p)->residual(Q, Qn.data(), resid + (size_t)s * U);
         }
         std::memcpy(Q, Qn.data(), n * sizeof(double));  // RhoSolver.cpp:513-517
+    }
+    return 0;
+}
+
+// EXTENSION: CFL time step of the state Q (the reference's DT is a macro, Time.cpp:62)
+double oracle_cfl_dt(void* hv, double cfl, const double* Q) {
+    Handle* h = (Handle*)hv;
+    return h->dim == 2 ? ((Ctx<2>*)h->p)->cflDt(Q, cfl) : ((Ctx<3>*)h->p)->cflDt(Q, cfl);
+}
+
+// nsteps steps, each with dt = oracle_cfl_dt of its start state; dts (optional) receives them
+int oracle_run_cfl(void* hv, double cfl, int nsteps, double* Q, double* dts) {
+    Handle* h = (Handle*)hv;
+    const int U = h->dim + 2;
+    size_t n = (size_t)(h->dim == 2 ? ((Ctx<2>*)h->p)->m.ncells : ((Ctx<3>*)h->p)->m.ncells) * U;
+    std::vector<double> Qn(n);
+    for (int s = 0; s < nsteps; s++) {
+        const double dt = oracle_cfl_dt(hv, cfl, Q);
+        if (dts) dts[s] = dt;
+        oracle_solve(hv, dt, Q, Qn.data());
+        std::memcpy(Q, Qn.data(), n * sizeof(double));
     }
     return 0;
 }
