@@ -76,6 +76,12 @@ def build_workload(args):
         Q[:, 4] = (1.0 + pert) / 0.4
         desc = (f"unit-cube {n}^3 hexes x 6 Kuhn tets, Roe, 2nd order, explicit, all walls, "
                 "smooth acoustic init rho=p=1+0.1*sin*sin*sin")
+        if getattr(args, "shock", 0):
+            # SURVEY 8d's input: SOD split + smooth perturbation (runs with the limiter extension)
+            Q[:, 0] = np.where(x[:, 0] > 0.5, 0.125, 1.0) + 0.1 * pert
+            Q[:, 4] = (np.where(x[:, 0] > 0.5, 0.1, 1.0) + 0.1 * pert) / 0.4
+            desc = (f"unit-cube {n}^3 hexes x 6 Kuhn tets, Roe, 2nd order + limiter, all walls, "
+                    "SOD split at x=0.5 + 1e-2*sin*sin*sin on rho and p")
     elif args.workload == "step":
         raw = host.forward_step_raw(args.n)
         f = host.flatten_raw(raw)
@@ -140,16 +146,27 @@ class ClockSampler:
                     samples=len(sm), reasons=sorted(reasons))
 
 
-def cpu_baseline(args, nsteps=3, n=None):
+def scheme_kwargs(args):
+    """gradient / limiter choice (extension; defaults = the reference scheme)"""
+    return dict(gradient=args.gradient, limiter=args.limiter, limiter_k=args.limiter_k)
+
+
+def cpu_baseline(args, nsteps=None, n=None, budget_s=12.0):
     """Oracle (kind "port": the reference cannot be compiled without Eigen) on
-    the host cores, on a bounded sample of the same workload."""
+    the host cores, on a bounded sample of the same workload: about `budget_s`
+    seconds of CPU work (the step count is sized from one warm-up step)."""
     from oracle import oracle
     from mstgpu import host
     n = n or args.cpu_n
     a = argparse.Namespace(**vars(args)); a.n = n
     f, Q, _ = build_workload(a)
-    o = oracle.Oracle(f, order=2, flux="roe", nthreads=0)
+    o = oracle.Oracle(f, order=args.order, flux=args.flux, nthreads=0, viscous=args.viscous, **scheme_kwargs(args))
     o.run(DT, 1, Q)  # warm-up (page faults of the work arrays)
+    t = time.perf_counter()
+    o.run(DT, 1, Q)
+    t1 = time.perf_counter() - t
+    if nsteps is None:
+        nsteps = int(min(60, max(3, round(budget_s / max(t1, 1e-3)))))
     t = time.perf_counter()
     o.run(DT, nsteps, Q)
     el = time.perf_counter() - t
@@ -161,11 +178,21 @@ def cpu_baseline(args, nsteps=3, n=None):
 def run_reference(args, rank):
     if rank != 0:
         return
+    if args.workload == "lusgs":
+        c = lusgs_cpu(args, budget_s=max(5.0, 10.0 * args.steps / 20))
+        out = dict(impl="reference", metric="cell_updates_per_sec", value=c["value"], unit="cell-updates/s",
+                   n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=None, higher_is_better=True,
+                   scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
+                   config=dict(workload=f"lusgs box{args.n}: block-5 LU-SGS, {LUSGS_ITERS} iterations per solve (bounded sample)"),
+                   cpu_baseline=c, e2e=dict(value=c["value"], unit="cell-updates/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                   gpu_launches=0)
+        print(json.dumps(out), flush=True)
+        return
     f_desc = None
     from oracle import oracle
     a = argparse.Namespace(**vars(args)); a.n = args.cpu_n
     f, Q, desc = build_workload(a)
-    o = oracle.Oracle(f, order=2, flux="roe", nthreads=0)
+    o = oracle.Oracle(f, order=args.order, flux=args.flux, nthreads=0, viscous=args.viscous, **scheme_kwargs(args))
     for _ in range(args.warmup):
         o.run(DT, 1, Q)
     t = time.perf_counter()
@@ -178,11 +205,142 @@ def run_reference(args, rank):
                n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * el / args.steps,
                higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
                config=dict(workload=f"{args.workload}{args.n}: " + desc.replace(f"{args.cpu_n}^3", f"{args.n}^3"),
-                           flux="roe", order=2, dt=DT),
+                           flux=args.flux, order=args.order, dt=DT),
                cpu_baseline=dict(value=val, unit="cell-updates/s", cores=o.nthreads, kind="port", sample=sample),
                e2e=dict(value=val, unit="cell-updates/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                gpu_launches=0)
     print(json.dumps(out), flush=True)
+
+
+def lusgs_system(args, n):
+    """Pattern of an implicit operator on the box mesh (device cell order) + its colour sweep order."""
+    import mstgpu
+    from mstgpu import host
+    t = time.time()
+    f = host.flatten_raw(host.box_tets_raw(n, n, n))
+    rowptr, col = mstgpu.mesh_adjacency(f)
+    order, ncol = mstgpu.lusgs_color_order(rowptr, col)
+    rows = np.repeat(np.arange(rowptr.size - 1, dtype=np.int32), np.diff(rowptr))
+    dpos = np.nonzero(col == rows)[0]
+    log(f"[bench] lusgs pattern: {rowptr.size - 1} rows, {col.size} blocks, {ncol} colours in {time.time() - t:.1f}s")
+    return f, rowptr, col, order, ncol, dpos
+
+
+LUSGS_ITERS = 5   # LU_INTERVAL, R/include/CONST.h:58
+LUSGS_B = 5       # DIMU of a 3-D mesh
+
+
+def lusgs_bytes_per_row(nnz_per_row):
+    """per iteration the off-diagonal blocks are read twice (val for U x / L ux, the
+    D^-1-scaled copies in the sweeps), the diagonal blocks three times, ~7 vector passes; once per
+    solve the blocks are read and their scaled copies / D / D^-1 written."""
+    BB, off = 8 * LUSGS_B * LUSGS_B, nnz_per_row - 1.0
+    per_iter = 2 * off * BB + 3 * BB + 7 * 8 * LUSGS_B
+    setup = nnz_per_row * BB + off * BB + 2 * BB
+    return per_iter, setup
+
+
+def run_lusgs(args, rank, world):
+    """BASELINE config 5's sweep: the reference's block LU-SGS (SparseSolver<MT,VCT>::solveILU,
+    R/lusolver/SparseSolver.cpp:54-104) on the 50 M-tet adjacency, colour-ordered, 5 iterations,
+    device-resident.  One "cell update" = one row through one whole solve."""
+    import torch
+    import mstgpu
+    if world > 1:
+        raise SystemExit("bench.py --workload lusgs: replicas only (the sweep does not shard yet, DESIGN.md 5)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(0)
+    f, rowptr, col, order, ncol, dpos = lusgs_system(args, args.n)
+    n, nnz, B = rowptr.size - 1, col.size, LUSGS_B
+    t = time.time()
+    solver = mstgpu.LuSgs(rowptr, col, B, device=0, sweep_order=order)
+    lev = solver.levels()
+    g = torch.Generator(device="cuda"); g.manual_seed(20231017)
+    val = torch.empty((nnz, B, B), dtype=torch.float64, device="cuda")
+    step = 1 << 22
+    for i in range(0, nnz, step):  # diagonally dominant random blocks, generated in place on the device
+        val[i:i + step] = (torch.rand((min(step, nnz - i), B, B), generator=g, dtype=torch.float64, device="cuda") - 0.5) * 0.2
+    eye = torch.eye(B, dtype=torch.float64, device="cuda") * 3.0
+    dp = torch.from_numpy(dpos).cuda()
+    for i in range(0, n, step):
+        val[dp[i:i + step]] += eye
+    b = torch.rand((n, B), generator=g, dtype=torch.float64, device="cuda")
+    x0 = torch.ones((n, B), dtype=torch.float64, device="cuda")
+    x = x0.clone()
+    torch.cuda.synchronize()
+    dev_bytes = solver.device_bytes + val.numel() * 8 + 3 * n * B * 8
+    log(f"[bench] lusgs solver built in {time.time() - t:.1f}s, levels fwd/bwd {lev}, {dev_bytes / 2**30:.1f} GiB on device")
+    for _ in range(args.warmup):
+        x.copy_(x0); solver.solve_device(val.data_ptr(), b.data_ptr(), x.data_ptr(), LUSGS_ITERS)
+    clocks = ClockSampler(0); clocks.start(); time.sleep(0.3)
+    l0 = solver.launch_count
+    ms = 0.0
+    w0 = time.perf_counter()
+    for _ in range(args.steps):  # every solve starts from the same x0 (untimed reset), as every time step would
+        x.copy_(x0); torch.cuda.synchronize()
+        ms += solver.solve_device(val.data_ptr(), b.data_ptr(), x.data_ptr(), LUSGS_ITERS)
+    wall = time.perf_counter() - w0
+    clk = clocks.stop()
+    launches = solver.launch_count - l0
+    value = n * args.steps / (ms * 1e-3)
+    # fixed point: the iteration converges to A x = b; the residual of the block system after 5 sweeps
+    peak, peak_src = measured_peaks()
+    per_iter, setup = lusgs_bytes_per_row(nnz / n)
+    algo = LUSGS_ITERS * per_iter + setup
+    achieved = algo * n / (ms / args.steps * 1e-3) / 1e9
+    roof = dict(bound="hbm", kernel="LU-SGS solve (k_scale + 5 x [k_ux, k_rhs, sweeps, k_mid, sweeps, k_fin])",
+                achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None, peak_source=peak_src,
+                algorithmic_bytes_per_cell=algo, bytes_per_row_iteration=per_iter, bytes_per_row_setup=setup)
+    # e2e: the reference's calling convention -- host arrays in (setELE / setD / setRHSb), host x out
+    e2e = None
+    if n * (nnz / n) * B * B * 8 < 24e9:
+        hv, hb, hx = val.cpu().numpy(), b.cpu().numpy(), x0.cpu().numpy()
+        solver.solve(hv, hb, hx, LUSGS_ITERS)
+        e0 = time.perf_counter()
+        ne = 2
+        for _ in range(ne):
+            solver.solve(hv, hb, hx, LUSGS_ITERS)
+        e2e_s = (time.perf_counter() - e0) / ne
+        e2e = dict(value=n / e2e_s, unit="cell-updates/s", h2d_bytes_per_step=int(hv.nbytes + hb.nbytes + hx.nbytes),
+                   d2h_bytes_per_step=int(hx.nbytes), ms_per_step=e2e_s * 1e3, steps=ne)
+    cpu = None
+    if not args.no_cpu:
+        cpu = lusgs_cpu(args)
+    out = dict(metric="cell_updates_per_sec", value=value, unit="cell-updates/s", n_gpus=1, steps=args.steps,
+               warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None,
+               dtype="f64", data="synthetic",
+               config=dict(workload=f"lusgs box{args.n}: block-5 LU-SGS (reference SparseSolver::solveILU algebra), "
+                                    f"{LUSGS_ITERS} iterations per solve, pattern = tet adjacency of the {args.n}^3 x 6 box "
+                                    f"in Hilbert order, {ncol}-colour sweep order, random diagonally dominant blocks",
+                           rows=n, blocks=int(nnz), colours=ncol, levels=list(lev),
+                           l2="inputs larger than L2" if nnz * 200 > 2 ** 28 else "inputs smaller than L2: flush not applied"),
+               clocks=clk, e2e=e2e, gpu_launches=launches, roofline=roof, cpu_baseline=cpu,
+               wall_ms_per_step=wall * 1e3 / args.steps, device_gib=dev_bytes / 2 ** 30)
+    print(json.dumps(out), flush=True)
+
+
+def lusgs_cpu(args, budget_s=12.0):
+    """The oracle's restatement of SparseSolver::solveILU (pinned bit-exactly to the reference build),
+    one thread (the reference's sweeps are sequential), on a bounded sample."""
+    from oracle import oracle
+    _, rowptr, col, order, ncol, dpos = lusgs_system(args, min(args.cpu_n, 48))
+    n, nnz, B = rowptr.size - 1, col.size, LUSGS_B
+    rng = np.random.default_rng(1)
+    val = (rng.random((nnz, B, B)) - 0.5) * 0.2
+    val[dpos] += 3.0 * np.eye(B)
+    b = rng.random((n, B)); x0 = np.ones((n, B))
+    t = time.perf_counter()
+    oracle.lusgs(rowptr, col, val, b, x0, B, LUSGS_ITERS)
+    t1 = time.perf_counter() - t
+    reps = int(min(50, max(1, round(budget_s / max(t1, 1e-3)))))
+    t = time.perf_counter()
+    for _ in range(reps):
+        oracle.lusgs(rowptr, col, val, b, x0, B, LUSGS_ITERS)
+    el = time.perf_counter() - t
+    return dict(value=n * reps / el, unit="cell-updates/s", cores=1, kind="port",
+                sample=f"lusgs box n={min(args.cpu_n, 48)}: {n} rows x {reps} solves of {LUSGS_ITERS} iterations in {el:.2f}s "
+                       "(oracle/lusgs_oracle.cpp, sequential like the reference)")
 
 
 def run_ours(args, rank, world):
@@ -207,7 +365,8 @@ def run_ours(args, rank, world):
         log(f"[bench] rank {rank}: {part.n_owned} owned + {part.n_local - part.n_owned} ghost cells, "
             f"{part.n_neighbors} neighbours, partition in {time.time() - t:.1f}s")
         ctx = mstgpu.Context(part, order=args.order, flux=args.flux, device=local, kernel=args.kernel, inletQ=inlet,
-                             viscous=args.viscous, tile_cells=args.tile_cells, block_threads=args.block_threads, renumber=args.renumber)
+                             viscous=args.viscous, tile_cells=args.tile_cells, block_threads=args.block_threads, renumber=args.renumber,
+                             **scheme_kwargs(args))
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             idt = torch.frombuffer(bytearray(mstgpu.comm_unique_id()), dtype=torch.uint8).cuda()
@@ -218,13 +377,23 @@ def run_ours(args, rank, world):
         del f["cf_idx"]
     else:
         ctx = mstgpu.Context(f, order=args.order, flux=args.flux, device=local, kernel=args.kernel, inletQ=inlet,
-                             viscous=args.viscous, tile_cells=args.tile_cells, block_threads=args.block_threads, renumber=args.renumber)
+                             viscous=args.viscous, tile_cells=args.tile_cells, block_threads=args.block_threads, renumber=args.renumber,
+                             **scheme_kwargs(args))
         nc = nc_total
     log(f"[bench] context built in {time.time() - t:.1f}s, {ctx.device_bytes / 2**30:.2f} GiB on device")
     ctx.set_state(Q0)
     dt_run = DT if args.workload == "box" else 2e-5
+    if args.cfl > 0:
+        # extension: every step at its own global CFL step, computed on the device (+ allreduce(min))
+        ctx.step = lambda dt, n: ctx.step_cfl(args.cfl, n)
     ctx.step(dt_run, args.warmup)
     ctx.sync()
+    graph_ms = None
+    if args.graph and world == 1 and args.cfl <= 0:
+        # the same K steps issued as pairs from a CUDA graph (no per-kernel events): launch-bound meshes
+        ctx.step(dt_run, 4)
+        ctx.sync()
+        graph_ms = ctx.step_timed(dt_run, args.steps)
     # ---- timed region: K steps, state resident in HBM -------------------------
     ctx.enable_kernel_timing(True)
     l0 = ctx.launch_count
@@ -235,7 +404,10 @@ def run_ours(args, rank, world):
         dist.barrier()
     torch.cuda.synchronize()
     w0 = time.perf_counter()
-    ms = ctx.step_timed(dt_run, args.steps)
+    if args.cfl > 0:
+        ms = ctx.step_cfl_timed(args.cfl, args.steps)  # CUDA events on the solver's own stream
+    else:
+        ms = ctx.step_timed(dt_run, args.steps)
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
@@ -255,7 +427,11 @@ def run_ours(args, rank, world):
 
     # ---- roofline of the dominant kernel --------------------------------------
     peak, peak_src = measured_peaks()
-    ab = ALGO_BYTES[(D, args.order)]
+    ab = dict(ALGO_BYTES[(D, args.order)])
+    if args.order == 2 and args.limiter != "none":
+        # limiter pass: Q in, gradient in + out, r = fc - cc per (cell, face), eps^2
+        fpc = 2.0 if D == 3 else 1.5
+        ab["step"] += 8 * U + 2 * 8 * U * D + 2 * fpc * 8 * D + 8
     per_kernel = {k: (v[0] / max(v[1], 1)) for k, v in kt.items()}
     dom = max(per_kernel, key=per_kernel.get)
     if args.viscous:
@@ -318,7 +494,8 @@ def run_ours(args, rank, world):
                scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
                config=dict(workload=f"{args.workload}{args.n}: {desc}", cells=nc_total, faces=f["nfaces"], flux=args.flux,
                            parallelism=f"{world} partition(s), Hilbert ranges, 2 ghost layers, NCCL send/recv + allreduce(max)",
-                           order=args.order, viscous=args.viscous, dt=DT if args.workload == "box" else 2e-5, kernel=args.kernel, tile_cells=args.tile_cells, renumber=args.renumber,
+                           order=args.order, viscous=args.viscous, gradient=args.gradient, limiter=args.limiter, cfl=args.cfl,
+                           graph_ms_per_step=None if graph_ms is None else graph_ms / args.steps, dt=DT if args.workload == "box" else 2e-5, kernel=args.kernel, tile_cells=args.tile_cells, renumber=args.renumber,
                            block_threads=args.block_threads, l2="inputs larger than L2 (state + tables >> 126 MB)"
                            if nc_total * U * 8 > 2 ** 28 else "inputs smaller than L2: flush not applied"),
                clocks=clk, e2e=e2e, gpu_launches=launches, roofline=roof, cpu_baseline=cpu,
@@ -340,7 +517,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="box", choices=["box", "step"])
+    ap.add_argument("--workload", default="box", choices=["box", "step", "lusgs"])
     ap.add_argument("--size", "--n", dest="n", type=int, default=203, help="hexes per side (box) or 1/h (step)")
     ap.add_argument("--cpu-n", type=int, default=96, help="size of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
@@ -351,6 +528,13 @@ def main():
     ap.add_argument("--order", type=int, default=2, choices=[1, 2])
     ap.add_argument("--viscous", type=int, default=0, choices=[0, 1], help="laminar viscous term (split-kernel path)")
     ap.add_argument("--block-threads", type=int, default=0)
+    ap.add_argument("--gradient", default="gg", choices=["gg", "lsq"], help="extension: least-squares gradient")
+    ap.add_argument("--limiter", default="none", choices=["none", "bj", "venkat"], help="extension: slope limiter")
+    ap.add_argument("--limiter-k", type=float, default=5.0)
+    ap.add_argument("--cfl", type=float, default=0.0, help="extension: > 0 = global CFL time step instead of DT")
+    ap.add_argument("--shock", type=int, default=0, choices=[0, 1],
+                    help="box init: 1 = SOD split at x = 0.5 + perturbation (SURVEY 8d; needs --limiter and --cfl)")
+    ap.add_argument("--graph", type=int, default=0, choices=[0, 1], help="also time the K steps issued from the CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -358,6 +542,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":
         run_reference(args, rank)
+    elif args.workload == "lusgs":
+        run_lusgs(args, rank, world)
     else:
         run_ours(args, rank, world)
 

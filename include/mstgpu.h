@@ -160,6 +160,8 @@ int mstgpu_cfl_dt(mstgpu_ctx* ctx, double cfl, double* dt);
 /* nsteps steps, each at the CFL step of its own start state; dt never visits the
  * host.  *time_advanced (optional) = sum of the steps taken.  Collective. */
 int mstgpu_step_cfl(mstgpu_ctx* ctx, double cfl, int32_t nsteps, double* time_advanced);
+/* Same, bracketed by CUDA events on the solver's own stream; *ms = elapsed (ms may be NULL). */
+int mstgpu_step_cfl_timed(mstgpu_ctx* ctx, double cfl, int32_t nsteps, double* time_advanced, float* ms);
 /* L-inf relative change of the LAST step, DIMU doubles (Time.cpp:69-76). */
 int mstgpu_residual_linf(mstgpu_ctx* ctx, double* out_dimu);
 int mstgpu_sync(mstgpu_ctx* ctx);
@@ -222,12 +224,25 @@ int mstgpu_comm_init(mstgpu_ctx* ctx, int32_t nranks, int32_t rank, const char* 
 typedef struct mstgpu_lusgs mstgpu_lusgs;
 int mstgpu_lusgs_create(mstgpu_lusgs** out, int32_t n, int32_t block, const int32_t* rowptr, const int32_t* col,
                         int32_t device);
+/* Same with a sweep order: sweep_new2old[i] = row visited i-th (a permutation, e.g. from
+ * mstgpu_lusgs_color_order; NULL = storage order).  The result is that of the reference's solver on
+ * the permuted system P A P^T, P b -- but the matrix, b and x stay in STORAGE order (locality of
+ * the mesh numbering is kept; only the dependency levels and the order of a row's terms change). */
+int mstgpu_lusgs_create_ordered(mstgpu_lusgs** out, int32_t n, int32_t block, const int32_t* rowptr,
+                                const int32_t* col, const int32_t* sweep_new2old, int32_t device);
 void mstgpu_lusgs_destroy(mstgpu_lusgs* h);
 /* x: in = start vector (the constructors' pOldX), out = solution.  max_iter = LU_INTERVAL
  * (CONST.h:58).  early_exit != 0 applies the scalar version's stop test
  * 1e-20 < res < 1e-7 (SparseSolverNUM.cpp:205).  res_hist: [max_iter] or NULL. */
 int mstgpu_lusgs_solve(mstgpu_lusgs* h, const double* val, const double* b, double* x, int32_t max_iter,
                        int32_t early_exit, double* res_hist, int32_t* iters_done);
+/* Device-resident solve: d_val / d_b / d_x are DEVICE pointers in the layout of mstgpu_lusgs_solve
+ * (x in place); nothing crosses PCIe.  Runs max_iter iterations (the block version's fixed count).
+ * *ms (optional) = CUDA-event time of the whole solve on the solver's stream. */
+int mstgpu_lusgs_solve_device(mstgpu_lusgs* h, const double* d_val, const double* d_b, double* d_x, int32_t max_iter,
+                              float* ms);
+int64_t mstgpu_lusgs_launch_count(mstgpu_lusgs* h);
+int64_t mstgpu_lusgs_device_bytes(mstgpu_lusgs* h);
 int mstgpu_lusgs_levels(mstgpu_lusgs* h, int32_t* forward_levels, int32_t* backward_levels);
 /* host only: greedy colouring of the symmetrised pattern; rows sorted by colour */
 int mstgpu_lusgs_color_order(int32_t n, const int32_t* rowptr, const int32_t* col, int32_t* perm_new2old,
@@ -238,6 +253,13 @@ const char* mstgpu_lusgs_last_error(void);
  * inspection and CPU tests.  cell_new2old [ncells], face_new2old [nfaces]. */
 int mstgpu_plan_permutation(const mstgpu_mesh* mesh, const mstgpu_config* cfg,
                             int32_t* cell_new2old, int32_t* face_new2old);
+
+/* Host-only: the pattern of an implicit operator on this mesh -- CSR adjacency through interior
+ * faces plus the diagonal, columns ascending, cells in the DEVICE order mstgpu_create would use
+ * (mstgpu_plan_permutation) -- ready for mstgpu_lusgs_create[_ordered].  rowptr [ncells+1];
+ * col may be NULL for a sizing call (rowptr[ncells] entries are needed), col_cap = its capacity. */
+int mstgpu_mesh_adjacency(const mstgpu_mesh* mesh, const mstgpu_config* cfg, int32_t* rowptr, int32_t* col,
+                          int64_t col_cap);
 
 /* Host-only: statistics of the tiling the fused kernel would use.
  * out[0]=tiles out[1]=max smem bytes out[2]=mean smem bytes out[3]=sum ring1

@@ -38,6 +38,8 @@ struct mstgpu_lusgs {
     double *val = nullptr, *D = nullptr, *Dinv = nullptr, *LD = nullptr, *UD = nullptr;
     double *b = nullptr, *x = nullptr, *rhs = nullptr, *rhs1 = nullptr, *ux = nullptr;
     unsigned long long* res = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int64_t launches = 0;
     std::string err;
 };
 
@@ -86,6 +88,51 @@ __device__ void d_inverse(const double* m, double* inv) {
     for (int i = 0; i < B; i++) for (int j = 0; j < B; j++) inv[i * B + j] = w[i][B + j];
 }
 
+// ---- thread mapping ---------------------------------------------------------------------------------
+// A block row (B scalar rows) is handled by B adjacent lanes, lane i owning scalar row i of every
+// B x B block it meets: consecutive lanes read consecutive 8*B-byte block rows, so the block arrays
+// (AoS, 8*B*B bytes per entry, rows in storage order) stream through fully used sectors, and the
+// vectors are written B doubles per group.  A group never straddles a warp: a warp takes
+// RPW = 32 / B block rows (lanes >= RPW * B idle), so the B values of a row can be exchanged with
+// shuffles where one lane needs its siblings' results (M v with v computed by the group).
+template <int B>
+struct Grp {
+    static constexpr int RPW = 32 / B;
+    int row, i, base;  // index of the group's item, scalar row within the block, first lane of the group
+    bool on;
+    __device__ __forceinline__ Grp(int nitems) {
+        const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        const int rl = lane / B;
+        i = lane - rl * B;
+        base = rl * B;
+        row = warp * RPW + rl;
+        on = rl < RPW && row < nitems;
+    }
+    static int grid(int nitems, int threads) {
+        const int warps = (nitems + RPW - 1) / RPW, wpb = threads / 32;
+        return (warps + wpb - 1) / wpb;
+    }
+    // (M v)_i where lane k of the group holds v_k; every lane of the warp must call it
+    __device__ __forceinline__ double matvec_lanes(const double* m_row, double vi) const {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < B; k++) {
+            const double vk = __shfl_sync(0xffffffffu, vi, base + k);
+            if (on) s = (k == 0) ? m_row[0] * vk : s + m_row[k] * vk;
+        }
+        return s;
+    }
+};
+
+// row i of a B x B block times a vector in memory: same order of operations as d_matvec
+template <int B>
+__device__ __forceinline__ double row_dot(const double* m_row, const double* v) {
+    double s = m_row[0] * v[0];
+#pragma unroll
+    for (int k = 1; k < B; k++) s += m_row[k] * v[k];
+    return s;
+}
+
 // D = sum of the row's diagonal entries (addD), Dinv = D^-1
 template <int B>
 __global__ void k_diag(int n, const int* Dptr, const int* Dpos, const double* val, double* D, double* Dinv) {
@@ -100,99 +147,94 @@ __global__ void k_diag(int n, const int* Dptr, const int* Dpos, const double* va
     for (int q = 0; q < B * B; q++) { D[(size_t)r * B * B + q] = d[q]; Dinv[(size_t)r * B * B + q] = di[q]; }
 }
 
-// XD[e] = X[e] * Dinv[col[e]]   (the reference's (L * D^-1) factor, SparseSolver.cpp:86,96)
+// XD[e] = X[e] * Dinv[col[e]]   (the reference's (L * D^-1) factor, SparseSolver.cpp:86,96); thread per (entry, row)
 template <int B>
-__global__ void k_scale(int ne, const int* col, const int* pos, const double* val, const double* D, const double* Dinv,
+__global__ void k_scale(size_t ne, const int* col, const int* pos, const double* val, const double* D, const double* Dinv,
                         double* XD) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= ne) return;
-    const double* a = val + (size_t)pos[e] * B * B;
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ne * B) return;
+    const size_t e = g / B;
+    const int i = (int)(g - e * B);
+    const double* a = val + (size_t)pos[e] * B * B + i * B;
     if (B == 1) { XD[e] = a[0] * (1. / D[col[e]]); return; }  // SparseSolverNUM.cpp:181: L * (1./D)
     const double* di = Dinv + (size_t)col[e] * B * B;
-    for (int i = 0; i < B; i++)
-        for (int j = 0; j < B; j++) {
-            double s = a[i * B] * di[j];
-            for (int k = 1; k < B; k++) s += a[i * B + k] * di[k * B + j];
-            XD[(size_t)e * B * B + i * B + j] = s;
-        }
+#pragma unroll
+    for (int j = 0; j < B; j++) {
+        double s = a[0] * di[j];
+#pragma unroll
+        for (int k = 1; k < B; k++) s += a[k] * di[k * B + j];
+        XD[e * B * B + i * B + j] = s;
+    }
 }
 
-// ux[r] = D^-1 (sum_{c>r} U[r,c] x[c])     (SparseSolverNUM.cpp:158-166)
+// ux[r] = D^-1 (sum_{c after r} U[r,c] x[c])     (SparseSolverNUM.cpp:158-166)
 template <int B>
 __global__ void k_ux(int n, const int* Uptr, const int* Ucol, const int* Upos, const double* val, const double* D,
                      const double* Dinv, const double* x, double* ux) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    double acc[B], t[B];
-    for (int q = 0; q < B; q++) acc[q] = 0.0;
-    for (int k = Uptr[r]; k < Uptr[r + 1]; k++) {
-        d_matvec<B>(val + (size_t)Upos[k] * B * B, x + (size_t)Ucol[k] * B, t);
-        for (int q = 0; q < B; q++) acc[q] += t[q];
-    }
-    if (B == 1) { ux[r] = acc[0] / D[r]; return; }
-    d_matvec<B>(Dinv + (size_t)r * B * B, acc, t);
-    for (int q = 0; q < B; q++) ux[(size_t)r * B + q] = t[q];
+    const Grp<B> g(n);
+    const int r = g.row, i = g.i;
+    double acc = 0.0;
+    if (g.on)
+        for (int k = Uptr[r]; k < Uptr[r + 1]; k++)
+            acc += row_dot<B>(val + (size_t)Upos[k] * B * B + i * B, x + (size_t)Ucol[k] * B);
+    if (B == 1) { if (g.on) ux[r] = acc / D[r]; return; }
+    const double t = g.matvec_lanes(g.on ? Dinv + (size_t)r * B * B + i * B : nullptr, acc);
+    if (g.on) ux[(size_t)r * B + i] = t;
 }
 
-// rhs[r] = b[r] + sum_{c<r} L[r,c] ux[c]   (SparseSolverNUM.cpp:167-175)
+// rhs[r] = b[r] + sum_{c before r} L[r,c] ux[c]   (SparseSolverNUM.cpp:167-175)
 template <int B>
 __global__ void k_rhs(int n, const int* Lptr, const int* Lcol, const int* Lpos, const double* val, const double* b,
                       const double* ux, double* rhs) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    double acc[B], t[B];
-    for (int q = 0; q < B; q++) acc[q] = 0.0;
-    for (int k = Lptr[r]; k < Lptr[r + 1]; k++) {
-        d_matvec<B>(val + (size_t)Lpos[k] * B * B, ux + (size_t)Lcol[k] * B, t);
-        for (int q = 0; q < B; q++) acc[q] += t[q];
-    }
-    for (int q = 0; q < B; q++) rhs[(size_t)r * B + q] = b[(size_t)r * B + q] + acc[q];
+    const Grp<B> g(n);
+    if (!g.on) return;
+    const int r = g.row, i = g.i;
+    double acc = 0.0;
+    for (int k = Lptr[r]; k < Lptr[r + 1]; k++)
+        acc += row_dot<B>(val + (size_t)Lpos[k] * B * B + i * B, ux + (size_t)Lcol[k] * B);
+    rhs[(size_t)r * B + i] = b[(size_t)r * B + i] + acc;
 }
 
-// one level of a triangular sweep: v[r] -= sum_k XD[k] v[col[k]], k ascending (forward) or descending (backward)
+// one level of a triangular sweep: v[r] -= sum_k XD[k] v[col[k]], k in sweep order (forward) or reversed (backward)
 template <int B, bool FWD>
 __global__ void k_sweep_level(int nrows, const int* rows, const int* ptr, const int* col, const double* XD, double* v) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nrows) return;
-    const int r = rows[i];
-    double acc[B], t[B];
-    for (int q = 0; q < B; q++) acc[q] = v[(size_t)r * B + q];
+    const Grp<B> g(nrows);
+    if (!g.on) return;
+    const int r = rows[g.row], i = g.i;
+    double acc = v[(size_t)r * B + i];
     const int k0 = ptr[r], k1 = ptr[r + 1];
     for (int kk = 0; kk < k1 - k0; kk++) {
         const int k = FWD ? k0 + kk : k1 - 1 - kk;
-        d_matvec<B>(XD + (size_t)k * B * B, v + (size_t)col[k] * B, t);
-        for (int q = 0; q < B; q++) acc[q] -= t[q];
+        acc -= row_dot<B>(XD + (size_t)k * B * B + i * B, v + (size_t)col[k] * B);
     }
-    for (int q = 0; q < B; q++) v[(size_t)r * B + q] = acc[q];
+    v[(size_t)r * B + i] = acc;
 }
 
 // X1 = D^-1 rhs; rhs1 = D X1   (SparseSolverNUM.cpp:184-187)
 template <int B>
 __global__ void k_mid(int n, const double* D, const double* Dinv, const double* rhs, double* rhs1) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    double x1[B], t[B];
-    if (B == 1) { x1[0] = (1. / D[r]) * rhs[r]; rhs1[r] = D[r] * x1[0]; return; }
-    d_matvec<B>(Dinv + (size_t)r * B * B, rhs + (size_t)r * B, x1);
-    d_matvec<B>(D + (size_t)r * B * B, x1, t);
-    for (int q = 0; q < B; q++) rhs1[(size_t)r * B + q] = t[q];
+    const Grp<B> g(n);
+    const int r = g.row, i = g.i;
+    if (B == 1) { if (g.on) { const double x1 = (1. / D[r]) * rhs[r]; rhs1[r] = D[r] * x1; } return; }
+    const double x1 = g.on ? row_dot<B>(Dinv + (size_t)r * B * B + i * B, rhs + (size_t)r * B) : 0.0;
+    const double t = g.matvec_lanes(g.on ? D + (size_t)r * B * B + i * B : nullptr, x1);
+    if (g.on) rhs1[(size_t)r * B + i] = t;
 }
 
 // xnew = D^-1 rhs1; residual (scalar only); x = xnew   (SparseSolverNUM.cpp:194-203)
 template <int B>
 __global__ void k_fin(int n, const double* D, const double* Dinv, const double* rhs1, double* x, unsigned long long* res) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const Grp<B> g(n);
+    const int r = g.row, i = g.i;
     double rr = 0.0;
-    if (r < n) {
+    if (g.on) {
         if (B == 1) {
             const double xn = (1. / D[r]) * rhs1[r];
             const double q = fabs(x[r] - xn) / x[r];
             rr = (q > 0.0) ? q : 0.0;
             x[r] = xn;
         } else {
-            double t[B];
-            d_matvec<B>(Dinv + (size_t)r * B * B, rhs1 + (size_t)r * B, t);
-            for (int q = 0; q < B; q++) x[(size_t)r * B + q] = t[q];
+            x[(size_t)r * B + i] = row_dot<B>(Dinv + (size_t)r * B * B + i * B, rhs1 + (size_t)r * B);
         }
     }
     if (B == 1) {
@@ -208,32 +250,33 @@ int up(mstgpu_lusgs* h, T** d, const std::vector<T>& v) {
     return 0;
 }
 
+// the sweeps on DEVICE arrays (val: caller's CSR order; x: start vector in, solution out)
 template <int B>
-int solve_impl(mstgpu_lusgs* h, const double* val, const double* b, double* x, int max_iter, int early_exit,
+int solve_core(mstgpu_lusgs* h, const double* val, const double* b, double* x, int max_iter, int early_exit,
                double* res_hist, int32_t* iters_done) {
-    const int n = h->n, BB = B * B, T = 128;
+    const int n = h->n, T = 128;
     cudaStream_t s = h->stream;
-    LCK(cudaMemcpyAsync(h->val, val, (size_t)h->nnz * BB * 8, cudaMemcpyHostToDevice, s));
-    LCK(cudaMemcpyAsync(h->b, b, (size_t)n * B * 8, cudaMemcpyHostToDevice, s));
-    LCK(cudaMemcpyAsync(h->x, x, (size_t)n * B * 8, cudaMemcpyHostToDevice, s));
-    k_diag<B><<<(n + T - 1) / T, T, 0, s>>>(n, h->Dptr, h->Dpos, h->val, h->D, h->Dinv);
-    if (h->nL) k_scale<B><<<(h->nL + T - 1) / T, T, 0, s>>>(h->nL, h->Lcol, h->Lpos, h->val, h->D, h->Dinv, h->LD);
-    if (h->nU) k_scale<B><<<(h->nU + T - 1) / T, T, 0, s>>>(h->nU, h->Ucol, h->Upos, h->val, h->D, h->Dinv, h->UD);
+    using G = Grp<B>;
+    k_diag<B><<<(n + T - 1) / T, T, 0, s>>>(n, h->Dptr, h->Dpos, val, h->D, h->Dinv);
+    if (h->nL) k_scale<B><<<(unsigned)(((size_t)h->nL * B + T - 1) / T), T, 0, s>>>((size_t)h->nL, h->Lcol, h->Lpos, val, h->D, h->Dinv, h->LD);
+    if (h->nU) k_scale<B><<<(unsigned)(((size_t)h->nU * B + T - 1) / T), T, 0, s>>>((size_t)h->nU, h->Ucol, h->Upos, val, h->D, h->Dinv, h->UD);
+    h->launches += 3;
     int it = 0;
     for (; it < max_iter; it++) {
         LCK(cudaMemsetAsync(h->res, 0, 8, s));
-        k_ux<B><<<(n + T - 1) / T, T, 0, s>>>(n, h->Uptr, h->Ucol, h->Upos, h->val, h->D, h->Dinv, h->x, h->ux);
-        k_rhs<B><<<(n + T - 1) / T, T, 0, s>>>(n, h->Lptr, h->Lcol, h->Lpos, h->val, h->b, h->ux, h->rhs);
+        k_ux<B><<<G::grid(n, T), T, 0, s>>>(n, h->Uptr, h->Ucol, h->Upos, val, h->D, h->Dinv, x, h->ux);
+        k_rhs<B><<<G::grid(n, T), T, 0, s>>>(n, h->Lptr, h->Lcol, h->Lpos, val, b, h->ux, h->rhs);
         for (size_t l = 1; l + 1 < h->fptr.size(); l++) {  // level 0 has no dependencies: nothing to subtract
             const int cnt = h->fptr[l + 1] - h->fptr[l];
-            k_sweep_level<B, true><<<(cnt + T - 1) / T, T, 0, s>>>(cnt, h->frows + h->fptr[l], h->Lptr, h->Lcol, h->LD, h->rhs);
+            k_sweep_level<B, true><<<G::grid(cnt, T), T, 0, s>>>(cnt, h->frows + h->fptr[l], h->Lptr, h->Lcol, h->LD, h->rhs);
         }
-        k_mid<B><<<(n + T - 1) / T, T, 0, s>>>(n, h->D, h->Dinv, h->rhs, h->rhs1);
+        k_mid<B><<<G::grid(n, T), T, 0, s>>>(n, h->D, h->Dinv, h->rhs, h->rhs1);
         for (size_t l = 1; l + 1 < h->bptr.size(); l++) {
             const int cnt = h->bptr[l + 1] - h->bptr[l];
-            k_sweep_level<B, false><<<(cnt + T - 1) / T, T, 0, s>>>(cnt, h->brows + h->bptr[l], h->Uptr, h->Ucol, h->UD, h->rhs1);
+            k_sweep_level<B, false><<<G::grid(cnt, T), T, 0, s>>>(cnt, h->brows + h->bptr[l], h->Uptr, h->Ucol, h->UD, h->rhs1);
         }
-        k_fin<B><<<(n + T - 1) / T, T, 0, s>>>(n, h->D, h->Dinv, h->rhs1, h->x, h->res);
+        k_fin<B><<<G::grid(n, T), T, 0, s>>>(n, h->D, h->Dinv, h->rhs1, x, h->res);
+        h->launches += 4 + (int64_t)(h->fptr.size() > 2 ? h->fptr.size() - 2 : 0) + (int64_t)(h->bptr.size() > 2 ? h->bptr.size() - 2 : 0);
         if (B == 1 && (res_hist || early_exit)) {
             unsigned long long bits = 0;
             LCK(cudaMemcpyAsync(&bits, h->res, 8, cudaMemcpyDeviceToHost, s));
@@ -245,9 +288,28 @@ int solve_impl(mstgpu_lusgs* h, const double* val, const double* b, double* x, i
         }
     }
     LCK(cudaGetLastError());
+    if (iters_done) *iters_done = it;
+    return MSTGPU_OK;
+}
+
+// host arrays in, host x out (the reference's calling convention: setELE / setD / setRHSb ... getPNewX)
+template <int B>
+int solve_impl(mstgpu_lusgs* h, const double* val, const double* b, double* x, int max_iter, int early_exit,
+               double* res_hist, int32_t* iters_done) {
+    const int n = h->n, BB = B * B;
+    cudaStream_t s = h->stream;
+    if (!h->val) {
+        LCK(cudaMalloc((void**)&h->val, std::max<size_t>(1, h->nnz) * BB * 8));
+        LCK(cudaMalloc((void**)&h->b, (size_t)n * B * 8));
+        LCK(cudaMalloc((void**)&h->x, (size_t)n * B * 8));
+    }
+    LCK(cudaMemcpyAsync(h->val, val, (size_t)h->nnz * BB * 8, cudaMemcpyHostToDevice, s));
+    LCK(cudaMemcpyAsync(h->b, b, (size_t)n * B * 8, cudaMemcpyHostToDevice, s));
+    LCK(cudaMemcpyAsync(h->x, x, (size_t)n * B * 8, cudaMemcpyHostToDevice, s));
+    int rc = solve_core<B>(h, h->val, h->b, h->x, max_iter, early_exit, res_hist, iters_done);
+    if (rc) return rc;
     LCK(cudaMemcpyAsync(x, h->x, (size_t)n * B * 8, cudaMemcpyDeviceToHost, s));
     LCK(cudaStreamSynchronize(s));
-    if (iters_done) *iters_done = it;
     return MSTGPU_OK;
 }
 
@@ -257,65 +319,111 @@ extern "C" {
 
 const char* mstgpu_lusgs_last_error(void) { return g_lusgs_error.c_str(); }
 
-int mstgpu_lusgs_color_order(int32_t n, const int32_t* rowptr, const int32_t* col, int32_t* perm_new2old,
-                             int32_t* ncolors) {
-    if (n <= 0 || !rowptr || !col || !perm_new2old) { g_lusgs_error = "bad argument"; return MSTGPU_ERR_ARG; }
-    // greedy first-fit colouring in the given order on the symmetrised pattern
-    std::vector<std::vector<int>> adj(n);
+// greedy first-fit colouring of the symmetrised pattern, rows visited in storage order; O(nnz), CSR only
+static int color_rows(int32_t n, const int32_t* rowptr, const int32_t* col, std::vector<int>& color, int& nc) {
+    // transpose pattern (for unsymmetric input): tptr / tcol
+    std::vector<int64_t> tptr((size_t)n + 1, 0);
     for (int r = 0; r < n; r++)
         for (int k = rowptr[r]; k < rowptr[r + 1]; k++) {
             const int c = col[k];
             if (c < 0 || c >= n) { g_lusgs_error = "column out of range"; return MSTGPU_ERR_ARG; }
-            if (c != r) { adj[r].push_back(c); adj[c].push_back(r); }
+            if (c != r) tptr[(size_t)c + 1]++;
         }
-    std::vector<int> color(n, -1), used;
-    int nc = 0;
+    for (int r = 0; r < n; r++) tptr[r + 1] += tptr[r];
+    std::vector<int> tcol((size_t)tptr[n]);
+    {
+        std::vector<int64_t> pos(tptr.begin(), tptr.end() - 1);
+        for (int r = 0; r < n; r++)
+            for (int k = rowptr[r]; k < rowptr[r + 1]; k++)
+                if (col[k] != r) tcol[(size_t)pos[col[k]]++] = r;
+    }
+    color.assign(n, -1);
+    nc = 0;
+    unsigned long long used;  // colours 0..63 as a bit mask (a mesh graph needs a handful)
     for (int r = 0; r < n; r++) {
-        used.assign(nc + 1, 0);
-        for (int c : adj[r]) if (color[c] >= 0) used[color[c]] = 1;
+        used = 0;
+        for (int k = rowptr[r]; k < rowptr[r + 1]; k++)
+            if (col[k] != r && color[col[k]] >= 0 && color[col[k]] < 64) used |= 1ULL << color[col[k]];
+        for (int64_t k = tptr[r]; k < tptr[r + 1]; k++)
+            if (color[tcol[(size_t)k]] >= 0 && color[tcol[(size_t)k]] < 64) used |= 1ULL << color[tcol[(size_t)k]];
         int k = 0;
-        while (k < nc && used[k]) k++;
+        while (k < 63 && ((used >> k) & 1)) k++;
         color[r] = k;
         nc = std::max(nc, k + 1);
     }
-    std::vector<int> order(n);
-    for (int i = 0; i < n; i++) order[i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return color[a] < color[b]; });
-    for (int i = 0; i < n; i++) perm_new2old[i] = order[i];
+    return MSTGPU_OK;
+}
+
+int mstgpu_lusgs_color_order(int32_t n, const int32_t* rowptr, const int32_t* col, int32_t* perm_new2old,
+                             int32_t* ncolors) {
+    if (n <= 0 || !rowptr || !col || !perm_new2old) { g_lusgs_error = "bad argument"; return MSTGPU_ERR_ARG; }
+    std::vector<int> color;
+    int nc = 0;
+    int rc = color_rows(n, rowptr, col, color, nc);
+    if (rc) return rc;
+    // counting sort by colour (stable: storage order within a colour)
+    std::vector<int64_t> start((size_t)nc + 1, 0);
+    for (int r = 0; r < n; r++) start[(size_t)color[r] + 1]++;
+    for (int c = 0; c < nc; c++) start[c + 1] += start[c];
+    for (int r = 0; r < n; r++) perm_new2old[start[color[r]]++] = r;
     if (ncolors) *ncolors = nc;
     return MSTGPU_OK;
 }
 
 int mstgpu_lusgs_create(mstgpu_lusgs** out, int32_t n, int32_t block, const int32_t* rowptr, const int32_t* col,
                         int32_t device) {
+    return mstgpu_lusgs_create_ordered(out, n, block, rowptr, col, nullptr, device);
+}
+
+int mstgpu_lusgs_create_ordered(mstgpu_lusgs** out, int32_t n, int32_t block, const int32_t* rowptr, const int32_t* col,
+                                const int32_t* sweep_new2old, int32_t device) {
     mstgpu_lusgs* h = nullptr;
     if (!out || n <= 0 || !rowptr || !col) { g_lusgs_error = "bad argument"; return MSTGPU_ERR_ARG; }
     *out = nullptr;
     if (block != 1 && block != 4 && block != 5) { g_lusgs_error = "block size must be 1, 4 or 5"; return MSTGPU_ERR_ARG; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_lusgs_error = "no CUDA device"; return MSTGPU_ERR_CUDA; }
+    // rank[r] = position of row r in the sweep; the sweeps are those of the reference on P A P^T, data unmoved
+    std::vector<int> rank;
+    if (sweep_new2old) {
+        rank.assign(n, -1);
+        for (int i = 0; i < n; i++) {
+            const int r = sweep_new2old[i];
+            if (r < 0 || r >= n || rank[r] >= 0) { g_lusgs_error = "sweep order is not a permutation"; return MSTGPU_ERR_ARG; }
+            rank[r] = i;
+        }
+    }
+    auto rk = [&](int r) { return sweep_new2old ? rank[r] : r; };
     std::vector<int> Lptr(n + 1, 0), Uptr(n + 1, 0), Dptr(n + 1, 0), Lcol, Lpos, Ucol, Upos, Dpos;
+    std::vector<std::pair<int, int>> lo, hi;  // (rank of column, index into the row)
     for (int r = 0; r < n; r++) {
+        lo.clear(); hi.clear();
         for (int k = rowptr[r]; k < rowptr[r + 1]; k++) {
             const int c = col[k];
             if (c < 0 || c >= n) { g_lusgs_error = "column out of range"; return MSTGPU_ERR_ARG; }
             if (k > rowptr[r] && col[k - 1] > c) { g_lusgs_error = "columns must be ascending within a row"; return MSTGPU_ERR_ARG; }
             if (c == r) Dpos.push_back(k);
-            else if (c < r) { Lcol.push_back(c); Lpos.push_back(k); }
-            else { Ucol.push_back(c); Upos.push_back(k); }
+            else if (rk(c) < rk(r)) lo.push_back({rk(c), k});
+            else hi.push_back({rk(c), k});
         }
+        // the reference subtracts a row's terms by ascending (permuted) column index
+        if (sweep_new2old) { std::sort(lo.begin(), lo.end()); std::sort(hi.begin(), hi.end()); }
+        for (auto& e : lo) { Lcol.push_back(col[e.second]); Lpos.push_back(e.second); }
+        for (auto& e : hi) { Ucol.push_back(col[e.second]); Upos.push_back(e.second); }
         Lptr[r + 1] = (int)Lcol.size(); Uptr[r + 1] = (int)Ucol.size(); Dptr[r + 1] = (int)Dpos.size();
         if (Dptr[r + 1] == Dptr[r]) { g_lusgs_error = "row without a diagonal entry"; return MSTGPU_ERR_ARG; }
     }
-    // dependency levels
+    // dependency levels, rows visited in sweep order
     std::vector<int> lf(n, 0), lb(n, 0);
     int nlf = 0, nlb = 0;
-    for (int r = 0; r < n; r++) {
+    for (int i = 0; i < n; i++) {
+        const int r = sweep_new2old ? sweep_new2old[i] : i;
         int l = 0;
         for (int k = Lptr[r]; k < Lptr[r + 1]; k++) l = std::max(l, lf[Lcol[k]] + 1);
         lf[r] = l; nlf = std::max(nlf, l + 1);
     }
-    for (int r = n - 1; r >= 0; r--) {
+    for (int i = n - 1; i >= 0; i--) {
+        const int r = sweep_new2old ? sweep_new2old[i] : i;
         int l = 0;
         for (int k = Uptr[r]; k < Uptr[r + 1]; k++) l = std::max(l, lb[Ucol[k]] + 1);
         lb[r] = l; nlb = std::max(nlb, l + 1);
@@ -326,7 +434,7 @@ int mstgpu_lusgs_create(mstgpu_lusgs** out, int32_t n, int32_t block, const int3
         for (int l = 0; l < nl; l++) ptr[l + 1] += ptr[l];
         rows.resize(n);
         std::vector<int> pos(ptr.begin(), ptr.end() - 1);
-        for (int r = 0; r < n; r++) rows[pos[lev[r]]++] = r;
+        for (int r = 0; r < n; r++) rows[pos[lev[r]]++] = r;  // storage order within a level
     };
     h = new mstgpu_lusgs;
     h->n = n; h->B = block; h->nnz = rowptr[n]; h->nL = (int)Lcol.size(); h->nU = (int)Ucol.size();
@@ -337,18 +445,20 @@ int mstgpu_lusgs_create(mstgpu_lusgs** out, int32_t n, int32_t block, const int3
         if (device >= 0) LCK(cudaSetDevice(device));
         LCK(cudaGetDevice(&h->device));
         LCK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        LCK(cudaEventCreate(&h->ev0));
+        LCK(cudaEventCreate(&h->ev1));
         int r;
         if ((r = up(h, &h->Lptr, Lptr)) || (r = up(h, &h->Lcol, Lcol)) || (r = up(h, &h->Lpos, Lpos))) return r;
         if ((r = up(h, &h->Uptr, Uptr)) || (r = up(h, &h->Ucol, Ucol)) || (r = up(h, &h->Upos, Upos))) return r;
         if ((r = up(h, &h->Dptr, Dptr)) || (r = up(h, &h->Dpos, Dpos))) return r;
         if ((r = up(h, &h->frows, frows)) || (r = up(h, &h->brows, brows))) return r;
         const size_t BB = (size_t)block * block;
-        LCK(cudaMalloc((void**)&h->val, std::max<size_t>(1, h->nnz) * BB * 8));
+        // val / b / x buffers of the host-array entry point are allocated at its first use
         LCK(cudaMalloc((void**)&h->D, n * BB * 8));
         LCK(cudaMalloc((void**)&h->Dinv, n * BB * 8));
         LCK(cudaMalloc((void**)&h->LD, std::max<size_t>(1, h->nL) * BB * 8));
         LCK(cudaMalloc((void**)&h->UD, std::max<size_t>(1, h->nU) * BB * 8));
-        for (double** p : {&h->b, &h->x, &h->rhs, &h->rhs1, &h->ux}) LCK(cudaMalloc((void**)p, (size_t)n * block * 8));
+        for (double** p : {&h->rhs, &h->rhs1, &h->ux}) LCK(cudaMalloc((void**)p, (size_t)n * block * 8));
         LCK(cudaMalloc((void**)&h->res, 8));
         return 0;
     }();
@@ -366,6 +476,8 @@ void mstgpu_lusgs_destroy(mstgpu_lusgs* h) {
                     (void*)h->Dinv, (void*)h->LD, (void*)h->UD, (void*)h->b, (void*)h->x, (void*)h->rhs, (void*)h->rhs1,
                     (void*)h->ux, (void*)h->res})
         if (p) cudaFree(p);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -386,6 +498,38 @@ int mstgpu_lusgs_solve(mstgpu_lusgs* h, const double* val, const double* b, doub
         case 4: return solve_impl<4>(h, val, b, x, max_iter, early_exit, res_hist, iters_done);
         default: return solve_impl<5>(h, val, b, x, max_iter, early_exit, res_hist, iters_done);
     }
+}
+
+int mstgpu_lusgs_solve_device(mstgpu_lusgs* h, const double* d_val, const double* d_b, double* d_x, int32_t max_iter,
+                              float* ms) {
+    if (!h || !d_val || !d_b || !d_x || max_iter < 0) { g_lusgs_error = "bad argument"; return MSTGPU_ERR_ARG; }
+    LCK(cudaSetDevice(h->device));
+    LCK(cudaStreamSynchronize(h->stream));
+    if (ms) LCK(cudaEventRecord(h->ev0, h->stream));
+    int rc;
+    switch (h->B) {
+        case 1: rc = solve_core<1>(h, d_val, d_b, d_x, max_iter, 0, nullptr, nullptr); break;
+        case 4: rc = solve_core<4>(h, d_val, d_b, d_x, max_iter, 0, nullptr, nullptr); break;
+        default: rc = solve_core<5>(h, d_val, d_b, d_x, max_iter, 0, nullptr, nullptr); break;
+    }
+    if (rc) return rc;
+    if (ms) {
+        LCK(cudaEventRecord(h->ev1, h->stream));
+        LCK(cudaEventSynchronize(h->ev1));
+        LCK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    } else {
+        LCK(cudaStreamSynchronize(h->stream));
+    }
+    return MSTGPU_OK;
+}
+
+int64_t mstgpu_lusgs_launch_count(mstgpu_lusgs* h) { return h ? h->launches : -1; }
+
+int64_t mstgpu_lusgs_device_bytes(mstgpu_lusgs* h) {
+    if (!h) return -1;
+    const int64_t BB = (int64_t)h->B * h->B;
+    return ((int64_t)h->n * 2 + h->nL + h->nU) * BB * 8 + (int64_t)h->n * h->B * 8 * 3 +
+           ((int64_t)h->n * 5 + 3 + 2LL * (h->nL + h->nU)) * 4;
 }
 
 }  // extern "C"

@@ -10,6 +10,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -117,6 +118,13 @@ struct mstgpu_ctx {
     cudaEvent_t ev_halo = nullptr, ev_done = nullptr;
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
+    // multi-step CUDA graph: two ping-pong steps, the tile classes of a step as parallel
+    // branches; one executable per starting buffer, rebuilt when dt changes
+    cudaGraphExec_t step_graph[2] = {nullptr, nullptr};
+    double step_graph_dt = 0.0;
+    cudaStream_t fork_stream = nullptr;  // non-null while a step is captured: odd classes go here
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int64_t graph_launches = 0;
     // extension tables / CFL stepping (mstgpu_config.gradient / limiter, mstgpu_step_cfl)
     double *lsq = nullptr, *eps2 = nullptr;
     unsigned long long* dtmin = nullptr;  // bit pattern of the smallest cell time step
@@ -380,20 +388,6 @@ __global__ void __launch_bounds__(256) k_gradient_lsq(int nc, int nslot, const d
         for (int d = 0; d < D; d++) G[((size_t)c * U + k) * D + d] = t[k][d];
 }
 
-// slope limiter value for one face of one cell (mode 1 Barth-Jespersen, 2 Venkatakrishnan)
-__device__ __forceinline__ double limiter_phi(int mode, double dl, double dmax, double dmin, double e2) {
-    if (mode == 1) {
-        if (dl > 0.0) return fmin(1.0, dmax / dl);
-        if (dl < 0.0) return fmin(1.0, dmin / dl);
-        return 1.0;
-    }
-    if (fabs(dl) < 1e-150) return 1.0;
-    const double dm = dl > 0.0 ? dmax : dmin;
-    const double num = (dm * dm + e2) * dl + 2.0 * dl * dl * dm;
-    const double den = dl * (dm * dm + 2.0 * dl * dl + dm * dl + e2);
-    return num / den;
-}
-
 // G[c][k][:] *= phi[c][k]: min / max over the cell and its face neighbours, slope tested at the
 // face centres of the cell
 template <int D>
@@ -408,11 +402,12 @@ __global__ void __launch_bounds__(256) k_limit(int nc, int nslot, int mode, cons
     constexpr int U = D + 2;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nc) return;
-    double qc[U], qmin[U], qmax[U], phi[U], g[U][D];
+    double qc[U], qmin[U], qmax[U], g[U][D];
+    LimiterAcc acc[U];
 #pragma unroll
     for (int k = 0; k < U; k++) {
         qc[k] = qmin[k] = qmax[k] = Q[(size_t)c * U + k];
-        phi[k] = 1.0;
+        acc[k].init(mode);
 #pragma unroll
         for (int d = 0; d < D; d++) g[k][d] = G[((size_t)c * U + k) * D + d];
     }
@@ -443,13 +438,15 @@ __global__ void __launch_bounds__(256) k_limit(int nc, int nslot, int mode, cons
             double dl = 0.0;
 #pragma unroll
             for (int d = 0; d < D; d++) dl += g[k][d] * r[d];
-            phi[k] = fmin(phi[k], limiter_phi(mode, dl, qmax[k] - qc[k], qmin[k] - qc[k], e2));
+            acc[k].add(mode, dl, qmax[k] - qc[k], qmin[k] - qc[k], e2);
         }
     }
 #pragma unroll
-    for (int k = 0; k < U; k++)
+    for (int k = 0; k < U; k++) {
+        const double phi = acc[k].phi(mode, qmax[k] - qc[k], qmin[k] - qc[k]);
 #pragma unroll
-        for (int d = 0; d < D; d++) G[((size_t)c * U + k) * D + d] = g[k][d] * phi[k];
+        for (int d = 0; d < D; d++) G[((size_t)c * U + k) * D + d] = g[k][d] * phi;
+    }
 }
 
 // min over the warp of POSITIVE doubles (their order is the order of their bit patterns)
@@ -720,9 +717,11 @@ int launch_tiles_lim(mstgpu_ctx* ctx, double dt, const double* dtd, const double
         configured_smem = ctx->tile_smem;
     }
     // which: 0 = tiles without ghost cells, 1 = tiles whose rings hold ghost cells, 2 = all
+    int ci = 0;
     for (const auto& tc : ctx->tile_classes) {
         if (which != 2 && (int)tc.halo != which) continue;
-        kern<<<tc.count, NT, tc.smem, st>>>(ctx->ta, tc.first, want_resid, ctx->dcfg, dt, dtd, Qo, Qn, ctx->resid, ctx->nanflag);
+        cudaStream_t s = (ctx->fork_stream && (ci++ & 1)) ? ctx->fork_stream : st;
+        kern<<<tc.count, NT, tc.smem, s>>>(ctx->ta, tc.first, want_resid, ctx->dcfg, dt, dtd, Qo, Qn, ctx->resid, ctx->nanflag);
         ctx->launches++;
     }
     return MSTGPU_OK;
@@ -764,10 +763,67 @@ int cfl_on_device(mstgpu_ctx* ctx, double cfl, const double* Q) {
     return MSTGPU_OK;
 }
 
+// Two fixed-dt steps (Q[cur] -> Q[cur^1] -> Q[cur]) captured once as a CUDA graph: the host issues
+// one launch per pair of steps, and the tile classes of a step (separate launches because their
+// shared-memory sizes differ) run as parallel branches instead of one behind the other's tail.
+template <int D>
+int build_step_graph(mstgpu_ctx* ctx, double dt, int start_cur) {
+    const bool fork = ctx->tile_classes.size() > 1;
+    cudaGraph_t g = nullptr;
+    // which = 3 selects no tile class: only the kernel's shared-memory attribute is set, outside the capture
+    int r = launch_tiles_any<D>(ctx, dt, nullptr, ctx->Q[0], ctx->Q[1], 0, 3, ctx->stream);
+    if (r) return r;
+    CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    const int64_t before = ctx->launches;
+    for (int s = 0; s < 2 && r == MSTGPU_OK; s++) {
+        const double* Qc = ctx->Q[start_cur ^ s];
+        double* Qn = ctx->Q[start_cur ^ s ^ 1];
+        if (fork) {
+            cudaEventRecord(ctx->ev_fork, ctx->stream);
+            cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0);
+            ctx->fork_stream = ctx->stream2;
+        }
+        r = launch_tiles_any<D>(ctx, dt, nullptr, Qc, Qn, 0, 2, ctx->stream);
+        ctx->fork_stream = nullptr;
+        if (fork) {
+            cudaEventRecord(ctx->ev_join, ctx->stream2);
+            cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
+        }
+    }
+    ctx->graph_launches = ctx->launches - before;
+    ctx->launches = before;
+    cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+    if (r != MSTGPU_OK) { if (g) cudaGraphDestroy(g); return r; }
+    if (e != cudaSuccess) { set_error(ctx, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e)); return MSTGPU_ERR_CUDA; }
+    e = cudaGraphInstantiate(&ctx->step_graph[start_cur], g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) { set_error(ctx, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); return MSTGPU_ERR_CUDA; }
+    return MSTGPU_OK;
+}
+
 template <int D>
 int step_tiles_impl(mstgpu_ctx* ctx, double dt, int nsteps, double cfl) {
     const double* dtd = cfl > 0.0 ? ctx->dt_dev : nullptr;
     const bool overlap = ctx->partitioned && !ctx->halo.empty();
+    // long fixed-dt runs on one GPU: pairs of steps from the graph, the last one or two steps (the
+    // observable residual belongs to the last) launched directly
+    static const bool no_graph = getenv("MSTGPU_NO_GRAPH") != nullptr;
+    if (!overlap && !ctx->comm && cfl <= 0.0 && !ctx->ktiming && !no_graph && nsteps >= 4) {
+        if (ctx->step_graph_dt != dt) {
+            for (auto& ge : ctx->step_graph) if (ge) { cudaGraphExecDestroy(ge); ge = nullptr; }
+            ctx->step_graph_dt = dt;
+        }
+        if (!ctx->step_graph[ctx->cur]) {
+            int r = build_step_graph<D>(ctx, dt, ctx->cur);
+            if (r) return r;
+        }
+        const int pairs = (nsteps - 1) / 2;
+        for (int i = 0; i < pairs; i++) CK(cudaGraphLaunch(ctx->step_graph[ctx->cur], ctx->stream));
+        ctx->launches += pairs * ctx->graph_launches;
+        nsteps -= 2 * pairs;  // cur is unchanged after an even number of steps
+        ctx->stepped = true;
+        ctx->probes_valid = false;
+    }
     if (overlap && !ctx->comm) { set_error(ctx, "partitioned context without a communicator: call mstgpu_comm_init"); return MSTGPU_ERR_STATE; }
     if (overlap && nsteps > 0) CK(cudaEventRecord(ctx->ev_done, ctx->stream));
     for (int s = 0; s < nsteps; s++) {
@@ -1002,6 +1058,8 @@ static int create_impl(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_c
         }
         CK(cudaEventCreateWithFlags(&ctx->ev_halo, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
         CK(cudaEventCreate(&ctx->ev0));
         CK(cudaEventCreate(&ctx->ev1));
         int r;
@@ -1154,6 +1212,9 @@ void mstgpu_destroy(mstgpu_ctx* ctx) {
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev_halo) cudaEventDestroy(ctx->ev_halo);
     if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    for (auto ge : ctx->step_graph) if (ge) cudaGraphExecDestroy(ge);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -1233,13 +1294,26 @@ int mstgpu_cfl_dt(mstgpu_ctx* ctx, double cfl, double* dt) {
 }
 
 int mstgpu_step_cfl(mstgpu_ctx* ctx, double cfl, int32_t nsteps, double* time_advanced) {
+    return mstgpu_step_cfl_timed(ctx, cfl, nsteps, time_advanced, nullptr);
+}
+
+int mstgpu_step_cfl_timed(mstgpu_ctx* ctx, double cfl, int32_t nsteps, double* time_advanced, float* ms) {
     if (!ctx) return MSTGPU_ERR_ARG;
     if (!ctx->has_state) { set_error(ctx, "step before set_state"); return MSTGPU_ERR_STATE; }
     if (nsteps < 0) { set_error(ctx, "nsteps < 0"); return MSTGPU_ERR_ARG; }
     if (!(cfl > 0.0)) { set_error(ctx, "cfl must be > 0"); return MSTGPU_ERR_ARG; }
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemsetAsync(ctx->dt_dev + 1, 0, sizeof(double), ctx->stream));
+    if (ms) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    }
     int rc = (ctx->D == 2) ? step_impl<2>(ctx, 0.0, nsteps, cfl) : step_impl<3>(ctx, 0.0, nsteps, cfl);
+    if (rc == MSTGPU_OK && ms) {
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(cudaEventSynchronize(ctx->ev1));
+        CK(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    }
     if (ctx->ktiming) drain_timers(ctx);
     if (rc) return rc;
     if (time_advanced) {
@@ -1379,6 +1453,41 @@ int mstgpu_comm_init(mstgpu_ctx* ctx, int32_t nranks, int32_t rank, const char* 
     std::memcpy(&id, id128, 128);
     NK(g_nccl.CommInitRank(&ctx->comm, nranks, id, rank));
     ctx->nranks = nranks; ctx->rank = rank;
+    return MSTGPU_OK;
+}
+
+int mstgpu_mesh_adjacency(const mstgpu_mesh* mesh, const mstgpu_config* cfg, int32_t* rowptr, int32_t* col, int64_t col_cap) {
+    if (!mesh || !cfg || !rowptr) { set_error(nullptr, "null argument"); return MSTGPU_ERR_ARG; }
+    Plan p;
+    std::string perr = build_plan(*mesh, *cfg, p);
+    if (!perr.empty()) { set_error(nullptr, perr); return MSTGPU_ERR_ARG; }
+    const int nc = p.nc;
+    rowptr[0] = 0;
+    for (int c = 0; c < nc; c++) {
+        int cnt = 1;
+        for (int j = 0; j < p.nslot; j++) {
+            const int v = p.cf[(size_t)j * nc + c];
+            if (v >= 0 && ((v & 1) ? p.fc0[v >> 1] : p.fc1[v >> 1]) >= 0) cnt++;
+        }
+        const int64_t next = (int64_t)rowptr[c] + cnt;
+        if (next > 0x7fffffffLL) { set_error(nullptr, "adjacency does not fit 32-bit offsets"); return MSTGPU_ERR_ARG; }
+        rowptr[c + 1] = (int32_t)next;
+    }
+    if (!col) return MSTGPU_OK;  // sizing call
+    if (col_cap < rowptr[nc]) { set_error(nullptr, "col buffer too small"); return MSTGPU_ERR_ARG; }
+#pragma omp parallel for schedule(static)
+    for (int c = 0; c < nc; c++) {
+        int32_t* out = col + rowptr[c];
+        int n = 0;
+        out[n++] = c;
+        for (int j = 0; j < p.nslot; j++) {
+            const int v = p.cf[(size_t)j * nc + c];
+            if (v < 0) continue;
+            const int nb = (v & 1) ? p.fc0[v >> 1] : p.fc1[v >> 1];
+            if (nb >= 0) out[n++] = nb;
+        }
+        std::sort(out, out + n);
+    }
     return MSTGPU_OK;
 }
 

@@ -33,6 +33,42 @@ struct DevCfg {
     int32_t order, flux, viscous, limiter;  // limiter: extension (0 none, 1 Barth-Jespersen, 2 Venkatakrishnan)
 };
 
+// ---- slope limiter (extension; formulas of oracle/rho_oracle.cpp limitGradient) ------------------
+// phi = min over the cell's faces of phi_j(D_j).  FP64 divisions are the expensive instruction, so the
+// minimum is taken BEFORE dividing:
+//  * Barth-Jespersen: min_j dmax/D_j over D_j > 0 equals dmax / max_j D_j exactly (IEEE division is
+//    monotone), likewise for D_j < 0 -> two divisions per variable, bit-identical to the per-face form;
+//  * Venkatakrishnan: the fractions N_j/M_j (both positive after dividing the textbook numerator and
+//    denominator by D_j) are compared by cross-multiplication, one division at the end (<= 1 ulp from
+//    the per-face form).
+struct LimiterAcc {
+    double a, b;  // BJ: largest positive / smallest negative slope;  Venkat: best numerator / denominator
+    __device__ __forceinline__ void init(int mode) {
+        if (mode == 1) { a = 0.0; b = 0.0; }
+        else { a = 1.0; b = 1.0; }
+    }
+    __device__ __forceinline__ void add(int mode, double dl, double dmax, double dmin, double e2) {
+        if (mode == 1) {
+            a = fmax(a, dl);
+            b = fmin(b, dl);
+        } else if (fabs(dl) >= 1e-150) {
+            const double dm = dl > 0.0 ? dmax : dmin;
+            const double c = dm * dm + e2, x = dl * dm;
+            const double n = c + 2.0 * x, m = c + x + 2.0 * dl * dl;
+            if (n * b < a * m) { a = n; b = m; }
+        }
+    }
+    __device__ __forceinline__ double phi(int mode, double dmax, double dmin) const {
+        if (mode == 1) {
+            double p = 1.0;
+            if (a > 0.0) p = fmin(p, dmax / a);
+            if (b < 0.0) p = fmin(p, dmin / b);
+            return p;
+        }
+        return a / b;
+    }
+};
+
 template <int D>
 struct Prim {  // per-state quantities shared by all coordinate directions
     double r;      // 1/rho

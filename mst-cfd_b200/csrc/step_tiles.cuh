@@ -98,21 +98,6 @@ __device__ __forceinline__ double warp_max_nonneg(double x) {
 #define MST_TILE_MINB(NT) ((NT) >= 256 ? 2 : 3)
 #endif
 
-// slope limiter value at one face centre (extension; same formulas as k_limit of the split path
-// and oracle/rho_oracle.cpp limitGradient): mode 1 Barth-Jespersen, 2 Venkatakrishnan
-__device__ __forceinline__ double tile_limiter_phi(int mode, double dl, double dmax, double dmin, double e2) {
-    if (mode == 1) {
-        if (dl > 0.0) return fmin(1.0, dmax / dl);
-        if (dl < 0.0) return fmin(1.0, dmin / dl);
-        return 1.0;
-    }
-    if (fabs(dl) < 1e-150) return 1.0;
-    const double dm = dl > 0.0 ? dmax : dmin;
-    const double num = (dm * dm + e2) * dl + 2.0 * dl * dl * dm;
-    const double den = dl * (dm * dm + 2.0 * dl * dl + dm * dl + e2);
-    return num / den;
-}
-
 template <int D, int ORDER, int NT, int NS, bool LIM = false>
 __global__ void __launch_bounds__(NT, MST_TILE_MINB(NT)) k_step_tiles(TileArrays ta, int tile_base, int want_resid, DevCfg cfg, double dt_val,
                                                    const double* __restrict__ dt_dev,
@@ -198,15 +183,16 @@ __global__ void __launch_bounds__(NT, MST_TILE_MINB(NT)) k_step_tiles(TileArrays
 #pragma unroll
                 for (int m = 1; m < NS; m++) { qmax = fmax(qmax, q[m]); qmin = fmin(qmin, q[m]); }
                 const double dmax = qmax - q[0], dmin = qmin - q[0];
-                double ph = 1.0;
+                LimiterAcc acc;
+                acc.init(cfg.limiter);
 #pragma unroll
                 for (int j = 0; j < nslot; j++) {
                     double dl = wj[j][0] * q[0];
 #pragma unroll
                     for (int m = 1; m < NS; m++) dl += wj[j][m] * q[m];
-                    ph = fmin(ph, tile_limiter_phi(cfg.limiter, dl, dmax, dmin, e2));
+                    acc.add(cfg.limiter, dl, dmax, dmin, e2);
                 }
-                philim[k * nCLp + i] = ph;
+                philim[k * nCLp + i] = acc.phi(cfg.limiter, dmax, dmin);
             }
         }
         __syncthreads();

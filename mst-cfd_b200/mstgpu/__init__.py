@@ -23,13 +23,14 @@ LIB_PATH = os.environ.get("MSTGPU_LIB", os.path.join(_ROOT, "libmstgpu.so"))  # 
 EXPORTS = [
     "mstgpu_default_config", "mstgpu_create", "mstgpu_destroy", "mstgpu_set_state",
     "mstgpu_get_state", "mstgpu_get_prev_state", "mstgpu_step", "mstgpu_step_timed",
-    "mstgpu_residual_linf", "mstgpu_sync", "mstgpu_cfl_dt", "mstgpu_step_cfl", "mstgpu_debug_gradient", "mstgpu_debug_face_flux",
+    "mstgpu_residual_linf", "mstgpu_sync", "mstgpu_cfl_dt", "mstgpu_step_cfl", "mstgpu_step_cfl_timed", "mstgpu_debug_gradient", "mstgpu_debug_face_flux",
     "mstgpu_launch_count", "mstgpu_enable_kernel_timing", "mstgpu_kernel_time",
     "mstgpu_device_bytes", "mstgpu_plan_permutation", "mstgpu_tile_stats",
     "mstgpu_partition_create", "mstgpu_partition_destroy", "mstgpu_partition_mesh", "mstgpu_partition_sizes",
     "mstgpu_partition_cell_ids", "mstgpu_partition_neighbor", "mstgpu_create_partitioned",
     "mstgpu_comm_unique_id", "mstgpu_comm_init", "mstgpu_lusgs_create", "mstgpu_lusgs_destroy",
-    "mstgpu_lusgs_solve", "mstgpu_lusgs_levels", "mstgpu_lusgs_color_order", "mstgpu_lusgs_last_error",
+    "mstgpu_lusgs_solve", "mstgpu_lusgs_levels", "mstgpu_lusgs_create_ordered", "mstgpu_lusgs_solve_device",
+    "mstgpu_lusgs_launch_count", "mstgpu_lusgs_device_bytes", "mstgpu_mesh_adjacency", "mstgpu_lusgs_color_order", "mstgpu_lusgs_last_error",
     "mstgpu_last_error", "mstgpu_version",
 ]
 
@@ -91,6 +92,7 @@ def lib():
         L.mstgpu_step_timed.argtypes = [vp, dbl, i32, C.POINTER(C.c_float)]
         L.mstgpu_cfl_dt.argtypes = [vp, dbl, C.POINTER(dbl)]
         L.mstgpu_step_cfl.argtypes = [vp, dbl, i32, C.POINTER(dbl)]
+        L.mstgpu_step_cfl_timed.argtypes = [vp, dbl, i32, C.POINTER(dbl), C.POINTER(C.c_float)]
         L.mstgpu_residual_linf.argtypes = [vp, vp]
         L.mstgpu_sync.argtypes = [vp]
         L.mstgpu_debug_gradient.argtypes = [vp, vp]
@@ -117,6 +119,13 @@ def lib():
         L.mstgpu_comm_unique_id.argtypes = [vp]
         L.mstgpu_comm_init.argtypes = [vp, i32, i32, vp]
         L.mstgpu_lusgs_create.argtypes = [C.POINTER(vp), i32, i32, vp, vp, i32]
+        L.mstgpu_lusgs_create_ordered.argtypes = [C.POINTER(vp), i32, i32, vp, vp, vp, i32]
+        L.mstgpu_lusgs_solve_device.argtypes = [vp, vp, vp, vp, i32, C.POINTER(C.c_float)]
+        L.mstgpu_lusgs_launch_count.argtypes = [vp]
+        L.mstgpu_lusgs_launch_count.restype = i64
+        L.mstgpu_lusgs_device_bytes.argtypes = [vp]
+        L.mstgpu_lusgs_device_bytes.restype = i64
+        L.mstgpu_mesh_adjacency.argtypes = [C.POINTER(MstMesh), C.POINTER(MstConfig), vp, vp, i64]
         L.mstgpu_lusgs_destroy.argtypes = [vp]
         L.mstgpu_lusgs_destroy.restype = None
         L.mstgpu_lusgs_solve.argtypes = [vp, vp, vp, vp, i32, i32, vp, C.POINTER(i32)]
@@ -163,6 +172,22 @@ def plan_permutation(flat: dict, renumber: int = 2):
     if rc != 0:
         raise MstGpuError(f"plan_permutation failed ({rc}): {lib().mstgpu_last_error(None).decode()}")
     return c, f
+
+
+def mesh_adjacency(flat: dict, renumber: int = 2):
+    """(rowptr, col): CSR cell adjacency + diagonal in the device cell order (host only)."""
+    m, keep = _mesh_struct(flat)
+    cfg = default_config(int(flat["dim"]))
+    cfg.renumber = renumber
+    rowptr = np.empty(int(flat["ncells"]) + 1, dtype=np.int32)
+    rc = lib().mstgpu_mesh_adjacency(C.byref(m), C.byref(cfg), rowptr.ctypes.data, None, 0)
+    if rc != 0:
+        raise MstGpuError(f"mesh_adjacency failed ({rc}): {lib().mstgpu_last_error(None).decode()}")
+    col = np.empty(int(rowptr[-1]), dtype=np.int32)
+    rc = lib().mstgpu_mesh_adjacency(C.byref(m), C.byref(cfg), rowptr.ctypes.data, col.ctypes.data, col.size)
+    if rc != 0:
+        raise MstGpuError(f"mesh_adjacency failed ({rc}): {lib().mstgpu_last_error(None).decode()}")
+    return rowptr, col
 
 
 def tile_stats(flat: dict, order: int = 2, tile_cells: int = 0, renumber: int = 2) -> dict:
@@ -384,6 +409,12 @@ class Context:
         self._check(lib().mstgpu_step_cfl(self.h, cfl, nsteps, C.byref(t)), "step_cfl")
         return float(t.value)
 
+    def step_cfl_timed(self, cfl: float, nsteps: int = 1) -> float:
+        """step_cfl bracketed by CUDA events on the solver's stream; returns milliseconds."""
+        t, ms = C.c_double(), C.c_float()
+        self._check(lib().mstgpu_step_cfl_timed(self.h, cfl, nsteps, C.byref(t), C.byref(ms)), "step_cfl_timed")
+        return float(ms.value)
+
     def residual(self):
         out = np.empty(self.U)
         self._check(lib().mstgpu_residual_linf(self.h, out.ctypes.data), "residual_linf")
@@ -466,12 +497,16 @@ class LuSgs:
     """GPU LU-SGS solver for one sparsity pattern (mirror of the reference's
     SparseSolverNUM for block = 1 and SparseSolver<MT,VCT> for block = DIMU)."""
 
-    def __init__(self, rowptr, col, block=1, device=-1):
+    def __init__(self, rowptr, col, block=1, device=-1, sweep_order=None):
+        """sweep_order: new2old permutation of the rows (e.g. lusgs_color_order); the data stay in
+        storage order, the sweeps are those of the reference on the permuted system."""
         self.rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
         self.col = np.ascontiguousarray(col, dtype=np.int32)
         self.n, self.block = self.rowptr.shape[0] - 1, block
         h = C.c_void_p()
-        rc = lib().mstgpu_lusgs_create(C.byref(h), self.n, block, self.rowptr.ctypes.data, self.col.ctypes.data, device)
+        so = None if sweep_order is None else np.ascontiguousarray(sweep_order, dtype=np.int32)
+        rc = lib().mstgpu_lusgs_create_ordered(C.byref(h), self.n, block, self.rowptr.ctypes.data, self.col.ctypes.data,
+                                               None if so is None else so.ctypes.data, device)
         if rc != 0:
             raise MstGpuError(f"lusgs_create failed ({rc}): {lib().mstgpu_lusgs_last_error().decode()}")
         self.h = h
@@ -493,6 +528,22 @@ class LuSgs:
         if rc != 0:
             raise MstGpuError(f"lusgs_solve failed ({rc}): {lib().mstgpu_lusgs_last_error().decode()}")
         return x, hist[:it.value], it.value
+
+    def solve_device(self, d_val: int, d_b: int, d_x: int, max_iter=5) -> float:
+        """Device pointers in, x updated in place on the device; returns the CUDA-event time in ms."""
+        ms = C.c_float()
+        rc = lib().mstgpu_lusgs_solve_device(self.h, d_val, d_b, d_x, max_iter, C.byref(ms))
+        if rc != 0:
+            raise MstGpuError(f"lusgs_solve_device failed ({rc}): {lib().mstgpu_lusgs_last_error().decode()}")
+        return float(ms.value)
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().mstgpu_lusgs_launch_count(self.h))
+
+    @property
+    def device_bytes(self) -> int:
+        return int(lib().mstgpu_lusgs_device_bytes(self.h))
 
     def close(self):
         if getattr(self, "h", None):

@@ -63,3 +63,60 @@ def test_scalar_early_exit_and_errors():
     bad = col.copy(); bad[0] = rowptr.size + 5
     with pytest.raises(mstgpu.MstGpuError, match="out of range"):
         mstgpu.LuSgs(rowptr, bad, 1)
+
+
+@pytest.mark.parametrize("block", [1, 5])
+def test_sweep_order_without_moving_the_data(block):
+    """Colour-ordered sweeps on the matrix in STORAGE order == the reference's solver on the explicitly
+    permuted system P A P^T (oracle), mapped back."""
+    rowptr, col, val, b, x0 = system("2d-stairW-1", block, 11)
+    n = rowptr.size - 1
+    perm, ncol = mstgpu.lusgs_color_order(rowptr, col)
+    s = mstgpu.LuSgs(rowptr, col, block, sweep_order=perm)
+    f, bk = s.levels()
+    assert f <= ncol and bk <= ncol
+    xg, _, _ = s.solve(val, b, x0, 5)
+    Ab = sp.csr_matrix((np.arange(col.size) + 1, col, rowptr), shape=(n, n))[perm][:, perm].tocsr()
+    Ab.sort_indices()
+    valp = val[Ab.data - 1]
+    xo, _, _ = oracle.lusgs(Ab.indptr, Ab.indices, valp, b[perm], x0[perm], block, 5)
+    assert _rel(xg[perm], xo) <= 1e-12
+    # and bit-identical to the GPU solve of the explicitly permuted system
+    xp, _, _ = mstgpu.LuSgs(Ab.indptr, Ab.indices, block).solve(valp, b[perm], x0[perm], 5)
+    assert np.array_equal(xg[perm], xp)
+    with pytest.raises(mstgpu.MstGpuError, match="permutation"):
+        mstgpu.LuSgs(rowptr, col, block, sweep_order=np.zeros(n, np.int32))
+
+
+def test_device_resident_solve_on_a_tet_mesh_pattern():
+    """BASELINE config 5 in small: block-5 system on the tet adjacency (device cell order), colour
+    sweeps, arrays resident on the device -- same bits as the host-array entry point, == oracle."""
+    import torch
+    from conftest import box_flat
+    f = box_flat(7, 6, 5)
+    rowptr, col = mstgpu.mesh_adjacency(f)
+    n, nnz, B = rowptr.size - 1, col.size, 5
+    assert n == f["ncells"] and nnz == n + 2 * f["nint"]
+    rows = np.repeat(np.arange(n), np.diff(rowptr))
+    assert np.all(np.diff(col)[np.diff(rows) == 0] > 0)  # ascending within a row
+    rng = np.random.default_rng(3)
+    val = (rng.random((nnz, B, B)) - 0.5) * 0.2
+    val[col == rows] += 3.0 * np.eye(B)
+    b = rng.random((n, B)); x0 = np.ones((n, B))
+    perm, ncol = mstgpu.lusgs_color_order(rowptr, col)
+    assert ncol <= 6
+    s = mstgpu.LuSgs(rowptr, col, B, sweep_order=perm)
+    xh, _, _ = s.solve(val, b, x0, 5)
+    dv, db, dx = torch.from_numpy(val).cuda(), torch.from_numpy(b).cuda(), torch.from_numpy(x0).cuda()
+    ms = s.solve_device(dv.data_ptr(), db.data_ptr(), dx.data_ptr(), 5)
+    assert ms > 0 and s.launch_count > 0
+    assert np.array_equal(dx.cpu().numpy(), xh)
+    Ab = sp.csr_matrix((np.arange(col.size) + 1, col, rowptr), shape=(n, n))[perm][:, perm].tocsr()
+    Ab.sort_indices()
+    xo, _, _ = oracle.lusgs(Ab.indptr, Ab.indices, val[Ab.data - 1], b[perm], x0[perm], B, 5)
+    assert _rel(xh[perm], xo) <= 1e-12
+    # 60 sweeps reach the solution of A x = b
+    x60, _, _ = s.solve(val, b, x0, 60)
+    A = sp.bsr_matrix((val, col, rowptr), shape=(n * B, n * B)).tocsc()
+    xs = sp.linalg.spsolve(A, b.ravel()).reshape(n, B)
+    assert np.abs(x60 - xs).max() < 1e-9 * np.abs(xs).max()
