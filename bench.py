@@ -161,14 +161,21 @@ def cpu_baseline(args, nsteps=None, n=None, budget_s=12.0):
     a = argparse.Namespace(**vars(args)); a.n = n
     f, Q, _ = build_workload(a)
     o = oracle.Oracle(f, order=args.order, flux=args.flux, nthreads=0, viscous=args.viscous, **scheme_kwargs(args))
-    o.run(DT, 1, Q)  # warm-up (page faults of the work arrays)
+    if getattr(args, "implicit", 0):
+        # implicit step: OpenMP assembly + the reference's sequential block LU-SGS (lusgs_oracle.cpp)
+        def run(k, Q=Q):
+            for _ in range(k):
+                Q = o.step_implicit(args.implicit_dt, Q, LUSGS_ITERS)
+    else:
+        run = lambda k: o.run(DT, k, Q)
+    run(1)  # warm-up (page faults of the work arrays)
     t = time.perf_counter()
-    o.run(DT, 1, Q)
+    run(1)
     t1 = time.perf_counter() - t
     if nsteps is None:
-        nsteps = int(min(60, max(3, round(budget_s / max(t1, 1e-3)))))
+        nsteps = int(min(60, max(1 if getattr(args, "implicit", 0) else 3, round(budget_s / max(t1, 1e-3)))))
     t = time.perf_counter()
-    o.run(DT, nsteps, Q)
+    run(nsteps)
     el = time.perf_counter() - t
     return dict(value=f["ncells"] * nsteps / el, unit="cell-updates/s", cores=o.nthreads, kind="port",
                 sample=f"{args.workload} n={n}: {f['ncells']} cells x {nsteps} steps in {el:.2f}s "
@@ -383,6 +390,15 @@ def run_ours(args, rank, world):
     log(f"[bench] context built in {time.time() - t:.1f}s, {ctx.device_bytes / 2**30:.2f} GiB on device")
     ctx.set_state(Q0)
     dt_run = DT if args.workload == "box" else 2e-5
+    if args.implicit:
+        # BASELINE config 5: every step = explicit residual + block assembly + 5 LU-SGS sweeps (colour-ordered)
+        if world > 1:
+            raise SystemExit("bench.py --implicit: replicas only (the sweeps do not shard yet, DESIGN.md 5)")
+        t = time.time()
+        ctx.implicit_setup(True)
+        log(f"[bench] implicit setup in {time.time() - t:.1f}s, {ctx.device_bytes / 2**30:.2f} GiB on device")
+        dt_run = args.implicit_dt
+        ctx.step = lambda dt, n: ctx.step_implicit(dt, n, LUSGS_ITERS)
     if args.cfl > 0:
         # extension: every step at its own global CFL step, computed on the device (+ allreduce(min))
         ctx.step = lambda dt, n: ctx.step_cfl(args.cfl, n)
@@ -404,7 +420,9 @@ def run_ours(args, rank, world):
         dist.barrier()
     torch.cuda.synchronize()
     w0 = time.perf_counter()
-    if args.cfl > 0:
+    if args.implicit:
+        ms = ctx.step_implicit(dt_run, args.steps, LUSGS_ITERS)  # CUDA events on the solver's own stream
+    elif args.cfl > 0:
         ms = ctx.step_cfl_timed(args.cfl, args.steps)  # CUDA events on the solver's own stream
     else:
         ms = ctx.step_timed(dt_run, args.steps)
@@ -418,7 +436,8 @@ def run_ours(args, rank, world):
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms = float(tms.item())
     launches = ctx.launch_count - l0
-    kt = {k: ctx.kernel_time(k) for k in ("gradient", "flux", "update", "step_tiles", "halo_pack")}
+    kt = {k: ctx.kernel_time(k) for k in ("gradient", "gradient_lsq", "limiter", "flux", "update", "step_tiles", "halo_pack",
+                                           "assemble", "lusgs", "increment")}
     kt = {k: v for k, v in kt.items() if v[1] > 0}
     ctx.enable_kernel_timing(False)
     res = ctx.residual()
@@ -436,7 +455,15 @@ def run_ours(args, rank, world):
     dom = max(per_kernel, key=per_kernel.get)
     if args.viscous:
         ab = dict(ab, step=616, flux_update=368) if (D, args.order) == (3, 2) else ab  # + eta per face
-    if "step_tiles" in per_kernel:
+    if args.implicit:
+        # the LU-SGS solve dominates an implicit step: its own algorithmic bytes over its duration
+        nnz_row = 1.0 + 2.0 * (f["nint"] / nc_total)
+        per_iter, setup = lusgs_bytes_per_row(nnz_row)
+        abytes = LUSGS_ITERS * per_iter + setup
+        achieved = abytes * nc / (per_kernel["lusgs"] * 1e-3) / 1e9
+        kname = "LU-SGS solve of the implicit step (k_diag, k_scale, 5 x [k_ux, k_rhs, sweeps, k_mid, sweeps, k_fin])"
+        ab["step"] = ab["step"] + abytes + nnz_row * 8 * U * U + 2 * 8 * U  # + assembly writes, increment
+    elif "step_tiles" in per_kernel:
         # fused kernel: one launch does both passes of SURVEY.md 8(d) -> the whole
         # step's algorithmic bytes (600 B per tet cell-update) over its duration
         achieved = ab["step"] * nc / (per_kernel["step_tiles"] * 1e-3) / 1e9
@@ -453,7 +480,7 @@ def run_ours(args, rank, world):
         # from the committed ncu --set full capture, scaled per cell
         tj = json.load(open(tp))
         key = "step_tiles" if "step_tiles" in per_kernel else "flux_update"
-        if key in tj:
+        if key in tj and not args.implicit and args.limiter == "none":
             traffic = tj[key]["bytes_per_cell"] * nc
     roof = dict(bound="hbm", kernel=kname, achieved=achieved, peak=peak, unit="GB/s",
                 frac=achieved / peak, traffic=traffic, peak_source=peak_src,
@@ -495,6 +522,7 @@ def run_ours(args, rank, world):
                config=dict(workload=f"{args.workload}{args.n}: {desc}", cells=nc_total, faces=f["nfaces"], flux=args.flux,
                            parallelism=f"{world} partition(s), Hilbert ranges, 2 ghost layers, NCCL send/recv + allreduce(max)",
                            order=args.order, viscous=args.viscous, gradient=args.gradient, limiter=args.limiter, cfl=args.cfl,
+                           implicit=None if not args.implicit else dict(dt=args.implicit_dt, lusgs_iterations=LUSGS_ITERS, sweeps="colour-ordered"),
                            graph_ms_per_step=None if graph_ms is None else graph_ms / args.steps, dt=DT if args.workload == "box" else 2e-5, kernel=args.kernel, tile_cells=args.tile_cells, renumber=args.renumber,
                            block_threads=args.block_threads, l2="inputs larger than L2 (state + tables >> 126 MB)"
                            if nc_total * U * 8 > 2 ** 28 else "inputs smaller than L2: flush not applied"),
@@ -534,6 +562,9 @@ def main():
     ap.add_argument("--cfl", type=float, default=0.0, help="extension: > 0 = global CFL time step instead of DT")
     ap.add_argument("--shock", type=int, default=0, choices=[0, 1],
                     help="box init: 1 = SOD split at x = 0.5 + perturbation (SURVEY 8d; needs --limiter and --cfl)")
+    ap.add_argument("--implicit", type=int, default=0, choices=[0, 1],
+                    help="config 5: implicit steps (block assembly + 5 colour-ordered LU-SGS sweeps)")
+    ap.add_argument("--implicit-dt", type=float, default=1e-3)
     ap.add_argument("--graph", type=int, default=0, choices=[0, 1], help="also time the K steps issued from the CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -162,6 +162,20 @@ int mstgpu_cfl_dt(mstgpu_ctx* ctx, double cfl, double* dt);
 int mstgpu_step_cfl(mstgpu_ctx* ctx, double cfl, int32_t nsteps, double* time_advanced);
 /* Same, bracketed by CUDA events on the solver's own stream; *ms = elapsed (ms may be NULL). */
 int mstgpu_step_cfl_timed(mstgpu_ctx* ctx, double cfl, int32_t nsteps, double* time_advanced, float* ms);
+/* ---- implicit step: the LU-SGS sweeps of the reference's lusolver applied to rhoSolver -------------
+ * The reference ships the solver (R/lusolver/SparseSolver.cpp:54-104) but never calls it from
+ * rhoSolver, so the operator is build-defined: linearised backward Euler with
+ * first-order flux Jacobians,
+ *   [V_i/dt I + sum_f 1/2 (A(Q_i,S) + lam_f I)] dQ_i + sum_f 1/2 (A(Q_j,S) - lam_f I) dQ_j = -R_i(Q),
+ * R = the explicit residual of mstgpu_step (same fluxes, same gather), solved by `lusgs_iters`
+ * sweeps of the reference's block algorithm from dQ = 0; Q += dQ.  dt -> 0 recovers mstgpu_step.
+ * setup builds the block pattern once (colour_sweeps != 0: colour-ordered sweeps, one level per
+ * colour; 0: storage order, one level per wavefront); step_implicit calls it with colours if needed.
+ * sweep_order: [ncells] reference cell ids in sweep order (for checking against the reference solver
+ * on the permuted system).  *ms (optional) = CUDA-event time of the call. */
+int mstgpu_implicit_setup(mstgpu_ctx* ctx, int32_t colour_sweeps);
+int mstgpu_implicit_sweep_order(mstgpu_ctx* ctx, int32_t* order_ref_ids);
+int mstgpu_step_implicit(mstgpu_ctx* ctx, double dt, int32_t nsteps, int32_t lusgs_iters, float* ms);
 /* L-inf relative change of the LAST step, DIMU doubles (Time.cpp:69-76). */
 int mstgpu_residual_linf(mstgpu_ctx* ctx, double* out_dimu);
 int mstgpu_sync(mstgpu_ctx* ctx);

@@ -315,6 +315,22 @@ int solve_impl(mstgpu_lusgs* h, const double* val, const double* b, double* x, i
 
 }  // namespace
 
+// in-library entry for the implicit step of mstgpu.cu: the sweeps on the caller's stream, no sync
+namespace mst {
+int lusgs_solve_async(mstgpu_lusgs* h, cudaStream_t st, const double* val, const double* b, double* x, int iters) {
+    cudaStream_t own = h->stream;
+    h->stream = st;
+    int rc;
+    switch (h->B) {
+        case 1: rc = solve_core<1>(h, val, b, x, iters, 0, nullptr, nullptr); break;
+        case 4: rc = solve_core<4>(h, val, b, x, iters, 0, nullptr, nullptr); break;
+        default: rc = solve_core<5>(h, val, b, x, iters, 0, nullptr, nullptr); break;
+    }
+    h->stream = own;
+    return rc;
+}
+}  // namespace mst
+
 extern "C" {
 
 const char* mstgpu_lusgs_last_error(void) { return g_lusgs_error.c_str(); }

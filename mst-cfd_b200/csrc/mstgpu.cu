@@ -27,6 +27,11 @@
 
 using namespace mst;
 
+namespace mst {
+// csrc/lusgs.cu: the sweeps on the caller's stream, device arrays, no synchronisation
+int lusgs_solve_async(mstgpu_lusgs* h, cudaStream_t st, const double* val, const double* b, double* x, int iters);
+}
+
 #define CK(call)                                                                       \
     do {                                                                               \
         cudaError_t e_ = (call);                                                       \
@@ -125,6 +130,11 @@ struct mstgpu_ctx {
     cudaStream_t fork_stream = nullptr;  // non-null while a step is captured: odd classes go here
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int64_t graph_launches = 0;
+    // implicit step (extension): block system + the reference's LU-SGS sweeps (csrc/lusgs.cu)
+    mstgpu_lusgs* imp_solver = nullptr;
+    int32_t *imp_dpos = nullptr, *imp_pos = nullptr;
+    double *imp_val = nullptr, *imp_b = nullptr, *imp_x = nullptr;
+    std::vector<int32_t> imp_sweep;  // sweep order, device cell ids (empty = storage order)
     // extension tables / CFL stepping (mstgpu_config.gradient / limiter, mstgpu_step_cfl)
     double *lsq = nullptr, *eps2 = nullptr;
     unsigned long long* dtmin = nullptr;  // bit pattern of the smallest cell time step
@@ -514,6 +524,138 @@ __global__ void k_cfl_finish(double cfl, unsigned long long* dtmin, double* dt, 
     *dtmin = 0x7FF0000000000000ULL;
 }
 
+// ---- implicit step (extension): the block system the LU-SGS sweeps solve ---------------------------
+// A(Q,S) = d(F(Q).S)/dQ for a perfect gas, U x U row-major (same expressions as the oracle's fluxJacobian)
+template <int D>
+__device__ __forceinline__ void flux_jacobian(const double (&q)[D + 2], const double (&S)[D], double gamma, double (&A)[(D + 2) * (D + 2)]) {
+    constexpr int U = D + 2;
+    const double r = 1.0 / q[0];
+    double u[D], un = 0.0, q2 = 0.0;
+#pragma unroll
+    for (int a = 0; a < D; a++) { u[a] = q[a + 1] * r; un += u[a] * S[a]; q2 += u[a] * u[a]; }
+    const double g1 = gamma - 1.0;
+    const double phi = 0.5 * g1 * q2;
+    const double p = (q[U - 1] - 0.5 * q[0] * q2) * g1;
+    const double H = (q[U - 1] + p) * r;
+#pragma unroll
+    for (int i = 0; i < U * U; i++) A[i] = 0.0;
+#pragma unroll
+    for (int b = 0; b < D; b++) A[1 + b] = S[b];
+#pragma unroll
+    for (int a = 0; a < D; a++) {
+        A[(1 + a) * U] = S[a] * phi - u[a] * un;
+#pragma unroll
+        for (int b = 0; b < D; b++) A[(1 + a) * U + 1 + b] = u[a] * S[b] - g1 * u[b] * S[a] + (a == b ? un : 0.0);
+        A[(1 + a) * U + U - 1] = g1 * S[a];
+    }
+    A[(U - 1) * U] = (phi - H) * un;
+#pragma unroll
+    for (int b = 0; b < D; b++) A[(U - 1) * U + 1 + b] = H * S[b] - g1 * u[b] * un;
+    A[(U - 1) * U + U - 1] = gamma * un;
+}
+
+template <int D>
+__device__ __forceinline__ double spectral_radius(const double (&q)[D + 2], const double (&S)[D], double gamma) {
+    constexpr int U = D + 2;
+    const double r = 1.0 / q[0];
+    double un = 0.0, q2 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int a = 0; a < D; a++) { un += q[a + 1] * r * S[a]; q2 += q[a + 1] * q[a + 1]; s2 += S[a] * S[a]; }
+    const double p = (q[U - 1] - 0.5 * q2 * r) * (gamma - 1.0);
+    return fabs(un) + sqrt(gamma * p * r) * sqrt(s2);
+}
+
+// one thread per cell: diagonal block and the off-diagonal blocks of its row, written at their CSR
+// positions (dpos / pos, built once by mstgpu_implicit_setup)
+template <int D>
+__global__ void __launch_bounds__(128) k_assemble_implicit(int n, int nc, int nslot, double gamma, double dt,
+                                                           const double* __restrict__ Q,
+                                                           const int32_t* __restrict__ cf,
+                                                           const int32_t* __restrict__ fc0,
+                                                           const int32_t* __restrict__ fc1,
+                                                           const double* __restrict__ Sd,
+                                                           const double* __restrict__ vol,
+                                                           const int32_t* __restrict__ dpos,
+                                                           const int32_t* __restrict__ pos,
+                                                           double* __restrict__ val) {
+    constexpr int U = D + 2, UU = U * U;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    double qi[U], Dg[UU], A[UU];
+#pragma unroll
+    for (int k = 0; k < U; k++) qi[k] = Q[(size_t)c * U + k];
+#pragma unroll
+    for (int i = 0; i < UU; i++) Dg[i] = 0.0;
+    const double vdt = vol[c] / dt;
+#pragma unroll
+    for (int k = 0; k < U; k++) Dg[k * U + k] = vdt;
+    for (int j = 0; j < nslot; j++) {
+        const int v = cf[(size_t)j * nc + c];
+        if (v < 0) continue;
+        const int f = v >> 1;
+        const double sg = (v & 1) ? -1.0 : 1.0;
+        const int nb = (v & 1) ? fc0[f] : fc1[f];
+        double S[D];
+#pragma unroll
+        for (int d = 0; d < D; d++) S[d] = sg * Sd[(size_t)f * D + d];
+        double lam = spectral_radius<D>(qi, S, gamma);
+        double qj[U];
+        if (nb >= 0) {
+#pragma unroll
+            for (int k = 0; k < U; k++) qj[k] = Q[(size_t)nb * U + k];
+            lam = fmax(lam, spectral_radius<D>(qj, S, gamma));
+        }
+        flux_jacobian<D>(qi, S, gamma, A);
+#pragma unroll
+        for (int i = 0; i < UU; i++) Dg[i] += 0.5 * A[i];
+#pragma unroll
+        for (int k = 0; k < U; k++) Dg[k * U + k] += 0.5 * lam;
+        if (nb >= 0) {
+            flux_jacobian<D>(qj, S, gamma, A);
+            double* O = val + (size_t)pos[(size_t)j * nc + c] * UU;
+#pragma unroll
+            for (int i = 0; i < UU; i++) {
+                double o = 0.5 * A[i];
+                if (i / U == i % U) o -= 0.5 * lam;
+                O[i] = o;
+            }
+        }
+    }
+    double* Dd = val + (size_t)dpos[c] * UU;
+#pragma unroll
+    for (int i = 0; i < UU; i++) Dd[i] = Dg[i];
+}
+
+// Q_new = Q_old + dQ, with the residual of Time.cpp:69-76 and the NaN flag
+template <int U>
+__global__ void __launch_bounds__(256) k_add_increment(int n, const double* __restrict__ Qold, const double* __restrict__ dq,
+                                                       double* __restrict__ Qnew,
+                                                       unsigned long long* __restrict__ resid, int* __restrict__ nanflag) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    double r[U];
+#pragma unroll
+    for (int k = 0; k < U; k++) r[k] = 0.0;
+    bool bad = false;
+    if (c < n) {
+#pragma unroll
+        for (int k = 0; k < U; k++) {
+            const double qo = Qold[(size_t)c * U + k];
+            const double qn = qo + dq[(size_t)c * U + k];
+            Qnew[(size_t)c * U + k] = qn;
+            const double x = fabs(qn - qo) / qo;
+            r[k] = (x > 0.0) ? x : 0.0;
+            bad |= (qn != qn);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r[k] = fmax(r[k], __shfl_xor_sync(0xffffffffu, r[k], o));
+        if ((threadIdx.x & 31) == 0 && r[k] > 0.0) atomicMax(&resid[k], (unsigned long long)__double_as_longlong(r[k]));
+    }
+    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(nanflag, 1);
+}
+
 __device__ __forceinline__ double warp_max(double x) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
@@ -521,7 +663,7 @@ __device__ __forceinline__ double warp_max(double x) {
 }
 
 template <int D>
-__global__ void __launch_bounds__(256) k_update(int nc, int n_upd, int nslot, double dt_val,
+__global__ void __launch_bounds__(256) k_update(int nc, int n_upd, int nslot, int mode, double dt_val,
                                                 const double* __restrict__ dt_dev,
                                                 const double* __restrict__ Qold,
                                                 const double* __restrict__ Phi,
@@ -553,10 +695,11 @@ __global__ void __launch_bounds__(256) k_update(int nc, int n_upd, int nslot, do
 #pragma unroll
         for (int k = 0; k < U; k++) {
             const double qo = Qold[(size_t)c * U + k];
-            const double qn = qo - s * acc[k];
+            // mode 2: residual-vector mode (implicit step): -R_i instead of the update
+            const double qn = (mode & 2) ? -acc[k] : qo - s * acc[k];
             Qnew[(size_t)c * U + k] = qn;
             // Time.cpp:72: signed denominator; NaN never wins, +inf can
-            const double x = fabs(qn - qo) / qo;
+            const double x = (mode & 2) ? 0.0 : fabs(qn - qo) / qo;
             r[k] = (x > 0.0) ? x : 0.0;
             bad |= (qn != qn);
         }
@@ -918,7 +1061,7 @@ int step_impl(mstgpu_ctx* ctx, double dt, int nsteps, double cfl = 0.0) {
         {
             KTimer t(ctx, "update");
             k_update<D><<<(ctx->n_owned + 255) / 256, 256, 0, ctx->stream>>>(
-                nc, ctx->n_owned, ctx->nslot, dt, dtd, Qo, ctx->Phi, ctx->cf, ctx->vol, Qn, ctx->resid, ctx->nanflag);
+                nc, ctx->n_owned, ctx->nslot, 1, dt, dtd, Qo, ctx->Phi, ctx->cf, ctx->vol, Qn, ctx->resid, ctx->nanflag);
         }
         ctx->cur ^= 1;  // RhoSolver::updateNewToOld as a pointer swap
     }
@@ -959,6 +1102,62 @@ int fetch_permuted(mstgpu_ctx* ctx, const double* dsrc, const int32_t* new2old, 
 }
 
 }  // namespace
+
+template <int D>
+static int step_implicit_impl(mstgpu_ctx* ctx, double dt, int nsteps, int iters) {
+    constexpr int U = D + 2;
+    const int nc = ctx->nc;
+    for (int s = 0; s < nsteps; s++) {
+        const double* Qc = ctx->Q[ctx->cur];
+        double* Qn = ctx->Q[ctx->cur ^ 1];
+        // b = -R(Q): the explicit path's fluxes and gather in residual-vector mode
+        if (ctx->use_tiles) {
+            int r = launch_tiles_any<D>(ctx, dt, nullptr, Qc, ctx->imp_b, 2, 2, ctx->stream);
+            if (r) return r;
+        } else {
+            int r = ensure_stage_buffers(ctx);
+            if (r) return r;
+            launch_gradient_stage<D>(ctx, Qc);
+            const int nf = ctx->nf;
+            {
+                KTimer t(ctx, "flux");
+                if (ctx->cfg.order == 2)
+                    k_flux<D, 2><<<(nf + 127) / 128, 128, 0, ctx->stream>>>(nf, ctx->dcfg, Qc, ctx->G, ctx->fc0, ctx->fc1, ctx->meta, ctx->Sd,
+                                                                             ctx->dx0, ctx->dx1, ctx->Phi, ctx->Gp, ctx->eta);
+                else
+                    k_flux<D, 1><<<(nf + 127) / 128, 128, 0, ctx->stream>>>(nf, ctx->dcfg, Qc, ctx->G, ctx->fc0, ctx->fc1, ctx->meta, ctx->Sd,
+                                                                             ctx->dx0, ctx->dx1, ctx->Phi, ctx->Gp, ctx->eta);
+            }
+            KTimer t(ctx, "update");
+            k_update<D><<<(nc + 255) / 256, 256, 0, ctx->stream>>>(nc, nc, ctx->nslot, 2, dt, nullptr, Qc, ctx->Phi, ctx->cf, ctx->vol,
+                                                                   ctx->imp_b, ctx->resid, ctx->nanflag);
+            ctx->probes_valid = true;
+        }
+        {
+            KTimer t(ctx, "assemble");
+            k_assemble_implicit<D><<<(nc + 127) / 128, 128, 0, ctx->stream>>>(nc, nc, ctx->nslot, ctx->dcfg.gamma, dt, Qc, ctx->cf, ctx->fc0,
+                                                                              ctx->fc1, ctx->Sd, ctx->vol, ctx->imp_dpos, ctx->imp_pos, ctx->imp_val);
+        }
+        CK(cudaMemsetAsync(ctx->imp_x, 0, (size_t)nc * U * sizeof(double), ctx->stream));  // dQ starts from 0
+        {
+            KTimer t(ctx, "lusgs");
+            const int64_t l0 = mstgpu_lusgs_launch_count(ctx->imp_solver);
+            int r = lusgs_solve_async(ctx->imp_solver, ctx->stream, ctx->imp_val, ctx->imp_b, ctx->imp_x, iters);
+            if (r) { set_error(ctx, std::string("lusgs: ") + mstgpu_lusgs_last_error()); return r; }
+            ctx->launches += mstgpu_lusgs_launch_count(ctx->imp_solver) - l0 - 1;
+        }
+        CK(cudaMemsetAsync(ctx->resid, 0, 8 * sizeof(unsigned long long), ctx->stream));
+        {
+            KTimer t(ctx, "increment");
+            k_add_increment<U><<<(nc + 255) / 256, 256, 0, ctx->stream>>>(nc, Qc, ctx->imp_x, Qn, ctx->resid, ctx->nanflag);
+        }
+        ctx->cur ^= 1;
+    }
+    CK(cudaGetLastError());
+    ctx->stepped = nsteps > 0 || ctx->stepped;
+    if (nsteps > 0 && ctx->use_tiles) ctx->probes_valid = false;
+    return MSTGPU_OK;
+}
 
 // cells per tile: the largest tile that still lets two CTAs share an SM (228 KB of shared
 // memory); the limiter extension adds a [U][own + ring 1] table, so its tiles are smaller
@@ -1201,7 +1400,9 @@ void mstgpu_destroy(mstgpu_ctx* ctx) {
     if (ctx->sendbuf) cudaFree(ctx->sendbuf);
     void* ptrs[] = {ctx->Q[0], ctx->Q[1], ctx->G, ctx->Gp, ctx->Phi, ctx->stage, ctx->Sd, ctx->dx0, ctx->dx1, ctx->eta,
                     ctx->vol, ctx->fc0, ctx->fc1, ctx->cf, ctx->cell_new2old, ctx->face_new2old, ctx->meta,
-                    ctx->resid, ctx->nanflag, ctx->lsq, ctx->eps2, ctx->dtmin, ctx->dt_dev};
+                    ctx->resid, ctx->nanflag, ctx->lsq, ctx->eps2, ctx->dtmin, ctx->dt_dev, ctx->imp_dpos, ctx->imp_pos,
+                    ctx->imp_val, ctx->imp_b, ctx->imp_x};
+    if (ctx->imp_solver) mstgpu_lusgs_destroy(ctx->imp_solver);
     for (void* q : ptrs)
         if (q) cudaFree(q);
     for (void* q : ctx->tile_allocs)
@@ -1321,6 +1522,104 @@ int mstgpu_step_cfl_timed(mstgpu_ctx* ctx, double cfl, int32_t nsteps, double* t
         CK(cudaStreamSynchronize(ctx->stream));
     }
     return MSTGPU_OK;
+}
+
+// ---- implicit step (extension; SURVEY.md 8a row L: the reference has the LU-SGS solver but no
+// rhoSolver call site, so the operator is build-defined -- see oracle/rho_oracle.cpp implicitSystem) ----
+int mstgpu_implicit_setup(mstgpu_ctx* ctx, int32_t colour_sweeps) {
+    if (!ctx) return MSTGPU_ERR_ARG;
+    if (ctx->partitioned) { set_error(ctx, "implicit step: not available on a partitioned context yet (DESIGN.md 5)"); return MSTGPU_ERR_STATE; }
+    if (ctx->imp_solver) return MSTGPU_OK;
+    CK(cudaSetDevice(ctx->device));
+    const int nc = ctx->nc, nslot = ctx->nslot, U = ctx->U;
+    // the connectivity lives on the device (the host copies were dropped after upload)
+    std::vector<int32_t> cf((size_t)nslot * nc), fc0(ctx->nf), fc1(ctx->nf);
+    CK(cudaMemcpy(cf.data(), ctx->cf, cf.size() * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(fc0.data(), ctx->fc0, fc0.size() * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(fc1.data(), ctx->fc1, fc1.size() * 4, cudaMemcpyDeviceToHost));
+    auto nb_of = [&](int c, int j) -> int {
+        const int v = cf[(size_t)j * nc + c];
+        if (v < 0) return -1;
+        return (v & 1) ? fc0[v >> 1] : fc1[v >> 1];
+    };
+    std::vector<int32_t> rowptr((size_t)nc + 1, 0);
+    for (int c = 0; c < nc; c++) {
+        int cnt = 1;
+        for (int j = 0; j < nslot; j++) cnt += nb_of(c, j) >= 0 ? 1 : 0;
+        const int64_t next = (int64_t)rowptr[c] + cnt;
+        if (next > 0x7fffffffLL) { set_error(ctx, "implicit system does not fit 32-bit offsets"); return MSTGPU_ERR_ARG; }
+        rowptr[c + 1] = (int32_t)next;
+    }
+    const size_t nnz = (size_t)rowptr[nc];
+    std::vector<int32_t> col(nnz), dpos(nc), pos((size_t)nslot * nc, -1);
+#pragma omp parallel for schedule(static)
+    for (int c = 0; c < nc; c++) {
+        int32_t* out = col.data() + rowptr[c];
+        int n = 0;
+        out[n++] = c;
+        for (int j = 0; j < nslot; j++) { const int nb = nb_of(c, j); if (nb >= 0) out[n++] = nb; }
+        std::sort(out, out + n);
+        dpos[c] = rowptr[c] + (int32_t)(std::lower_bound(out, out + n, c) - out);
+        for (int j = 0; j < nslot; j++) {
+            const int nb = nb_of(c, j);
+            if (nb >= 0) pos[(size_t)j * nc + c] = rowptr[c] + (int32_t)(std::lower_bound(out, out + n, nb) - out);
+        }
+    }
+    std::vector<int32_t> order;
+    if (colour_sweeps) {
+        order.resize(nc);
+        int32_t ncol = 0;
+        if (mstgpu_lusgs_color_order(nc, rowptr.data(), col.data(), order.data(), &ncol) != MSTGPU_OK) {
+            set_error(ctx, std::string("colour order: ") + mstgpu_lusgs_last_error());
+            return MSTGPU_ERR_ARG;
+        }
+    }
+    int rc = mstgpu_lusgs_create_ordered(&ctx->imp_solver, nc, U, rowptr.data(), col.data(),
+                                         colour_sweeps ? order.data() : nullptr, ctx->device);
+    if (rc != MSTGPU_OK) { set_error(ctx, std::string("lusgs: ") + mstgpu_lusgs_last_error()); return rc; }
+    ctx->dev_bytes += mstgpu_lusgs_device_bytes(ctx->imp_solver);
+    ctx->imp_sweep = order;
+    int r;
+    if ((r = upload(ctx, &ctx->imp_dpos, dpos))) return r;
+    if ((r = upload(ctx, &ctx->imp_pos, pos))) return r;
+    if ((r = dalloc(ctx, &ctx->imp_val, nnz * U * U))) return r;
+    if ((r = dalloc(ctx, &ctx->imp_b, (size_t)nc * U + 2 * U))) return r;  // + 2 rows: bulk stores of the fused kernel
+    if ((r = dalloc(ctx, &ctx->imp_x, (size_t)nc * U))) return r;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MSTGPU_OK;
+}
+
+int mstgpu_implicit_sweep_order(mstgpu_ctx* ctx, int32_t* order_ref_ids) {
+    if (!ctx || !order_ref_ids) return MSTGPU_ERR_ARG;
+    if (!ctx->imp_solver) { set_error(ctx, "implicit_sweep_order before implicit_setup"); return MSTGPU_ERR_STATE; }
+    for (int i = 0; i < ctx->nc; i++) {
+        const int dev = ctx->imp_sweep.empty() ? i : ctx->imp_sweep[i];
+        order_ref_ids[i] = ctx->plan.cell_new2old[dev];
+    }
+    return MSTGPU_OK;
+}
+
+int mstgpu_step_implicit(mstgpu_ctx* ctx, double dt, int32_t nsteps, int32_t lusgs_iters, float* ms) {
+    if (!ctx) return MSTGPU_ERR_ARG;
+    if (!ctx->has_state) { set_error(ctx, "step before set_state"); return MSTGPU_ERR_STATE; }
+    if (nsteps < 0 || lusgs_iters < 0 || !(dt > 0.0)) { set_error(ctx, "step_implicit: bad dt / nsteps / iterations"); return MSTGPU_ERR_ARG; }
+    if (!ctx->imp_solver) {
+        int r = mstgpu_implicit_setup(ctx, 1);
+        if (r) return r;
+    }
+    CK(cudaSetDevice(ctx->device));
+    if (ms) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    }
+    int rc = (ctx->D == 2) ? step_implicit_impl<2>(ctx, dt, nsteps, lusgs_iters) : step_implicit_impl<3>(ctx, dt, nsteps, lusgs_iters);
+    if (rc == MSTGPU_OK && ms) {
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(cudaEventSynchronize(ctx->ev1));
+        CK(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    }
+    if (ctx->ktiming) drain_timers(ctx);
+    return rc;
 }
 
 int mstgpu_sync(mstgpu_ctx* ctx) {

@@ -306,9 +306,10 @@ __global__ void __launch_bounds__(NT, MST_TILE_MINB(NT)) k_step_tiles(TileArrays
 #pragma unroll
         for (int k = 0; k < U; k++) {
             const double qo = Qs[lc * U + k];
-            const double qn = qo - s * acc[k];
+            // bit 1 of want_resid: residual-vector mode (implicit step): -R_i instead of the update
+            const double qn = (want_resid & 2) ? -acc[k] : qo - s * acc[k];
             Qs[lc * U + k] = qn;
-            if (want_resid) {  // only the last step of a multi-step call can be observed (mstgpu_residual_linf)
+            if (want_resid & 1) {  // only the last step of a multi-step call can be observed (mstgpu_residual_linf)
                 const double x = fabs(qn - qo) * __drcp_rn(qo);  // Time.cpp:72 (|d|/q; reporting only, 1 ulp)
                 r[k] = fmax(r[k], (x > 0.0) ? x : 0.0);
             }
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(NT, MST_TILE_MINB(NT)) k_step_tiles(TileArrays
     }
     __shared__ double sm[U][NT / 32];
     const int lane = tid & 31, wid = tid >> 5;
-    if (want_resid) {
+    if (want_resid & 1) {
 #pragma unroll
         for (int k = 0; k < U; k++) {
             const double m = warp_max_nonneg(r[k]);
@@ -333,7 +334,7 @@ __global__ void __launch_bounds__(NT, MST_TILE_MINB(NT)) k_step_tiles(TileArrays
             for (int k = 0; k < U; k++) Qnew[(size_t)(d.cb + even) * U + k] = Qs[even * U + k];
         bulk_commit_wait_read();
     }
-    if (want_resid && tid >= 32 && tid < 32 + U) {
+    if ((want_resid & 1) && tid >= 32 && tid < 32 + U) {
         const int k = tid - 32;
         double m = 0.0;
         for (int w = 0; w < NT / 32; w++) m = fmax(m, sm[k][w]);

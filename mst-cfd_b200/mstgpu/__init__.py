@@ -23,7 +23,8 @@ LIB_PATH = os.environ.get("MSTGPU_LIB", os.path.join(_ROOT, "libmstgpu.so"))  # 
 EXPORTS = [
     "mstgpu_default_config", "mstgpu_create", "mstgpu_destroy", "mstgpu_set_state",
     "mstgpu_get_state", "mstgpu_get_prev_state", "mstgpu_step", "mstgpu_step_timed",
-    "mstgpu_residual_linf", "mstgpu_sync", "mstgpu_cfl_dt", "mstgpu_step_cfl", "mstgpu_step_cfl_timed", "mstgpu_debug_gradient", "mstgpu_debug_face_flux",
+    "mstgpu_residual_linf", "mstgpu_sync", "mstgpu_cfl_dt", "mstgpu_step_cfl", "mstgpu_step_cfl_timed", "mstgpu_implicit_setup",
+    "mstgpu_implicit_sweep_order", "mstgpu_step_implicit", "mstgpu_debug_gradient", "mstgpu_debug_face_flux",
     "mstgpu_launch_count", "mstgpu_enable_kernel_timing", "mstgpu_kernel_time",
     "mstgpu_device_bytes", "mstgpu_plan_permutation", "mstgpu_tile_stats",
     "mstgpu_partition_create", "mstgpu_partition_destroy", "mstgpu_partition_mesh", "mstgpu_partition_sizes",
@@ -93,6 +94,9 @@ def lib():
         L.mstgpu_cfl_dt.argtypes = [vp, dbl, C.POINTER(dbl)]
         L.mstgpu_step_cfl.argtypes = [vp, dbl, i32, C.POINTER(dbl)]
         L.mstgpu_step_cfl_timed.argtypes = [vp, dbl, i32, C.POINTER(dbl), C.POINTER(C.c_float)]
+        L.mstgpu_implicit_setup.argtypes = [vp, i32]
+        L.mstgpu_implicit_sweep_order.argtypes = [vp, vp]
+        L.mstgpu_step_implicit.argtypes = [vp, dbl, i32, i32, C.POINTER(C.c_float)]
         L.mstgpu_residual_linf.argtypes = [vp, vp]
         L.mstgpu_sync.argtypes = [vp]
         L.mstgpu_debug_gradient.argtypes = [vp, vp]
@@ -413,6 +417,20 @@ class Context:
         """step_cfl bracketed by CUDA events on the solver's stream; returns milliseconds."""
         t, ms = C.c_double(), C.c_float()
         self._check(lib().mstgpu_step_cfl_timed(self.h, cfl, nsteps, C.byref(t), C.byref(ms)), "step_cfl_timed")
+        return float(ms.value)
+
+    def implicit_setup(self, colour_sweeps: bool = True):
+        self._check(lib().mstgpu_implicit_setup(self.h, 1 if colour_sweeps else 0), "implicit_setup")
+
+    def implicit_sweep_order(self) -> np.ndarray:
+        out = np.empty(self.ncells, dtype=np.int32)
+        self._check(lib().mstgpu_implicit_sweep_order(self.h, out.ctypes.data), "implicit_sweep_order")
+        return out
+
+    def step_implicit(self, dt: float, nsteps: int = 1, lusgs_iters: int = 5) -> float:
+        """Implicit steps (LU-SGS sweeps of the reference's lusolver); returns the CUDA-event time in ms."""
+        ms = C.c_float()
+        self._check(lib().mstgpu_step_implicit(self.h, dt, nsteps, lusgs_iters, C.byref(ms)), "step_implicit")
         return float(ms.value)
 
     def residual(self):

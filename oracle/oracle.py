@@ -62,6 +62,8 @@ def lib():
         L.oracle_cfl_dt.restype = C.c_double
         L.oracle_cfl_dt.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
         L.oracle_run_cfl.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+        L.oracle_implicit_system.restype = C.c_int64
+        L.oracle_implicit_system.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_riemann.argtypes = [C.c_int, C.c_int, C.POINTER(OmCfg), C.c_void_p,
                                      C.c_void_p, C.c_int, C.c_void_p]
@@ -171,6 +173,34 @@ class Oracle:
         dts = np.zeros(nsteps)
         lib().oracle_run_cfl(self.h, cfl, nsteps, Q.ctypes.data, dts.ctypes.data)
         return Q, dts
+
+    def implicit_system(self, dt: float, Q: np.ndarray):
+        """(rowptr, col, val [nnz,U,U], b [nc,U]) of one implicit step (extension; reference cell order)."""
+        Q = np.ascontiguousarray(Q, dtype=np.float64)
+        nc, U = self.flat["ncells"], self.U
+        rowptr = np.zeros(nc + 1, dtype=np.int32)
+        nnz = lib().oracle_implicit_system(self.h, dt, Q.ctypes.data, rowptr.ctypes.data, None, None, None)
+        col = np.zeros(nnz, dtype=np.int32); val = np.zeros((nnz, U, U)); b = np.zeros((nc, U))
+        lib().oracle_implicit_system(self.h, dt, Q.ctypes.data, rowptr.ctypes.data, col.ctypes.data, val.ctypes.data, b.ctypes.data)
+        return rowptr, col, val, b
+
+    def step_implicit(self, dt: float, Q: np.ndarray, iters: int = 5, sweep_order=None) -> np.ndarray:
+        """One implicit step: assemble, `iters` LU-SGS sweeps of the REFERENCE block solver
+        (lusgs_oracle.cpp == SparseSolver<MT,VCT>::solveILU) from dQ = 0, Q + dQ.  sweep_order
+        (new2old, reference cell ids): the solver runs on the explicitly permuted system P A P^T."""
+        import scipy.sparse as sp
+        rowptr, col, val, b = self.implicit_system(dt, Q)
+        nc, U = self.flat["ncells"], self.U
+        x0 = np.zeros((nc, U))
+        if sweep_order is None:
+            x, _, _ = lusgs(rowptr, col, val, b, x0, U, iters)
+            return Q + x.reshape(nc, U)
+        perm = np.asarray(sweep_order)
+        Ab = sp.csr_matrix((np.arange(col.size) + 1, col, rowptr), shape=(nc, nc))[perm][:, perm].tocsr()
+        Ab.sort_indices()
+        xp, _, _ = lusgs(Ab.indptr, Ab.indices, val[Ab.data - 1], b[perm], x0[perm], U, iters)
+        x = np.empty((nc, U)); x[perm] = xp.reshape(nc, U)
+        return Q + x
 
     def probe(self):
         """(Qf [nf,U], G [nc,U,D], F [nf,D,U]) of the last solve()."""

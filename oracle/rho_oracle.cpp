@@ -738,6 +738,122 @@ struct Ctx {
         if (cfg.viscous) viscousTerm(Qold, dt, Qnew);
     }
 
+    // ---- EXTENSION: implicit operator for the LU-SGS sweeps (the reference has
+    // the solver, R/lusolver/SparseSolver.cpp:54-104, but no rhoSolver call site, so WHAT it solves is
+    // build-defined).  Linearised backward Euler with first-order flux Jacobians (Yoon-Jameson):
+    //   [V_i/dt I + sum_f 1/2 (A(Q_i,S) + lam_f I)] dQ_i + sum_{f interior} 1/2 (A(Q_j,S) - lam_f I) dQ_j = -R_i
+    // S = outward area vector of cell i on face f, A(Q,S) = d(F(Q).S)/dQ (perfect gas), lam(Q,S) =
+    // |u.S| + a|S|, lam_f = max over the two cells (own cell on boundary faces), R_i = sum_f Phi_f the
+    // explicit residual of solve().  dt -> 0 recovers the explicit step.
+    static void fluxJacobian(const double* q, const double* S, double gamma, double* A /* U x U row-major */) {
+        const double r = 1.0 / q[0];
+        double u[D], un = 0.0, q2 = 0.0;
+        for (int a = 0; a < D; a++) { u[a] = q[a + 1] * r; un += u[a] * S[a]; q2 += u[a] * u[a]; }
+        const double g1 = gamma - 1.0;
+        const double phi = 0.5 * g1 * q2;
+        const double p = (q[U - 1] - 0.5 * q[0] * q2) * g1;
+        const double H = (q[U - 1] + p) * r;
+        for (int i = 0; i < U * U; i++) A[i] = 0.0;
+        for (int b = 0; b < D; b++) A[0 * U + 1 + b] = S[b];
+        for (int a = 0; a < D; a++) {
+            A[(1 + a) * U + 0] = S[a] * phi - u[a] * un;
+            for (int b = 0; b < D; b++) A[(1 + a) * U + 1 + b] = u[a] * S[b] - g1 * u[b] * S[a] + (a == b ? un : 0.0);
+            A[(1 + a) * U + U - 1] = g1 * S[a];
+        }
+        A[(U - 1) * U + 0] = (phi - H) * un;
+        for (int b = 0; b < D; b++) A[(U - 1) * U + 1 + b] = H * S[b] - g1 * u[b] * un;
+        A[(U - 1) * U + U - 1] = gamma * un;
+    }
+    static double spectralRadius(const double* q, const double* S, double gamma) {
+        const double r = 1.0 / q[0];
+        double un = 0.0, q2 = 0.0, s2 = 0.0;
+        for (int a = 0; a < D; a++) { un += q[a + 1] * r * S[a]; q2 += q[a + 1] * q[a + 1]; s2 += S[a] * S[a]; }
+        const double p = (q[U - 1] - 0.5 * q2 * r) * (gamma - 1.0);
+        return std::fabs(un) + std::sqrt(gamma * p * r) * std::sqrt(s2);
+    }
+
+    // R_i = sum_f sum_d Sout[d] F[:,d]: the gather of solve() without the update
+    void residualVector(const double* Q, double* R) {
+        if (cfg.order == 2) {
+            updateGradFlux(Q);
+            if (cfg.gradient == 1) lsqGradient(Q);
+            if (cfg.limiter != 0) limitGradient(Q);
+        }
+        if (cfg.flux == 0) updateFaceFlux<Roe<D>>(Q);
+        else updateFaceFlux<Ausm<D>>(Q);
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+        for (int c = 0; c < m.ncells; c++) {
+            double acc[U];
+            for (int k = 0; k < U; k++) acc[k] = 0.0;
+            for (int j = m.cf_ptr[c]; j < m.cf_ptr[c + 1]; j++) {
+                int f = m.cf_idx[j];
+                double sg = soutSign(c, f);
+                for (int d = 0; d < D; d++) {
+                    double s = sg * m.S[(size_t)f * D + d];
+                    const double* colp = &F[((size_t)f * D + d) * U];
+                    for (int k = 0; k < U; k++) acc[k] += s * colp[k];
+                }
+            }
+            for (int k = 0; k < U; k++) R[(size_t)c * U + k] = acc[k];
+        }
+    }
+
+    // CSR by row, columns ascending, blocks U x U row-major; b = -R.  rowptr [nc+1]; col / val may be
+    // null for a sizing call.  Returns the number of blocks.
+    int64_t implicitSystem(double dt, const double* Q, int32_t* rowptr, int32_t* col, double* val, double* b) {
+        const int nc = m.ncells;
+        rowptr[0] = 0;
+        for (int c = 0; c < nc; c++) {
+            int cnt = 1;
+            for (int j = m.cf_ptr[c]; j < m.cf_ptr[c + 1]; j++) {
+                const int f = m.cf_idx[j];
+                if (m.ftype[f] == 2 && m.c1[f] >= 0) cnt++;
+            }
+            rowptr[c + 1] = rowptr[c] + cnt;
+        }
+        if (!col || !val || !b) return rowptr[nc];
+        std::vector<double> R((size_t)nc * U);
+        residualVector(Q, R.data());
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+        for (int c = 0; c < nc; c++) {
+            int32_t* cols = col + rowptr[c];
+            double* blk = val + (size_t)rowptr[c] * U * U;
+            int n = 0;
+            cols[n++] = c;
+            for (int j = m.cf_ptr[c]; j < m.cf_ptr[c + 1]; j++) {
+                const int f = m.cf_idx[j];
+                if (m.ftype[f] == 2 && m.c1[f] >= 0) cols[n++] = (m.c0[f] == c) ? m.c1[f] : m.c0[f];
+            }
+            std::sort(cols, cols + n);
+            for (size_t i = 0; i < (size_t)n * U * U; i++) blk[i] = 0.0;
+            auto at = [&](int cc) { return blk + (size_t)(std::lower_bound(cols, cols + n, cc) - cols) * U * U; };
+            double* Dg = at(c);
+            for (int k = 0; k < U; k++) Dg[k * U + k] = m.vol[c] / dt;
+            const double* qi = Q + (size_t)c * U;
+            for (int j = m.cf_ptr[c]; j < m.cf_ptr[c + 1]; j++) {
+                const int f = m.cf_idx[j];
+                const double sg = soutSign(c, f);
+                double S[D], A[U * U];
+                for (int d = 0; d < D; d++) S[d] = sg * m.S[(size_t)f * D + d];
+                const bool interior = (m.ftype[f] == 2 && m.c1[f] >= 0);
+                const int nb = interior ? ((m.c0[f] == c) ? m.c1[f] : m.c0[f]) : -1;
+                double lam = spectralRadius(qi, S, cfg.gamma);
+                if (nb >= 0) lam = std::fmax(lam, spectralRadius(Q + (size_t)nb * U, S, cfg.gamma));
+                fluxJacobian(qi, S, cfg.gamma, A);
+                for (int i = 0; i < U * U; i++) Dg[i] += 0.5 * A[i];
+                for (int k = 0; k < U; k++) Dg[k * U + k] += 0.5 * lam;
+                if (nb >= 0) {
+                    double* O = at(nb);
+                    fluxJacobian(Q + (size_t)nb * U, S, cfg.gamma, A);
+                    for (int i = 0; i < U * U; i++) O[i] += 0.5 * A[i];
+                    for (int k = 0; k < U; k++) O[k * U + k] -= 0.5 * lam;
+                }
+            }
+            for (int k = 0; k < U; k++) b[(size_t)c * U + k] = -R[(size_t)c * U + k];
+        }
+        return rowptr[nc];
+    }
+
     // R/time/Time.cpp:69-76: signed denominator, NaN never wins, +inf can
     void residual(const double* Qold, const double* Qnew, double* r) const {
         // the reference loop is serial; max is exact under any association, so
@@ -837,6 +953,13 @@ int oracle_run_cfl(void* hv, double cfl, int nsteps, double* Q, double* dts) {
         std::memcpy(Q, Qn.data(), n * sizeof(double));
     }
     return 0;
+}
+
+// EXTENSION: block system of one implicit step (see Ctx::implicitSystem); col / val / b may be NULL to size
+int64_t oracle_implicit_system(void* hv, double dt, const double* Q, int32_t* rowptr, int32_t* col, double* val, double* b) {
+    Handle* h = (Handle*)hv;
+    return h->dim == 2 ? ((Ctx<2>*)h->p)->implicitSystem(dt, Q, rowptr, col, val, b)
+                       : ((Ctx<3>*)h->p)->implicitSystem(dt, Q, rowptr, col, val, b);
 }
 
 // stage probes (valid after oracle_solve): Qf nfaces*U, G ncells*U*D

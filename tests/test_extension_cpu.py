@@ -167,3 +167,66 @@ def test_config_is_validated_without_a_gpu():
             mstgpu.Context(f, order=2, **bad)
     with pytest.raises(mstgpu.MstGpuError, match="unknown config field"):
         mstgpu.make_config(3, limitr=1)
+
+
+# ---- implicit operator (oracle side) -----------------------------------------------------------------
+
+def test_implicit_system_blocks_follow_the_stated_operator():
+    """off-diagonal O_ij = 1/2 (A(Q_j,S) - lam I), and the Euler flux is homogeneous of degree one:
+    A(Q,S) Q = F(Q).S, so (2 O_ij + lam I) Q_j must be the physical flux of Q_j through S."""
+    f = box_flat(4, 3, 3)
+    D, U = 3, 5
+    Q = mesh_np.random_state(f, seed=6)
+    o = oracle.Oracle(f, order=2, flux="roe")
+    dt = 1e-3
+    rowptr, col, val, b = o.implicit_system(dt, Q)
+    assert rowptr[-1] == f["ncells"] + 2 * f["nint"] and val.shape == (rowptr[-1], U, U)
+    rows = np.repeat(np.arange(f["ncells"]), np.diff(rowptr))
+    assert np.all(np.diff(col)[np.diff(rows) == 0] > 0)
+    S_all = f["S"].reshape(-1, D) * f["dac"][:, None]  # outward from c0
+
+    def lam(q, S):
+        u = q[1:4] / q[0]
+        p = (q[4] - 0.5 * q[0] * (u @ u)) * 0.4
+        return abs(u @ S) + np.sqrt(1.4 * p / q[0]) * np.linalg.norm(S)
+
+    def flux(q, S):
+        u = q[1:4] / q[0]
+        p = (q[4] - 0.5 * q[0] * (u @ u)) * 0.4
+        un = u @ S
+        return np.concatenate([[q[0] * un], q[1:4] * un + p * S, [(q[4] + p) * un]])
+
+    checked = 0
+    for fa in range(0, f["nint"], 7):
+        i, j = f["c0"][fa], f["c1"][fa]
+        S = S_all[fa]
+        l = max(lam(Q[i], S), lam(Q[j], S))
+        k = rowptr[i] + np.searchsorted(col[rowptr[i]:rowptr[i + 1]], j)
+        assert col[k] == j
+        assert np.allclose((2 * val[k] + l * np.eye(U)) @ Q[j], flux(Q[j], S), rtol=1e-11, atol=1e-13)
+        k2 = rowptr[j] + np.searchsorted(col[rowptr[j]:rowptr[j + 1]], i)
+        assert np.allclose((2 * val[k2] + l * np.eye(U)) @ Q[i], flux(Q[i], -S), rtol=1e-11, atol=1e-13)
+        checked += 1
+    assert checked > 20
+    # b = -R: the explicit step is Q - dt/V R
+    Qe = o.solve(dt, Q)
+    assert np.allclose(Q + dt / f["vol"][:, None] * b, Qe, rtol=1e-12, atol=1e-14)
+
+
+def test_implicit_step_limits():
+    f = load_flat("2d-stair-un-5-tri")
+    Q0 = mesh_np.random_state(f, seed=8)
+    o = oracle.Oracle(f, order=2, flux="roe", limiter="bj")
+    dt = 1e-10
+    Qi, Qe = o.step_implicit(dt, Q0, 5), o.solve(dt, Q0)
+    assert np.abs(Qi - Qe).max() <= 1e-4 * np.abs(Qe - Q0).max()
+    # a gas at rest in a closed box stays exactly at rest
+    fb = box_flat(3, 3, 3)
+    Qr = np.tile(np.array([1.0, 0, 0, 0, 2.5]), (fb["ncells"], 1))
+    ob = oracle.Oracle(fb, order=2, flux="roe")
+    assert np.abs(ob.step_implicit(1e-2, Qr, 5) - Qr).max() < 1e-13
+    # a sweep order changes the 5-sweep iterate, not the converged solution
+    perm = np.random.default_rng(0).permutation(f["ncells"])
+    a = o.step_implicit(1e-3, Q0, 60)
+    bq = o.step_implicit(1e-3, Q0, 60, sweep_order=perm)
+    assert np.abs(a - bq).max() < 1e-9 * np.abs(a).max()
