@@ -88,6 +88,15 @@ def build_workload(args):
         u = 3.0 * np.sqrt(1.4)
         Q = np.tile(np.array([1.0, u, 0.0, 1.0 / 0.4 + 0.5 * u * u]), (f["ncells"], 1))
         desc = f"forward-facing step h=1/{args.n}, triangles"
+    elif args.workload == "sphere":
+        # BASELINE config 3: flow over a sphere, cubed-sphere shell, 24 tets per hex; Mach 0.5 in +x
+        n = args.n if args.n != 203 else 42
+        m = max(2, round(n * 40 / 42))
+        f = host.flatten_raw(host.sphere_shell_raw(n, m))
+        u = 0.5 * np.sqrt(1.4)
+        Q = np.tile(np.array([1.0, u, 0.0, 0.0, 1.0 / 0.4 + 0.5 * u * u]), (f["ncells"], 1))
+        desc = (f"cubed-sphere shell r in [0.5, 10], 6 x {n}^2 x {m} hexes x 24 tets, sphere = wall, outer = inlet / outlet, "
+                "Mach 0.5 free stream")
     else:
         raise SystemExit("unknown workload")
     log(f"[bench] mesh: {f['ncells']} cells, {f['nfaces']} faces in {time.time() - t:.1f}s")
@@ -146,6 +155,17 @@ class ClockSampler:
                     samples=len(sm), reasons=sorted(reasons))
 
 
+def run_params(args, Q0):
+    """(dt, inlet state) of a workload: the inlet of the step / sphere cases is their free stream"""
+    dt = {"box": DT, "step": 2e-5, "sphere": 2e-4}.get(args.workload, DT)
+    inlet = (list(Q0[0]) + [0.0] * 5)[:5] if args.workload in ("step", "sphere") else None
+    return dt, inlet
+
+
+def cpu_sample_size(args):
+    return {"box": args.cpu_n, "step": max(args.cpu_n, 200), "sphere": min(args.cpu_n, 20)}.get(args.workload, args.cpu_n)
+
+
 def scheme_kwargs(args):
     """gradient / limiter choice (extension; defaults = the reference scheme)"""
     return dict(gradient=args.gradient, limiter=args.limiter, limiter_k=args.limiter_k)
@@ -157,10 +177,11 @@ def cpu_baseline(args, nsteps=None, n=None, budget_s=12.0):
     seconds of CPU work (the step count is sized from one warm-up step)."""
     from oracle import oracle
     from mstgpu import host
-    n = n or args.cpu_n
+    n = n or cpu_sample_size(args)
     a = argparse.Namespace(**vars(args)); a.n = n
     f, Q, _ = build_workload(a)
-    o = oracle.Oracle(f, order=args.order, flux=args.flux, nthreads=0, viscous=args.viscous, **scheme_kwargs(args))
+    DT, inlet = run_params(args, Q)
+    o = oracle.Oracle(f, order=args.order, flux=args.flux, nthreads=0, viscous=args.viscous, inletQ=inlet, **scheme_kwargs(args))
     if getattr(args, "implicit", 0):
         # implicit step: OpenMP assembly + the reference's sequential block LU-SGS (lusgs_oracle.cpp)
         def run(k, Q=Q):
@@ -197,16 +218,22 @@ def run_reference(args, rank):
         return
     f_desc = None
     from oracle import oracle
-    a = argparse.Namespace(**vars(args)); a.n = args.cpu_n
+    a = argparse.Namespace(**vars(args)); a.n = cpu_sample_size(args)
     f, Q, desc = build_workload(a)
-    o = oracle.Oracle(f, order=args.order, flux=args.flux, nthreads=0, viscous=args.viscous, **scheme_kwargs(args))
-    for _ in range(args.warmup):
-        o.run(DT, 1, Q)
+    DT, inlet = run_params(args, Q)
+    o = oracle.Oracle(f, order=args.order, flux=args.flux, nthreads=0, viscous=args.viscous, inletQ=inlet, **scheme_kwargs(args))
+    if args.implicit:
+        def adv(k, Q=Q):
+            for _ in range(k):
+                Q = o.step_implicit(args.implicit_dt, Q, LUSGS_ITERS)
+    else:
+        adv = lambda k: o.run(DT, k, Q)
+    adv(min(args.warmup, 3))
     t = time.perf_counter()
-    o.run(DT, args.steps, Q)
+    adv(args.steps)
     el = time.perf_counter() - t
     val = f["ncells"] * args.steps / el
-    sample = (f"{args.workload} n={args.cpu_n}: {f['ncells']} cells per step "
+    sample = (f"{args.workload} n={a.n}: {f['ncells']} cells per step "
               f"(bounded sample of the n={args.n} workload), {o.nthreads} threads of {os.cpu_count()} cpus")
     out = dict(impl="reference", metric="cell_updates_per_sec", value=val, unit="cell-updates/s",
                n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * el / args.steps,
@@ -364,7 +391,7 @@ def run_ours(args, rank, world):
 
     f, Q0, desc = build_workload(args)
     nc_total, U, D = f["ncells"], f["dim"] + 2, f["dim"]
-    inlet = list(Q0[0]) + [0.0] * (5 - U) if args.workload == "step" else None  # Mach-3 inlet state
+    dt_run, inlet = run_params(args, Q0)  # the inlet of the step / sphere cases is their free stream
     t = time.time()
     if world > 1:
         # one partition per GPU (equal ranges of the Hilbert curve), 2 ghost layers
@@ -389,7 +416,6 @@ def run_ours(args, rank, world):
         nc = nc_total
     log(f"[bench] context built in {time.time() - t:.1f}s, {ctx.device_bytes / 2**30:.2f} GiB on device")
     ctx.set_state(Q0)
-    dt_run = DT if args.workload == "box" else 2e-5
     if args.implicit:
         # BASELINE config 5: every step = explicit residual + block assembly + 5 LU-SGS sweeps (colour-ordered)
         if world > 1:
@@ -523,7 +549,7 @@ def run_ours(args, rank, world):
                            parallelism=f"{world} partition(s), Hilbert ranges, 2 ghost layers, NCCL send/recv + allreduce(max)",
                            order=args.order, viscous=args.viscous, gradient=args.gradient, limiter=args.limiter, cfl=args.cfl,
                            implicit=None if not args.implicit else dict(dt=args.implicit_dt, lusgs_iterations=LUSGS_ITERS, sweeps="colour-ordered"),
-                           graph_ms_per_step=None if graph_ms is None else graph_ms / args.steps, dt=DT if args.workload == "box" else 2e-5, kernel=args.kernel, tile_cells=args.tile_cells, renumber=args.renumber,
+                           graph_ms_per_step=None if graph_ms is None else graph_ms / args.steps, dt=dt_run, kernel=args.kernel, tile_cells=args.tile_cells, renumber=args.renumber,
                            block_threads=args.block_threads, l2="inputs larger than L2 (state + tables >> 126 MB)"
                            if nc_total * U * 8 > 2 ** 28 else "inputs smaller than L2: flush not applied"),
                clocks=clk, e2e=e2e, gpu_launches=launches, roofline=roof, cpu_baseline=cpu,
@@ -545,7 +571,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="box", choices=["box", "step", "lusgs"])
+    ap.add_argument("--workload", default="box", choices=["box", "step", "sphere", "lusgs"])
     ap.add_argument("--size", "--n", dest="n", type=int, default=203, help="hexes per side (box) or 1/h (step)")
     ap.add_argument("--cpu-n", type=int, default=96, help="size of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true")

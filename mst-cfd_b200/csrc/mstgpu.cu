@@ -565,8 +565,9 @@ __device__ __forceinline__ double spectral_radius(const double (&q)[D + 2], cons
     return fabs(un) + sqrt(gamma * p * r) * sqrt(s2);
 }
 
-// one thread per cell: diagonal block and the off-diagonal blocks of its row, written at their CSR
-// positions (dpos / pos, built once by mstgpu_implicit_setup)
+// One thread per cell computes the diagonal block and the off-diagonal blocks of its row; each block is
+// staged in shared memory and written by the whole CTA, so the 8*U*U-byte blocks leave as contiguous runs
+// (a thread writing its own 200 bytes would touch 7 sectors with 25 separate stores).
 template <int D>
 __global__ void __launch_bounds__(128) k_assemble_implicit(int n, int nc, int nslot, double gamma, double dt,
                                                            const double* __restrict__ Q,
@@ -578,52 +579,67 @@ __global__ void __launch_bounds__(128) k_assemble_implicit(int n, int nc, int ns
                                                            const int32_t* __restrict__ dpos,
                                                            const int32_t* __restrict__ pos,
                                                            double* __restrict__ val) {
-    constexpr int U = D + 2, UU = U * U;
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n) return;
+    constexpr int U = D + 2, UU = U * U, NT = 128;
+    __shared__ double blk[NT][UU + 1];  // + 1: the rows of different threads start in different banks
+    __shared__ int dst[NT];
+    const int tid = threadIdx.x;
+    const int c = blockIdx.x * NT + tid;
+    const bool on = c < n;
+    auto flush = [&]() {
+        __syncthreads();
+        for (int i = tid; i < NT * UU; i += NT) {
+            const int t = i / UU, e = i - t * UU;
+            if (dst[t] >= 0) val[(size_t)dst[t] * UU + e] = blk[t][e];
+        }
+        __syncthreads();
+    };
     double qi[U], Dg[UU], A[UU];
 #pragma unroll
-    for (int k = 0; k < U; k++) qi[k] = Q[(size_t)c * U + k];
+    for (int k = 0; k < U; k++) qi[k] = on ? Q[(size_t)c * U + k] : 1.0;
 #pragma unroll
     for (int i = 0; i < UU; i++) Dg[i] = 0.0;
-    const double vdt = vol[c] / dt;
+    const double vdt = on ? vol[c] / dt : 0.0;
 #pragma unroll
     for (int k = 0; k < U; k++) Dg[k * U + k] = vdt;
     for (int j = 0; j < nslot; j++) {
-        const int v = cf[(size_t)j * nc + c];
-        if (v < 0) continue;
-        const int f = v >> 1;
-        const double sg = (v & 1) ? -1.0 : 1.0;
-        const int nb = (v & 1) ? fc0[f] : fc1[f];
-        double S[D];
+        const int v = on ? cf[(size_t)j * nc + c] : -1;
+        int nb = -1;
+        if (v >= 0) {
+            const int f = v >> 1;
+            const double sg = (v & 1) ? -1.0 : 1.0;
+            nb = (v & 1) ? fc0[f] : fc1[f];
+            double S[D];
 #pragma unroll
-        for (int d = 0; d < D; d++) S[d] = sg * Sd[(size_t)f * D + d];
-        double lam = spectral_radius<D>(qi, S, gamma);
-        double qj[U];
-        if (nb >= 0) {
+            for (int d = 0; d < D; d++) S[d] = sg * Sd[(size_t)f * D + d];
+            double lam = spectral_radius<D>(qi, S, gamma);
+            double qj[U];
+            if (nb >= 0) {
 #pragma unroll
-            for (int k = 0; k < U; k++) qj[k] = Q[(size_t)nb * U + k];
-            lam = fmax(lam, spectral_radius<D>(qj, S, gamma));
-        }
-        flux_jacobian<D>(qi, S, gamma, A);
+                for (int k = 0; k < U; k++) qj[k] = Q[(size_t)nb * U + k];
+                lam = fmax(lam, spectral_radius<D>(qj, S, gamma));
+            }
+            flux_jacobian<D>(qi, S, gamma, A);
 #pragma unroll
-        for (int i = 0; i < UU; i++) Dg[i] += 0.5 * A[i];
+            for (int i = 0; i < UU; i++) Dg[i] += 0.5 * A[i];
 #pragma unroll
-        for (int k = 0; k < U; k++) Dg[k * U + k] += 0.5 * lam;
-        if (nb >= 0) {
-            flux_jacobian<D>(qj, S, gamma, A);
-            double* O = val + (size_t)pos[(size_t)j * nc + c] * UU;
+            for (int k = 0; k < U; k++) Dg[k * U + k] += 0.5 * lam;
+            if (nb >= 0) {
+                flux_jacobian<D>(qj, S, gamma, A);
 #pragma unroll
-            for (int i = 0; i < UU; i++) {
-                double o = 0.5 * A[i];
-                if (i / U == i % U) o -= 0.5 * lam;
-                O[i] = o;
+                for (int i = 0; i < UU; i++) {
+                    double o = 0.5 * A[i];
+                    if (i / U == i % U) o -= 0.5 * lam;
+                    blk[tid][i] = o;
+                }
             }
         }
+        dst[tid] = nb >= 0 ? pos[(size_t)j * nc + c] : -1;
+        flush();
     }
-    double* Dd = val + (size_t)dpos[c] * UU;
 #pragma unroll
-    for (int i = 0; i < UU; i++) Dd[i] = Dg[i];
+    for (int i = 0; i < UU; i++) blk[tid][i] = Dg[i];
+    dst[tid] = on ? dpos[c] : -1;
+    flush();
 }
 
 // Q_new = Q_old + dQ, with the residual of Time.cpp:69-76 and the NaN flag
@@ -647,13 +663,21 @@ __global__ void __launch_bounds__(256) k_add_increment(int n, const double* __re
             bad |= (qn != qn);
         }
     }
+    __shared__ double sm[U][8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < U; k++) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) r[k] = fmax(r[k], __shfl_xor_sync(0xffffffffu, r[k], o));
-        if ((threadIdx.x & 31) == 0 && r[k] > 0.0) atomicMax(&resid[k], (unsigned long long)__double_as_longlong(r[k]));
+        if (lane == 0) sm[k][wid] = r[k];
     }
-    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(nanflag, 1);
+    const bool anybad = __syncthreads_or(bad);
+    if (threadIdx.x < U) {
+        double m = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) m = fmax(m, sm[threadIdx.x][w]);
+        if (m > 0.0) atomicMax(&resid[threadIdx.x], (unsigned long long)__double_as_longlong(m));
+    }
+    if (anybad && threadIdx.x == 0) atomicOr(nanflag, 1);
 }
 
 __device__ __forceinline__ double warp_max(double x) {

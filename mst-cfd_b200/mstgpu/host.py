@@ -121,3 +121,96 @@ def raw_zones_from_ftype(raw: dict) -> dict:
     out["zones"] = [dict(id=k, start=int(s), end=int(e), type=int(ft[s]), name="")
                     for k, (s, e) in enumerate(zip(starts, ends))]
     return out
+
+
+def tets_to_raw(nodes: np.ndarray, tets: np.ndarray, boundary_type) -> dict:
+    """Raw mesh tables of a conforming tetrahedral mesh given as (nodes, cell -> 4 nodes): faces are
+    found by matching sorted node triples (twice = interior, once = boundary).  boundary_type(fc) maps
+    the boundary face centres [nb,3] to zone types; boundary faces are grouped by type, interior first."""
+    nc = tets.shape[0]
+    combos = np.array([[0, 1, 2], [0, 1, 3], [0, 2, 3], [1, 2, 3]])
+    tri = np.sort(tets[:, combos].reshape(-1, 3), axis=1)           # [4 nc, 3]
+    cell = np.repeat(np.arange(nc, dtype=np.int64), 4)
+    nn = int(nodes.shape[0])
+    key = (tri[:, 0].astype(np.int64) * nn + tri[:, 1]) * nn + tri[:, 2]
+    order = np.argsort(key, kind="stable")
+    key, tri, cell = key[order], tri[order], cell[order]
+    first = np.ones(key.size, bool); first[1:] = key[1:] != key[:-1]
+    idx = np.flatnonzero(first)
+    cnt = np.diff(np.append(idx, key.size))
+    if cnt.max() > 2:
+        raise ValueError("non-manifold face")
+    inter = idx[cnt == 2]
+    bnd = idx[cnt == 1]
+    fc_b = nodes[tri[bnd]].mean(axis=1)
+    bt = np.asarray(boundary_type(fc_b), dtype=np.int32)
+    bo = np.argsort(bt, kind="stable")
+    bnd, bt = bnd[bo], bt[bo]
+    face_nodes = np.concatenate([tri[inter], tri[bnd]]).astype(np.int32)
+    c0 = np.concatenate([np.minimum(cell[inter], cell[inter + 1]), cell[bnd]]).astype(np.int32)
+    c1 = np.concatenate([np.maximum(cell[inter], cell[inter + 1]), np.full(bnd.size, -1)]).astype(np.int32)
+    ftype = np.concatenate([np.full(inter.size, 2, np.int32), bt])
+    return dict(dim=3, ncells=nc, nodes=np.ascontiguousarray(nodes, dtype=np.float64), face_nodes=face_nodes,
+                c0=c0, c1=c1, ftype=ftype, nint=int(inter.size))
+
+
+def sphere_shell_raw(n=42, m=40, r0=0.5, r1=10.0) -> dict:
+    """BASELINE config 3: cubed-sphere shell r in [r0, r1] around a sphere, 6 patches x n^2 x m
+    hexahedra (geometric radial stretching), each split into 24 tetrahedra about its centroid and its
+    face centres (always conforming): n = 42, m = 40 -> 10 160 640 tets.  Sphere = wall (3), outer
+    boundary = inlet (10) upstream (x < 0) / outlet (5) downstream."""
+    # surface lattice of the cube [0, n]^3: nodes with a coordinate on 0 or n, numbered by coordinates
+    g = np.arange(n + 1)
+    I, J, K = np.meshgrid(g, g, g, indexing="ij")
+    on = (I == 0) | (I == n) | (J == 0) | (J == n) | (K == 0) | (K == n)
+    sid = -np.ones((n + 1,) * 3, dtype=np.int64)
+    sid[on] = np.arange(int(on.sum()))
+    ns = int(on.sum())
+    # equi-angular direction of every surface node
+    t = np.tan(np.pi / 4 * (2.0 * np.stack([I[on], J[on], K[on]], axis=1) / n - 1.0))
+    dirs = t / np.linalg.norm(t, axis=1, keepdims=True)
+    radii = r0 * (r1 / r0) ** (np.arange(m + 1) / m)
+    shell_nodes = (radii[:, None, None] * dirs[None]).reshape(-1, 3)   # node (layer l, surface s) = l * ns + s
+    # surface quads of the 6 cube faces
+    quads = []
+    a, b = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    a, b = a.ravel(), b.ravel()
+    for ax in range(3):
+        for side in (0, n):
+            def nid(da, db):
+                c = [None, None, None]
+                c[ax] = np.full(a.size, side)
+                c[(ax + 1) % 3] = a + da
+                c[(ax + 2) % 3] = b + db
+                return sid[c[0], c[1], c[2]]
+            quads.append(np.stack([nid(0, 0), nid(1, 0), nid(1, 1), nid(0, 1)], axis=1))
+    quads = np.concatenate(quads)                                        # [6 n^2, 4]
+    nq = quads.shape[0]
+    lay = np.arange(m)
+    lo = (lay[:, None, None] * ns + quads[None]).reshape(-1, 4)          # inner quad of each hex
+    hi = lo + ns
+    nh = lo.shape[0]
+    hexes = np.concatenate([lo, hi], axis=1)                             # 0-3 inner, 4-7 outer
+    # hex faces as node quads (local ids), each split about its centre
+    hf = np.array([[0, 1, 2, 3], [4, 5, 6, 7], [0, 1, 5, 4], [1, 2, 6, 5], [2, 3, 7, 6], [3, 0, 4, 7]])
+    fq = hexes[:, hf]                                                    # [nh, 6, 4] global node ids
+    # face-centre nodes: unique per geometric face (shared between the two hexes of an interior quad)
+    fkey = np.sort(fq.reshape(-1, 4), axis=1)
+    nn0 = shell_nodes.shape[0]
+    uniq, inv = np.unique(fkey, axis=0, return_inverse=True)
+    fcen = shell_nodes[uniq].mean(axis=1)
+    fc_id = nn0 + inv.reshape(nh, 6)
+    hc_id = nn0 + uniq.shape[0] + np.arange(nh)
+    hcen = shell_nodes[hexes].mean(axis=1)
+    nodes = np.concatenate([shell_nodes, fcen, hcen])
+    # 24 tets: (corner e, corner e+1, face centre, hex centre) for every edge of every face
+    e0 = fq
+    e1 = np.roll(fq, -1, axis=2)
+    tets = np.stack([e0, e1, np.broadcast_to(fc_id[:, :, None], e0.shape),
+                     np.broadcast_to(hc_id[:, None, None], e0.shape)], axis=3).reshape(-1, 4)
+
+    def btype(fc):
+        r = np.linalg.norm(fc, axis=1)
+        return np.where(r < np.sqrt(r0 * r1), 3, np.where(fc[:, 0] < 0.0, 10, 5))
+
+    return tets_to_raw(nodes, tets, btype)

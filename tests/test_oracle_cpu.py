@@ -307,3 +307,39 @@ def test_viscous_dissipates_a_shear_layer():
     band = (np.abs(y - 0.6) < 0.1) & (f["cc"][:, 0] < 0.5)
     grad = lambda q: np.abs(q[band, 1] / q[band, 0]).mean()
     assert np.isfinite(a).all() and grad(a) != grad(b)
+
+
+def test_config3_sphere_shell_mesh():
+    """BASELINE config 3: cubed-sphere shell, 24 conforming tets per hex; 42 x 42 x 40 per patch gives
+    10 160 640 cells (checked by formula; a small instance is generated and checked geometrically)."""
+    from mstgpu import host
+    assert 6 * 42 * 42 * 40 * 24 == 10_160_640
+    n, m = 5, 4
+    raw = host.sphere_shell_raw(n, m)
+    assert raw["ncells"] == 6 * n * n * m * 24
+    nb = raw["c0"].size - raw["nint"]
+    assert nb == 2 * 6 * n * n * 4                       # inner + outer surface, 4 triangles per quad
+    assert 4 * raw["ncells"] == 2 * raw["nint"] + nb     # every tet has 4 faces
+    f = host.flatten_raw(raw)
+    assert (f["vol"] > 0).all()
+    S = f["S"].reshape(-1, 3) * f["dac"][:, None]
+    acc = np.zeros((f["ncells"], 3))
+    np.add.at(acc, f["c0"], S)
+    it = f["c1"] >= 0
+    np.add.at(acc, f["c1"][it], -S[it])
+    assert np.abs(acc).max() < 1e-12                     # closed cells
+    ft = f["ftype"][raw["nint"]:]
+    fc = f["fc"].reshape(-1, 3)[raw["nint"]:]
+    r = np.linalg.norm(fc, axis=1)
+    assert set(np.unique(ft)) == {3, 5, 10}
+    assert (r[ft == 3] < 0.6).all() and (r[ft != 3] > 9.0).all()
+    assert (fc[ft == 10, 0] < 0).all() and (fc[ft == 5, 0] >= 0).all()
+    # shell volume tends to 4/3 pi (10^3 - 0.5^3) from below
+    assert 0.9 < f["vol"].sum() / (4 / 3 * np.pi * (1000 - 0.125)) < 1.0
+    # free stream is preserved away from the walls by the oracle (closed cells, inviscid)
+    u = 0.5 * np.sqrt(1.4)
+    q = np.array([1.0, u, 0.0, 0.0, 2.5 + 0.5 * u * u])
+    Q0 = np.tile(q, (f["ncells"], 1))
+    Q1 = oracle.Oracle(f, order=2, flux="roe", inletQ=q).solve(1e-4, Q0)
+    wallcells = np.zeros(f["ncells"], bool); wallcells[f["c0"][raw["nint"]:][ft == 3]] = True
+    assert np.abs(Q1[~wallcells] - Q0[~wallcells]).max() < 1e-12

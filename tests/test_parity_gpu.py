@@ -344,3 +344,30 @@ def test_hexahedra_seven_point_stencil(order, kernel):
     Q1 = o.run(1e-4, 3, Q0)
     g.step(1e-4, 3)
     assert rel_linf(g.get_state(), Q1) <= 1e-11
+
+
+@pytest.mark.parametrize("viscous,kernel", [(1, "split"), (0, "tiles"), (0, "split")])
+def test_config3_sphere_shell_roe_viscous(viscous, kernel):
+    """BASELINE config 3 in small: flow over a sphere on the cubed-sphere shell (24 tets per hex), Roe,
+    second order, laminar viscous term (extension), wall / inlet / outlet zones; 1 and 20 steps."""
+    import mstgpu
+    from mstgpu import host
+    f = host.flatten_raw(host.sphere_shell_raw(6, 5))
+    u = 0.5 * np.sqrt(1.4)
+    q = np.array([1.0, u, 0.0, 0.0, 2.5 + 0.5 * u * u])
+    rng = np.random.default_rng(7)
+    Q0 = np.tile(q, (f["ncells"], 1)) * (1.0 + 0.05 * rng.standard_normal((f["ncells"], 5)))
+    kw = dict(order=2, flux="roe", viscous=viscous, inletQ=q, mu=1e-2, kappa=10.0)  # viscous term large enough to matter
+    o = oracle.Oracle(f, **kw)
+    dt = o.cfl_dt(0.2, Q0)
+    ctx = mstgpu.Context(f, kernel=kernel, **kw)
+    ctx.set_state(Q0)
+    ctx.step(dt, 1)
+    assert rel_linf(ctx.get_state(), o.solve(dt, Q0)) <= 1e-12
+    ctx.step(dt, 19)
+    assert rel_linf(ctx.get_state(), o.run(dt, 20, Q0)) <= 1e-10
+    if viscous:
+        # the viscous term is not a no-op in this test
+        oi = oracle.Oracle(f, **dict(kw, viscous=0))
+        assert rel_linf(o.solve(dt, Q0), oi.solve(dt, Q0)) > 1e-6
+    ctx.close()
