@@ -244,6 +244,15 @@ int mstgpu_lusgs_create(mstgpu_lusgs** out, int32_t n, int32_t block, const int3
  * the mesh numbering is kept; only the dependency levels and the order of a row's terms change). */
 int mstgpu_lusgs_create_ordered(mstgpu_lusgs** out, int32_t n, int32_t block, const int32_t* rowptr,
                                 const int32_t* col, const int32_t* sweep_new2old, int32_t device);
+/* One partition of a distributed system: n rows this rank owns, columns in
+ * [n, ncols) are rows other ranks own ("ghost columns").  Their couplings are LAGGED: every
+ * iteration first forms b - sum_ghost A[r,c] x[c] with the x the caller holds for them (x has ncols
+ * rows; the caller refreshes the ghost rows between iterations, e.g. one iteration per call) -- block
+ * Jacobi across partitions, the reference's sweeps inside each. */
+int mstgpu_lusgs_create_partitioned(mstgpu_lusgs** out, int32_t n, int32_t ncols, int32_t block, const int32_t* rowptr,
+                                    const int32_t* col, const int32_t* sweep_new2old, int32_t device);
+int mstgpu_lusgs_color_order_partitioned(int32_t n, int32_t ncols, const int32_t* rowptr, const int32_t* col,
+                                         int32_t* perm_new2old, int32_t* ncolors);
 void mstgpu_lusgs_destroy(mstgpu_lusgs* h);
 /* x: in = start vector (the constructors' pOldX), out = solution.  max_iter = LU_INTERVAL
  * (CONST.h:58).  early_exit != 0 applies the scalar version's stop test

@@ -29,10 +29,12 @@ thread_local std::string g_lusgs_error;
 struct mstgpu_lusgs {
     int n = 0, B = 1, device = 0;
     cudaStream_t stream = nullptr;
-    int nnz = 0, nL = 0, nU = 0;
+    int nnz = 0, nL = 0, nU = 0, nG = 0, ncols = 0;
     // strictly-lower / strictly-upper CSR by row; pos = index of the entry in the caller's val array
     int *Lptr = nullptr, *Lcol = nullptr, *Lpos = nullptr, *Uptr = nullptr, *Ucol = nullptr, *Upos = nullptr;
     int *Dptr = nullptr, *Dpos = nullptr;  // diagonal entries per row (summed)
+    int *Gptr = nullptr, *Gcol = nullptr, *Gpos = nullptr;  // entries in ghost columns (>= n): lagged, moved to the right-hand side
+    double* beff = nullptr;
     std::vector<int> fptr, bptr;           // level pointers (host)
     int *frows = nullptr, *brows = nullptr;
     double *val = nullptr, *D = nullptr, *Dinv = nullptr, *LD = nullptr, *UD = nullptr;
@@ -182,6 +184,20 @@ __global__ void k_ux(int n, const int* Uptr, const int* Ucol, const int* Upos, c
     if (g.on) ux[(size_t)r * B + i] = t;
 }
 
+// beff[r] = b[r] - sum_{ghost columns c} A[r,c] x[c]: couplings to rows another partition owns, with the
+// x the caller supplied for them (the previous iteration's values: block Jacobi across partitions)
+template <int B>
+__global__ void k_ghost_rhs(int n, const int* Gptr, const int* Gcol, const int* Gpos, const double* val, const double* b,
+                            const double* x, double* beff) {
+    const Grp<B> g(n);
+    if (!g.on) return;
+    const int r = g.row, i = g.i;
+    double acc = b[(size_t)r * B + i];
+    for (int k = Gptr[r]; k < Gptr[r + 1]; k++)
+        acc -= row_dot<B>(val + (size_t)Gpos[k] * B * B + i * B, x + (size_t)Gcol[k] * B);
+    beff[(size_t)r * B + i] = acc;
+}
+
 // rhs[r] = b[r] + sum_{c before r} L[r,c] ux[c]   (SparseSolverNUM.cpp:167-175)
 template <int B>
 __global__ void k_rhs(int n, const int* Lptr, const int* Lcol, const int* Lpos, const double* val, const double* b,
@@ -253,19 +269,27 @@ int up(mstgpu_lusgs* h, T** d, const std::vector<T>& v) {
 // the sweeps on DEVICE arrays (val: caller's CSR order; x: start vector in, solution out)
 template <int B>
 int solve_core(mstgpu_lusgs* h, const double* val, const double* b, double* x, int max_iter, int early_exit,
-               double* res_hist, int32_t* iters_done) {
+               double* res_hist, int32_t* iters_done, bool setup = true) {
     const int n = h->n, T = 128;
     cudaStream_t s = h->stream;
     using G = Grp<B>;
-    k_diag<B><<<(n + T - 1) / T, T, 0, s>>>(n, h->Dptr, h->Dpos, val, h->D, h->Dinv);
-    if (h->nL) k_scale<B><<<(unsigned)(((size_t)h->nL * B + T - 1) / T), T, 0, s>>>((size_t)h->nL, h->Lcol, h->Lpos, val, h->D, h->Dinv, h->LD);
-    if (h->nU) k_scale<B><<<(unsigned)(((size_t)h->nU * B + T - 1) / T), T, 0, s>>>((size_t)h->nU, h->Ucol, h->Upos, val, h->D, h->Dinv, h->UD);
-    h->launches += 3;
+    if (setup) {  // D, D^-1 and the scaled copies depend on the matrix only
+        k_diag<B><<<(n + T - 1) / T, T, 0, s>>>(n, h->Dptr, h->Dpos, val, h->D, h->Dinv);
+        if (h->nL) k_scale<B><<<(unsigned)(((size_t)h->nL * B + T - 1) / T), T, 0, s>>>((size_t)h->nL, h->Lcol, h->Lpos, val, h->D, h->Dinv, h->LD);
+        if (h->nU) k_scale<B><<<(unsigned)(((size_t)h->nU * B + T - 1) / T), T, 0, s>>>((size_t)h->nU, h->Ucol, h->Upos, val, h->D, h->Dinv, h->UD);
+        h->launches += 3;
+    }
     int it = 0;
     for (; it < max_iter; it++) {
         LCK(cudaMemsetAsync(h->res, 0, 8, s));
+        const double* bb = b;
+        if (h->nG) {
+            k_ghost_rhs<B><<<G::grid(n, T), T, 0, s>>>(n, h->Gptr, h->Gcol, h->Gpos, val, b, x, h->beff);
+            h->launches++;
+            bb = h->beff;
+        }
         k_ux<B><<<G::grid(n, T), T, 0, s>>>(n, h->Uptr, h->Ucol, h->Upos, val, h->D, h->Dinv, x, h->ux);
-        k_rhs<B><<<G::grid(n, T), T, 0, s>>>(n, h->Lptr, h->Lcol, h->Lpos, val, b, h->ux, h->rhs);
+        k_rhs<B><<<G::grid(n, T), T, 0, s>>>(n, h->Lptr, h->Lcol, h->Lpos, val, bb, h->ux, h->rhs);
         for (size_t l = 1; l + 1 < h->fptr.size(); l++) {  // level 0 has no dependencies: nothing to subtract
             const int cnt = h->fptr[l + 1] - h->fptr[l];
             k_sweep_level<B, true><<<G::grid(cnt, T), T, 0, s>>>(cnt, h->frows + h->fptr[l], h->Lptr, h->Lcol, h->LD, h->rhs);
@@ -301,11 +325,11 @@ int solve_impl(mstgpu_lusgs* h, const double* val, const double* b, double* x, i
     if (!h->val) {
         LCK(cudaMalloc((void**)&h->val, std::max<size_t>(1, h->nnz) * BB * 8));
         LCK(cudaMalloc((void**)&h->b, (size_t)n * B * 8));
-        LCK(cudaMalloc((void**)&h->x, (size_t)n * B * 8));
+        LCK(cudaMalloc((void**)&h->x, (size_t)h->ncols * B * 8));
     }
     LCK(cudaMemcpyAsync(h->val, val, (size_t)h->nnz * BB * 8, cudaMemcpyHostToDevice, s));
     LCK(cudaMemcpyAsync(h->b, b, (size_t)n * B * 8, cudaMemcpyHostToDevice, s));
-    LCK(cudaMemcpyAsync(h->x, x, (size_t)n * B * 8, cudaMemcpyHostToDevice, s));
+    LCK(cudaMemcpyAsync(h->x, x, (size_t)h->ncols * B * 8, cudaMemcpyHostToDevice, s));  // ghost rows: the caller's values
     int rc = solve_core<B>(h, h->val, h->b, h->x, max_iter, early_exit, res_hist, iters_done);
     if (rc) return rc;
     LCK(cudaMemcpyAsync(x, h->x, (size_t)n * B * 8, cudaMemcpyDeviceToHost, s));
@@ -317,14 +341,14 @@ int solve_impl(mstgpu_lusgs* h, const double* val, const double* b, double* x, i
 
 // in-library entry for the implicit step of mstgpu.cu: the sweeps on the caller's stream, no sync
 namespace mst {
-int lusgs_solve_async(mstgpu_lusgs* h, cudaStream_t st, const double* val, const double* b, double* x, int iters) {
+int lusgs_solve_async(mstgpu_lusgs* h, cudaStream_t st, const double* val, const double* b, double* x, int iters, bool setup) {
     cudaStream_t own = h->stream;
     h->stream = st;
     int rc;
     switch (h->B) {
-        case 1: rc = solve_core<1>(h, val, b, x, iters, 0, nullptr, nullptr); break;
-        case 4: rc = solve_core<4>(h, val, b, x, iters, 0, nullptr, nullptr); break;
-        default: rc = solve_core<5>(h, val, b, x, iters, 0, nullptr, nullptr); break;
+        case 1: rc = solve_core<1>(h, val, b, x, iters, 0, nullptr, nullptr, setup); break;
+        case 4: rc = solve_core<4>(h, val, b, x, iters, 0, nullptr, nullptr, setup); break;
+        default: rc = solve_core<5>(h, val, b, x, iters, 0, nullptr, nullptr, setup); break;
     }
     h->stream = own;
     return rc;
@@ -336,14 +360,15 @@ extern "C" {
 const char* mstgpu_lusgs_last_error(void) { return g_lusgs_error.c_str(); }
 
 // greedy first-fit colouring of the symmetrised pattern, rows visited in storage order; O(nnz), CSR only
-static int color_rows(int32_t n, const int32_t* rowptr, const int32_t* col, std::vector<int>& color, int& nc) {
+static int color_rows(int32_t n, const int32_t* rowptr, const int32_t* col, std::vector<int>& color, int& nc, int32_t ncols = -1) {
+    if (ncols < n) ncols = n;  // columns in [n, ncols) are ghost columns: no row to colour against
     // transpose pattern (for unsymmetric input): tptr / tcol
     std::vector<int64_t> tptr((size_t)n + 1, 0);
     for (int r = 0; r < n; r++)
         for (int k = rowptr[r]; k < rowptr[r + 1]; k++) {
             const int c = col[k];
-            if (c < 0 || c >= n) { g_lusgs_error = "column out of range"; return MSTGPU_ERR_ARG; }
-            if (c != r) tptr[(size_t)c + 1]++;
+            if (c < 0 || c >= ncols) { g_lusgs_error = "column out of range"; return MSTGPU_ERR_ARG; }
+            if (c != r && c < n) tptr[(size_t)c + 1]++;
         }
     for (int r = 0; r < n; r++) tptr[r + 1] += tptr[r];
     std::vector<int> tcol((size_t)tptr[n]);
@@ -351,7 +376,7 @@ static int color_rows(int32_t n, const int32_t* rowptr, const int32_t* col, std:
         std::vector<int64_t> pos(tptr.begin(), tptr.end() - 1);
         for (int r = 0; r < n; r++)
             for (int k = rowptr[r]; k < rowptr[r + 1]; k++)
-                if (col[k] != r) tcol[(size_t)pos[col[k]]++] = r;
+                if (col[k] != r && col[k] < n) tcol[(size_t)pos[col[k]]++] = r;
     }
     color.assign(n, -1);
     nc = 0;
@@ -359,7 +384,7 @@ static int color_rows(int32_t n, const int32_t* rowptr, const int32_t* col, std:
     for (int r = 0; r < n; r++) {
         used = 0;
         for (int k = rowptr[r]; k < rowptr[r + 1]; k++)
-            if (col[k] != r && color[col[k]] >= 0 && color[col[k]] < 64) used |= 1ULL << color[col[k]];
+            if (col[k] != r && col[k] < n && color[col[k]] >= 0 && color[col[k]] < 64) used |= 1ULL << color[col[k]];
         for (int64_t k = tptr[r]; k < tptr[r + 1]; k++)
             if (color[tcol[(size_t)k]] >= 0 && color[tcol[(size_t)k]] < 64) used |= 1ULL << color[tcol[(size_t)k]];
         int k = 0;
@@ -372,10 +397,15 @@ static int color_rows(int32_t n, const int32_t* rowptr, const int32_t* col, std:
 
 int mstgpu_lusgs_color_order(int32_t n, const int32_t* rowptr, const int32_t* col, int32_t* perm_new2old,
                              int32_t* ncolors) {
+    return mstgpu_lusgs_color_order_partitioned(n, n, rowptr, col, perm_new2old, ncolors);
+}
+
+int mstgpu_lusgs_color_order_partitioned(int32_t n, int32_t ncols, const int32_t* rowptr, const int32_t* col,
+                                         int32_t* perm_new2old, int32_t* ncolors) {
     if (n <= 0 || !rowptr || !col || !perm_new2old) { g_lusgs_error = "bad argument"; return MSTGPU_ERR_ARG; }
     std::vector<int> color;
     int nc = 0;
-    int rc = color_rows(n, rowptr, col, color, nc);
+    int rc = color_rows(n, rowptr, col, color, nc, ncols);
     if (rc) return rc;
     // counting sort by colour (stable: storage order within a colour)
     std::vector<int64_t> start((size_t)nc + 1, 0);
@@ -393,7 +423,13 @@ int mstgpu_lusgs_create(mstgpu_lusgs** out, int32_t n, int32_t block, const int3
 
 int mstgpu_lusgs_create_ordered(mstgpu_lusgs** out, int32_t n, int32_t block, const int32_t* rowptr, const int32_t* col,
                                 const int32_t* sweep_new2old, int32_t device) {
+    return mstgpu_lusgs_create_partitioned(out, n, n, block, rowptr, col, sweep_new2old, device);
+}
+
+int mstgpu_lusgs_create_partitioned(mstgpu_lusgs** out, int32_t n, int32_t ncols, int32_t block, const int32_t* rowptr,
+                                    const int32_t* col, const int32_t* sweep_new2old, int32_t device) {
     mstgpu_lusgs* h = nullptr;
+    if (ncols < n) { g_lusgs_error = "ncols < n"; return MSTGPU_ERR_ARG; }
     if (!out || n <= 0 || !rowptr || !col) { g_lusgs_error = "bad argument"; return MSTGPU_ERR_ARG; }
     *out = nullptr;
     if (block != 1 && block != 4 && block != 5) { g_lusgs_error = "block size must be 1, 4 or 5"; return MSTGPU_ERR_ARG; }
@@ -410,15 +446,16 @@ int mstgpu_lusgs_create_ordered(mstgpu_lusgs** out, int32_t n, int32_t block, co
         }
     }
     auto rk = [&](int r) { return sweep_new2old ? rank[r] : r; };
-    std::vector<int> Lptr(n + 1, 0), Uptr(n + 1, 0), Dptr(n + 1, 0), Lcol, Lpos, Ucol, Upos, Dpos;
+    std::vector<int> Lptr(n + 1, 0), Uptr(n + 1, 0), Dptr(n + 1, 0), Gptr(n + 1, 0), Lcol, Lpos, Ucol, Upos, Dpos, Gcol, Gpos;
     std::vector<std::pair<int, int>> lo, hi;  // (rank of column, index into the row)
     for (int r = 0; r < n; r++) {
         lo.clear(); hi.clear();
         for (int k = rowptr[r]; k < rowptr[r + 1]; k++) {
             const int c = col[k];
-            if (c < 0 || c >= n) { g_lusgs_error = "column out of range"; return MSTGPU_ERR_ARG; }
+            if (c < 0 || c >= ncols) { g_lusgs_error = "column out of range"; return MSTGPU_ERR_ARG; }
             if (k > rowptr[r] && col[k - 1] > c) { g_lusgs_error = "columns must be ascending within a row"; return MSTGPU_ERR_ARG; }
-            if (c == r) Dpos.push_back(k);
+            if (c >= n) { Gcol.push_back(c); Gpos.push_back(k); }
+            else if (c == r) Dpos.push_back(k);
             else if (rk(c) < rk(r)) lo.push_back({rk(c), k});
             else hi.push_back({rk(c), k});
         }
@@ -427,6 +464,7 @@ int mstgpu_lusgs_create_ordered(mstgpu_lusgs** out, int32_t n, int32_t block, co
         for (auto& e : lo) { Lcol.push_back(col[e.second]); Lpos.push_back(e.second); }
         for (auto& e : hi) { Ucol.push_back(col[e.second]); Upos.push_back(e.second); }
         Lptr[r + 1] = (int)Lcol.size(); Uptr[r + 1] = (int)Ucol.size(); Dptr[r + 1] = (int)Dpos.size();
+        Gptr[r + 1] = (int)Gcol.size();
         if (Dptr[r + 1] == Dptr[r]) { g_lusgs_error = "row without a diagonal entry"; return MSTGPU_ERR_ARG; }
     }
     // dependency levels, rows visited in sweep order
@@ -454,6 +492,7 @@ int mstgpu_lusgs_create_ordered(mstgpu_lusgs** out, int32_t n, int32_t block, co
     };
     h = new mstgpu_lusgs;
     h->n = n; h->B = block; h->nnz = rowptr[n]; h->nL = (int)Lcol.size(); h->nU = (int)Ucol.size();
+    h->nG = (int)Gcol.size(); h->ncols = ncols;
     std::vector<int> frows, brows;
     bucket(lf, nlf, h->fptr, frows);
     bucket(lb, nlb, h->bptr, brows);
@@ -467,6 +506,10 @@ int mstgpu_lusgs_create_ordered(mstgpu_lusgs** out, int32_t n, int32_t block, co
         if ((r = up(h, &h->Lptr, Lptr)) || (r = up(h, &h->Lcol, Lcol)) || (r = up(h, &h->Lpos, Lpos))) return r;
         if ((r = up(h, &h->Uptr, Uptr)) || (r = up(h, &h->Ucol, Ucol)) || (r = up(h, &h->Upos, Upos))) return r;
         if ((r = up(h, &h->Dptr, Dptr)) || (r = up(h, &h->Dpos, Dpos))) return r;
+        if (h->nG) {
+            if ((r = up(h, &h->Gptr, Gptr)) || (r = up(h, &h->Gcol, Gcol)) || (r = up(h, &h->Gpos, Gpos))) return r;
+            LCK(cudaMalloc((void**)&h->beff, (size_t)n * block * 8));
+        }
         if ((r = up(h, &h->frows, frows)) || (r = up(h, &h->brows, brows))) return r;
         const size_t BB = (size_t)block * block;
         // val / b / x buffers of the host-array entry point are allocated at its first use
@@ -490,7 +533,7 @@ void mstgpu_lusgs_destroy(mstgpu_lusgs* h) {
     for (void* p : {(void*)h->Lptr, (void*)h->Lcol, (void*)h->Lpos, (void*)h->Uptr, (void*)h->Ucol, (void*)h->Upos,
                     (void*)h->Dptr, (void*)h->Dpos, (void*)h->frows, (void*)h->brows, (void*)h->val, (void*)h->D,
                     (void*)h->Dinv, (void*)h->LD, (void*)h->UD, (void*)h->b, (void*)h->x, (void*)h->rhs, (void*)h->rhs1,
-                    (void*)h->ux, (void*)h->res})
+                    (void*)h->ux, (void*)h->res, (void*)h->Gptr, (void*)h->Gcol, (void*)h->Gpos, (void*)h->beff})
         if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);

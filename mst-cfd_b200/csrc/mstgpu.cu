@@ -29,7 +29,7 @@ using namespace mst;
 
 namespace mst {
 // csrc/lusgs.cu: the sweeps on the caller's stream, device arrays, no synchronisation
-int lusgs_solve_async(mstgpu_lusgs* h, cudaStream_t st, const double* val, const double* b, double* x, int iters);
+int lusgs_solve_async(mstgpu_lusgs* h, cudaStream_t st, const double* val, const double* b, double* x, int iters, bool setup);
 }
 
 #define CK(call)                                                                       \
@@ -1130,10 +1130,16 @@ int fetch_permuted(mstgpu_ctx* ctx, const double* dsrc, const int32_t* new2old, 
 template <int D>
 static int step_implicit_impl(mstgpu_ctx* ctx, double dt, int nsteps, int iters) {
     constexpr int U = D + 2;
-    const int nc = ctx->nc;
+    const int nc = ctx->nc, nrow = ctx->n_owned;
+    const bool dist = ctx->partitioned && !ctx->halo.empty();
+    if (dist && !ctx->comm) { set_error(ctx, "partitioned context without a communicator: call mstgpu_comm_init"); return MSTGPU_ERR_STATE; }
     for (int s = 0; s < nsteps; s++) {
-        const double* Qc = ctx->Q[ctx->cur];
+        double* Qc = ctx->Q[ctx->cur];
         double* Qn = ctx->Q[ctx->cur ^ 1];
+        if (dist) {
+            int r = halo_exchange(ctx, Qc, ctx->stream);
+            if (r) return r;
+        }
         // b = -R(Q): the explicit path's fluxes and gather in residual-vector mode
         if (ctx->use_tiles) {
             int r = launch_tiles_any<D>(ctx, dt, nullptr, Qc, ctx->imp_b, 2, 2, ctx->stream);
@@ -1153,27 +1159,39 @@ static int step_implicit_impl(mstgpu_ctx* ctx, double dt, int nsteps, int iters)
                                                                              ctx->dx0, ctx->dx1, ctx->Phi, ctx->Gp, ctx->eta);
             }
             KTimer t(ctx, "update");
-            k_update<D><<<(nc + 255) / 256, 256, 0, ctx->stream>>>(nc, nc, ctx->nslot, 2, dt, nullptr, Qc, ctx->Phi, ctx->cf, ctx->vol,
-                                                                   ctx->imp_b, ctx->resid, ctx->nanflag);
+            k_update<D><<<(nrow + 255) / 256, 256, 0, ctx->stream>>>(nc, nrow, ctx->nslot, 2, dt, nullptr, Qc, ctx->Phi, ctx->cf, ctx->vol,
+                                                                     ctx->imp_b, ctx->resid, ctx->nanflag);
             ctx->probes_valid = true;
         }
         {
             KTimer t(ctx, "assemble");
-            k_assemble_implicit<D><<<(nc + 127) / 128, 128, 0, ctx->stream>>>(nc, nc, ctx->nslot, ctx->dcfg.gamma, dt, Qc, ctx->cf, ctx->fc0,
-                                                                              ctx->fc1, ctx->Sd, ctx->vol, ctx->imp_dpos, ctx->imp_pos, ctx->imp_val);
+            k_assemble_implicit<D><<<(nrow + 127) / 128, 128, 0, ctx->stream>>>(nrow, nc, ctx->nslot, ctx->dcfg.gamma, dt, Qc, ctx->cf, ctx->fc0,
+                                                                                ctx->fc1, ctx->Sd, ctx->vol, ctx->imp_dpos, ctx->imp_pos, ctx->imp_val);
         }
         CK(cudaMemsetAsync(ctx->imp_x, 0, (size_t)nc * U * sizeof(double), ctx->stream));  // dQ starts from 0
         {
             KTimer t(ctx, "lusgs");
             const int64_t l0 = mstgpu_lusgs_launch_count(ctx->imp_solver);
-            int r = lusgs_solve_async(ctx->imp_solver, ctx->stream, ctx->imp_val, ctx->imp_b, ctx->imp_x, iters);
+            int r = MSTGPU_OK;
+            if (!dist) {
+                r = lusgs_solve_async(ctx->imp_solver, ctx->stream, ctx->imp_val, ctx->imp_b, ctx->imp_x, iters, true);
+            } else {
+                // one sweep pair per call; the neighbours' dQ of this sweep become the next one's lagged ghost values
+                for (int it = 0; it < iters && r == MSTGPU_OK; it++) {
+                    r = lusgs_solve_async(ctx->imp_solver, ctx->stream, ctx->imp_val, ctx->imp_b, ctx->imp_x, 1, it == 0);
+                    if (r == MSTGPU_OK && it + 1 < iters) {
+                        r = halo_exchange(ctx, ctx->imp_x, ctx->stream);
+                        if (r) return r;
+                    }
+                }
+            }
             if (r) { set_error(ctx, std::string("lusgs: ") + mstgpu_lusgs_last_error()); return r; }
             ctx->launches += mstgpu_lusgs_launch_count(ctx->imp_solver) - l0 - 1;
         }
         CK(cudaMemsetAsync(ctx->resid, 0, 8 * sizeof(unsigned long long), ctx->stream));
         {
             KTimer t(ctx, "increment");
-            k_add_increment<U><<<(nc + 255) / 256, 256, 0, ctx->stream>>>(nc, Qc, ctx->imp_x, Qn, ctx->resid, ctx->nanflag);
+            k_add_increment<U><<<(nrow + 255) / 256, 256, 0, ctx->stream>>>(nrow, Qc, ctx->imp_x, Qn, ctx->resid, ctx->nanflag);
         }
         ctx->cur ^= 1;
     }
@@ -1552,10 +1570,11 @@ int mstgpu_step_cfl_timed(mstgpu_ctx* ctx, double cfl, int32_t nsteps, double* t
 // rhoSolver call site, so the operator is build-defined -- see oracle/rho_oracle.cpp implicitSystem) ----
 int mstgpu_implicit_setup(mstgpu_ctx* ctx, int32_t colour_sweeps) {
     if (!ctx) return MSTGPU_ERR_ARG;
-    if (ctx->partitioned) { set_error(ctx, "implicit step: not available on a partitioned context yet (DESIGN.md 5)"); return MSTGPU_ERR_STATE; }
     if (ctx->imp_solver) return MSTGPU_OK;
     CK(cudaSetDevice(ctx->device));
-    const int nc = ctx->nc, nslot = ctx->nslot, U = ctx->U;
+    // rows = the cells this context advances; on a partition the ghost cells (ids >= n_owned) are
+    // columns only, their couplings lagged by one sweep (block Jacobi across partitions)
+    const int nc = ctx->nc, nrow = ctx->n_owned, nslot = ctx->nslot, U = ctx->U;
     // the connectivity lives on the device (the host copies were dropped after upload)
     std::vector<int32_t> cf((size_t)nslot * nc), fc0(ctx->nf), fc1(ctx->nf);
     CK(cudaMemcpy(cf.data(), ctx->cf, cf.size() * 4, cudaMemcpyDeviceToHost));
@@ -1566,18 +1585,18 @@ int mstgpu_implicit_setup(mstgpu_ctx* ctx, int32_t colour_sweeps) {
         if (v < 0) return -1;
         return (v & 1) ? fc0[v >> 1] : fc1[v >> 1];
     };
-    std::vector<int32_t> rowptr((size_t)nc + 1, 0);
-    for (int c = 0; c < nc; c++) {
+    std::vector<int32_t> rowptr((size_t)nrow + 1, 0);
+    for (int c = 0; c < nrow; c++) {
         int cnt = 1;
         for (int j = 0; j < nslot; j++) cnt += nb_of(c, j) >= 0 ? 1 : 0;
         const int64_t next = (int64_t)rowptr[c] + cnt;
         if (next > 0x7fffffffLL) { set_error(ctx, "implicit system does not fit 32-bit offsets"); return MSTGPU_ERR_ARG; }
         rowptr[c + 1] = (int32_t)next;
     }
-    const size_t nnz = (size_t)rowptr[nc];
-    std::vector<int32_t> col(nnz), dpos(nc), pos((size_t)nslot * nc, -1);
+    const size_t nnz = (size_t)rowptr[nrow];
+    std::vector<int32_t> col(nnz), dpos(nrow), pos((size_t)nslot * nc, -1);
 #pragma omp parallel for schedule(static)
-    for (int c = 0; c < nc; c++) {
+    for (int c = 0; c < nrow; c++) {
         int32_t* out = col.data() + rowptr[c];
         int n = 0;
         out[n++] = c;
@@ -1591,15 +1610,15 @@ int mstgpu_implicit_setup(mstgpu_ctx* ctx, int32_t colour_sweeps) {
     }
     std::vector<int32_t> order;
     if (colour_sweeps) {
-        order.resize(nc);
+        order.resize(nrow);
         int32_t ncol = 0;
-        if (mstgpu_lusgs_color_order(nc, rowptr.data(), col.data(), order.data(), &ncol) != MSTGPU_OK) {
+        if (mstgpu_lusgs_color_order_partitioned(nrow, nc, rowptr.data(), col.data(), order.data(), &ncol) != MSTGPU_OK) {
             set_error(ctx, std::string("colour order: ") + mstgpu_lusgs_last_error());
             return MSTGPU_ERR_ARG;
         }
     }
-    int rc = mstgpu_lusgs_create_ordered(&ctx->imp_solver, nc, U, rowptr.data(), col.data(),
-                                         colour_sweeps ? order.data() : nullptr, ctx->device);
+    int rc = mstgpu_lusgs_create_partitioned(&ctx->imp_solver, nrow, nc, U, rowptr.data(), col.data(),
+                                             colour_sweeps ? order.data() : nullptr, ctx->device);
     if (rc != MSTGPU_OK) { set_error(ctx, std::string("lusgs: ") + mstgpu_lusgs_last_error()); return rc; }
     ctx->dev_bytes += mstgpu_lusgs_device_bytes(ctx->imp_solver);
     ctx->imp_sweep = order;
@@ -1608,6 +1627,7 @@ int mstgpu_implicit_setup(mstgpu_ctx* ctx, int32_t colour_sweeps) {
     if ((r = upload(ctx, &ctx->imp_pos, pos))) return r;
     if ((r = dalloc(ctx, &ctx->imp_val, nnz * U * U))) return r;
     if ((r = dalloc(ctx, &ctx->imp_b, (size_t)nc * U + 2 * U))) return r;  // + 2 rows: bulk stores of the fused kernel
+    CK(cudaMemsetAsync(ctx->imp_b, 0, ((size_t)nc * U + 2 * U) * sizeof(double), ctx->stream));
     if ((r = dalloc(ctx, &ctx->imp_x, (size_t)nc * U))) return r;
     CK(cudaStreamSynchronize(ctx->stream));
     return MSTGPU_OK;
@@ -1616,7 +1636,7 @@ int mstgpu_implicit_setup(mstgpu_ctx* ctx, int32_t colour_sweeps) {
 int mstgpu_implicit_sweep_order(mstgpu_ctx* ctx, int32_t* order_ref_ids) {
     if (!ctx || !order_ref_ids) return MSTGPU_ERR_ARG;
     if (!ctx->imp_solver) { set_error(ctx, "implicit_sweep_order before implicit_setup"); return MSTGPU_ERR_STATE; }
-    for (int i = 0; i < ctx->nc; i++) {
+    for (int i = 0; i < ctx->n_owned; i++) {  // a partition's ids are its own (mstgpu_partition_cell_ids maps them)
         const int dev = ctx->imp_sweep.empty() ? i : ctx->imp_sweep[i];
         order_ref_ids[i] = ctx->plan.cell_new2old[dev];
     }

@@ -31,6 +31,7 @@ EXPORTS = [
     "mstgpu_partition_cell_ids", "mstgpu_partition_neighbor", "mstgpu_create_partitioned",
     "mstgpu_comm_unique_id", "mstgpu_comm_init", "mstgpu_lusgs_create", "mstgpu_lusgs_destroy",
     "mstgpu_lusgs_solve", "mstgpu_lusgs_levels", "mstgpu_lusgs_create_ordered", "mstgpu_lusgs_solve_device",
+    "mstgpu_lusgs_create_partitioned", "mstgpu_lusgs_color_order_partitioned",
     "mstgpu_lusgs_launch_count", "mstgpu_lusgs_device_bytes", "mstgpu_mesh_adjacency", "mstgpu_lusgs_color_order", "mstgpu_lusgs_last_error",
     "mstgpu_last_error", "mstgpu_version",
 ]

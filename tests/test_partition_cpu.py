@@ -128,3 +128,40 @@ def test_two_process_gloo_halo_exchange():
     ref, rr = o.run(1e-4, 4, Q0, residuals=True)
     assert np.array_equal(got, ref, equal_nan=True)
     assert np.allclose(res, rr[-1], rtol=1e-12)
+
+
+@pytest.mark.parametrize("nparts", [1, 2, 3])
+def test_partitioned_implicit_step_definition(nparts):
+    """The lagged-ghost (block-Jacobi across partitions) implicit step of tests/implicit_partitioned.py:
+    with one partition it IS the single-domain step; with several it converges to the same
+    solution of the linear system as the sweeps are iterated (the 5-sweep iterates differ)."""
+    import implicit_partitioned as ip
+    f = box_flat(6, 5, 4, bc=(10, 5, 3, 7, 3, 3))
+    inlet = np.array([1.0, 0.4, 0.0, 0.0, 2.58])
+    kw = dict(order=2, flux="roe", inletQ=inlet, limiter="venkat", limiter_k=2.0)
+    Q0 = mesh_np.random_state(f, seed=4)
+    single = oracle.Oracle(f, **kw)
+    dt = 10 * single.cfl_dt(1.0, Q0)
+    parts = [mstgpu.Partition(f, nparts, r, order=2) for r in range(nparts)]
+    locs = [P.local_flat() for P in parts]
+    ors = [oracle.Oracle(lf, qf_copy_from=lf["nint"], **kw) for lf in locs]
+
+    def run(iters):
+        Qs = [np.zeros((P.n_local, 5)) for P in parts]
+        for P, Q in zip(parts, Qs):
+            Q[:P.n_owned] = Q0[P.cell_ids[:P.n_owned]]
+        ip.step(ors, parts, Qs, dt, iters)
+        out = np.empty_like(Q0)
+        for P, Q in zip(parts, Qs):
+            out[P.cell_ids[:P.n_owned]] = Q[:P.n_owned]
+        return out
+
+    if nparts == 1:
+        # same rows in the partition's own numbering: the single-domain step with that sweep order
+        order = parts[0].cell_ids[:parts[0].n_owned]
+        assert np.allclose(run(5), single.step_implicit(dt, Q0, 5, sweep_order=order), rtol=1e-13, atol=1e-13)
+    conv = single.step_implicit(dt, Q0, 80)
+    assert np.abs(run(80) - conv).max() < 1e-9 * np.abs(conv).max()
+    if nparts > 1:
+        d5 = np.abs(run(5) - single.step_implicit(dt, Q0, 5)).max()
+        assert 0 < d5 < 0.05 * np.abs(conv - Q0).max()  # a different iterate, close to the same answer
