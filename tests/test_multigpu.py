@@ -22,7 +22,10 @@ def _ngpu():
         return 0
 
 
-def _worker(rank, world, port, case, kernel, q):
+EXT = dict(limiter="bj", gradient="lsq")  # extension scheme for the CFL variant
+
+
+def _worker(rank, world, port, case, kernel, q, cfl=0.0):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -33,14 +36,18 @@ def _worker(rank, world, port, case, kernel, q):
     inlet = np.array([1.0, 0.4, 0.0, 0.0, 2.58]) if case == "box" else None
     Q0 = mesh_np.random_state(f, seed=4)
     P = mstgpu.Partition(f, world, rank, order=2)
-    ctx = mstgpu.Context(P, order=2, flux="roe", inletQ=inlet, device=rank, kernel=kernel)
+    ctx = mstgpu.Context(P, order=2, flux="roe", inletQ=inlet, device=rank, kernel=kernel, **(EXT if cfl > 0 else {}))
     idt = torch.zeros(128, dtype=torch.uint8)
     if rank == 0:
         idt = torch.frombuffer(bytearray(mstgpu.comm_unique_id()), dtype=torch.uint8).clone()
     dist.broadcast(idt, 0)
     ctx.comm_init(world, rank, bytes(idt.numpy().tobytes()))
     ctx.set_state(Q0[P.cell_ids[:P.n_owned]])
-    ctx.step(1e-4, 5)
+    if cfl > 0:
+        t = ctx.step_cfl(cfl, 5)  # global time step: min over ranks on the device (ncclAllReduce(min))
+        assert t > 0
+    else:
+        ctx.step(1e-4, 5)
     res = ctx.residual()  # collective
     full = torch.zeros((f["ncells"], f["dim"] + 2), dtype=torch.float64)
     full[torch.from_numpy(P.cell_ids[:P.n_owned].astype(np.int64))] = torch.from_numpy(ctx.get_state())
@@ -75,6 +82,31 @@ def test_two_gpus_match_one(case, kernel):
     assert np.array_equal(got, one.get_state(), equal_nan=True)  # same arithmetic per cell
     assert np.array_equal(res, one.residual())
     ref = oracle.Oracle(f, order=2, flux="roe", inletQ=inlet).run(1e-4, 5, Q0)
+    assert rel_linf(got, ref) <= 1e-11
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("kernel", ["tiles", "split"])
+def test_two_gpus_limited_scheme_at_the_global_cfl_step(kernel):
+    import torch.multiprocessing as mp
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    port = 29650 + (os.getpid() % 2000)
+    procs = [mpc.Process(target=_worker, args=(r, 2, port, "box", kernel, q, 0.4)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got, res = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    f = box_flat(12, 10, 8, bc=(10, 5, 3, 7, 3, 3))
+    inlet = np.array([1.0, 0.4, 0.0, 0.0, 2.58])
+    Q0 = mesh_np.random_state(f, seed=4)
+    one = mstgpu.Context(f, order=2, flux="roe", inletQ=inlet, kernel=kernel, **EXT)
+    one.set_state(Q0)
+    one.step_cfl(0.4, 5)
+    assert np.array_equal(got, one.get_state(), equal_nan=True)  # same dt (a minimum is exact), same arithmetic per cell
+    ref, _ = oracle.Oracle(f, order=2, flux="roe", inletQ=inlet, **EXT).run_cfl(0.4, 5, Q0)
     assert rel_linf(got, ref) <= 1e-11
 
 
