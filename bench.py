@@ -579,7 +579,7 @@ def main():
     ap.add_argument("--renumber", type=int, default=2, help="0 none, 1 Morton, 2 Hilbert")
     ap.add_argument("--flux", default="roe", choices=["roe", "ausm"])
     ap.add_argument("--order", type=int, default=2, choices=[1, 2])
-    ap.add_argument("--viscous", type=int, default=0, choices=[0, 1], help="laminar viscous term (split-kernel path)")
+    ap.add_argument("--viscous", type=int, default=0, choices=[0, 1], help="laminar viscous term (extension; fused kernel at second order)")
     ap.add_argument("--block-threads", type=int, default=0)
     ap.add_argument("--gradient", default="gg", choices=["gg", "lsq"], help="extension: least-squares gradient")
     ap.add_argument("--limiter", default="none", choices=["none", "bj", "venkat"], help="extension: slope limiter")

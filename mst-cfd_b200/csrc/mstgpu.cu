@@ -875,9 +875,9 @@ int halo_exchange(mstgpu_ctx* ctx, double* Q, cudaStream_t st) {
     return MSTGPU_OK;
 }
 
-template <int D, int ORDER, int NT, int NS, bool LIM>
+template <int D, int ORDER, int NT, int NS, bool LIM, bool VISC>
 int launch_tiles_lim(mstgpu_ctx* ctx, double dt, const double* dtd, const double* Qo, double* Qn, int want_resid, int which, cudaStream_t st) {
-    auto kern = k_step_tiles<D, ORDER, NT, NS, LIM>;
+    auto kern = k_step_tiles<D, ORDER, NT, NS, LIM, VISC>;
     static thread_local size_t configured_smem = 0;
     if (configured_smem < ctx->tile_smem) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->tile_smem));
@@ -896,8 +896,13 @@ int launch_tiles_lim(mstgpu_ctx* ctx, double dt, const double* dtd, const double
 
 template <int D, int ORDER, int NT, int NS>
 int launch_tiles(mstgpu_ctx* ctx, double dt, const double* dtd, const double* Qo, double* Qn, int wr, int which, cudaStream_t st) {
-    if (ORDER == 2 && ctx->cfg.limiter != 0) return launch_tiles_lim<D, 2, NT, NS, true>(ctx, dt, dtd, Qo, Qn, wr, which, st);
-    return launch_tiles_lim<D, ORDER, NT, NS, false>(ctx, dt, dtd, Qo, Qn, wr, which, st);
+    if (ORDER == 2) {
+        const bool lim = ctx->cfg.limiter != 0, visc = ctx->cfg.viscous != 0;
+        if (lim && visc) return launch_tiles_lim<D, 2, NT, NS, true, true>(ctx, dt, dtd, Qo, Qn, wr, which, st);
+        if (lim) return launch_tiles_lim<D, 2, NT, NS, true, false>(ctx, dt, dtd, Qo, Qn, wr, which, st);
+        if (visc) return launch_tiles_lim<D, 2, NT, NS, false, true>(ctx, dt, dtd, Qo, Qn, wr, which, st);
+    }
+    return launch_tiles_lim<D, ORDER, NT, NS, false, false>(ctx, dt, dtd, Qo, Qn, wr, which, st);
 }
 
 template <int D, int NS>
@@ -1203,7 +1208,11 @@ static int step_implicit_impl(mstgpu_ctx* ctx, double dt, int nsteps, int iters)
 
 // cells per tile: the largest tile that still lets two CTAs share an SM (228 KB of shared
 // memory); the limiter extension adds a [U][own + ring 1] table, so its tiles are smaller
-static int default_tile_cells(const mstgpu_config& cfg) { return (cfg.order == 2 && cfg.limiter != 0) ? 384 : 512; }
+static int default_tile_cells(const mstgpu_config& cfg) {
+    if (cfg.order != 2) return 512;
+    if (cfg.viscous != 0) return cfg.limiter != 0 ? 192 : 256;  // + [(D+1) D][own + ring 1] primitive gradients
+    return cfg.limiter != 0 ? 384 : 512;
+}
 
 extern "C" {
 
@@ -1214,14 +1223,14 @@ int mstgpu_tile_stats(const mstgpu_mesh* mesh, const mstgpu_config* cfg, int64_t
     if (!perr.empty()) { set_error(nullptr, perr); return MSTGPU_ERR_ARG; }
     TilePack tp;
     int T = cfg->tile_cells > 0 ? cfg->tile_cells : default_tile_cells(*cfg);
-    perr = build_tiles(p, p.nc, T, cfg->order, tp, cfg->order == 2 ? cfg->limiter : 0);
+    perr = build_tiles(p, p.nc, T, cfg->order, tp, tile_ext(cfg->order, cfg->limiter, cfg->viscous));
     if (!perr.empty()) { set_error(nullptr, perr); return MSTGPU_ERR_ARG; }
     for (int i = 0; i < 12; i++) out[i] = 0;
     out[0] = tp.ntiles; out[1] = (int64_t)tp.max_smem;
     out[3] = tp.sum_r1; out[4] = tp.sum_r2; out[5] = tp.sum_FB; out[6] = tp.sum_FA; out[7] = (int64_t)tp.packets.size();
     double sum = 0;
     for (const TileDesc& d : tp.desc) {
-        const size_t b = tile_layout(p.D, cfg->order, p.nslot, d.n_own, d.n_r1, d.n_r2, d.nFB, cfg->limiter).total;
+        const size_t b = tile_layout(p.D, cfg->order, p.nslot, d.n_own, d.n_r1, d.n_r2, d.nFB, tile_ext(cfg->order, cfg->limiter, cfg->viscous)).total;
         sum += (double)b;
         out[8 + (b <= 56 * 1024 ? 0 : b <= 75 * 1024 ? 1 : b <= 113 * 1024 ? 2 : 3)]++;
     }
@@ -1276,8 +1285,9 @@ static int create_impl(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_c
     }
     ctx = new mstgpu_ctx;
     ctx->cfg = *cfg;
-    // the laminar viscous term lives in the split-kernel path (the fused tile kernel is inviscid)
-    ctx->use_tiles = cfg->kernel != 0 && cfg->viscous == 0;
+    // the fused tile kernel carries the laminar viscous term at second order (it shares the rings of the
+    // reconstruction); first order + viscous runs the split kernels
+    ctx->use_tiles = cfg->kernel != 0 && (cfg->viscous == 0 || cfg->order == 2);
     mstgpu_config pcfg = *cfg;
     if (part) pcfg.qf_copy_from = 0x7fffffff;  // already folded into the partition's eta table
     std::string perr = build_plan(*mesh, pcfg, ctx->plan, part ? part->n_owned : -1);
@@ -1326,7 +1336,7 @@ static int create_impl(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_c
         if (ctx->use_tiles) {
             TilePack tp;
             int T = cfg->tile_cells > 0 ? cfg->tile_cells : default_tile_cells(*cfg);
-            std::string terr = build_tiles(p, ctx->n_owned, T, cfg->order, tp, cfg->order == 2 ? cfg->limiter : 0);
+            std::string terr = build_tiles(p, ctx->n_owned, T, cfg->order, tp, tile_ext(cfg->order, cfg->limiter, cfg->viscous));
             if (!terr.empty()) { set_error(ctx, terr); return MSTGPU_ERR_ARG; }
             int dev_smem = 0;
             CK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
@@ -1343,7 +1353,7 @@ static int create_impl(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_c
                 int ccount[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                 for (int t = 0; t < tp.ntiles; t++) {
                     const TileDesc& d = tp.desc[t];
-                    const size_t b = tile_layout(p.D, cfg->order, p.nslot, d.n_own, d.n_r1, d.n_r2, d.nFB, cfg->limiter).total;
+                    const size_t b = tile_layout(p.D, cfg->order, p.nslot, d.n_own, d.n_r1, d.n_r2, d.nFB, tile_ext(cfg->order, cfg->limiter, cfg->viscous)).total;
                     int c = 0;
                     while (c < 3 && b > lim[c]) c++;
                     // tiles whose rings reach into the ghost cells wait for the halo exchange
@@ -1419,7 +1429,7 @@ static int create_impl(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_c
     d.gamma = cfg->gamma; d.gm1 = cfg->gamma - 1.0; d.delta = cfg->delta;
     d.delta2 = cfg->delta * cfg->delta; d.inv2delta = 1.0 / (2.0 * cfg->delta); d.eor = cfg->eor;
     d.astar_fac = 2.0 * (cfg->gamma - 1.0) / (cfg->gamma + 1.0);
-    d.mu = cfg->mu; d.lambda = -0.666667 * cfg->mu; d.kappa = cfg->kappa; d.cv = cfg->cv;
+    d.mu = cfg->mu; d.lambda = -0.666667 * cfg->mu; d.kappa = cfg->kappa; d.cv = cfg->cv; d.inv_cv = 1.0 / cfg->cv;
     for (int k = 0; k < 5; k++) d.inletQ[k] = cfg->inletQ[k];
     d.order = cfg->order; d.flux = cfg->flux; d.viscous = cfg->viscous; d.limiter = cfg->order == 2 ? cfg->limiter : 0;
     // the big host tables are no longer needed

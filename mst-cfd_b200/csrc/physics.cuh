@@ -28,7 +28,7 @@ namespace mst {
 struct DevCfg {
     double gamma, gm1, delta, delta2, inv2delta, eor;
     double astar_fac;  // 2 (g-1)/(g+1)      SolverAusm.cpp:6
-    double mu, lambda, kappa, cv;
+    double mu, lambda, kappa, cv, inv_cv;
     double inletQ[5];
     int32_t order, flux, viscous, limiter;  // limiter: extension (0 none, 1 Barth-Jespersen, 2 Venkatakrishnan)
 };

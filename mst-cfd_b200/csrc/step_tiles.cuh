@@ -98,7 +98,7 @@ __device__ __forceinline__ double warp_max_nonneg(double x) {
 #define MST_TILE_MINB(NT) ((NT) >= 256 ? 2 : 3)
 #endif
 
-template <int D, int ORDER, int NT, int NS, bool LIM = false>
+template <int D, int ORDER, int NT, int NS, bool LIM = false, bool VISC = false>
 __global__ void __launch_bounds__(NT, MST_TILE_MINB(NT)) k_step_tiles(TileArrays ta, int tile_base, int want_resid, DevCfg cfg, double dt_val,
                                                    const double* __restrict__ dt_dev,
                                                    const double* __restrict__ Qold,
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(NT, MST_TILE_MINB(NT)) k_step_tiles(TileArrays
     const int tid = threadIdx.x;
     const int n_own = d.n_own, n_ring = d.n_r1 + d.n_r2;
     const int nFB = d.nFB;
-    const TileLayout L = tile_layout(D, ORDER, nslot, d.n_own, d.n_r1, d.n_r2, d.nFB, LIM ? 1 : 0);
+    const TileLayout L = tile_layout(D, ORDER, nslot, d.n_own, d.n_r1, d.n_r2, d.nFB, (LIM ? 1 : 0) | (VISC ? 2 : 0));
     const double dt = dt_dev ? *dt_dev : dt_val;  // device-resident dt: CFL stepping (extension)
     const int nFBp = L.nFBp, ncp = L.ncp;
     const unsigned char* pk = ta.packets + d.pk_off;
@@ -198,6 +198,51 @@ __global__ void __launch_bounds__(NT, MST_TILE_MINB(NT)) k_step_tiles(TileArrays
         __syncthreads();
     }
 
+    // ---- phase 1v (viscous extension only): Green-Gauss gradient of the face primitives (u_i, T) of every
+    // cell next to a flux face (own + ring 1), as k_gradient forms it: face state = eta-weighted mean of the
+    // two cell states, primitives of THAT state, summed with the outward area vectors (pre-divided by V).
+    constexpr int P = D + 1;
+    double* Gps = reinterpret_cast<double*>(smem + L.Gps);  // [(k*D+d)][nCLp]
+    if (VISC) {
+        const int nCL = n_own + d.n_r1, nCLp = L.nCLp;
+        const double* __restrict__ vw_g = reinterpret_cast<const double*>(pk + L.vw);
+        const uint16_t* __restrict__ lid_g = reinterpret_cast<const uint16_t*>(pk + L.lid);
+        constexpr int W = 2 + D;
+        for (int i = tid; i < nCL; i += NT) {
+            double q0[U], t[P][D];
+#pragma unroll
+            for (int k = 0; k < U; k++) q0[k] = Qs[i * U + k];
+#pragma unroll
+            for (int k = 0; k < P; k++)
+#pragma unroll
+                for (int dd = 0; dd < D; dd++) t[k][dd] = 0.0;
+#pragma unroll
+            for (int j = 0; j < nslot; j++) {
+                const int c = lid_g[j * nCLp + i];
+                const double e0 = vw_g[(j * W + 0) * nCLp + i], e1 = vw_g[(j * W + 1) * nCLp + i];
+                double qf[U], pr[P], m2 = 0.0;
+#pragma unroll
+                for (int k = 0; k < U; k++) qf[k] = e0 * q0[k] + e1 * Qs[c * U + k];
+                // one FP64 division per face state (the split path divides six times: ~20 issue slots each)
+                const double rf = 1.0 / qf[0];
+#pragma unroll
+                for (int a = 0; a < D; a++) { pr[a] = qf[a + 1] * rf; m2 += qf[a + 1] * qf[a + 1]; }
+                pr[D] = (qf[U - 1] - 0.5 * m2 * rf) * rf * cfg.inv_cv;  // T, FUNCTION.cpp:8-11
+#pragma unroll
+                for (int dd = 0; dd < D; dd++) {
+                    const double sv = vw_g[(j * W + 2 + dd) * nCLp + i];
+#pragma unroll
+                    for (int k = 0; k < P; k++) t[k][dd] += pr[k] * sv;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < P; k++)
+#pragma unroll
+                for (int dd = 0; dd < D; dd++) Gps[(k * D + dd) * nCLp + i] = t[k][dd];
+        }
+        __syncthreads();
+    }
+
     // ---- phase 2: reconstruction (fixed stencil) + flux on every face with an owned cell ----
     for (int f = tid; f < nFB; f += NT) {
         const uint32_t mt = fmeta_g[f];
@@ -207,6 +252,7 @@ __global__ void __launch_bounds__(NT, MST_TILE_MINB(NT)) k_step_tiles(TileArrays
 #pragma unroll
         for (int dd = 0; dd < D; dd++) S[dd] = fSd_g[dd * nFBp + f];
         double A[U], B[U], phi[U];
+        double visc[VISC ? U : 1];
         bool live = true;
         if (ORDER == 2) {
             uint32_t id[NS - 1];
@@ -258,6 +304,53 @@ __global__ void __launch_bounds__(NT, MST_TILE_MINB(NT)) k_step_tiles(TileArrays
                 for (int k = 0; k < U; k++) ra[k] = A[k];
                 live = boundary_states<D>(type, qa, ra, S, cfg, A, B);
             }
+            if (VISC) {
+                // laminar viscous flux (corrected formulation, see k_flux): tau = mu (grad u + grad u^T) +
+                // lambda div(u) I, energy flux u.tau + k grad T; face values by the eta interpolation.
+                // Kept in phi[] and combined with the convective flux below.
+                const double e = reinterpret_cast<const double*>(pk + L.feta)[f];
+                const int nCLp = L.nCLp;
+                double qf[U], gf[P][D];
+                if (interior) {
+#pragma unroll
+                    for (int k = 0; k < U; k++) qf[k] = e * qa[k] + (1.0 - e) * qb[k];
+#pragma unroll
+                    for (int k = 0; k < P; k++)
+#pragma unroll
+                        for (int dd = 0; dd < D; dd++)
+                            gf[k][dd] = e * Gps[(k * D + dd) * nCLp + la] + (1.0 - e) * Gps[(k * D + dd) * nCLp + lb];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < U; k++) qf[k] = qa[k];
+#pragma unroll
+                    for (int k = 0; k < P; k++)
+#pragma unroll
+                        for (int dd = 0; dd < D; dd++) gf[k][dd] = Gps[(k * D + dd) * nCLp + la];
+                }
+                double uf[D], div = 0.0;
+                const double rqf = 1.0 / qf[0];
+#pragma unroll
+                for (int i = 0; i < D; i++) { uf[i] = qf[i + 1] * rqf; div += gf[i][i]; }
+                double en = 0.0, fv[D];
+#pragma unroll
+                for (int i = 0; i < D; i++) fv[i] = 0.0;
+#pragma unroll
+                for (int j = 0; j < D; j++) {
+                    double w = 0.0;
+#pragma unroll
+                    for (int i = 0; i < D; i++) {
+                        double tij = cfg.mu * (gf[i][j] + gf[j][i]);
+                        if (i == j) tij += cfg.lambda * div;
+                        fv[i] += tij * S[j];
+                        w += uf[i] * tij;
+                    }
+                    en += (w + cfg.kappa * gf[D][j]) * S[j];
+                }
+                visc[0] = 0.0;
+#pragma unroll
+                for (int i = 0; i < D; i++) visc[i + 1] = fv[i];
+                visc[U - 1] = en;
+            }
         } else {
             const uint32_t ab = idx_g[f];
             const int la = ab & 0xFFFFu, lb = ab >> 16;
@@ -276,6 +369,10 @@ __global__ void __launch_bounds__(NT, MST_TILE_MINB(NT)) k_step_tiles(TileArrays
         } else {
 #pragma unroll
             for (int k = 0; k < U; k++) phi[k] = 0.0;
+        }
+        if (VISC) {
+#pragma unroll
+            for (int k = 0; k < U; k++) phi[k] -= visc[k];
         }
 #pragma unroll
         for (int k = 0; k < U; k++) Phis[k * nFBp + f] = phi[k];

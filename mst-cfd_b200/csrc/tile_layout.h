@@ -25,23 +25,31 @@ struct TileLayout {
                      //                   row m-1 = stencil entry m >= 2 (entry 1 is the cell across the face)
     uint32_t fSd;    // f64 [D][nFBp]     area vector, outward from c0
     uint32_t fmeta;  // u32 [nFBp]        zone type | left/right flags << 8
-    // limiter extension (lim != 0): per cell of the tile and of ring 1 ("limited cells", local ids 0..nCL-1)
-    uint32_t lw;     // f64 [nslot][NS][nCLp]  slope at face centre j:  D_j = sum_m lw[j][m] Q_stencil(m)
+    // extensions (ext bit 0: limiter, bit 1: viscous term): per cell of the tile and of ring 1
+    // ("stencil cells", local ids 0..nCL-1)
+    uint32_t lw;     // f64 [nslot][NS][nCLp]  (limiter) slope at face centre j:  D_j = sum_m lw[j][m] Q_stencil(m)
     uint32_t lid;    // u16 [nslot][nCLp]      local ids of the face neighbours (own id where there is none)
-    uint32_t le2;    // f64 [nCLp]             Venkatakrishnan eps^2
+    uint32_t le2;    // f64 [nCLp]             (limiter) Venkatakrishnan eps^2
+    uint32_t vw;     // f64 [nslot][2+D][nCLp] (viscous) per face slot: weight of the cell, weight of the neighbour
+                     //                        in the face state, outward area vector / V
+    uint32_t feta;   // f64 [nFBp]             (viscous) eta of the flux face (1 where the face state is Q[c0])
     uint32_t slots;  // u16 [nslot][ncp]  per owned cell: local face << 1 | side, 0xFFFF = pad
     uint32_t cvol;   // f64 [ncp]         1 / cell volume
     uint32_t pk_bytes;
     // shared memory
     uint32_t mbar, Qs, Phis, cells_s, total;  // cells_s: copy of the packet's slots + cvol block
-    uint32_t philim;                          // f64 [U][nCLp] limiter value per limited cell (lim != 0)
+    uint32_t philim;                          // f64 [U][nCLp] limiter value per stencil cell (ext & 1)
+    uint32_t Gps;                             // f64 [(D+1)*D][nCLp] primitive gradients (u_i, T) per stencil cell (ext & 2)
     uint32_t nFBp, ncp, nCLp;
 };
 
 MST_HD uint32_t up16(uint32_t x) { return (x + 15u) & ~15u; }
 
 // NS = stencil size of the second-order reconstruction = 1 + max faces per cell
-MST_HD TileLayout tile_layout(int D, int order, int nslot, int n_own, int n_r1, int n_r2, int nFB, int lim = 0) {
+// ext: bit 0 = limiter tables, bit 1 = viscous tables (both need order == 2: rings 1 and 2)
+MST_HD int tile_ext(int order, int limiter, int viscous) { return order == 2 ? ((limiter != 0 ? 1 : 0) | (viscous != 0 ? 2 : 0)) : 0; }
+
+MST_HD TileLayout tile_layout(int D, int order, int nslot, int n_own, int n_r1, int n_r2, int nFB, int ext = 0) {
     const uint32_t U = (uint32_t)D + 2u;
     const uint32_t NS = (order == 2) ? (uint32_t)nslot + 1u : 1u;
     TileLayout L;
@@ -53,11 +61,14 @@ MST_HD TileLayout tile_layout(int D, int order, int nslot, int n_own, int n_r1, 
     L.idx = o; o += up16((NS > 1u ? NS - 1u : 1u) * L.nFBp * 4u);
     L.fSd = o; o += up16((uint32_t)D * L.nFBp * 8u);
     L.fmeta = o; o += up16(L.nFBp * 4u);
-    const bool limited = lim != 0 && order == 2;
-    L.nCLp = limited ? (((uint32_t)(n_own + n_r1) + 3u) & ~3u) : 0u;
-    L.lw = o; o += up16((uint32_t)nslot * NS * L.nCLp * 8u);
+    if (order != 2) ext = 0;
+    const bool limited = (ext & 1) != 0, visc = (ext & 2) != 0;
+    L.nCLp = ext ? (((uint32_t)(n_own + n_r1) + 3u) & ~3u) : 0u;
+    L.lw = o; if (limited) o += up16((uint32_t)nslot * NS * L.nCLp * 8u);
     L.lid = o; o += up16((uint32_t)nslot * L.nCLp * 2u);
-    L.le2 = o; o += up16(L.nCLp * 8u);
+    L.le2 = o; if (limited) o += up16(L.nCLp * 8u);
+    L.vw = o; if (visc) o += up16((uint32_t)nslot * (2u + (uint32_t)D) * L.nCLp * 8u);
+    L.feta = o; if (visc) o += up16(L.nFBp * 8u);
     L.slots = o; o += up16((uint32_t)nslot * L.ncp * 2u);
     L.cvol = o; o += up16(L.ncp * 8u);
     L.pk_bytes = o;
@@ -66,7 +77,8 @@ MST_HD TileLayout tile_layout(int D, int order, int nslot, int n_own, int n_r1, 
     L.Qs = s; s += up16(((n_loc + 1u) & ~1u) * U * 8u);
     L.Phis = s; s += up16(U * L.nFBp * 8u);
     L.cells_s = s; s += L.pk_bytes - L.slots;
-    L.philim = s; s += up16(U * L.nCLp * 8u);
+    L.philim = s; if (limited) s += up16(U * L.nCLp * 8u);
+    L.Gps = s; if (visc) s += up16(((uint32_t)D + 1u) * (uint32_t)D * L.nCLp * 8u);
     L.total = s;
     return L;
 }

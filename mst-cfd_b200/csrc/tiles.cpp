@@ -39,11 +39,13 @@ inline int up(int x, int m) { return (x + m - 1) / m * m; }
 
 }  // namespace
 
-std::string build_tiles(const Plan& p, int n_update, int T, int order, TilePack& tp, int limiter) {
+std::string build_tiles(const Plan& p, int n_update, int T, int order, TilePack& tp, int ext) {
+    if (order != 2) ext = 0;
+    const int limiter = ext & 1, visc = ext & 2;
     const int D = p.D, nc = p.nc, nslot = p.nslot, NS = nslot + 1;
     if (T < 32 || T > 2048 || (T & 1)) return "tile size must be even, 32..2048";
     if (n_update <= 0 || n_update > nc) return "n_update out of range";
-    tp.T = T; tp.order = order; tp.D = D; tp.nslot = nslot; tp.limiter = limiter;
+    tp.T = T; tp.order = order; tp.D = D; tp.nslot = nslot; tp.ext = ext;
     const bool lsq = !p.lsq.empty();
     tp.ntiles = (n_update + T - 1) / T;
     tp.desc.assign(tp.ntiles, TileDesc{});
@@ -62,7 +64,7 @@ std::string build_tiles(const Plan& p, int n_update, int T, int order, TilePack&
             int64_t ro = 0, po = 0;
             for (int t = 0; t < nt; t++) {
                 TileDesc& d = tp.desc[t];
-                const TileLayout L = tile_layout(D, order, nslot, d.n_own, d.n_r1, d.n_r2, d.nFB, limiter);
+                const TileLayout L = tile_layout(D, order, nslot, d.n_own, d.n_r1, d.n_r2, d.nFB, ext);
                 d.ring_off = ro; d.pk_off = po;
                 ro += up(d.n_r1 + d.n_r2, 4);
                 po += L.pk_bytes;
@@ -128,7 +130,7 @@ std::string build_tiles(const Plan& p, int n_update, int T, int order, TilePack&
                     continue;
                 }
                 // ---- fill ---------------------------------------------------------
-                const TileLayout L = tile_layout(D, order, nslot, n_own, n_r1, n_r2, nFB, limiter);
+                const TileLayout L = tile_layout(D, order, nslot, n_own, n_r1, n_r2, nFB, ext);
                 unsigned char* pk = tp.packets.data() + d.pk_off;
                 double* w = reinterpret_cast<double*>(pk + L.w);
                 uint32_t* idx = reinterpret_cast<uint32_t*>(pk + L.idx);
@@ -205,10 +207,53 @@ std::string build_tiles(const Plan& p, int n_update, int T, int order, TilePack&
                     std::swap(beta[1], beta[1 + jself]);
                     std::swap(cells[1], cells[1 + jself]);
                 };
-                if (limiter != 0 && order == 2) {
+                if (ext) {
+                    // face-neighbour ids of the stencil cells (own + ring 1); own id where a slot has no neighbour
+                    uint16_t* lid = reinterpret_cast<uint16_t*>(pk + L.lid);
+                    const uint32_t nCLp = L.nCLp;
+                    for (uint32_t i = 0; i < nCLp; i++)
+                        for (int m = 0; m < nslot; m++) {
+                            int v = 0;
+                            if ((int)i < n_own + n_r1) {
+                                const int c = (int)i < n_own ? cb + (int)i : s.ring[i - n_own];
+                                int g, side;
+                                const int nb = nb_of(c, m, g, side);
+                                v = nb >= 0 ? local_of(nb) : (int)i;
+                            }
+                            lid[(size_t)m * nCLp + i] = (uint16_t)v;
+                        }
+                }
+                if (visc) {
+                    // viscous term: Green-Gauss gradient of the face primitives needs, per face slot of a stencil
+                    // cell, the two interpolation weights of the face state and the outward area vector / V
+                    double* vw = reinterpret_cast<double*>(pk + L.vw);
+                    double* feta = reinterpret_cast<double*>(pk + L.feta);
+                    const uint32_t nCLp = L.nCLp;
+                    const int W = 2 + D;
+                    for (int i = 0; i < n_own + n_r1; i++) {
+                        const int c = i < n_own ? cb + i : s.ring[i - n_own];
+                        for (int j = 0; j < nslot; j++) {
+                            int g, side;
+                            const int nb = nb_of(c, j, g, side);
+                            double e0 = 1.0, e1 = 0.0, S[3] = {0.0, 0.0, 0.0};  // pad slot: contributes nothing
+                            if (g >= 0) {
+                                const double e = p.eta[g];
+                                if (nb >= 0) { e0 = side ? (1.0 - e) : e; e1 = side ? e : (1.0 - e); }
+                                for (int k = 0; k < D; k++) S[k] = (side ? -1.0 : 1.0) * p.Sd[(size_t)g * D + k] / p.vol[c];
+                            }
+                            vw[((size_t)j * W + 0) * nCLp + i] = e0;
+                            vw[((size_t)j * W + 1) * nCLp + i] = e1;
+                            for (int k = 0; k < D; k++) vw[((size_t)j * W + 2 + k) * nCLp + i] = S[k];
+                        }
+                    }
+                    for (int i = n_own + n_r1; i < (int)nCLp; i++)
+                        for (int j = 0; j < nslot; j++) vw[((size_t)j * W + 0) * nCLp + i] = 1.0;
+                    for (int lf = 0; lf < nFB; lf++) feta[lf] = p.eta[s.flist[lf]];
+                    for (uint32_t lf = (uint32_t)nFB; lf < L.nFBp; lf++) feta[lf] = 1.0;
+                }
+                if (limiter) {
                     // limiter tables of the cells whose reconstruction the tile evaluates: own + ring 1
                     double* lw = reinterpret_cast<double*>(pk + L.lw);
-                    uint16_t* lid = reinterpret_cast<uint16_t*>(pk + L.lid);
                     double* le2 = reinterpret_cast<double*>(pk + L.le2);
                     const uint32_t nCLp = L.nCLp;
                     for (int i = 0; i < n_own + n_r1; i++) {
@@ -225,12 +270,8 @@ std::string build_tiles(const Plan& p, int n_update, int T, int order, TilePack&
                             }
                             project(c, side ? &p.dx1[(size_t)g * D] : &p.dx0[(size_t)g * D], 0.0, beta, cells);
                             for (int m = 0; m < NS; m++) lw[((size_t)j * NS + m) * nCLp + i] = beta[m];
-                            if (j == 0)
-                                for (int m = 0; m < nslot; m++) lid[(size_t)m * nCLp + i] = (uint16_t)cells[1 + m];
                         }
                     }
-                    for (uint32_t i = (uint32_t)(n_own + n_r1); i < nCLp; i++)
-                        for (int m = 0; m < nslot; m++) lid[(size_t)m * nCLp + i] = 0;
                 }
                 for (int lf = 0; lf < nFB; lf++) {
                     const int f = s.flist[lf];

@@ -38,7 +38,7 @@ struct TileDesc {
 };
 
 struct TilePack {
-    int T = 0, ntiles = 0, order = 2, D = 0, nslot = 0, limiter = 0;
+    int T = 0, ntiles = 0, order = 2, D = 0, nslot = 0, ext = 0;
     std::vector<TileDesc> desc;
     std::vector<int32_t> ring;           // device-order cell ids of ring cells
     std::vector<unsigned char> packets;  // concatenated packets, layout = tile_layout()
@@ -47,7 +47,7 @@ struct TilePack {
 };
 
 // n_update: cells [0, n_update) are advanced (the rest are ghosts, read only)
-// limiter != 0 (extension): the packets also carry the limiter tables of tile_layout.h
-std::string build_tiles(const Plan& p, int n_update, int T, int order, TilePack& tp, int limiter = 0);
+// ext (tile_ext()): the packets also carry the limiter / viscous tables of tile_layout.h
+std::string build_tiles(const Plan& p, int n_update, int T, int order, TilePack& tp, int ext = 0);
 
 }  // namespace mst

@@ -262,24 +262,28 @@ def test_large_box_properties():
 
 @pytest.mark.parametrize("dim", [2, 3])
 @pytest.mark.parametrize("order", [1, 2])
-def test_viscous_extension(dim, order):
-    """Laminar viscous term (documented extension): GPU
-    (split-kernel path) vs the oracle's corrected formulation; viscous wall =
-    negated momentum ghost (RhoSolver.cpp:301-305)."""
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("limiter", ["none", "venkat"])
+def test_viscous_extension(dim, order, kernel, limiter):
+    """Laminar viscous term (documented extension): GPU (fused tile kernel at second
+    order, split kernels otherwise) vs the oracle's corrected formulation; viscous wall = negated
+    momentum ghost (RhoSolver.cpp:301-305)."""
+    if limiter != "none" and order == 1:
+        pytest.skip("the limiter acts on the second-order reconstruction")
     if dim == 2:
         f = load_flat("2d-stairW-1"); inlet = None
     else:
         f = box_flat(6, 5, 4, bc=(10, 5, 3, 7, 3, 3), l=(1.0, 0.8, 0.6)); inlet = np.array([1.0, 0.4, 0.0, 0.0, 2.58])
     Q0 = mesh_np.random_state(f, seed=6)
-    kw = dict(order=order, flux="roe", viscous=1, mu=0.01, kappa=0.5, inletQ=inlet)
+    kw = dict(order=order, flux="roe", viscous=1, mu=0.01, kappa=0.5, inletQ=inlet, limiter=limiter, limiter_k=2.0)
     o = oracle.Oracle(f, **kw)
-    g = mstgpu.Context(f, **kw)
+    g = mstgpu.Context(f, kernel=kernel, **kw)
     g.set_state(Q0)
     Q1 = o.run(1e-5, 1, Q0)
     g.step(1e-5, 1)
     assert rel_linf(g.get_state(), Q1) <= TOL_1STEP
     # the term is active: the inviscid result differs
-    Qi = oracle.Oracle(f, order=order, flux="roe", viscous=0, inletQ=inlet).run(1e-5, 1, Q0)
+    Qi = oracle.Oracle(f, **dict(kw, viscous=0)).run(1e-5, 1, Q0)
     assert rel_linf(Q1, Qi) > 1e-8
     Q5 = o.run(1e-5, 4, Q1)
     g.step(1e-5, 4)
@@ -346,7 +350,7 @@ def test_hexahedra_seven_point_stencil(order, kernel):
     assert rel_linf(g.get_state(), Q1) <= 1e-11
 
 
-@pytest.mark.parametrize("viscous,kernel", [(1, "split"), (0, "tiles"), (0, "split")])
+@pytest.mark.parametrize("viscous,kernel", [(1, "split"), (1, "tiles"), (0, "tiles"), (0, "split")])
 def test_config3_sphere_shell_roe_viscous(viscous, kernel):
     """BASELINE config 3 in small: flow over a sphere on the cubed-sphere shell (24 tets per hex), Roe,
     second order, laminar viscous term (extension), wall / inlet / outlet zones; 1 and 20 steps."""
