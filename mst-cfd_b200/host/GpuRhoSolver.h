@@ -47,6 +47,12 @@ struct Options {
     int device = -1;
     double inletQ[5] = {0, 0, 0, 0, 0};
     bool have_inlet = false;
+    // options the reference does not have; the defaults are the reference's scheme
+    int gradient = MSTGPU_GRAD_GREEN_GAUSS;  // or MSTGPU_GRAD_LSQ
+    int limiter = MSTGPU_LIMITER_NONE;       // or _BARTH_JESPERSEN / _VENKATAKRISHNAN
+    double limiter_k = 5.0;
+    bool implicit = false;                   // solve() = residual + block assembly + LU-SGS sweeps of R/lusolver
+    int lusgs_iterations = 5;                // LU_INTERVAL (CONST.h:58)
 };
 
 // Flatten the reference's pointer-graph mesh into the tables of mstgpu_mesh,
@@ -128,6 +134,7 @@ public:
             mstgpu_default_config(&cfg, ND);
             const Options& o = options();
             cfg.order = o.order; cfg.flux = o.flux; cfg.viscous = o.viscous; cfg.device = o.device;
+            cfg.gradient = o.gradient; cfg.limiter = o.limiter; cfg.limiter_k = o.limiter_k;
             if (o.have_inlet) for (int k = 0; k < 5; k++) cfg.inletQ[k] = o.inletQ[k];
             check(mstgpu_create(&sc->ctx, &fm.m, &cfg), nullptr, "mstgpu_create");
             sc->ncells = fm.m.ncells; sc->U = ND + 2;
@@ -139,7 +146,10 @@ public:
     // host wrote AllData's old array, e.g. a restart) uploads the state.
     void solve() {
         if (!sc->state_on_device) upload_old();
-        check(mstgpu_step(sc->ctx, DT, 1), sc->ctx, "mstgpu_step");
+        if (options().implicit)
+            check(mstgpu_step_implicit(sc->ctx, DT, 1, options().lusgs_iterations, nullptr), sc->ctx, "mstgpu_step_implicit");
+        else
+            check(mstgpu_step(sc->ctx, DT, 1), sc->ctx, "mstgpu_step");
         sc->new_on_host = sc->old_on_host = false;
     }
     Vec* getNewValue() {  // RhoSolver.cpp:507-509
