@@ -27,6 +27,20 @@ def lib():
         L.msthost_grid_tris_sizes.restype = None
         L.msthost_grid_tris.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double] + [vp] * 7
         L.msthost_flatten.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int] + [vp] * 4 + [C.c_int] + [vp] * 9
+        L.msthost_last_error.restype = C.c_char_p
+        L.msthost_msh_read.argtypes = [C.c_char_p, C.POINTER(vp)]
+        L.msthost_msh_parse.argtypes = [C.c_char_p, C.c_int64, C.POINTER(vp)]
+        L.msthost_msh_free.argtypes = [vp]
+        L.msthost_msh_free.restype = None
+        L.msthost_msh_sizes.argtypes = [vp, i64p]
+        L.msthost_msh_tables.argtypes = [vp] * 7
+        L.msthost_msh_zone_name.argtypes = [vp, C.c_int32]
+        L.msthost_msh_zone_name.restype = C.c_char_p
+        L.msthost_node_faces.argtypes = [C.c_int64, C.c_int64, C.c_int32, vp, vp, vp]
+        L.msthost_cell_nodes.argtypes = [C.c_int32, C.c_int64, C.c_int32] + [vp] * 6
+        L.msthost_plt_write.argtypes = [C.c_char_p, C.c_int32, C.c_int64, C.c_int64] + [vp] * 4 + [C.c_int32, C.c_int32]
+        L.msthost_plt_write_binary.argtypes = [C.c_char_p, C.c_int32, C.c_int64, C.c_int64] + [vp] * 4 + [C.c_int32]
+        L.msthost_msh_write.argtypes = [C.c_char_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32] + [vp] * 4 + [C.c_int32, vp]
         _lib = L
     return _lib
 
@@ -66,6 +80,104 @@ def flatten_raw(raw: dict, flag_convention: str = "consistent") -> dict:
         raise RuntimeError("msthost_flatten failed")
     return dict(dim=dim, ncells=nc, nfaces=nf, nint=nint, c0=c0, c1=c1, S=S, dac=dac, fc=fc,
                 eta=eta, flag=flag, ftype=ftype, cc=cc, vol=vol, cf_ptr=cf_ptr, cf_idx=cf_idx)
+
+
+def _msh_handle_to_raw(L, h) -> dict:
+    try:
+        sz = (C.c_int64 * 8)()
+        L.msthost_msh_sizes(h, sz)
+        dim, nn, nc, nf, nint, nz, npf = (int(v) for v in sz[:7])
+        nodes = np.empty((nn, dim)); fn = np.empty((nf, npf), dtype=np.int32)
+        c0 = np.empty(nf, dtype=np.int32); c1 = np.empty(nf, dtype=np.int32); ft = np.empty(nf, dtype=np.int32)
+        zt = np.empty((nz, 5), dtype=np.int32)
+        L.msthost_msh_tables(h, _p(nodes), _p(fn), _p(c0), _p(c1), _p(ft), _p(zt))
+        zones = [dict(id=int(z[0]), start=int(z[1]), end=int(z[2]), type=int(z[3]), npf=int(z[4]),
+                      name=L.msthost_msh_zone_name(h, k).decode("ascii", "replace")) for k, z in enumerate(zt)]
+    finally:
+        L.msthost_msh_free(h)
+    return dict(dim=dim, ncells=nc, nodes=nodes, face_nodes=fn, c0=c0, c1=c1, ftype=ft, nint=nint, zones=zones)
+
+
+def read_msh(path: str) -> dict:
+    """Native reader for the Fluent ASCII .msh subset of the reference's MshBlock
+    (R/mesh/MshBlock.cpp:75-271, host/mshread.cpp): raw tables, same keys as the generators."""
+    L = lib()
+    h = C.c_void_p()
+    rc = L.msthost_msh_read(os.fsencode(path), C.byref(h))
+    if rc != 0:
+        raise RuntimeError(f"msthost_msh_read({path}): {L.msthost_last_error().decode()}")
+    return _msh_handle_to_raw(L, h)
+
+
+def parse_msh(text: bytes) -> dict:
+    """read_msh on a memory image of the file."""
+    L = lib()
+    h = C.c_void_p()
+    rc = L.msthost_msh_parse(text, len(text), C.byref(h))
+    if rc != 0:
+        raise RuntimeError(f"msthost_msh_parse: {L.msthost_last_error().decode()}")
+    return _msh_handle_to_raw(L, h)
+
+
+def write_msh(path: str, raw: dict):
+    """Raw tables -> .msh file the reference's own reader accepts (multi-threaded writer)."""
+    L = lib()
+    raw = raw if "zones" in raw else raw_zones_from_ftype(raw)
+    nodes = np.ascontiguousarray(raw["nodes"], dtype=np.float64)
+    fn = np.ascontiguousarray(raw["face_nodes"], dtype=np.int32)
+    c0 = np.ascontiguousarray(raw["c0"], dtype=np.int32); c1 = np.ascontiguousarray(raw["c1"], dtype=np.int32)
+    zt = np.array([[z.get("id", k + 7), z["start"], z["end"], z["type"],
+                    z.get("npf", int((fn[z["start"]] >= 0).sum()) if z["end"] > z["start"] else fn.shape[1])]
+                   for k, z in enumerate(raw["zones"])], dtype=np.int32).reshape(-1, 5)
+    rc = L.msthost_msh_write(os.fsencode(path), int(raw["dim"]), nodes.shape[0], int(raw["ncells"]), c0.shape[0],
+                             fn.shape[1], _p(nodes), _p(fn), _p(c0), _p(c1), zt.shape[0], _p(zt))
+    if rc != 0:
+        raise RuntimeError(f"msthost_msh_write({path}): {L.msthost_last_error().decode()}")
+
+
+def node_faces(raw: dict):
+    """(nf_ptr, nf_idx): a node's faces in the order Node::addNbFace builds it (R/mesh/Node.cpp:13-15)."""
+    fn = np.ascontiguousarray(raw["face_nodes"], dtype=np.int32)
+    nn = int(np.asarray(raw["nodes"]).shape[0])
+    ptr = np.empty(nn + 1, dtype=np.int32)
+    idx = np.empty(int((fn >= 0).sum()), dtype=np.int32)
+    if lib().msthost_node_faces(nn, fn.shape[0], fn.shape[1], _p(fn), _p(ptr), _p(idx)) != 0:
+        raise RuntimeError("msthost_node_faces failed")
+    return ptr, idx
+
+
+def cell_nodes(raw: dict, flat: dict):
+    """(cn_ptr, cn_idx): Cell::getBeginItPNbNodes as the reference builds it (MshBlock.cpp:335-368)."""
+    fn = np.ascontiguousarray(raw["face_nodes"], dtype=np.int32)
+    nodes = np.ascontiguousarray(raw["nodes"], dtype=np.float64)
+    nc = int(flat["ncells"])
+    ptr = np.empty(nc + 1, dtype=np.int32)
+    L = lib()
+    args = (int(raw["dim"]), nc, fn.shape[1], _p(fn), _p(flat["cf_ptr"]), _p(flat["cf_idx"]), _p(nodes))
+    if L.msthost_cell_nodes(*args, _p(ptr), None) != 0:
+        raise RuntimeError("msthost_cell_nodes failed")
+    idx = np.empty(int(ptr[-1]), dtype=np.int32)
+    if L.msthost_cell_nodes(*args, _p(ptr), _p(idx)) != 0:
+        raise RuntimeError("msthost_cell_nodes failed")
+    return ptr, idx
+
+
+def plt_write(path: str, raw: dict, fields: np.ndarray, cn_ptr, cn_idx, zone_t: int = 0, felnum: int = 4, binary: bool = False):
+    """The reference's node-averaged Tecplot file (Work.cpp:204-319) from node fields [nnodes, dim+4]
+    (mstgpu.Context.node_fields); byte-identical to the reference's own writer.  binary=True: raw dump."""
+    nodes = np.ascontiguousarray(raw["nodes"], dtype=np.float64)
+    fields = np.ascontiguousarray(fields, dtype=np.float64)
+    dim = int(raw["dim"])
+    assert fields.shape == (nodes.shape[0], dim + 4)
+    L = lib()
+    if binary:
+        rc = L.msthost_plt_write_binary(os.fsencode(path), dim, nodes.shape[0], cn_ptr.size - 1, _p(nodes), _p(fields),
+                                        _p(cn_ptr), _p(cn_idx), int(zone_t))
+    else:
+        rc = L.msthost_plt_write(os.fsencode(path), dim, nodes.shape[0], cn_ptr.size - 1, _p(nodes), _p(fields),
+                                 _p(cn_ptr), _p(cn_idx), int(zone_t), int(felnum))
+    if rc != 0:
+        raise RuntimeError(f"msthost_plt_write({path}) failed ({rc})")
 
 
 def box_tets_raw(nx, ny, nz, lx=1.0, ly=1.0, lz=1.0, bc=(3, 3, 3, 3, 3, 3)) -> dict:
