@@ -180,6 +180,22 @@ int mstgpu_step_implicit(mstgpu_ctx* ctx, double dt, int32_t nsteps, int32_t lus
 int mstgpu_residual_linf(mstgpu_ctx* ctx, double* out_dimu);
 int mstgpu_sync(mstgpu_ctx* ctx);
 
+/* ---- output path: replaces the arithmetic of
+ * Work::writedataRhoBasedMshNodePlt (R/work/Work.cpp:243-304), which the reference runs on the
+ * host after reading the whole cell state back.
+ *   mstgpu_output_setup  once: the node -> faces lists in the order Node::addNbFace builds them
+ *                        (R/mesh/Node.cpp:13-15; nf_ptr [nnodes+1], nf_idx), the mesh the context was
+ *                        created from (c0, c1, eta, ftype are read), and the per-node weight of
+ *                        Work.cpp:292-293, 1 / Face::getArea() of face[node id] (NULL = 1).
+ *   mstgpu_node_fields   out [nnodes][D+4] = rho, u_i, T, p, Ma of every node for the CURRENT
+ *                        state, bit-identical to the reference's numbers (the columns it prints
+ *                        after the coordinates, Work.cpp:299-303).  Zone types its switch does not
+ *                        list (symmetry) read an uninitialised array there; Q[c0] here.
+ * Not available on a partitioned context (gather the state with mstgpu_get_state instead). */
+int mstgpu_output_setup(mstgpu_ctx* ctx, const mstgpu_mesh* mesh, int32_t nnodes, const int32_t* nf_ptr,
+                        const int32_t* nf_idx, const double* node_weight);
+int mstgpu_node_fields(mstgpu_ctx* ctx, double* out);
+
 /* Stage probes of the last step, reference order.
  * gradient: [ncells][DIMU][D]; face flux: [nfaces][DIMU] =
  * sum_d (dac*S)[d] * F[:,d], i.e. the flux through the face oriented out of c0. */

@@ -141,6 +141,10 @@ struct mstgpu_ctx {
     double* dt_dev = nullptr;             // [0] dt of the running step, [1] time advanced
     unsigned long long* resid = nullptr;  // [U] bit patterns of non-negative doubles
     int* nanflag = nullptr;
+    // output path (csrc/output.cuh): node -> faces CSR, per-face cells (device order) and eta, node weights
+    int32_t *out_nf_ptr = nullptr, *out_nf_idx = nullptr, *out_c0 = nullptr, *out_c1 = nullptr;
+    double *out_eta = nullptr, *out_w = nullptr, *out_fields = nullptr;
+    int out_nn = 0;
     int cur = 0;          // Q[cur] = current ("old") state
     bool has_state = false, stepped = false;
     int64_t launches = 0, dev_bytes = 0;
@@ -1453,7 +1457,8 @@ void mstgpu_destroy(mstgpu_ctx* ctx) {
     void* ptrs[] = {ctx->Q[0], ctx->Q[1], ctx->G, ctx->Gp, ctx->Phi, ctx->stage, ctx->Sd, ctx->dx0, ctx->dx1, ctx->eta,
                     ctx->vol, ctx->fc0, ctx->fc1, ctx->cf, ctx->cell_new2old, ctx->face_new2old, ctx->meta,
                     ctx->resid, ctx->nanflag, ctx->lsq, ctx->eps2, ctx->dtmin, ctx->dt_dev, ctx->imp_dpos, ctx->imp_pos,
-                    ctx->imp_val, ctx->imp_b, ctx->imp_x};
+                    ctx->imp_val, ctx->imp_b, ctx->imp_x, ctx->out_nf_ptr, ctx->out_nf_idx, ctx->out_c0, ctx->out_c1,
+                    ctx->out_eta, ctx->out_w, ctx->out_fields};
     if (ctx->imp_solver) mstgpu_lusgs_destroy(ctx->imp_solver);
     for (void* q : ptrs)
         if (q) cudaFree(q);
@@ -1856,3 +1861,5 @@ int mstgpu_plan_permutation(const mstgpu_mesh* mesh, const mstgpu_config* cfg, i
 }
 
 }  // extern "C"
+
+#include "output.cuh"

@@ -107,6 +107,7 @@ struct SharedContext {
     int ncells = 0, U = 0;
     bool state_on_device = false;  // device holds the current state
     bool new_on_host = false, old_on_host = false;
+    bool output_ready = false;     // mstgpu_output_setup done (nodeFields)
     ~SharedContext() { if (ctx) mstgpu_destroy(ctx); }
 };
 
@@ -182,6 +183,32 @@ public:
     // extras a GPU-aware host can use instead of reading both arrays every step
     void residual(double* out_dimu) { check(mstgpu_residual_linf(sc->ctx, out_dimu), sc->ctx, "mstgpu_residual_linf"); }
     void invalidateDeviceState() { sc->state_on_device = false; }  // call after writing AllData by hand
+
+    // Output path: rho, u_i, T, p, Ma of every node for the current state, [nnodes][ND + 4], computed on the
+    // device -- the numbers Work::writedataRhoBasedMshNodePlt prints after the coordinates
+    // (R/work/Work.cpp:243-304), bit-identical, without downloading the cell state.  The node -> faces lists
+    // and the per-node weight 1 / area(face[node id]) (Work.cpp:292) are taken from the host's own mesh once.
+    void nodeFields(std::vector<double>& out) {
+        if (!sc->state_on_device) upload_old();
+        const int nn = pMesh->getNumOfNodes();
+        if (!sc->output_ready) {
+            FlatMesh<Mesh> fm;
+            fm.build(pMesh, ND);
+            auto* nodes = pMesh->getBeginItNodesList();
+            auto* faces = pMesh->getBeginItFacesList();
+            std::vector<int32_t> ptr((size_t)nn + 1, 0), idx;
+            std::vector<double> w((size_t)nn);
+            for (int i = 0; i < nn; i++) {
+                for (auto it = nodes[i].getBeginItPNbFaces(); it < nodes[i].getEndItPNbFaces(); it++) idx.push_back((*it)->getId());
+                ptr[(size_t)i + 1] = (int32_t)idx.size();
+                w[(size_t)i] = 1 / faces[i].getArea();
+            }
+            check(mstgpu_output_setup(sc->ctx, &fm.m, nn, ptr.data(), idx.data(), w.data()), sc->ctx, "mstgpu_output_setup");
+            sc->output_ready = true;
+        }
+        out.resize((size_t)nn * (ND + 4));
+        check(mstgpu_node_fields(sc->ctx, out.data()), sc->ctx, "mstgpu_node_fields");
+    }
     static void release(Mesh* mesh, Data* data) { registry().erase({(const void*)mesh, (const void*)data}); }
 
 private:

@@ -31,10 +31,15 @@
 
 namespace {
 
-// ostream << fixed << setprecision(15) << v  (setw(15) never pads: 17 characters at least)
-inline char* put_fixed15(char* p, double v) {
+// ostream << fixed << setprecision(15) [<< setw(15)] << v.  A finite number has 17 characters at least, so
+// setw(15) only shows on nan / inf, which are right-aligned in 15 columns like iostream does.
+inline char* put_fixed15(char* p, double v, bool setw15) {
     if (std::isfinite(v)) return std::to_chars(p, p + 340, v, std::chars_format::fixed, 15).ptr;
-    return p + snprintf(p, 16, "%.15f", v);  // nan / -nan / inf / -inf exactly as printf spells them
+    char t[16];
+    const int n = snprintf(t, sizeof t, "%.15f", v);  // nan / -nan / inf / -inf exactly as printf spells them
+    if (setw15) for (int k = n; k < 15; k++) *p++ = ' ';
+    memcpy(p, t, (size_t)n);
+    return p + n;
 }
 
 }  // namespace
@@ -117,8 +122,9 @@ int msthost_plt_write(const char* path, int32_t dim, int64_t nnodes, int64_t nce
     }
     const int numw = (int)std::floor(std::log10(big)) + 1 + 1 + 1 + 15 + 2;
     bool ok = msthost::emit_records(fp, nnodes, (D + W) * (numw + 1) + 2, [&](int64_t i, char* p) {
-        for (int d = 0; d < D; d++) { p = put_fixed15(p, nodes[i * D + d]); *p++ = ' '; }
-        for (int k = 0; k < W; k++) { p = put_fixed15(p, fields[i * W + k]); *p++ = ' '; }
+        // setw(15) is in front of the coordinates, rho, u_i and T only (Work.cpp:297-303)
+        for (int d = 0; d < D; d++) { p = put_fixed15(p, nodes[i * D + d], true); *p++ = ' '; }
+        for (int k = 0; k < W; k++) { p = put_fixed15(p, fields[i * W + k], k < D + 2); *p++ = ' '; }
         *p++ = '\n';
         return p;
     });

@@ -33,6 +33,7 @@ EXPORTS = [
     "mstgpu_lusgs_solve", "mstgpu_lusgs_levels", "mstgpu_lusgs_create_ordered", "mstgpu_lusgs_solve_device",
     "mstgpu_lusgs_create_partitioned", "mstgpu_lusgs_color_order_partitioned",
     "mstgpu_lusgs_launch_count", "mstgpu_lusgs_device_bytes", "mstgpu_mesh_adjacency", "mstgpu_lusgs_color_order", "mstgpu_lusgs_last_error",
+    "mstgpu_output_setup", "mstgpu_node_fields",
     "mstgpu_last_error", "mstgpu_version",
 ]
 
@@ -100,6 +101,8 @@ def lib():
         L.mstgpu_step_implicit.argtypes = [vp, dbl, i32, i32, C.POINTER(C.c_float)]
         L.mstgpu_residual_linf.argtypes = [vp, vp]
         L.mstgpu_sync.argtypes = [vp]
+        L.mstgpu_output_setup.argtypes = [vp, C.POINTER(MstMesh), i32, vp, vp, vp]
+        L.mstgpu_node_fields.argtypes = [vp, vp]
         L.mstgpu_debug_gradient.argtypes = [vp, vp]
         L.mstgpu_debug_face_flux.argtypes = [vp, vp]
         L.mstgpu_launch_count.argtypes = [vp]
@@ -388,6 +391,24 @@ class Context:
 
     def get_state_ptr(self, ptr: int):
         self._check(lib().mstgpu_get_state(self.h, ptr), "get_state")
+
+    def output_setup(self, flat, nf_ptr, nf_idx, node_weight=None):
+        """Output path (Work.cpp:243-304 on the device): `flat` is the mesh the context was created
+        from, (nf_ptr, nf_idx) the node -> faces lists in Node::addNbFace order (host.node_faces),
+        node_weight the reference's 1 / area(face[node id]) (None = 1)."""
+        m, keep = _mesh_struct(flat)
+        nf_ptr = np.ascontiguousarray(nf_ptr, dtype=np.int32); nf_idx = np.ascontiguousarray(nf_idx, dtype=np.int32)
+        w = None if node_weight is None else np.ascontiguousarray(node_weight, dtype=np.float64)
+        self.nnodes = nf_ptr.size - 1
+        self._check(lib().mstgpu_output_setup(self.h, C.byref(m), self.nnodes, nf_ptr.ctypes.data, nf_idx.ctypes.data,
+                                              None if w is None else w.ctypes.data), "output_setup")
+
+    def node_fields(self, out=None):
+        """[nnodes, dim+4] = rho, u_i, T, p, Ma per node of the current state (bit-identical to the
+        numbers the reference's writer prints)."""
+        out = np.empty((self.nnodes, self.dim + 4)) if out is None else out
+        self._check(lib().mstgpu_node_fields(self.h, out.ctypes.data), "node_fields")
+        return out
 
     def get_prev_state(self):
         out = np.empty((self.ncells, self.U))

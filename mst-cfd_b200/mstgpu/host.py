@@ -146,6 +146,18 @@ def node_faces(raw: dict):
     return ptr, idx
 
 
+def node_weights(flat: dict, nnodes: int) -> np.ndarray:
+    """The per-node weight of the reference's node averaging: 1 / Face::getArea() of face[NODE id]
+    (the reference indexes its face list with the node index, R/work/Work.cpp:292-293)."""
+    S = np.asarray(flat["S"])[:nnodes]
+    if S.shape[0] < nnodes:
+        raise ValueError("the reference reads face[node id]: needs nfaces >= nnodes")
+    a2 = S[:, 0] * S[:, 0] + S[:, 1] * S[:, 1]
+    if S.shape[1] == 3:
+        a2 = a2 + S[:, 2] * S[:, 2]
+    return 1.0 / np.sqrt(a2)
+
+
 def cell_nodes(raw: dict, flat: dict):
     """(cn_ptr, cn_idx): Cell::getBeginItPNbNodes as the reference builds it (MshBlock.cpp:335-368)."""
     fn = np.ascontiguousarray(raw["face_nodes"], dtype=np.int32)

@@ -90,6 +90,14 @@ int main(int argc, char** argv) {
         dump(nm, "f8", allData.getP1OldCellQs(), (long long)nc * (DIMU), 8);
     }
     dump("resid_host_dev", "f8", resid.data(), (long long)resid.size(), 8);
+    {
+        // output path: node-averaged fields of the final state from the device (GpuRhoSolverT::nodeFields),
+        // fed by the reference's own Node / Face lists
+        GpuRhoSolver outSolver(&mesh, &fLog, &allData);
+        std::vector<double> nodeF;
+        outSolver.nodeFields(nodeF);
+        dump("node_fields", "f8", nodeF.data(), (long long)nodeF.size(), 8);
+    }
     GpuRhoSolver::release(&mesh, &allData);
     fclose(g_out);
     return 0;

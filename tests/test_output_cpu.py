@@ -73,21 +73,24 @@ def test_plt_file_against_a_fresh_run_of_the_reference_writer(tmp_path):
 
 
 def test_writer_spells_non_finite_and_negative_zero_like_iostream(tmp_path):
-    raw = dict(dim=2, nodes=np.array([[0.0, -0.0], [1.5, 2.25], [1e6, -3.0]]))
-    fld = np.array([[np.nan, -np.nan, np.inf, -np.inf, -0.0, 1.0 / 3.0],
+    raw = dict(dim=2, nodes=np.array([[0.0, -0.0], [1.5, 2.25], [1e6, -3.0], [0.1, 0.2]]))
+    fld = np.array([[np.nan, -np.nan, np.inf, -np.inf, -np.nan, np.inf],
+                    [-0.0, 1.0 / 3.0, -np.inf, 1e-20, np.nan, -0.0],
                     [1.0, 2.0, 3.0, 4.0, 5.0, 6.0],
                     [123456789.125, -1e-300, 5e-16, 4.9999e-16, 0.5, 2.5]])
     cp = np.array([0, 3], dtype=np.int32); ci = np.array([0, 1, 2], dtype=np.int32)
+    n = fld.shape[0]
     out = str(tmp_path / "x.plt")
     host.plt_write(out, raw, fld, cp, ci, zone_t=1, felnum=3)
     lines = open(out).read().split("\n")
     assert lines[2].endswith("ZONETYPE=FETRIANGLE")
     # glibc printf / libstdc++ num_put spell a NaN with the sign bit set "-nan" (Python drops the sign)
-    fmt = lambda v: ("-nan" if np.signbit(v) else "nan") if np.isnan(v) else "%.15f" % v
-    exp = lambda row: " ".join(fmt(v) for v in row) + " "
-    for i in range(3):
+    # setw(15) precedes the coordinates, rho, u, v, T (not p, Ma): it only shows on nan / inf
+    fmt = lambda v, k: ((("-nan" if np.signbit(v) else "nan") if np.isnan(v) else "%.15f" % v).rjust(15 if k < 6 else 0))
+    exp = lambda row: " ".join(fmt(v, k) for k, v in enumerate(row)) + " "
+    for i in range(n):
         assert lines[3 + i] == exp(list(raw["nodes"][i]) + list(fld[i]))
-    assert lines[6] == "1 2 3 "
+    assert lines[3 + n] == "1 2 3 "
 
 
 def test_binary_twin_round_trips(tmp_path):

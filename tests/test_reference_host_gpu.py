@@ -46,6 +46,23 @@ def test_reference_time_loop_on_the_gpu(case, tmp_path):
         Qg, Qr = d[f"Q{s}"].reshape(nc, -1), g[f"Q{s}"]
         tol = 1e-12 if s == 1 else 1e-9
         assert rel_linf(Qg, Qr) <= tol, (case, s)
+    # output path through the reference's own Node / Face lists: the device's node fields of the final state
+    # equal the restatement of Work.cpp:243-304 (itself pinned to the reference's writer, test_output_cpu.py)
+    # bit for bit
+    if "node_fields" in d and np.isfinite(d[f"Q{steps[-1]}"]).all():
+        from mstgpu import host
+        from oracle import output_np
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            f = mesh_np.flatten(raw, "consistent" if int(g["flagmode"]) == 1 else "as_shipped")
+        retag = str(g["retag"])
+        if retag != "-":
+            a, b = (int(x) for x in retag.split(":"))
+            f["ftype"] = np.where(f["ftype"] == a, b, f["ftype"]).astype(f["ftype"].dtype)
+        ptr, idx = host.node_faces(raw)
+        exp = output_np.node_fields(f, raw, d[f"Q{steps[-1]}"].reshape(nc, -1), ptr, idx)
+        assert np.array_equal(d["node_fields"].reshape(exp.shape), exp, equal_nan=True)
     # the residual the reference's host loop computes from the downloaded arrays equals the device reduction
     r = d["resid_host_dev"].reshape(-1, 2)
     fin = np.isfinite(r).all(axis=1)
