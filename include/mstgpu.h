@@ -202,6 +202,12 @@ int mstgpu_node_fields(mstgpu_ctx* ctx, double* out);
 int mstgpu_debug_gradient(mstgpu_ctx* ctx, double* grad);
 int mstgpu_debug_face_flux(mstgpu_ctx* ctx, double* phi);
 
+/* Experimental: launch variant of the default fused instantiation (3-D, second order, 256 threads, no
+ * extension): bit mask, 1 = L2 prefetch one tile ahead, 2 = persistent CTAs, 4 = cp.async ring rows;
+ * 0 = the measured default.  Same arithmetic in the same order: results are bit-identical.  The
+ * environment variable MSTGPU_TILE_VAR sets it at creation.  (csrc/step_tiles.cuh) */
+int mstgpu_set_tile_variant(mstgpu_ctx* ctx, int32_t variant);
+
 /* Introspection for the bench: kernels launched so far by this context and
  * per-kernel accumulated device time (ms) when timing is enabled. */
 int64_t mstgpu_launch_count(mstgpu_ctx* ctx);

@@ -106,6 +106,8 @@ struct mstgpu_ctx {
     TileArrays ta{};
     std::vector<void*> tile_allocs;
     int ntiles = 0, tile_T = 0, tile_NT = 0;
+    int tile_var = 0;   // MSTGPU_TILE_VAR: experimental variant of the default fused instantiation (0 = default)
+    int sm_count = 148;
     size_t tile_smem = 0;
     struct TileClass { int first, count; size_t smem; bool halo; };  // halo: a ring of the tile holds ghost cells
     std::vector<TileClass> tile_classes;  // tiles grouped by shared-memory need (CTAs per SM)
@@ -879,9 +881,9 @@ int halo_exchange(mstgpu_ctx* ctx, double* Q, cudaStream_t st) {
     return MSTGPU_OK;
 }
 
-template <int D, int ORDER, int NT, int NS, bool LIM, bool VISC>
-int launch_tiles_lim(mstgpu_ctx* ctx, double dt, const double* dtd, const double* Qo, double* Qn, int want_resid, int which, cudaStream_t st) {
-    auto kern = k_step_tiles<D, ORDER, NT, NS, LIM, VISC>;
+template <int D, int ORDER, int NT, int NS, bool LIM, bool VISC, int VAR>
+int launch_tiles_var(mstgpu_ctx* ctx, double dt, const double* dtd, const double* Qo, double* Qn, int want_resid, int which, cudaStream_t st) {
+    auto kern = k_step_tiles<D, ORDER, NT, NS, LIM, VISC, VAR>;
     static thread_local size_t configured_smem = 0;
     if (configured_smem < ctx->tile_smem) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->tile_smem));
@@ -892,10 +894,22 @@ int launch_tiles_lim(mstgpu_ctx* ctx, double dt, const double* dtd, const double
     for (const auto& tc : ctx->tile_classes) {
         if (which != 2 && (int)tc.halo != which) continue;
         cudaStream_t s = (ctx->fork_stream && (ci++ & 1)) ? ctx->fork_stream : st;
-        kern<<<tc.count, NT, tc.smem, s>>>(ctx->ta, tc.first, want_resid, ctx->dcfg, dt, dtd, Qo, Qn, ctx->resid, ctx->nanflag);
+        int grid = tc.count, wave = 0;
+        if (VAR & 3) {  // experimental variants: CTAs resident at once for this class's shared-memory size
+            int per_sm = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, tc.smem));
+            wave = std::max(1, per_sm) * ctx->sm_count;
+            if (VAR & 2) grid = std::min(tc.count, wave);
+        }
+        kern<<<grid, NT, tc.smem, s>>>(ctx->ta, tc.first, tc.count, wave, want_resid, ctx->dcfg, dt, dtd, Qo, Qn, ctx->resid, ctx->nanflag);
         ctx->launches++;
     }
     return MSTGPU_OK;
+}
+
+template <int D, int ORDER, int NT, int NS, bool LIM, bool VISC>
+int launch_tiles_lim(mstgpu_ctx* ctx, double dt, const double* dtd, const double* Qo, double* Qn, int want_resid, int which, cudaStream_t st) {
+    return launch_tiles_var<D, ORDER, NT, NS, LIM, VISC, 0>(ctx, dt, dtd, Qo, Qn, want_resid, which, st);
 }
 
 template <int D, int ORDER, int NT, int NS>
@@ -905,6 +919,18 @@ int launch_tiles(mstgpu_ctx* ctx, double dt, const double* dtd, const double* Qo
         if (lim && visc) return launch_tiles_lim<D, 2, NT, NS, true, true>(ctx, dt, dtd, Qo, Qn, wr, which, st);
         if (lim) return launch_tiles_lim<D, 2, NT, NS, true, false>(ctx, dt, dtd, Qo, Qn, wr, which, st);
         if (visc) return launch_tiles_lim<D, 2, NT, NS, false, true>(ctx, dt, dtd, Qo, Qn, wr, which, st);
+    }
+    if (D == 3 && ORDER == 2 && NT == 256 && NS == 5 && ctx->tile_var) {
+        // experimental variants of the default instantiation (step_tiles.cuh), bit-identical results
+        switch (ctx->tile_var) {
+            case 1: return launch_tiles_var<3, 2, 256, 5, false, false, 1>(ctx, dt, dtd, Qo, Qn, wr, which, st);
+            case 2: return launch_tiles_var<3, 2, 256, 5, false, false, 2>(ctx, dt, dtd, Qo, Qn, wr, which, st);
+            case 3: return launch_tiles_var<3, 2, 256, 5, false, false, 3>(ctx, dt, dtd, Qo, Qn, wr, which, st);
+            case 4: return launch_tiles_var<3, 2, 256, 5, false, false, 4>(ctx, dt, dtd, Qo, Qn, wr, which, st);
+            case 5: return launch_tiles_var<3, 2, 256, 5, false, false, 5>(ctx, dt, dtd, Qo, Qn, wr, which, st);
+            case 7: return launch_tiles_var<3, 2, 256, 5, false, false, 7>(ctx, dt, dtd, Qo, Qn, wr, which, st);
+            default: break;
+        }
     }
     return launch_tiles_lim<D, ORDER, NT, NS, false, false>(ctx, dt, dtd, Qo, Qn, wr, which, st);
 }
@@ -1346,6 +1372,8 @@ static int create_impl(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_c
             CK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
             if (tp.max_smem + 1024 > (size_t)dev_smem) { set_error(ctx, "tile needs more shared memory than the device has; lower tile_cells"); return MSTGPU_ERR_ARG; }
             ctx->ntiles = tp.ntiles; ctx->tile_T = T; ctx->tile_smem = tp.max_smem;
+            CK(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, ctx->device));
+            if (const char* v = getenv("MSTGPU_TILE_VAR")) ctx->tile_var = atoi(v);
             {
                 // The dynamic shared memory of a launch is what its LARGEST tile needs, and
                 // it decides how many CTAs share an SM.  A few outlier tiles (ragged blobs)
@@ -1729,6 +1757,16 @@ int mstgpu_debug_face_flux(mstgpu_ctx* ctx, double* phi) {
 }
 
 int64_t mstgpu_launch_count(mstgpu_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+int mstgpu_set_tile_variant(mstgpu_ctx* ctx, int32_t variant) {
+    if (!ctx) return MSTGPU_ERR_ARG;
+    if (variant < 0 || variant > 7 || variant == 6) { set_error(ctx, "tile variant must be 0-5 or 7"); return MSTGPU_ERR_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (auto& ge : ctx->step_graph) if (ge) { cudaGraphExecDestroy(ge); ge = nullptr; }  // the graph holds the old kernels
+    ctx->tile_var = variant;
+    return MSTGPU_OK;
+}
 
 int mstgpu_enable_kernel_timing(mstgpu_ctx* ctx, int32_t on) {
     if (!ctx) return MSTGPU_ERR_ARG;

@@ -129,6 +129,7 @@ int mstgpu_node_fields(mstgpu_ctx* ctx, double* out) {
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, ctx->out_fields, (size_t)nn * (ctx->D + 4) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->ktiming) drain_timers(ctx);
     return MSTGPU_OK;
 }
 

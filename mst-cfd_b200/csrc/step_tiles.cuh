@@ -98,17 +98,26 @@ __device__ __forceinline__ double warp_max_nonneg(double x) {
 #define MST_TILE_MINB(NT) ((NT) >= 256 ? 2 : 3)
 #endif
 
-template <int D, int ORDER, int NT, int NS, bool LIM = false, bool VISC = false>
-__global__ void __launch_bounds__(NT, MST_TILE_MINB(NT)) k_step_tiles(TileArrays ta, int tile_base, int want_resid, DevCfg cfg, double dt_val,
-                                                   const double* __restrict__ dt_dev,
-                                                   const double* __restrict__ Qold,
-                                                   double* __restrict__ Qnew,
-                                                   unsigned long long* __restrict__ resid,
-                                                   int* __restrict__ nanflag) {
+// Experimental variants of the default instantiation (MSTGPU_TILE_VAR, bit mask; 0 = the measured default):
+//   1  prefetch AHEAD: thread 0 pulls the packet and the owned state block of the tile this CTA slot will run
+//      NEXT (persistent: its own next tile; otherwise the tile one wave of CTAs later) into L2, so that the
+//      packet stream of phase 2 finds its lines in L2 from the first face on
+//   2  persistent CTAs: one launch of (resident CTAs) blocks per tile class, each looping over tiles
+//   4  ring rows by cp.async (LDGSTS): no register round trip, every row of a thread in flight at once
+// All variants run the same arithmetic in the same order: results are bit-identical to variant 0.
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+
+template <int D, int ORDER, int NT, int NS, bool LIM, bool VISC, int VAR>
+__device__ __forceinline__ void step_tile(const TileArrays& ta, const TileDesc d, const int pf_tile, const bool first, const bool pf_self,
+                                          const uint32_t parity, int want_resid, const DevCfg& cfg, double dt_val,
+                                          const double* __restrict__ dt_dev, const double* __restrict__ Qold,
+                                          double* __restrict__ Qnew, unsigned long long* __restrict__ resid,
+                                          int* __restrict__ nanflag) {
     constexpr int U = D + 2;
     constexpr int nslot = NS - 1;
     extern __shared__ __align__(128) unsigned char smem[];
-    const TileDesc d = ta.desc[tile_base + blockIdx.x];
     const int tid = threadIdx.x;
     const int n_own = d.n_own, n_ring = d.n_r1 + d.n_r2;
     const int nFB = d.nFB;
@@ -125,8 +134,10 @@ __global__ void __launch_bounds__(NT, MST_TILE_MINB(NT)) k_step_tiles(TileArrays
     const uint32_t bar = smem_u32(smem + L.mbar);
 
     // ---- phase 0: stage the states of the tile and its rings ------------------------
-    if (tid == 0) mbar_init(bar, 1);
-    __syncthreads();
+    if (first) {
+        if (tid == 0) mbar_init(bar, 1);
+        __syncthreads();
+    }
     if (tid == 0) {
         const uint32_t qbytes = (uint32_t)((n_own + 1) & ~1) * U * 8u;
         // slots + cvol are adjacent in the packet: one more bulk copy brings the phase-3
@@ -137,20 +148,38 @@ __global__ void __launch_bounds__(NT, MST_TILE_MINB(NT)) k_step_tiles(TileArrays
         bulk_g2s(smem_u32(smem + L.cells_s), pk + L.slots, cbytes, bar);
         // the packet is streamed from HBM by phase 2 / 3: start moving it into L2 now,
         // while the states are being staged
-        bulk_prefetch_l2(pk, L.pk_bytes);
+        if (pf_self) bulk_prefetch_l2(pk, L.pk_bytes);
+        if ((VAR & 1) && pf_tile >= 0) {
+            const TileDesc dn = ta.desc[pf_tile];
+            const TileLayout Ln = tile_layout(D, ORDER, nslot, dn.n_own, dn.n_r1, dn.n_r2, dn.nFB, (LIM ? 1 : 0) | (VISC ? 2 : 0));
+            bulk_prefetch_l2(ta.packets + dn.pk_off, Ln.pk_bytes);
+            bulk_prefetch_l2(Qold + (size_t)dn.cb * U, (uint32_t)((dn.n_own + 1) & ~1) * U * 8u);
+        }
     }
     // ring cells: one thread per cell, U independent loads of a contiguous 8*U-byte row.
     // (Batching several cells per thread -- ids first, then rows -- was measured: it helps the
     // 128-thread variant but costs registers and was 1 % slower for the default 256-thread one.)
-    for (int r = tid; r < n_ring; r += NT) {
-        const int g = ta.ring[d.ring_off + r];
-        double q[U];
+    if (VAR & 4) {
+        for (int r = tid; r < n_ring; r += NT) {
+            const int g = ta.ring[d.ring_off + r];
+            const double* src = Qold + (size_t)g * U;
+            const uint32_t dst = smem_u32(Qs + (n_own + r) * U);
 #pragma unroll
-        for (int k = 0; k < U; k++) q[k] = Qold[(size_t)g * U + k];
+            for (int k = 0; k < U; k++) cp_async8(dst + 8u * k, src + k);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else {
+        for (int r = tid; r < n_ring; r += NT) {
+            const int g = ta.ring[d.ring_off + r];
+            double q[U];
 #pragma unroll
-        for (int k = 0; k < U; k++) Qs[(n_own + r) * U + k] = q[k];
+            for (int k = 0; k < U; k++) q[k] = Qold[(size_t)g * U + k];
+#pragma unroll
+            for (int k = 0; k < U; k++) Qs[(n_own + r) * U + k] = q[k];
+        }
     }
-    mbar_wait(bar, 0);
+    mbar_wait(bar, parity);
     __syncthreads();
 
     // ---- phase 1 (limiter extension only): limiter value of every cell whose reconstruction the
@@ -438,6 +467,32 @@ __global__ void __launch_bounds__(NT, MST_TILE_MINB(NT)) k_step_tiles(TileArrays
         if (m > 0.0) atomicMax(&resid[k], (unsigned long long)__double_as_longlong(m));
     }
     if (anybad && tid == 64) atomicOr(nanflag, 1);
+}
+
+// n_class = tiles in this launch's class (persistent loop bound, prefetch bound); var_arg = prefetch distance in
+// tiles for the non-persistent prefetch-ahead variant (one wave of resident CTAs)
+template <int D, int ORDER, int NT, int NS, bool LIM = false, bool VISC = false, int VAR = 0>
+__global__ void __launch_bounds__(NT, MST_TILE_MINB(NT)) k_step_tiles(TileArrays ta, int tile_base, int n_class, int var_arg,
+                                                   int want_resid, DevCfg cfg, double dt_val,
+                                                   const double* __restrict__ dt_dev,
+                                                   const double* __restrict__ Qold,
+                                                   double* __restrict__ Qnew,
+                                                   unsigned long long* __restrict__ resid,
+                                                   int* __restrict__ nanflag) {
+    if (VAR & 2) {
+        uint32_t it = 0;
+        for (int t = blockIdx.x; t < n_class; t += gridDim.x, it++) {
+            const int tn = t + (int)gridDim.x;
+            step_tile<D, ORDER, NT, NS, LIM, VISC, VAR>(ta, ta.desc[tile_base + t], ((VAR & 1) && tn < n_class) ? tile_base + tn : -1, it == 0, !(VAR & 1) || it == 0, it & 1u,
+                                                        want_resid, cfg, dt_val, dt_dev, Qold, Qnew, resid, nanflag);
+            __syncthreads();  // the bulk store has read Qs (thread 0 waited for it): the next tile may overwrite it
+        }
+    } else {
+        const int tn = (int)blockIdx.x + var_arg;
+        step_tile<D, ORDER, NT, NS, LIM, VISC, VAR>(ta, ta.desc[tile_base + blockIdx.x], ((VAR & 1) && tn < n_class) ? tile_base + tn : -1,
+                                                    true, !(VAR & 1) || (int)blockIdx.x < var_arg, 0u, want_resid, cfg, dt_val, dt_dev, Qold,
+                                                    Qnew, resid, nanflag);
+    }
 }
 
 }  // namespace mst

@@ -33,7 +33,7 @@ EXPORTS = [
     "mstgpu_lusgs_solve", "mstgpu_lusgs_levels", "mstgpu_lusgs_create_ordered", "mstgpu_lusgs_solve_device",
     "mstgpu_lusgs_create_partitioned", "mstgpu_lusgs_color_order_partitioned",
     "mstgpu_lusgs_launch_count", "mstgpu_lusgs_device_bytes", "mstgpu_mesh_adjacency", "mstgpu_lusgs_color_order", "mstgpu_lusgs_last_error",
-    "mstgpu_output_setup", "mstgpu_node_fields",
+    "mstgpu_output_setup", "mstgpu_node_fields", "mstgpu_set_tile_variant",
     "mstgpu_last_error", "mstgpu_version",
 ]
 
@@ -103,6 +103,7 @@ def lib():
         L.mstgpu_sync.argtypes = [vp]
         L.mstgpu_output_setup.argtypes = [vp, C.POINTER(MstMesh), i32, vp, vp, vp]
         L.mstgpu_node_fields.argtypes = [vp, vp]
+        L.mstgpu_set_tile_variant.argtypes = [vp, i32]
         L.mstgpu_debug_gradient.argtypes = [vp, vp]
         L.mstgpu_debug_face_flux.argtypes = [vp, vp]
         L.mstgpu_launch_count.argtypes = [vp]
@@ -391,6 +392,10 @@ class Context:
 
     def get_state_ptr(self, ptr: int):
         self._check(lib().mstgpu_get_state(self.h, ptr), "get_state")
+
+    def set_tile_variant(self, variant: int):
+        """experimental launch variants of the default fused kernel (include/mstgpu.h); 0 = default"""
+        self._check(lib().mstgpu_set_tile_variant(self.h, int(variant)), "set_tile_variant")
 
     def output_setup(self, flat, nf_ptr, nf_idx, node_weight=None):
         """Output path (Work.cpp:243-304 on the device): `flat` is the mesh the context was created

@@ -85,7 +85,8 @@ def main():
         ms, n = ctx.kernel_time("node_fields")
         res["node_fields_kernel_ms"] = ms / max(n, 1)
         # algorithmic bytes of the kernel: per node-face entry id 4 + (c0, c1, eta) 16 + two state rows 64; per node ptr 4 + w 8 + out 48
-        res["node_fields_kernel_gbs"] = (idx.size * (4 + 16 + 64) + nn * 60) / (res["node_fields_kernel_ms"] * 1e-3) / 1e9
+        if res["node_fields_kernel_ms"] > 0:
+            res["node_fields_kernel_gbs"] = (idx.size * (4 + 16 + 64) + nn * 60) / (res["node_fields_kernel_ms"] * 1e-3) / 1e9
         ctx.close()
     else:
         from oracle import output_np
