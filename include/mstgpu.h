@@ -309,8 +309,10 @@ int mstgpu_mesh_adjacency(const mstgpu_mesh* mesh, const mstgpu_config* cfg, int
 /* Host-only: statistics of the tiling the fused kernel would use.
  * out[0]=tiles out[1]=max smem bytes out[2]=mean smem bytes out[3]=sum ring1
  * out[4]=sum ring2 out[5]=sum flux faces out[6]=sum local faces out[7]=packet bytes
- * out[8..11]=smem histogram: tiles needing <=56K, <=75K, <=113K, more */
-int mstgpu_tile_stats(const mstgpu_mesh* mesh, const mstgpu_config* cfg, int64_t* out12);
+ * out[8..11]=smem histogram: tiles needing <=56K, <=75K, <=113K, more
+ * out[12..14]=sum over tiles of the loop trips of a CTA: ceil(flux faces / NT), ceil(owned cells / NT),
+ * ceil(ring cells / NT); out[15]=NT.  (16 entries.) */
+int mstgpu_tile_stats(const mstgpu_mesh* mesh, const mstgpu_config* cfg, int64_t* out16);
 
 const char* mstgpu_last_error(mstgpu_ctx* ctx); /* ctx may be NULL (create errors) */
 const char* mstgpu_version(void);

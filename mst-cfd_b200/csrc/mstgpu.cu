@@ -1255,7 +1255,7 @@ int mstgpu_tile_stats(const mstgpu_mesh* mesh, const mstgpu_config* cfg, int64_t
     int T = cfg->tile_cells > 0 ? cfg->tile_cells : default_tile_cells(*cfg);
     perr = build_tiles(p, p.nc, T, cfg->order, tp, tile_ext(cfg->order, cfg->limiter, cfg->viscous));
     if (!perr.empty()) { set_error(nullptr, perr); return MSTGPU_ERR_ARG; }
-    for (int i = 0; i < 12; i++) out[i] = 0;
+    for (int i = 0; i < 16; i++) out[i] = 0;
     out[0] = tp.ntiles; out[1] = (int64_t)tp.max_smem;
     out[3] = tp.sum_r1; out[4] = tp.sum_r2; out[5] = tp.sum_FB; out[6] = tp.sum_FA; out[7] = (int64_t)tp.packets.size();
     double sum = 0;
@@ -1263,6 +1263,10 @@ int mstgpu_tile_stats(const mstgpu_mesh* mesh, const mstgpu_config* cfg, int64_t
         const size_t b = tile_layout(p.D, cfg->order, p.nslot, d.n_own, d.n_r1, d.n_r2, d.nFB, tile_ext(cfg->order, cfg->limiter, cfg->viscous)).total;
         sum += (double)b;
         out[8 + (b <= 56 * 1024 ? 0 : b <= 75 * 1024 ? 1 : b <= 113 * 1024 ? 2 : 3)]++;
+        // loop trips of a CTA of NT threads: flux faces (phase 2), owned cells (phase 3), ring rows (phase 0)
+        const int NT = cfg->block_threads == 128 ? 128 : (cfg->block_threads == 256 ? 256 : (T <= 96 ? 128 : 256));
+        out[12] += (d.nFB + NT - 1) / NT; out[13] += (d.n_own + NT - 1) / NT; out[14] += (d.n_r1 + d.n_r2 + NT - 1) / NT;
+        out[15] = NT;
     }
     out[2] = (int64_t)(sum / tp.ntiles);
     return MSTGPU_OK;

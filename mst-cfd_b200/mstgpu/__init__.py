@@ -204,12 +204,12 @@ def tile_stats(flat: dict, order: int = 2, tile_cells: int = 0, renumber: int = 
     m, keep = _mesh_struct(flat)
     cfg = default_config(int(flat["dim"]))
     cfg.order, cfg.tile_cells, cfg.renumber = order, tile_cells, renumber
-    out = np.zeros(12, dtype=np.int64)
+    out = np.zeros(16, dtype=np.int64)
     rc = lib().mstgpu_tile_stats(C.byref(m), C.byref(cfg), out.ctypes.data)
     if rc != 0:
         raise MstGpuError(f"tile_stats failed ({rc}): {lib().mstgpu_last_error(None).decode()}")
     keys = ("tiles", "max_smem", "mean_smem", "sum_ring1", "sum_ring2", "sum_flux_faces", "sum_local_faces",
-            "packet_bytes", "le56k", "le75k", "le113k", "more")
+            "packet_bytes", "le56k", "le75k", "le113k", "more", "face_trips", "cell_trips", "ring_trips", "block_threads")
     return dict(zip(keys, (int(x) for x in out)))
 
 
