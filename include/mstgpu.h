@@ -204,8 +204,10 @@ int mstgpu_debug_face_flux(mstgpu_ctx* ctx, double* phi);
 
 /* Experimental: launch variant of the default fused instantiation (3-D, second order, 256 threads, no
  * extension): bit mask, 1 = L2 prefetch one tile ahead, 2 = persistent CTAs, 4 = cp.async ring rows;
- * 0 = the measured default.  Same arithmetic in the same order: results are bit-identical.  The
- * environment variable MSTGPU_TILE_VAR sets it at creation.  (csrc/step_tiles.cuh) */
+ * 0 = the measured default.  2-D first order on triangles: 8 / 16 = registers sized for 4 / 3 resident
+ * CTAs per SM (the default picks 4 for AUSM+, 3 for Roe), 32 = the plain 2-CTA allocation.  Same arithmetic
+ * in the same order: results are bit-identical.  The environment variable MSTGPU_TILE_VAR sets it at
+ * creation.  (csrc/step_tiles.cuh) */
 int mstgpu_set_tile_variant(mstgpu_ctx* ctx, int32_t variant);
 
 /* Introspection for the bench: kernels launched so far by this context and

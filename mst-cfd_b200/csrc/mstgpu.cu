@@ -932,6 +932,15 @@ int launch_tiles(mstgpu_ctx* ctx, double dt, const double* dtd, const double* Qo
             default: break;
         }
     }
+    if (D == 2 && ORDER == 1 && NT == 256 && NS == 4 && !(ctx->tile_var & 32)) {
+        // 2-D first order on triangles is occupancy-bound (light flux, ~10 us of dependent latency per tile):
+        // the register allocation is sized for 4 (AUSM+) / 3 (Roe) resident CTAs per SM instead of 2.
+        // Measured on 998 046 triangles (profiles/r1c_ab_variants.json): AUSM+ 78.0 -> 60.6 us per step,
+        // Roe 57.4 -> 47.2 us; bit-identical results.  MSTGPU_TILE_VAR: 8 / 16 force one of the two, 32 = plain.
+        const bool four = (ctx->tile_var & 8) || (!(ctx->tile_var & 16) && ctx->cfg.flux == MSTGPU_FLUX_AUSM);
+        return four ? launch_tiles_var<2, 1, 256, 4, false, false, 8>(ctx, dt, dtd, Qo, Qn, wr, which, st)
+                    : launch_tiles_var<2, 1, 256, 4, false, false, 16>(ctx, dt, dtd, Qo, Qn, wr, which, st);
+    }
     return launch_tiles_lim<D, ORDER, NT, NS, false, false>(ctx, dt, dtd, Qo, Qn, wr, which, st);
 }
 
@@ -1764,7 +1773,7 @@ int64_t mstgpu_launch_count(mstgpu_ctx* ctx) { return ctx ? ctx->launches : -1; 
 
 int mstgpu_set_tile_variant(mstgpu_ctx* ctx, int32_t variant) {
     if (!ctx) return MSTGPU_ERR_ARG;
-    if (variant < 0 || variant > 7 || variant == 6) { set_error(ctx, "tile variant must be 0-5 or 7"); return MSTGPU_ERR_ARG; }
+    if (!(variant == 8 || variant == 16 || variant == 32 || (variant >= 0 && variant <= 7 && variant != 6))) { set_error(ctx, "tile variant must be 0-5, 7, 8, 16 or 32"); return MSTGPU_ERR_ARG; }
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     for (auto& ge : ctx->step_graph) if (ge) { cudaGraphExecDestroy(ge); ge = nullptr; }  // the graph holds the old kernels
