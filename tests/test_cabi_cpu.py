@@ -28,6 +28,35 @@ def test_library_exports_every_declared_symbol():
     assert set(mstgpu.EXPORTS) == set(names)
 
 
+def test_host_library_exports_every_declared_symbol():
+    """include/msthost.h vs libmsthost.so (reader, flattener, writers, generators)"""
+    from mstgpu import host
+    hdr = open(os.path.join(ROOT, "include", "msthost.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(msthost_[a-z_0-9]+)\s*\(", hdr)))
+    assert len(names) >= 17
+    L = host.lib()
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/msthost.h but not exported"
+
+
+@pytest.mark.skipif(have_gpu(), reason="checks the no-GPU failure mode")
+def test_native_driver_fails_loudly_without_gpu(tmp_path):
+    """mstrun (the reference's main program on the two C ABIs) reads and flattens the mesh on the host, then
+    must stop with the CUDA error: there is no CPU path behind it"""
+    import subprocess
+    from conftest import load_raw
+    from mstgpu import host
+    exe = os.path.join(ROOT, "mst-cfd_b200", "mstrun")
+    assert os.path.exists(exe), "mst-cfd_b200/mstrun is missing: make -C mst-cfd_b200"
+    msh = str(tmp_path / "m.msh")
+    host.write_msh(msh, load_raw("2d-stair-un-5-tri"))
+    r = subprocess.run([exe, msh, "--steps", "2", "--out", str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode != 0 and "mstgpu_create" in r.stderr and "cuda" in r.stderr.lower()
+    r = subprocess.run([exe, str(tmp_path / "nope.msh")], capture_output=True, text=True)
+    assert r.returncode != 0 and "cannot open" in r.stderr
+
+
 def test_version_and_default_config():
     assert b"sm_100a" in mstgpu.lib().mstgpu_version()
     c = mstgpu.default_config(2)
