@@ -932,6 +932,11 @@ int launch_tiles(mstgpu_ctx* ctx, double dt, const double* dtd, const double* Qo
             default: break;
         }
     }
+    if (D == 3 && ORDER == 2 && NT == 128 && NS == 5 && (ctx->tile_var & 72)) {
+        // experimental: small tiles, 128 threads, registers sized for 4 (8) / 5 (64) resident CTAs per SM
+        return (ctx->tile_var & 64) ? launch_tiles_var<3, 2, 128, 5, false, false, 64>(ctx, dt, dtd, Qo, Qn, wr, which, st)
+                                    : launch_tiles_var<3, 2, 128, 5, false, false, 8>(ctx, dt, dtd, Qo, Qn, wr, which, st);
+    }
     if (D == 2 && ORDER == 1 && NT == 256 && NS == 4 && !(ctx->tile_var & 32)) {
         // 2-D first order on triangles is occupancy-bound (light flux, ~10 us of dependent latency per tile):
         // the register allocation is sized for 4 (AUSM+) / 3 (Roe) resident CTAs per SM instead of 2.
@@ -1773,7 +1778,7 @@ int64_t mstgpu_launch_count(mstgpu_ctx* ctx) { return ctx ? ctx->launches : -1; 
 
 int mstgpu_set_tile_variant(mstgpu_ctx* ctx, int32_t variant) {
     if (!ctx) return MSTGPU_ERR_ARG;
-    if (!(variant == 8 || variant == 16 || variant == 32 || (variant >= 0 && variant <= 7 && variant != 6))) { set_error(ctx, "tile variant must be 0-5, 7, 8, 16 or 32"); return MSTGPU_ERR_ARG; }
+    if (!(variant == 8 || variant == 16 || variant == 32 || variant == 64 || (variant >= 0 && variant <= 7 && variant != 6))) { set_error(ctx, "tile variant must be 0-5, 7, 8, 16, 32 or 64"); return MSTGPU_ERR_ARG; }
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     for (auto& ge : ctx->step_graph) if (ge) { cudaGraphExecDestroy(ge); ge = nullptr; }  // the graph holds the old kernels

@@ -474,7 +474,7 @@ __device__ __forceinline__ void step_tile(const TileArrays& ta, const TileDesc d
 // n_class = tiles in this launch's class (persistent loop bound, prefetch bound); var_arg = prefetch distance in
 // tiles for the non-persistent prefetch-ahead variant (one wave of resident CTAs)
 template <int D, int ORDER, int NT, int NS, bool LIM = false, bool VISC = false, int VAR = 0>
-__global__ void __launch_bounds__(NT, (VAR & 8) ? 4 : (VAR & 16) ? 3 : MST_TILE_MINB(NT)) k_step_tiles(TileArrays ta, int tile_base, int n_class, int var_arg,
+__global__ void __launch_bounds__(NT, (VAR & 64) ? 5 : (VAR & 8) ? 4 : (VAR & 16) ? 3 : MST_TILE_MINB(NT)) k_step_tiles(TileArrays ta, int tile_base, int n_class, int var_arg,
                                                    int want_resid, DevCfg cfg, double dt_val,
                                                    const double* __restrict__ dt_dev,
                                                    const double* __restrict__ Qold,

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--workload", default="box", choices=["box", "step"], help="step: BASELINE config 2 (AUSM+, first order, Mach 3)")
     ap.add_argument("--order", type=int, default=0, help="0 = the workload's own (box 2, step 1)")
     ap.add_argument("--flux", default="", help="default: the workload's own (box roe, step ausm)")
+    ap.add_argument("--block-threads", type=int, default=0, help="CTA size of the fused kernel (128|256), 0 = default")
     ap.add_argument("--tiles", default="0", help="comma list of tile sizes (cells per tile), 0 = default; one context each")
     ap.add_argument("--out", default="")
     a = ap.parse_args()
@@ -51,7 +52,7 @@ def main():
     ref, rows = None, []
     for T in [int(s) for s in a.tiles.split(",")]:
         t = time.time()
-        ctx = mstgpu.Context(f, tile_cells=T, **kw)
+        ctx = mstgpu.Context(f, tile_cells=T, block_threads=a.block_threads, **kw)
         print(f"[ab] {f['ncells']} cells, T={T}: context in {time.time() - t:.1f}s", file=sys.stderr, flush=True)
         for v in [int(s) for s in a.variants.split(",")]:
             ctx.set_tile_variant(v)
