@@ -94,9 +94,12 @@ int mstgpu_output_setup(mstgpu_ctx* ctx, const mstgpu_mesh* mesh, int32_t nnodes
         eta[(size_t)f] = mesh->eta[f];
     }
     for (int i = 0; i < nnodes; i++) w[(size_t)i] = node_weight ? node_weight[i] : 1.0;
+    // a second call replaces the tables (nothing dangles if an upload below fails)
     for (void* q : {(void*)ctx->out_nf_ptr, (void*)ctx->out_nf_idx, (void*)ctx->out_c0, (void*)ctx->out_c1, (void*)ctx->out_eta,
                     (void*)ctx->out_w, (void*)ctx->out_fields})
         if (q) cudaFree(q);
+    ctx->out_nf_ptr = ctx->out_nf_idx = ctx->out_c0 = ctx->out_c1 = nullptr;
+    ctx->out_eta = ctx->out_w = ctx->out_fields = nullptr;
     ctx->out_nn = nnodes;
     int r;
     if ((r = upload(ctx, &ctx->out_nf_ptr, std::vector<int32_t>(nf_ptr, nf_ptr + nnodes + 1)))) return r;

@@ -449,7 +449,8 @@ int msthost_msh_write(const char* path, int32_t dim, int64_t nnodes, int64_t nce
     fprintf(fp, "(10 (0 1 %llx 0 %d))\n(10 (5 1 %llx 1 %d)\n(\n", (unsigned long long)nnodes, dim,
             (unsigned long long)nnodes, dim);
     using msthost::put_hex;
-    auto emit = [&](int64_t count, int width, auto&& line) { msthost::emit_records(fp, count, width, line); };
+    bool wrote = true;
+    auto emit = [&](int64_t count, int width, auto&& line) { wrote = msthost::emit_records(fp, count, width, line) && wrote; };
     emit(nnodes, 32 * dim, [&](int64_t i, char* p) {
         for (int d = 0; d < dim; d++) {
             if (d) *p++ = ' ';
@@ -479,7 +480,7 @@ int msthost_msh_write(const char* path, int32_t dim, int64_t nnodes, int64_t nce
         fprintf(fp, ")\n)\n");
     }
     fprintf(fp, "(0 \"Zone Sections\")\n");
-    const bool ok = fclose(fp) == 0;
+    const bool ok = (fclose(fp) == 0) && wrote;
     if (!ok) g_err = "write failed";
     return ok ? 0 : -2;
 }
