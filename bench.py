@@ -56,6 +56,18 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def sod_state(f):
+    """Time::initialization (R/time/Time.cpp:13-38) on the base state of CONST.h:70-75"""
+    U = f["dim"] + 2
+    Q = np.zeros((f["ncells"], U))
+    Q[:, 0] = 1.0
+    Q[:, U - 1] = 1 * (1 / 286.32 * 715.8 + 0.5 * (0 * 0 + 0 * 0))
+    right = f["cc"][:, 0] > 0.5
+    Q[right, 0] *= 0.125
+    Q[right, U - 1] *= 0.1
+    return Q
+
+
 def build_workload(args):
     """Returns (flat mesh, Q0, description)."""
     from mstgpu import host
@@ -97,6 +109,26 @@ def build_workload(args):
         Q = np.tile(np.array([1.0, u, 0.0, 0.0, 1.0 / 0.4 + 0.5 * u * u]), (f["ncells"], 1))
         desc = (f"cubed-sphere shell r in [0.5, 10], 6 x {n}^2 x {m} hexes x 24 tets, sphere = wall, outer = inlet / outlet, "
                 "Mach 0.5 free stream")
+    elif args.workload == "sod":
+        # BASELINE config 1: the reference's own SOD tube mesh (18 282 triangles; the raw tables of the shipped
+        # file are a test fixture), written as a .msh file once and read back by the native reader, so that both
+        # arms start from the same file like the reference program does
+        d = np.load(os.path.join(ROOT, "tests", "golden", "mesh_2d-shockwavepipe-2.npz"))
+        raw = dict(dim=int(d["dim"]), ncells=int(d["ncells"]), nodes=d["nodes"], face_nodes=d["face_nodes"], c0=d["c0"], c1=d["c1"],
+                   zones=[dict(start=int(a), end=int(b), type=int(t)) for a, b, t in zip(d["zone_start"], d["zone_end"], d["zone_type"])])
+        args.mesh = os.path.join(tempfile.mkdtemp(prefix="mstbench_"), "2d-shockwavepipe-2.msh")
+        host.write_msh(args.mesh, raw)
+        f = host.flatten_raw(host.read_msh(args.mesh))
+        Q = sod_state(f)
+        desc = "2d-shockwavepipe-2.msh (the reference's SOD case), Roe, 2nd order, explicit, DT = 1/STEP_TIME"
+    elif args.workload == "msh":
+        # any Fluent .msh file the reference's reader accepts (native reader, host/mshread.cpp), with the
+        # reference's SOD initial state (Time.cpp:13-38): BASELINE config 1 is --mesh .../2d-shockwavepipe-2.msh
+        if not args.mesh:
+            raise SystemExit("--workload msh needs --mesh FILE")
+        f = host.flatten_raw(host.read_msh(args.mesh))
+        Q = sod_state(f)
+        desc = f"{os.path.basename(args.mesh)} (native .msh reader), SOD initial state, DT = 1/STEP_TIME"
     else:
         raise SystemExit("unknown workload")
     log(f"[bench] mesh: {f['ncells']} cells, {f['nfaces']} faces in {time.time() - t:.1f}s")
@@ -157,7 +189,7 @@ class ClockSampler:
 
 def run_params(args, Q0):
     """(dt, inlet state) of a workload: the inlet of the step / sphere cases is their free stream"""
-    dt = {"box": DT, "step": 2e-5, "sphere": 2e-4}.get(args.workload, DT)
+    dt = {"box": DT, "step": 2e-5, "sphere": 2e-4, "msh": 2.5e-4, "sod": 2.5e-4}.get(args.workload, DT)
     inlet = (list(Q0[0]) + [0.0] * 5)[:5] if args.workload in ("step", "sphere") else None
     return dt, inlet
 
@@ -213,6 +245,31 @@ def run_reference(args, rank):
                    scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
                    config=dict(workload=f"lusgs box{args.n}: block-5 LU-SGS, {LUSGS_ITERS} iterations per solve (bounded sample)"),
                    cpu_baseline=c, e2e=dict(value=c["value"], unit="cell-updates/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                   gpu_launches=0)
+        print(json.dumps(out), flush=True)
+        return
+    ref_io = os.path.join(ROOT, "oracle", "_ref", "ref_io")
+    if args.workload == "sod" and args.order == 2 and args.flux == "roe" and os.path.exists(ref_io):
+        # BASELINE config 1 is the one case the reference itself can run: its own reader, Time::goNextTimeStep
+        # and RhoSolver (Roe, ACCURACY 2; oracle/_ref/ref_io = the reference's sources, oracle/refbuild), with
+        # the 8 OpenMP threads it hard-codes (CONST.h:7), on the same .msh file
+        f, Q, desc = build_workload(args)
+        tmp = os.path.dirname(args.mesh)
+        os.makedirs(os.path.join(tmp, "result"), exist_ok=True)
+        nst = args.steps + min(args.warmup, 3)
+        r = subprocess.run([ref_io, args.mesh, tmp, "-", "0", str(nst), "1"], check=True, capture_output=True, text=True)
+        tok = r.stdout.split()
+        el = float(tok[tok.index("step_ms") + 1]) * 1e-3
+        thr = int(tok[tok.index("threads") + 1])
+        val = f["ncells"] * nst / el
+        out = dict(impl="reference", metric="cell_updates_per_sec", value=val, unit="cell-updates/s",
+                   n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * el / nst,
+                   higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64", data="reference mesh",
+                   config=dict(workload=f"sod: " + desc, flux=args.flux, order=args.order, dt=2.5e-4),
+                   cpu_baseline=dict(value=val, unit="cell-updates/s", cores=thr, kind="reference",
+                                     sample=f"{f['ncells']} cells x {nst} steps of Time::goNextTimeStep in {el:.3f}s "
+                                            f"(oracle/_ref/ref_io, {thr} OpenMP threads as hard-coded, host has {os.cpu_count()} cpus)"),
+                   e2e=dict(value=val, unit="cell-updates/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                    gpu_launches=0)
         print(json.dumps(out), flush=True)
         return
@@ -570,7 +627,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="box", choices=["box", "step", "sphere", "lusgs"])
+    ap.add_argument("--workload", default="box", choices=["box", "step", "sphere", "lusgs", "msh", "sod"])
+    ap.add_argument("--mesh", default="", help="--workload msh: a Fluent .msh file (the subset the reference's reader accepts)")
     ap.add_argument("--size", "--n", dest="n", type=int, default=203, help="hexes per side (box) or 1/h (step)")
     ap.add_argument("--cpu-n", type=int, default=96, help="size of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true")

@@ -78,13 +78,16 @@ int main(int argc, char** argv) {
         fclose(f);
         for (int c = 0; c < nc; c++) w.allData.getP1NewCellQs()[c] = Q[c];
     }
+    t0 = now_ms();
     for (int s = 0; s < nsteps; s++) time1.goNextTimeStep();
+    const double step_ms = now_ms() - t0;
     w.fLog.flush();
     w.t = tnow;
     t0 = now_ms();
     w.writedataRhoBasedMshNodePlt(&w.mesh, Q, tnow);
     const double write_ms = now_ms() - t0;
     std::cout.clear();
-    printf("cells %d faces %d nodes %d read_ms %.3f write_ms %.3f\n", nc, nf, w.mesh.getNumOfNodes(), read_ms, write_ms);
+    printf("cells %d faces %d nodes %d read_ms %.3f write_ms %.3f steps %d step_ms %.3f threads %d\n", nc, nf,
+           w.mesh.getNumOfNodes(), read_ms, write_ms, nsteps, step_ms, NUM_CPU_THREADS);
     return 0;
 }
