@@ -135,3 +135,9 @@ def test_tiling_statistics(order):
     assert sh["max_smem"] < 227 * 1024
     if order == 2:
         assert sh["packet_bytes"] / nc < 400
+    # loop trips of a CTA (the tile-size predictor of DESIGN.md 8: padded phase-2 slots per cell)
+    NT = sh["block_threads"]
+    assert NT == 128   # tiles of <= 96 cells run 128-thread CTAs
+    assert sh["face_trips"] * NT >= sh["sum_flux_faces"] and sh["face_trips"] <= sh["sum_flux_faces"] / NT + sh["tiles"]
+    assert sh["cell_trips"] == sh["tiles"]                # 96 owned cells: one trip
+    assert sh["ring_trips"] * NT >= sh["sum_ring1"] + sh["sum_ring2"]
