@@ -63,4 +63,11 @@ if __name__ == "__main__":
         gold[name] = dict(mesh=mesh, seed=seed, t=t, retag=retag, bytes=len(data), sha256=hashlib.sha256(data).hexdigest(),
                           head=[ln.decode() for ln in lines[:6]], tail=[ln.decode() for ln in lines[-4:]])
         print(name, len(data), gold[name]["sha256"][:16])
+    # the residual log of the reference PROGRAM (Time.cpp:69-78): SOD, Roe / ACCURACY 2, consistent flags, 10 steps
+    msh = os.path.join(tmp, "2d-shockwavepipe-2.msh")
+    subprocess.run([os.path.join(REF, "ref_io"), msh, tmp, "-", "10", "10", "1"], check=True, stdout=subprocess.DEVNULL)
+    lines = [ln for ln in open(os.path.join(tmp, "result", "ref-log.lhblog")).read().split("\n") if ln.strip()]
+    gold["_log_sod_roe2_consistent_10steps"] = dict(
+        mesh="2d-shockwavepipe-2", lines=lines,
+        note="residual lines of Time.cpp:78 written by the reference program (ref_io <msh> <dir> - 10 10 1)")
     json.dump(gold, open(os.path.join(OUT, "ref_plt.json"), "w"), indent=1)

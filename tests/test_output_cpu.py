@@ -19,7 +19,9 @@ from msh_writer import write_msh
 from mstgpu import host
 from oracle import mesh_np, output_np
 
-GOLD = json.load(open(os.path.join(GOLDEN, "ref_plt.json")))
+_ALL = json.load(open(os.path.join(GOLDEN, "ref_plt.json")))
+GOLD = {k: v for k, v in _ALL.items() if not k.startswith("_")}     # .plt cases
+REF_LOG = _ALL["_log_sod_roe2_consistent_10steps"]                  # residual log of the reference program
 REF_IO = os.path.join(ROOT, "oracle", "_ref", "ref_io")
 
 
@@ -122,3 +124,18 @@ def test_cell_nodes_of_a_tet_box():
     for c in (0, 5, f["ncells"] - 1):
         faces = f["cf_idx"][f["cf_ptr"][c]:f["cf_ptr"][c + 1]]
         assert set(ci[cp[c]:cp[c + 1]]) == set(raw["face_nodes"][faces].ravel())
+
+
+def test_oracle_residuals_equal_the_reference_programs_log():
+    """Row I of SURVEY 8a (Time.cpp:69-76): the residual lines the reference PROGRAM logged for 10 SOD steps
+    (signed denominator, inf where the old momentum is zero) against the oracle's restatement"""
+    from conftest import load_flat
+    from oracle import oracle
+    f = load_flat("2d-shockwavepipe-2", "consistent")
+    _, r = oracle.Oracle(f, order=2, flux="roe").run(2.5e-4, 10, mesh_np.sod_initial_state(f), residuals=True)
+    ref = np.array([[float(x) for x in ln.split()] for ln in REF_LOG["lines"]])
+    assert ref.shape == (10, 4)
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(r[:, :4]), fin) and np.array_equal(np.isinf(r[:, :4]), np.isinf(ref))
+    # 15 printed decimals
+    assert np.abs(r[:, :4][fin] - ref[fin]).max() <= 1e-12 * np.abs(ref[fin]).max() + 5e-16
