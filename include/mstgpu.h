@@ -288,6 +288,13 @@ int mstgpu_lusgs_solve(mstgpu_lusgs* h, const double* val, const double* b, doub
  * *ms (optional) = CUDA-event time of the whole solve on the solver's stream. */
 int mstgpu_lusgs_solve_device(mstgpu_lusgs* h, const double* d_val, const double* d_b, double* d_x, int32_t max_iter,
                               float* ms);
+/* Experimental: mode 1 = fused iteration (csrc/lusgs.cu): the backward sweep leaves U x of the next
+ * iteration as a by-product and the right-hand side update is folded into the forward sweep, so the unscaled
+ * off-diagonal blocks are read once per solve instead of twice per iteration.  Same mathematics as
+ * SparseSolver.cpp:54-104, re-associated (6e-16 against the reference-pinned oracle on the CPU restatement,
+ * tests/lusgs_fused_np.py).  Mode 0 (default) runs the reference's passes one by one.  MSTGPU_LUSGS_MODE sets
+ * it at creation. */
+int mstgpu_lusgs_set_mode(mstgpu_lusgs* h, int32_t mode);
 int64_t mstgpu_lusgs_launch_count(mstgpu_lusgs* h);
 int64_t mstgpu_lusgs_device_bytes(mstgpu_lusgs* h);
 int mstgpu_lusgs_levels(mstgpu_lusgs* h, int32_t* forward_levels, int32_t* backward_levels);

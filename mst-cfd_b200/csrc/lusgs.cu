@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -39,6 +40,8 @@ struct mstgpu_lusgs {
     int *frows = nullptr, *brows = nullptr;
     double *val = nullptr, *D = nullptr, *Dinv = nullptr, *LD = nullptr, *UD = nullptr;
     double *b = nullptr, *x = nullptr, *rhs = nullptr, *rhs1 = nullptr, *ux = nullptr;
+    double* s = nullptr;  // mode 1: U x of the next iteration, a by-product of the backward sweep
+    int mode = 0;         // 0 = the reference's four passes per iteration, 1 = fused (see solve_core)
     unsigned long long* res = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t launches = 0;
@@ -226,6 +229,60 @@ __global__ void k_sweep_level(int nrows, const int* rows, const int* ptr, const 
     v[(size_t)r * B + i] = acc;
 }
 
+// ---- fused iteration (mode 1) ------------------------------------------------------------------------
+// With XD[r,c] = X[r,c] D_c^-1 (k_scale) the reference iteration (SparseSolver.cpp:54-104) is, in RHS space,
+//     s = U x;  rhs = b + LD s;  v[r] = rhs[r] - sum_{c<r} LD[r,c] v[c];  w0 = D (D^-1 v);
+//     w[r] = w0[r] - sum_{c>r} UD[r,c] w[c];  x = D^-1 w.
+// The backward sweep already forms sum_{c>r} UD[r,c] w[c] = sum U[r,c] x[c] = s[r] of the NEXT iteration, and
+// rhs + forward sweep collapse into v[r] = b[r] + sum_{c<r} LD[r,c] (s[c] - v[c]).  The unscaled blocks are then
+// read once per solve (first s) instead of twice per iteration: off-diagonal traffic 4 -> 2 block reads per
+// entry and iteration.  Same mathematics, re-associated: 6e-16 against the reference-pinned oracle after 5
+// iterations (tests/lusgs_fused_np.py restates exactly this order on the CPU).
+
+// s[r] = sum_{c after r} U[r,c] x[c]   (RHSUx of SparseSolver.cpp:64-69, before the D^-1)
+template <int B>
+__global__ void k_ux_raw(int n, const int* Uptr, const int* Ucol, const int* Upos, const double* val, const double* x, double* s) {
+    const Grp<B> g(n);
+    if (!g.on) return;
+    const int r = g.row, i = g.i;
+    double acc = 0.0;
+    for (int k = Uptr[r]; k < Uptr[r + 1]; k++)
+        acc += row_dot<B>(val + (size_t)Upos[k] * B * B + i * B, x + (size_t)Ucol[k] * B);
+    s[(size_t)r * B + i] = acc;
+}
+
+// one level of the fused forward sweep: v[r] = b[r] + sum_k LD[k] t[col[k]],  t[r] = s[r] - v[r]
+template <int B>
+__global__ void k_fwd_fused(int nrows, const int* rows, const int* ptr, const int* col, const double* LD, const double* b,
+                            const double* s, double* v, double* t) {
+    const Grp<B> g(nrows);
+    if (!g.on) return;
+    const int r = rows[g.row], i = g.i;
+    double acc = b[(size_t)r * B + i];
+    for (int k = ptr[r]; k < ptr[r + 1]; k++) acc += row_dot<B>(LD + (size_t)k * B * B + i * B, t + (size_t)col[k] * B);
+    v[(size_t)r * B + i] = acc;
+    t[(size_t)r * B + i] = s[(size_t)r * B + i] - acc;
+}
+
+// one level of the backward sweep that also leaves s[r] = sum_k UD[k] w[col[k]] (= U x of the next iteration);
+// w is updated exactly as k_sweep_level<B, false> does it
+template <int B>
+__global__ void k_bwd_fused(int nrows, const int* rows, const int* ptr, const int* col, const double* UD, double* w, double* s) {
+    const Grp<B> g(nrows);
+    if (!g.on) return;
+    const int r = rows[g.row], i = g.i;
+    double acc = w[(size_t)r * B + i], ss = 0.0;
+    const int k0 = ptr[r], k1 = ptr[r + 1];
+    for (int kk = 0; kk < k1 - k0; kk++) {
+        const int k = k1 - 1 - kk;
+        const double d = row_dot<B>(UD + (size_t)k * B * B + i * B, w + (size_t)col[k] * B);
+        acc -= d;
+        ss += d;
+    }
+    w[(size_t)r * B + i] = acc;
+    s[(size_t)r * B + i] = ss;
+}
+
 // X1 = D^-1 rhs; rhs1 = D X1   (SparseSolverNUM.cpp:184-187)
 template <int B>
 __global__ void k_mid(int n, const double* D, const double* Dinv, const double* rhs, double* rhs1) {
@@ -279,6 +336,13 @@ int solve_core(mstgpu_lusgs* h, const double* val, const double* b, double* x, i
         if (h->nU) k_scale<B><<<(unsigned)(((size_t)h->nU * B + T - 1) / T), T, 0, s>>>((size_t)h->nU, h->Ucol, h->Upos, val, h->D, h->Dinv, h->UD);
         h->launches += 3;
     }
+    const bool fused = h->mode == 1;
+    if (fused) {
+        if (!h->s) LCK(cudaMalloc((void**)&h->s, (size_t)n * B * 8));
+        // the only read of the unscaled off-diagonal blocks in this mode: U x of the start vector
+        k_ux_raw<B><<<G::grid(n, T), T, 0, s>>>(n, h->Uptr, h->Ucol, h->Upos, val, x, h->s);
+        h->launches++;
+    }
     int it = 0;
     for (; it < max_iter; it++) {
         LCK(cudaMemsetAsync(h->res, 0, 8, s));
@@ -288,6 +352,24 @@ int solve_core(mstgpu_lusgs* h, const double* val, const double* b, double* x, i
             h->launches++;
             bb = h->beff;
         }
+        if (fused) {
+            // forward: every level, level 0 included (v = b there, but t = s - v is needed by the later levels);
+            // h->rhs = v, h->ux = t
+            for (size_t l = 0; l + 1 < h->fptr.size(); l++) {
+                const int cnt = h->fptr[l + 1] - h->fptr[l];
+                if (cnt > 0)
+                    k_fwd_fused<B><<<G::grid(cnt, T), T, 0, s>>>(cnt, h->frows + h->fptr[l], h->Lptr, h->Lcol, h->LD, bb, h->s, h->rhs, h->ux);
+            }
+            k_mid<B><<<G::grid(n, T), T, 0, s>>>(n, h->D, h->Dinv, h->rhs, h->rhs1);
+            LCK(cudaMemsetAsync(h->s, 0, (size_t)n * B * 8, s));  // rows without upper entries (level 0): U x = 0
+            for (size_t l = 1; l + 1 < h->bptr.size(); l++) {
+                const int cnt = h->bptr[l + 1] - h->bptr[l];
+                if (cnt > 0)
+                    k_bwd_fused<B><<<G::grid(cnt, T), T, 0, s>>>(cnt, h->brows + h->bptr[l], h->Uptr, h->Ucol, h->UD, h->rhs1, h->s);
+            }
+            k_fin<B><<<G::grid(n, T), T, 0, s>>>(n, h->D, h->Dinv, h->rhs1, x, h->res);
+            h->launches += 2 + (int64_t)(h->fptr.size() > 1 ? h->fptr.size() - 1 : 0) + (int64_t)(h->bptr.size() > 2 ? h->bptr.size() - 2 : 0);
+        } else {
         k_ux<B><<<G::grid(n, T), T, 0, s>>>(n, h->Uptr, h->Ucol, h->Upos, val, h->D, h->Dinv, x, h->ux);
         k_rhs<B><<<G::grid(n, T), T, 0, s>>>(n, h->Lptr, h->Lcol, h->Lpos, val, bb, h->ux, h->rhs);
         for (size_t l = 1; l + 1 < h->fptr.size(); l++) {  // level 0 has no dependencies: nothing to subtract
@@ -301,6 +383,7 @@ int solve_core(mstgpu_lusgs* h, const double* val, const double* b, double* x, i
         }
         k_fin<B><<<G::grid(n, T), T, 0, s>>>(n, h->D, h->Dinv, h->rhs1, x, h->res);
         h->launches += 4 + (int64_t)(h->fptr.size() > 2 ? h->fptr.size() - 2 : 0) + (int64_t)(h->bptr.size() > 2 ? h->bptr.size() - 2 : 0);
+        }
         if (B == 1 && (res_hist || early_exit)) {
             unsigned long long bits = 0;
             LCK(cudaMemcpyAsync(&bits, h->res, 8, cudaMemcpyDeviceToHost, s));
@@ -522,6 +605,7 @@ int mstgpu_lusgs_create_partitioned(mstgpu_lusgs** out, int32_t n, int32_t ncols
         return 0;
     }();
     if (rc) { mstgpu_lusgs_destroy(h); return rc; }
+    if (const char* v = getenv("MSTGPU_LUSGS_MODE")) h->mode = atoi(v) == 1 ? 1 : 0;
     *out = h;
     return MSTGPU_OK;
 }
@@ -533,7 +617,7 @@ void mstgpu_lusgs_destroy(mstgpu_lusgs* h) {
     for (void* p : {(void*)h->Lptr, (void*)h->Lcol, (void*)h->Lpos, (void*)h->Uptr, (void*)h->Ucol, (void*)h->Upos,
                     (void*)h->Dptr, (void*)h->Dpos, (void*)h->frows, (void*)h->brows, (void*)h->val, (void*)h->D,
                     (void*)h->Dinv, (void*)h->LD, (void*)h->UD, (void*)h->b, (void*)h->x, (void*)h->rhs, (void*)h->rhs1,
-                    (void*)h->ux, (void*)h->res, (void*)h->Gptr, (void*)h->Gcol, (void*)h->Gpos, (void*)h->beff})
+                    (void*)h->ux, (void*)h->s, (void*)h->res, (void*)h->Gptr, (void*)h->Gcol, (void*)h->Gpos, (void*)h->beff})
         if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -587,8 +671,14 @@ int64_t mstgpu_lusgs_launch_count(mstgpu_lusgs* h) { return h ? h->launches : -1
 int64_t mstgpu_lusgs_device_bytes(mstgpu_lusgs* h) {
     if (!h) return -1;
     const int64_t BB = (int64_t)h->B * h->B;
-    return ((int64_t)h->n * 2 + h->nL + h->nU) * BB * 8 + (int64_t)h->n * h->B * 8 * 3 +
+    return ((int64_t)h->n * 2 + h->nL + h->nU) * BB * 8 + (int64_t)h->n * h->B * 8 * (3 + (h->s ? 1 : 0)) +
            ((int64_t)h->n * 5 + 3 + 2LL * (h->nL + h->nU)) * 4;
+}
+
+int mstgpu_lusgs_set_mode(mstgpu_lusgs* h, int32_t mode) {
+    if (!h || (mode != 0 && mode != 1)) { g_lusgs_error = "mode must be 0 (reference passes) or 1 (fused)"; return MSTGPU_ERR_ARG; }
+    h->mode = mode;
+    return MSTGPU_OK;
 }
 
 }  // extern "C"

@@ -33,7 +33,7 @@ EXPORTS = [
     "mstgpu_lusgs_solve", "mstgpu_lusgs_levels", "mstgpu_lusgs_create_ordered", "mstgpu_lusgs_solve_device",
     "mstgpu_lusgs_create_partitioned", "mstgpu_lusgs_color_order_partitioned",
     "mstgpu_lusgs_launch_count", "mstgpu_lusgs_device_bytes", "mstgpu_mesh_adjacency", "mstgpu_lusgs_color_order", "mstgpu_lusgs_last_error",
-    "mstgpu_output_setup", "mstgpu_node_fields", "mstgpu_set_tile_variant",
+    "mstgpu_output_setup", "mstgpu_node_fields", "mstgpu_set_tile_variant", "mstgpu_lusgs_set_mode",
     "mstgpu_last_error", "mstgpu_version",
 ]
 
@@ -130,6 +130,7 @@ def lib():
         L.mstgpu_lusgs_create.argtypes = [C.POINTER(vp), i32, i32, vp, vp, i32]
         L.mstgpu_lusgs_create_ordered.argtypes = [C.POINTER(vp), i32, i32, vp, vp, vp, i32]
         L.mstgpu_lusgs_solve_device.argtypes = [vp, vp, vp, vp, i32, C.POINTER(C.c_float)]
+        L.mstgpu_lusgs_set_mode.argtypes = [vp, i32]
         L.mstgpu_lusgs_launch_count.argtypes = [vp]
         L.mstgpu_lusgs_launch_count.restype = i64
         L.mstgpu_lusgs_device_bytes.argtypes = [vp]
@@ -555,6 +556,12 @@ class LuSgs:
         if rc != 0:
             raise MstGpuError(f"lusgs_create failed ({rc}): {lib().mstgpu_lusgs_last_error().decode()}")
         self.h = h
+
+    def set_mode(self, mode: int):
+        """0 = the reference's passes one by one (default), 1 = fused iteration (experimental, include/mstgpu.h)"""
+        rc = lib().mstgpu_lusgs_set_mode(self.h, int(mode))
+        if rc != 0:
+            raise MstGpuError(f"lusgs_set_mode failed ({rc}): {lib().mstgpu_lusgs_last_error().decode()}")
 
     def levels(self):
         a, b = C.c_int32(), C.c_int32()

@@ -58,3 +58,20 @@ def test_color_order_is_a_valid_colouring():
         c = c[c < r]
         lev[r] = (lev[c].max() + 1) if c.size else 0
     assert lev.max() + 1 <= ncol
+
+
+@pytest.mark.parametrize("block, mesh", [(1, "2d-stair-un-3-loose-tri"), (4, "2d-stair-un-5-tri"), (5, "2d-stair-un-5-tri")])
+def test_fused_iteration_is_the_reference_iteration_reassociated(block, mesh):
+    """mode 1 of csrc/lusgs.cu (mstgpu_lusgs_set_mode), restated on the CPU in the kernels' order of operations
+    (tests/lusgs_fused_np.py): the backward sweep's by-product is U x of the next iteration and the right-hand
+    side folds into the forward sweep.  Against the oracle, which equals the reference build bit for bit."""
+    import lusgs_fused_np
+    rowptr, col, val, b, x0 = system(mesh, block, 11)
+    xo, _, _ = oracle.lusgs(rowptr, col, val, b, x0, block, 5, early_exit=False)
+    xf = lusgs_fused_np.solve(rowptr, col, val, b, x0, block, 5)
+    assert np.abs(xf - xo.reshape(xf.shape)).max() <= 1e-13 * np.abs(xo).max()
+    # and from a zero start vector (the implicit step's case: the first U x vanishes)
+    z = np.zeros_like(x0)
+    xo, _, _ = oracle.lusgs(rowptr, col, val, b, z, block, 3, early_exit=False)
+    xf = lusgs_fused_np.solve(rowptr, col, val, b, z, block, 3)
+    assert np.abs(xf - xo.reshape(xf.shape)).max() <= 1e-13 * np.abs(xo).max()

@@ -120,3 +120,29 @@ def test_device_resident_solve_on_a_tet_mesh_pattern():
     A = sp.bsr_matrix((val, col, rowptr), shape=(n * B, n * B)).tocsc()
     xs = sp.linalg.spsolve(A, b.ravel()).reshape(n, B)
     assert np.abs(x60 - xs).max() < 1e-9 * np.abs(xs).max()
+
+
+@pytest.mark.parametrize("block", [1, 4, 5])
+def test_fused_mode_matches_the_reference_passes(block):
+    """mstgpu_lusgs_set_mode(1): half the off-diagonal block traffic per iteration, same iterate (re-associated):
+    against the oracle (reference order) and against mode 0 on the same handle, natural and colour sweep order"""
+    rowptr, col, val, b, x0 = system("2d-stairW-1", block, 13)
+    xo, ho, _ = oracle.lusgs(rowptr, col, val, b, x0, block, 5, early_exit=False)
+    s = mstgpu.LuSgs(rowptr, col, block)
+    x0_, h0, _ = s.solve(val, b, x0, 5)
+    s.set_mode(1)
+    x1, h1, _ = s.solve(val, b, x0, 5)
+    assert _rel(x1, xo) <= 1e-12 and _rel(x1, x0_) <= 1e-13
+    if block == 1:
+        assert np.allclose(h1, ho, rtol=1e-9)
+    xz, _, _ = s.solve(val, b, np.zeros_like(x0), 3)     # zero start vector: the implicit step's case
+    xoz, _, _ = oracle.lusgs(rowptr, col, val, b, np.zeros_like(x0), block, 3, early_exit=False)
+    assert _rel(xz, xoz) <= 1e-12
+    perm, _ = mstgpu.lusgs_color_order(rowptr, col)
+    so = mstgpu.LuSgs(rowptr, col, block, sweep_order=perm)
+    xa, _, _ = so.solve(val, b, x0, 5)
+    so.set_mode(1)
+    xb, _, _ = so.solve(val, b, x0, 5)
+    assert _rel(xb, xa) <= 1e-13
+    with pytest.raises(mstgpu.MstGpuError):
+        so.set_mode(2)
