@@ -40,6 +40,7 @@
 #include <vector>
 
 #include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -180,17 +181,38 @@ bool parse(const char* buf, int64_t n, Msh& m) {
             const char* e = L.e(i);
             kind[i] = (b == e) ? 2 : ((*b == '(' || *b == ')') ? 1 : 0);
         }
-        int64_t nd = 0, nh = 0;
-        for (int64_t i = 0; i < nl; i++) { nd += kind[i] == 0; nh += kind[i] == 1; }
-        hdr.reserve((size_t)nh);
-        data.reserve((size_t)nd);
-        for (int64_t i = 0; i < nl; i++) {
-            if (kind[i] == 0) data.push_back(i);
-            else if (kind[i] == 1) hdr.push_back(i);
-            else if (i > 0 && i + 1 < nl && kind[i - 1] == 0 && kind[i + 1] == 0)
-                // the reference would take it for a data line (MshBlock.cpp:92) and throw in stod()
-                return fail("blank line inside a data block (line " + std::to_string(i + 1) + ")");
+        // compaction in parallel: per-thread counts, prefix, fill (27 M lines for a 12.6 M-tet file)
+        const int nt = std::max(1, omp_get_max_threads());
+        std::vector<int64_t> cd((size_t)nt + 1, 0), chh((size_t)nt + 1, 0);
+        const int64_t chunk = (nl + nt - 1) / nt;
+        int64_t bad_blank = -1;
+#pragma omp parallel for schedule(static, 1)
+        for (int t = 0; t < nt; t++) {
+            const int64_t lo = std::min(nl, t * chunk), hi = std::min(nl, lo + chunk);
+            int64_t a = 0, b = 0;
+            for (int64_t i = lo; i < hi; i++) { a += kind[i] == 0; b += kind[i] == 1; }
+            cd[(size_t)t + 1] = a;
+            chh[(size_t)t + 1] = b;
         }
+        for (int t = 0; t < nt; t++) { cd[(size_t)t + 1] += cd[(size_t)t]; chh[(size_t)t + 1] += chh[(size_t)t]; }
+        data.resize((size_t)cd[(size_t)nt]);
+        hdr.resize((size_t)chh[(size_t)nt]);
+#pragma omp parallel for schedule(static, 1)
+        for (int t = 0; t < nt; t++) {
+            const int64_t lo = std::min(nl, t * chunk), hi = std::min(nl, lo + chunk);
+            int64_t a = cd[(size_t)t], b = chh[(size_t)t];
+            for (int64_t i = lo; i < hi; i++) {
+                if (kind[i] == 0) data[(size_t)a++] = i;
+                else if (kind[i] == 1) hdr[(size_t)b++] = i;
+                else if (i > 0 && i + 1 < nl && kind[i - 1] == 0 && kind[i + 1] == 0) {
+#pragma omp critical
+                    if (bad_blank < 0 || i < bad_blank) bad_blank = i;
+                }
+            }
+        }
+        // a blank line between two data lines: the reference would take it for a data line (MshBlock.cpp:92)
+        // and throw in stod()
+        if (bad_blank >= 0) return fail("blank line inside a data block (line " + std::to_string(bad_blank + 1) + ")");
     }
     int64_t cur = 0;  // next unread data line
     int64_t node_done = 0, face_done = 0;
@@ -344,17 +366,16 @@ int msthost_msh_read(const char* path, msthost_msh** out) {
     if (fd < 0) { g_err = std::string("cannot open ") + path; return -2; }  // MshBlock.cpp:79-82 prints and goes on
     struct stat st;
     if (fstat(fd, &st) != 0) { close(fd); g_err = "fstat failed"; return -2; }
-    std::vector<char> buf((size_t)st.st_size);
-    int64_t got = 0;
-    while (got < (int64_t)st.st_size) {
-        const ssize_t r = read(fd, buf.data() + got, (size_t)std::min<int64_t>((int64_t)st.st_size - got, (int64_t)1 << 30));
-        if (r <= 0) break;
-        got += r;
-    }
+    if (st.st_size == 0) { close(fd); g_err = "empty file"; return -3; }
+    // the file is parsed in place: mapped read-only, pages come in as the parser's threads touch them
+    void* map = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
     close(fd);
-    if (got != (int64_t)st.st_size) { g_err = "short read"; return -2; }
+    if (map == MAP_FAILED) { g_err = std::string("cannot map ") + path; return -2; }
+    madvise(map, (size_t)st.st_size, MADV_WILLNEED);
     Msh* m = new Msh();
-    if (!parse(buf.data(), got, *m)) { delete m; return -3; }
+    const bool ok = parse(static_cast<const char*>(map), (int64_t)st.st_size, *m);
+    munmap(map, (size_t)st.st_size);
+    if (!ok) { delete m; return -3; }
     *out = reinterpret_cast<msthost_msh*>(m);
     return 0;
 }
