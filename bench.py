@@ -6,9 +6,14 @@
 
 Workload (BASELINE.json configs[3], the one the metric is quoted on): synthetic
 unit-cube tet mesh, 203^3 hexes x 6 Kuhn tets = 50 192 562 cells, Roe flux,
-second order, explicit, all walls, SOD-type split at x = 0.5 plus a smooth
-perturbation on rho and p, DT = 1e-4.  A "step" is one RhoSolver::solve() +
-residual + new->old over the whole mesh.
+second order, explicit, all walls, smooth acoustic initial state
+rho = p = 1 + 0.1 sin(2 pi x) sin(2 pi y) sin(2 pi z) (SURVEY 8d's SOD split goes
+NaN under the reference's unlimited scheme on Kuhn tets; it is the
+`--shock 1 --limiter bj --cfl 0.4` line), DT = 1e-4.  A "step" is one
+RhoSolver::solve() + residual + new->old over the whole mesh.
+
+Both arms print the same `config`; `--impl reference` runs the CPU restatement on
+ALL host cores (whatever WORLD_SIZE says), on the same mesh at the same size.
 
 One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
 """
@@ -24,7 +29,11 @@ import time
 # torchrun pins OMP_NUM_THREADS=1; the host-side mesh / plan / partition builders
 # are OpenMP code, so give every rank its share of the cores before libgomp loads
 _world = int(os.environ.get("WORLD_SIZE", "1"))
-if os.environ.get("OMP_NUM_THREADS", "1") == "1":
+_ref_arm = any(a == "reference" or a == "--impl=reference" for a in sys.argv[1:])
+if _ref_arm:
+    # the reference arm runs on rank 0 alone and is the CPU baseline of every N: all host cores, always
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+elif os.environ.get("OMP_NUM_THREADS", "1") == "1":
     os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // _world))
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -203,6 +212,40 @@ def scheme_kwargs(args):
     return dict(gradient=args.gradient, limiter=args.limiter, limiter_k=args.limiter_k)
 
 
+def workload_config(args, world, ncells, nfaces, U, desc, dt_run):
+    """`config` of the JSON line: names the workload.  Built by this one function for BOTH arms, so the
+    reference arm's line describes the same job (same mesh, size, scheme, dt) as the GPU arm's."""
+    return dict(workload=f"{args.workload}{args.n}: {desc}", cells=int(ncells), faces=int(nfaces), flux=args.flux,
+                order=args.order, viscous=args.viscous, gradient=args.gradient, limiter=args.limiter, cfl=args.cfl,
+                implicit=None if not args.implicit else dict(dt=args.implicit_dt, lusgs_iterations=LUSGS_ITERS, sweeps="colour-ordered"),
+                dt=dt_run,
+                parallelism=f"{world} partition(s) on {world} GPU(s), Hilbert ranges, 2 ghost layers, halo exchange + allreduce(max); "
+                            "the CPU arm runs the whole mesh on one host",
+                l2="inputs larger than L2 (state + tables >> 126 MB)" if ncells * U * 8 > 2 ** 28
+                else "inputs smaller than L2: flush not applied")
+
+
+_M1, _M2, _GOLD = np.uint64(0xBF58476D1CE4E5B9), np.uint64(0x94D049BB133111EB), np.uint64(0x9E3779B97F4A7C15)
+
+
+def state_digest(Q, gids):
+    """Order-independent 64-bit digest of a set of state rows keyed by GLOBAL cell id: the sum mod 2^64 of
+    splitmix64(bits(Q[i, k]) xor golden * (gid_i * U + k + 1)).  Ranks add their partial sums, so equal
+    digests at N = 1, 2, 4, 8 mean every conserved variable of every cell has the same 64 bits."""
+    U = Q.shape[1]
+    tot = np.uint64(0)
+    with np.errstate(over="ignore"):
+        for a in range(0, Q.shape[0], 1 << 22):
+            q = np.ascontiguousarray(Q[a:a + (1 << 22)]).view(np.uint64)
+            key = (gids[a:a + (1 << 22)].astype(np.uint64)[:, None] * np.uint64(U) + np.arange(1, U + 1, dtype=np.uint64)[None, :]) * _GOLD
+            z = q ^ key
+            z = (z ^ (z >> np.uint64(30))) * _M1
+            z = (z ^ (z >> np.uint64(27))) * _M2
+            z = z ^ (z >> np.uint64(31))
+            tot = tot + z.sum(dtype=np.uint64)
+    return int(tot)
+
+
 def cpu_baseline(args, nsteps=None, n=None, budget_s=12.0):
     """Oracle (kind "port": the reference cannot be compiled without Eigen) on
     the host cores, on a bounded sample of the same workload: about `budget_s`
@@ -273,30 +316,39 @@ def run_reference(args, rank):
                    gpu_launches=0)
         print(json.dumps(out), flush=True)
         return
-    f_desc = None
     from oracle import oracle
-    a = argparse.Namespace(**vars(args)); a.n = cpu_sample_size(args)
+    # the SAME workload at the SAME size as the GPU arm (50.2 M tets by default: ~3-5 s per step on the box's
+    # cores, so --steps 20 ends within two minutes); --cpu-sample N runs an N^3 sample instead and says so
+    a = argparse.Namespace(**vars(args))
+    sampled = args.cpu_sample > 0
+    if sampled:
+        a.n = args.cpu_sample
     f, Q, desc = build_workload(a)
     DT, inlet = run_params(args, Q)
+    if args.implicit:
+        DT = args.implicit_dt
     o = oracle.Oracle(f, order=args.order, flux=args.flux, nthreads=0, viscous=args.viscous, inletQ=inlet, **scheme_kwargs(args))
     if args.implicit:
-        def adv(k, Q=Q):
+        def adv(k, Q):
             for _ in range(k):
                 Q = o.step_implicit(args.implicit_dt, Q, LUSGS_ITERS)
+            return Q
     else:
-        adv = lambda k: o.run(DT, k, Q)
-    adv(min(args.warmup, 3))
+        adv = lambda k, Q: o.run(DT, k, Q, residuals=True)[0]  # Time.cpp:69-76: the residual of every step
+    nw = min(args.warmup, 2)  # page faults of the work arrays; a CPU has no clocks to ramp
+    Q = adv(nw, Q)
     t = time.perf_counter()
-    adv(args.steps)
+    Q = adv(args.steps, Q)
     el = time.perf_counter() - t
     val = f["ncells"] * args.steps / el
-    sample = (f"{args.workload} n={a.n}: {f['ncells']} cells per step "
-              f"(bounded sample of the n={args.n} workload), {o.nthreads} threads of {os.cpu_count()} cpus")
+    sample = (f"{a.workload} n={a.n}: {f['ncells']} cells x {args.steps} timed steps (+{nw} warm-up) in {el:.2f}s, "
+              f"{'a SAMPLE of the n=%d workload, ' % args.n if sampled else 'the full workload, '}"
+              f"oracle/rho_oracle.cpp, {o.nthreads} OpenMP threads of {os.cpu_count()} cpus, residual every step")
+    log(f"[bench] reference arm: {sample}")
     out = dict(impl="reference", metric="cell_updates_per_sec", value=val, unit="cell-updates/s",
                n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * el / args.steps,
                higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
-               config=dict(workload=f"{args.workload}{args.n}: " + desc.replace(f"{args.cpu_n}^3", f"{args.n}^3"),
-                           flux=args.flux, order=args.order, dt=DT),
+               config=workload_config(a, args.gpus, f["ncells"], f["nfaces"], f["dim"] + 2, desc, DT),
                cpu_baseline=dict(value=val, unit="cell-updates/s", cores=o.nthreads, kind="port", sample=sample),
                e2e=dict(value=val, unit="cell-updates/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                gpu_launches=0)
@@ -486,12 +538,6 @@ def run_ours(args, rank, world):
         ctx.step = lambda dt, n: ctx.step_cfl(args.cfl, n)
     ctx.step(dt_run, args.warmup)
     ctx.sync()
-    graph_ms = None
-    if args.graph and world == 1 and args.cfl <= 0:
-        # the same K steps issued as pairs from a CUDA graph (no per-kernel events): launch-bound meshes
-        ctx.step(dt_run, 4)
-        ctx.sync()
-        graph_ms = ctx.step_timed(dt_run, args.steps)
     # ---- timed region: K steps, state resident in HBM -------------------------
     ctx.enable_kernel_timing(True)
     l0 = ctx.launch_count
@@ -526,6 +572,43 @@ def run_ours(args, rank, world):
     value = nc_total * args.steps / (ms * 1e-3)
     log(f"[bench] {args.steps} steps in {ms:.2f} ms (wall {wall * 1e3:.2f} ms), residual {res}")
 
+    # ---- state digest after W + K steps: order-independent, keyed by global cell id, summed over ranks.
+    # Every N runs the same W + K steps from the same initial state, so equal digests across the N = 1, 2, 4, 8
+    # lines are bit-identity of the partitioned runs with the single-GPU run.
+    gids = part.cell_ids[:part.n_owned] if world > 1 else np.arange(nc_total)
+    dg = state_digest(ctx.get_state(), gids)
+    if dist is not None:
+        tdg = torch.tensor([dg - (1 << 64) if dg >= (1 << 63) else dg], dtype=torch.int64, device="cuda")
+        dist.all_reduce(tdg, op=dist.ReduceOp.SUM)  # two's-complement wrap = sum mod 2^64
+        dg = int(tdg.item()) & ((1 << 64) - 1)
+    digest = dict(value=f"{dg:016x}", after_steps=args.warmup + args.steps,
+                  what="sum mod 2^64 over all cells and variables of splitmix64(bits(Q) ^ golden*(global_cell_id*U+k+1)), all-reduced over ranks")
+    log(f"[bench] state digest after {args.warmup + args.steps} steps: {dg:016x}")
+
+    # ---- the same K steps with the residual of EVERY step (Time.cpp:69-76 computes it each step; the timed
+    # region above is one mstgpu_step(dt, K) call, which reduces the residual of its last step only) ----------
+    every = None
+    if not args.implicit and args.cfl <= 0:
+        ms1 = 0.0
+        for _ in range(args.steps):
+            ms1 += ctx.step_timed(dt_run, 1)
+        if dist is not None:
+            t1 = torch.tensor([ms1], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t1, op=dist.ReduceOp.MAX)
+            ms1 = float(t1.item())
+        every = dict(value=nc_total * args.steps / (ms1 * 1e-3), unit="cell-updates/s", ms_per_step=ms1 / args.steps,
+                     what=f"{args.steps} calls of mstgpu_step(dt, 1): residual reduced on every step, one host call per step")
+    graph_ms = None
+    if args.graph and args.cfl <= 0 and not args.implicit:
+        # the same K steps issued as pairs from a CUDA graph (no per-kernel events): launch-bound meshes
+        ctx.step(dt_run, 4)
+        ctx.sync()
+        graph_ms = ctx.step_timed(dt_run, args.steps)
+        if dist is not None:
+            tg = torch.tensor([graph_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+            graph_ms = float(tg.item())
+
     # ---- roofline of the dominant kernel --------------------------------------
     peak, peak_src = measured_peaks()
     ab = dict(ALGO_BYTES[(D, args.order)])
@@ -555,17 +638,17 @@ def run_ours(args, rank, world):
         pass2_ms = per_kernel["flux"] + per_kernel["update"]
         achieved = ab["flux_update"] * nc / (pass2_ms * 1e-3) / 1e9
         kname, abytes = "flux+update (pass 2 of 8d)", ab["flux_update"]
-    traffic = None
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel: only where a committed ncu
+    # capture of THIS instantiation exists (profiles/traffic.json, keyed by dim/order/options); null otherwise
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel,
-        # from the committed ncu --set full capture, scaled per cell
+    if os.path.exists(tp) and "step_tiles" in per_kernel and not args.implicit:
         tj = json.load(open(tp))
-        key = "step_tiles" if "step_tiles" in per_kernel else "flux_update"
-        if key in tj and not args.implicit and args.limiter == "none":
-            traffic = tj[key]["bytes_per_cell"] * nc
+        key = f"step_tiles_d{D}_o{args.order}" + ("_visc" if args.viscous else "") + (f"_{args.limiter}" if args.limiter != "none" else "")
+        if key in tj:
+            traffic, traffic_src = tj[key]["bytes_per_cell"] * nc, f"profiles/traffic.json[{key}]: " + tj[key]["source"]
     roof = dict(bound="hbm", kernel=kname, achieved=achieved, peak=peak, unit="GB/s",
-                frac=achieved / peak, traffic=traffic, peak_source=peak_src,
+                frac=achieved / peak, traffic=traffic, traffic_source=traffic_src, peak_source=peak_src,
                 algorithmic_bytes_per_cell=abytes,
                 kernels_ms={k: round(v, 4) for k, v in per_kernel.items()}, dominant=dom,
                 step_frac=ab["step"] * value / 1e9 / peak)
@@ -601,14 +684,13 @@ def run_ours(args, rank, world):
     out = dict(metric="cell_updates_per_sec", value=value, unit="cell-updates/s", n_gpus=world,
                steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True,
                scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
-               config=dict(workload=f"{args.workload}{args.n}: {desc}", cells=nc_total, faces=f["nfaces"], flux=args.flux,
-                           parallelism=f"{world} partition(s), Hilbert ranges, 2 ghost layers, NCCL send/recv + allreduce(max)",
-                           order=args.order, viscous=args.viscous, gradient=args.gradient, limiter=args.limiter, cfl=args.cfl,
-                           implicit=None if not args.implicit else dict(dt=args.implicit_dt, lusgs_iterations=LUSGS_ITERS, sweeps="colour-ordered"),
-                           graph_ms_per_step=None if graph_ms is None else graph_ms / args.steps, dt=dt_run, kernel=args.kernel, tile_cells=args.tile_cells, renumber=args.renumber,
-                           block_threads=args.block_threads, l2="inputs larger than L2 (state + tables >> 126 MB)"
-                           if nc_total * U * 8 > 2 ** 28 else "inputs smaller than L2: flush not applied"),
+               config=workload_config(args, world, nc_total, f["nfaces"], U, desc, dt_run),
+               gpu_config=dict(kernel=args.kernel, tile_cells=args.tile_cells, renumber=args.renumber, block_threads=args.block_threads,
+                               graph_ms_per_step=None if graph_ms is None else graph_ms / args.steps,
+                               residual="reduced on the last step of the timed mstgpu_step(dt, K) call (SURVEY 8f.1: residual every k); "
+                                        "see every_step_residual for one call per step"),
                clocks=clk, e2e=e2e, gpu_launches=launches, roofline=roof, cpu_baseline=cpu,
+               state_digest=digest, every_step_residual=every,
                wall_ms_per_step=wall * 1e3 / args.steps, device_gib=ctx.device_bytes / 2 ** 30)
     if rank == 0:
         print(json.dumps(out), flush=True)
@@ -630,7 +712,8 @@ def main():
     ap.add_argument("--workload", default="box", choices=["box", "step", "sphere", "lusgs", "msh", "sod"])
     ap.add_argument("--mesh", default="", help="--workload msh: a Fluent .msh file (the subset the reference's reader accepts)")
     ap.add_argument("--size", "--n", dest="n", type=int, default=203, help="hexes per side (box) or 1/h (step)")
-    ap.add_argument("--cpu-n", type=int, default=96, help="size of the bounded CPU sample")
+    ap.add_argument("--cpu-n", type=int, default=96, help="size of the bounded CPU sample of the GPU arm's cpu_baseline leg")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="--impl reference: run an N^3 sample instead of the full workload (0 = full size)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--kernel", default="tiles", choices=["tiles", "split"])
     ap.add_argument("--tile-cells", type=int, default=0)

@@ -103,6 +103,9 @@ typedef struct mstgpu_mesh {
     const int32_t* cf_idx; /* face ids per cell, in the cell's own (file) order      */
 } mstgpu_mesh;
 
+#define MSTGPU_TILE_DIRECT 1 /* packet words loaded straight into registers */
+#define MSTGPU_TILE_STAGED 2 /* next face's weights / ids staged in shared memory by cp.async */
+
 typedef struct mstgpu_config {
     int32_t order;        /* ACCURACY 1|2 (CONST.h:6)                                */
     int32_t flux;         /* MSTGPU_FLUX_* (CONST.h:10)                              */
@@ -123,7 +126,8 @@ typedef struct mstgpu_config {
                              viscous = 1 always runs the three-kernel path            */
     int32_t tile_cells;   /* cells per tile of the fused kernel, 0 = default         */
     int32_t block_threads;/* CTA size of the fused kernel (128|256), 0 = default     */
-    int32_t reserved_;
+    int32_t tile_flags;   /* fused kernel, tets at second order: MSTGPU_TILE_DIRECT or
+                             MSTGPU_TILE_STAGED; 0 = the library's default               */
     /* ---- build-defined extension: named by the project's north star, ABSENT from the
      * reference (no limiter, Green-Gauss only, fixed DT: SURVEY.md fact 2, 8f.4).  The
      * defaults (0, 0) are the reference's scheme.  Checked against the oracle's own

@@ -107,6 +107,9 @@ struct mstgpu_ctx {
     std::vector<void*> tile_allocs;
     int ntiles = 0, tile_T = 0, tile_NT = 0;
     int tile_var = 0;   // MSTGPU_TILE_VAR: experimental variant of the default fused instantiation (0 = default)
+    std::map<const void*, size_t> smem_configured;  // dynamic shared memory opted in per kernel instantiation, on this context's device
+    bool tile_staged = false;  // packet stream staged through shared memory (step_tiles.cuh, VAR & 128)
+    int tile_ext = 0;          // tile_layout() ext argument of this context's tiles
     int sm_count = 148;
     size_t tile_smem = 0;
     struct TileClass { int first, count; size_t smem; bool halo; };  // halo: a ring of the tile holds ghost cells
@@ -884,7 +887,9 @@ int halo_exchange(mstgpu_ctx* ctx, double* Q, cudaStream_t st) {
 template <int D, int ORDER, int NT, int NS, bool LIM, bool VISC, int VAR>
 int launch_tiles_var(mstgpu_ctx* ctx, double dt, const double* dtd, const double* Qo, double* Qn, int want_resid, int which, cudaStream_t st) {
     auto kern = k_step_tiles<D, ORDER, NT, NS, LIM, VISC, VAR>;
-    static thread_local size_t configured_smem = 0;
+    // the opt-in to > 48 KB of dynamic shared memory is a per-DEVICE attribute of the function: remembered per
+    // context (a context lives on one device), not per thread -- one host thread may drive several devices
+    size_t& configured_smem = ctx->smem_configured[(const void*)kern];
     if (configured_smem < ctx->tile_smem) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->tile_smem));
         configured_smem = ctx->tile_smem;
@@ -952,6 +957,18 @@ int launch_tiles(mstgpu_ctx* ctx, double dt, const double* dtd, const double* Qo
 template <int D, int NS>
 int launch_tiles_ns(mstgpu_ctx* ctx, double dt, const double* dtd, const double* Qo, double* Qn, int wr, int which, cudaStream_t st) {
     const bool o2 = ctx->cfg.order == 2;
+    if constexpr (D == 3 && NS == 5) {
+        if (ctx->tile_staged && o2) {
+            if (ctx->tile_NT == 128) return launch_tiles_var<3, 2, 128, 5, false, false, 128 + 8>(ctx, dt, dtd, Qo, Qn, wr, which, st);
+            return launch_tiles_var<3, 2, 256, 5, false, false, 128>(ctx, dt, dtd, Qo, Qn, wr, which, st);
+        }
+        // wider CTAs for the default scheme (tets, second order, no extension): 2 x 320 threads at 96 registers
+        // or 2 x 384 threads at 80 registers per SM instead of 2 x 256 at 128
+        if (o2 && !ctx->cfg.limiter && !ctx->cfg.viscous && ctx->tile_NT == 320)
+            return launch_tiles_var<3, 2, 320, 5, false, false, 0>(ctx, dt, dtd, Qo, Qn, wr, which, st);
+        if (o2 && !ctx->cfg.limiter && !ctx->cfg.viscous && ctx->tile_NT == 384)
+            return launch_tiles_var<3, 2, 384, 5, false, false, 0>(ctx, dt, dtd, Qo, Qn, wr, which, st);
+    }
     if (ctx->tile_NT == 128) return o2 ? launch_tiles<D, 2, 128, NS>(ctx, dt, dtd, Qo, Qn, wr, which, st) : launch_tiles<D, 1, 128, NS>(ctx, dt, dtd, Qo, Qn, wr, which, st);
     return o2 ? launch_tiles<D, 2, 256, NS>(ctx, dt, dtd, Qo, Qn, wr, which, st) : launch_tiles<D, 1, 256, NS>(ctx, dt, dtd, Qo, Qn, wr, which, st);
 }
@@ -1252,7 +1269,25 @@ static int step_implicit_impl(mstgpu_ctx* ctx, double dt, int nsteps, int iters)
 
 // cells per tile: the largest tile that still lets two CTAs share an SM (228 KB of shared
 // memory); the limiter extension adds a [U][own + ring 1] table, so its tiles are smaller
-static int default_tile_cells(const mstgpu_config& cfg) {
+// staged packet stream: tets at second order without extensions, 128- or 256-thread CTAs
+static bool tile_staged_for(const mstgpu_config& cfg, int D, int nslot) {
+    if (!(D == 3 && nslot == 4 && cfg.order == 2 && !cfg.limiter && !cfg.viscous)) return false;
+    if (cfg.block_threads != 0 && cfg.block_threads != 128 && cfg.block_threads != 256) return false;
+    if (cfg.tile_flags & MSTGPU_TILE_DIRECT) return false;
+    if (cfg.tile_flags & MSTGPU_TILE_STAGED) return true;
+    static const char* env = getenv("MSTGPU_TILE_STAGED");
+    return env ? atoi(env) != 0 : false;
+}
+
+static int tile_threads_for(const mstgpu_config& cfg, int T, int D, int nslot) {
+    int NT = cfg.block_threads == 128 ? 128 : (cfg.block_threads == 256 ? 256 : (T <= 96 ? 128 : 256));
+    if ((cfg.block_threads == 320 || cfg.block_threads == 384) && D == 3 && nslot == 4 && cfg.order == 2 && !cfg.limiter && !cfg.viscous)
+        NT = cfg.block_threads;
+    return NT;
+}
+
+static int default_tile_cells(const mstgpu_config& cfg, bool staged = false) {
+    if (staged) return cfg.block_threads == 128 ? 208 : 416;  // + 80 B of landing slots per thread
     if (cfg.order != 2) return 512;
     if (cfg.viscous != 0) return cfg.limiter != 0 ? 192 : 256;  // + [(D+1) D][own + ring 1] primitive gradients
     return cfg.limiter != 0 ? 384 : 512;
@@ -1266,19 +1301,23 @@ int mstgpu_tile_stats(const mstgpu_mesh* mesh, const mstgpu_config* cfg, int64_t
     std::string perr = build_plan(*mesh, *cfg, p);
     if (!perr.empty()) { set_error(nullptr, perr); return MSTGPU_ERR_ARG; }
     TilePack tp;
-    int T = cfg->tile_cells > 0 ? cfg->tile_cells : default_tile_cells(*cfg);
-    perr = build_tiles(p, p.nc, T, cfg->order, tp, tile_ext(cfg->order, cfg->limiter, cfg->viscous));
+    const bool staged = tile_staged_for(*cfg, p.D, p.nslot);
+    int T = cfg->tile_cells > 0 ? cfg->tile_cells : default_tile_cells(*cfg, staged);
+    const int NTs = tile_threads_for(*cfg, T, p.D, p.nslot);
+    int ext = tile_ext(cfg->order, cfg->limiter, cfg->viscous);
+    if (staged) ext = tile_ext_staged(ext, NTs);
+    perr = build_tiles(p, p.nc, T, cfg->order, tp, ext);
     if (!perr.empty()) { set_error(nullptr, perr); return MSTGPU_ERR_ARG; }
     for (int i = 0; i < 16; i++) out[i] = 0;
     out[0] = tp.ntiles; out[1] = (int64_t)tp.max_smem;
     out[3] = tp.sum_r1; out[4] = tp.sum_r2; out[5] = tp.sum_FB; out[6] = tp.sum_FA; out[7] = (int64_t)tp.packets.size();
     double sum = 0;
     for (const TileDesc& d : tp.desc) {
-        const size_t b = tile_layout(p.D, cfg->order, p.nslot, d.n_own, d.n_r1, d.n_r2, d.nFB, tile_ext(cfg->order, cfg->limiter, cfg->viscous)).total;
+        const size_t b = tile_layout(p.D, cfg->order, p.nslot, d.n_own, d.n_r1, d.n_r2, d.nFB, ext).total;
         sum += (double)b;
         out[8 + (b <= 56 * 1024 ? 0 : b <= 75 * 1024 ? 1 : b <= 113 * 1024 ? 2 : 3)]++;
         // loop trips of a CTA of NT threads: flux faces (phase 2), owned cells (phase 3), ring rows (phase 0)
-        const int NT = cfg->block_threads == 128 ? 128 : (cfg->block_threads == 256 ? 256 : (T <= 96 ? 128 : 256));
+        const int NT = NTs;
         out[12] += (d.nFB + NT - 1) / NT; out[13] += (d.n_own + NT - 1) / NT; out[14] += (d.n_r1 + d.n_r2 + NT - 1) / NT;
         out[15] = NT;
     }
@@ -1301,6 +1340,7 @@ void mstgpu_default_config(mstgpu_config* cfg, int32_t dim) {
     cfg->kernel = 1;
     cfg->tile_cells = 0;
     cfg->block_threads = 0;
+    cfg->tile_flags = 0;
     cfg->gamma = 1.4;
     cfg->delta = 0.125;
     cfg->eor = 1e-10;
@@ -1383,9 +1423,19 @@ static int create_impl(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_c
         CK(cudaMemsetAsync(ctx->Q[1], 0, (nq + 2 * p.U) * sizeof(double), ctx->stream));
         if (ctx->use_tiles) {
             TilePack tp;
-            int T = cfg->tile_cells > 0 ? cfg->tile_cells : default_tile_cells(*cfg);
-            std::string terr = build_tiles(p, ctx->n_owned, T, cfg->order, tp, tile_ext(cfg->order, cfg->limiter, cfg->viscous));
+            ctx->tile_staged = tile_staged_for(*cfg, p.D, p.nslot);
+            int T = cfg->tile_cells > 0 ? cfg->tile_cells : default_tile_cells(*cfg, ctx->tile_staged);
+            ctx->tile_NT = tile_threads_for(*cfg, T, p.D, p.nslot);
+            ctx->tile_ext = tile_ext(cfg->order, cfg->limiter, cfg->viscous);
+            if (ctx->tile_staged) ctx->tile_ext = tile_ext_staged(ctx->tile_ext, ctx->tile_NT);
+            std::string terr = build_tiles(p, ctx->n_owned, T, cfg->order, tp, ctx->tile_ext);
             if (!terr.empty()) { set_error(ctx, terr); return MSTGPU_ERR_ARG; }
+            if (tp.open_stencils > 0) {
+                // the fused kernel derives the own-cell reconstruction weight from the closure of the cell
+                set_error(ctx, std::to_string(tp.open_stencils) + " face sides belong to cells that are not closed (sum of outward area vectors != 0): "
+                               "the fused kernel needs closed cells; use kernel = 0 (split kernels) for this mesh");
+                return MSTGPU_ERR_ARG;
+            }
             int dev_smem = 0;
             CK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
             if (tp.max_smem + 1024 > (size_t)dev_smem) { set_error(ctx, "tile needs more shared memory than the device has; lower tile_cells"); return MSTGPU_ERR_ARG; }
@@ -1403,7 +1453,7 @@ static int create_impl(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_c
                 int ccount[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                 for (int t = 0; t < tp.ntiles; t++) {
                     const TileDesc& d = tp.desc[t];
-                    const size_t b = tile_layout(p.D, cfg->order, p.nslot, d.n_own, d.n_r1, d.n_r2, d.nFB, tile_ext(cfg->order, cfg->limiter, cfg->viscous)).total;
+                    const size_t b = tile_layout(p.D, cfg->order, p.nslot, d.n_own, d.n_r1, d.n_r2, d.nFB, ctx->tile_ext).total;
                     int c = 0;
                     while (c < 3 && b > lim[c]) c++;
                     // tiles whose rings reach into the ghost cells wait for the halo exchange
@@ -1431,7 +1481,6 @@ static int create_impl(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_c
                     for (const auto& tc : ctx->tile_classes)
                         fprintf(stderr, "[mstgpu] tile class: %d tiles, %zu B smem, %s\n", tc.count, tc.smem, tc.halo ? "halo" : "interior");
             }
-            ctx->tile_NT = cfg->block_threads == 128 ? 128 : (cfg->block_threads == 256 ? 256 : (T <= 96 ? 128 : 256));
             TileDesc* ddesc; int32_t* dring; unsigned char* dpk;
             if ((r = upload(ctx, &ddesc, tp.desc))) return r;
             ctx->tile_allocs.push_back(ddesc);

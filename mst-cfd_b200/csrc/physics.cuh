@@ -109,6 +109,11 @@ __device__ __forceinline__ double entropy_fix(double x, const DevCfg& c) {
 }
 
 // phi = sum_d Sd[d] * RoeFlux_d(L,R),  (L,R) = flag[d] ? (A,B) : (B,A)
+//
+// Register budget first (the fused kernel lives or dies by resident warps): the central part
+// 1/2 (F_A + F_B) . S does not depend on the orientation, so it is contracted with the area vector up
+// front through the mass fluxes m_A.S, m_B.S -- after that A and B themselves are dead and only the
+// wave strengths (theta, shear, dq0), the Roe averages and S stay live through the three upwind parts.
 template <int D>
 __device__ __forceinline__ void roe_contract(const double (&A)[D + 2], const double (&B)[D + 2],
                                              uint32_t flags, const double (&Sd)[D],
@@ -118,88 +123,92 @@ __device__ __forceinline__ void roe_contract(const double (&A)[D + 2], const dou
     // (~20 issue slots each), so the reciprocals are shared: 1/rhoA and 1/rhoB
     // come from one division, 1/(1+w) and 1/g from another, 1/a from rsqrt, and
     // 1/(rho+EOR) from a three-term series (relative error (EOR/rho)^3).
-    Prim<D> a, b;
     const double rab = 1.0 / (A[0] * B[0]);
-    prim_with_r<D>(A, B[0] * rab, c, a);
-    prim_with_r<D>(B, A[0] * rab, c, b);
+    const double ra = B[0] * rab, rb = A[0] * rab;
+    double m2a = A[1] * A[1], m2b = B[1] * B[1], mna = Sd[0] * A[1], mnb = Sd[0] * B[1];
+#pragma unroll
+    for (int i = 1; i < D; i++) {
+        m2a += A[i + 1] * A[i + 1];
+        m2b += B[i + 1] * B[i + 1];
+        mna += Sd[i] * A[i + 1];  // mass flux through the face, m . S
+        mnb += Sd[i] * B[i + 1];
+    }
+    const double pa = (A[U - 1] - 0.5 * m2a * ra) * c.gm1;  // FUNCTION.cpp:12-15
+    const double pb = (B[U - 1] - 0.5 * m2b * rb) * c.gm1;
+    const double hta = (A[U - 1] + pa) * ra, htb = (B[U - 1] + pb) * rb;  // FUNCTION.cpp:3-7
     // Roe averages, SolverRoe.cpp:7-14 (symmetric under L<->R)
-    const double w = sqrt(fabs(B[0] * a.r));
+    const double w = sqrt(fabs(B[0] * ra));
     const double sw = 1.0 + w;
-    double un[D];
+    double uh[D];
     double qn2 = 0.0;
 #pragma unroll
     for (int i = 0; i < D; i++) {
-        un[i] = a.u[i] + w * b.u[i];
-        qn2 += un[i] * un[i];
+        uh[i] = A[i + 1] * ra + w * (B[i + 1] * rb);
+        qn2 += uh[i] * uh[i];
     }
-    const double Hn = a.ht + w * b.ht;
+    const double Hn = hta + w * htb;
     const double gn = Hn * sw - 0.5 * qn2;  // = g (1+w)^2
     const double z = 1.0 / (sw * gn);
     const double iw = z * gn;            // 1/(1+w)
     const double ig = sw * sw * sw * z;  // 1/g
-    double uh[D];
 #pragma unroll
-    for (int i = 0; i < D; i++) uh[i] = un[i] * iw;
+    for (int i = 0; i < D; i++) uh[i] *= iw;
     const double q2 = qn2 * iw * iw;
     const double H = Hn * iw;
-    const double g = H - 0.5 * q2;
-    const double ya = fabs(c.gm1 * g);
+    const double ya = fabs(c.gm1 * (H - 0.5 * q2));
     const double ia = rsqrt(ya);
     const double ah = ya * ia;
-    double dq[U];
-#pragma unroll
-    for (int k = 0; k < U; k++) dq[k] = B[k] - A[k];
-    // wave strengths of K^-1 dq that do not depend on the direction
-    double ud = 0.0;
-#pragma unroll
-    for (int i = 0; i < D; i++) ud += uh[i] * dq[i + 1];
-    const double theta = (0.5 * q2 * dq[0] - ud + dq[U - 1]) * ig;
-    double sh[D];  // shear strengths  dq[t+1] - u_t dq0
-#pragma unroll
-    for (int i = 0; i < D; i++) sh[i] = dq[i + 1] - uh[i] * dq[0];
     // (rho + EOR) denominators of the physical fluxes, SolverRoe.cpp:87-94:
     // 1/(rho+e) = r (1 - t + t^2 - ...), t = e r
-    const double ta = c.eor * a.r, tb = c.eor * b.r;
-    const double rea = a.r * (1.0 - ta + ta * ta);
-    const double reb = b.r * (1.0 - tb + tb * tb);
+    const double ta = c.eor * ra, tb = c.eor * rb;
+    const double fa = mna * (ra * (1.0 - ta + ta * ta));
+    const double fb = mnb * (rb * (1.0 - tb + tb * tb));
+    // central part: sum_d Sd[d] 1/2 (F_A,d + F_B,d)
+    const double ph = 0.5 * (pa + pb);
+    phi[0] = 0.5 * (mna + mnb);
 #pragma unroll
-    for (int k = 0; k < U; k++) phi[k] = 0.0;
+    for (int i = 0; i < D; i++) phi[i + 1] = 0.5 * (A[i + 1] * fa + B[i + 1] * fb) + ph * Sd[i];
+    phi[U - 1] = 0.5 * (hta * mna + htb * mnb);
+    // wave strengths of K^-1 dq that do not depend on the direction
+    const double dq0 = B[0] - A[0];
+    double sh[D];  // shear strengths  dq[t+1] - u_t dq0
+    double ud = 0.0;
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+        const double dm = B[i + 1] - A[i + 1];
+        ud += uh[i] * dm;
+        sh[i] = dm - uh[i] * dq0;
+    }
+    const double theta = (0.5 * q2 * dq0 - ud + (B[U - 1] - A[U - 1])) * ig;
+    const double hq2 = 0.5 * q2;
+    // upwind parts: - sum_d Sd[d] (+-1/2) K |L_d| K^-1 dq
 #pragma unroll
     for (int d = 0; d < D; d++) {
-        const double sgn = ((flags >> d) & 1u) ? 0.5 : -0.5;  // 1/2 * orientation
+        const double ss = ((flags >> d) & 1u) ? 0.5 * Sd[d] : -0.5 * Sd[d];  // 1/2 * orientation * area component
         const double beta = sh[d] * ia;
         const double lm = entropy_fix(fabs(uh[d] - ah), c);
         const double le = entropy_fix(fabs(uh[d]), c);
         const double lp = entropy_fix(fabs(uh[d] + ah), c);
         const double wm = lm * (0.5 * (theta - beta));
-        const double we = le * (dq[0] - theta);
+        const double we = le * (dq0 - theta);
         const double wp = lp * (0.5 * (theta + beta));
         const double sum = wm + we + wp;
         const double dif = ah * (wp - wm);
-        // physical fluxes 1/2 (F_A + F_B)
-        const double ma = A[d + 1], mb = B[d + 1];
-        double F[U];
-        F[0] = 0.5 * (ma + mb) - sgn * sum;
-        double en = H * (wm + wp) + uh[d] * dif + 0.5 * q2 * we;
+        double en = H * (wm + wp) + uh[d] * dif + hq2 * we;
+        phi[0] -= ss * sum;
 #pragma unroll
         for (int i = 0; i < D; i++) {
-            double fa = A[i + 1] * ma * rea;
-            double fb = B[i + 1] * mb * reb;
             double dis = uh[i] * sum;
             if (i == d) {
-                fa += a.p;
-                fb += b.p;
                 dis += dif;
             } else {
                 const double ws = le * sh[i];
                 dis += ws;
                 en += uh[i] * ws;
             }
-            F[i + 1] = 0.5 * (fa + fb) - sgn * dis;
+            phi[i + 1] -= ss * dis;
         }
-        F[U - 1] = 0.5 * (a.ht * ma + b.ht * mb) - sgn * en;
-#pragma unroll
-        for (int k = 0; k < U; k++) phi[k] += Sd[d] * F[k];
+        phi[U - 1] -= ss * en;
     }
 }
 

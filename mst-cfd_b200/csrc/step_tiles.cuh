@@ -110,6 +110,9 @@ __device__ __forceinline__ double warp_max_nonneg(double x) {
 __device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
 
 template <int D, int ORDER, int NT, int NS, bool LIM, bool VISC, int VAR>
 __device__ __forceinline__ void step_tile(const TileArrays& ta, const TileDesc d, const int pf_tile, const bool first, const bool pf_self,
@@ -123,7 +126,9 @@ __device__ __forceinline__ void step_tile(const TileArrays& ta, const TileDesc d
     const int tid = threadIdx.x;
     const int n_own = d.n_own, n_ring = d.n_r1 + d.n_r2;
     const int nFB = d.nFB;
-    const TileLayout L = tile_layout(D, ORDER, nslot, d.n_own, d.n_r1, d.n_r2, d.nFB, (LIM ? 1 : 0) | (VISC ? 2 : 0));
+    constexpr bool STG = ORDER == 2 && (VAR & 128) != 0;
+    constexpr int EXT = (LIM ? 1 : 0) | (VISC ? 2 : 0) | (STG ? (4 | (NT << 8)) : 0);
+    const TileLayout L = tile_layout(D, ORDER, nslot, d.n_own, d.n_r1, d.n_r2, d.nFB, EXT);
     const double dt = dt_dev ? *dt_dev : dt_val;  // device-resident dt: CFL stepping (extension)
     const int nFBp = L.nFBp, ncp = L.ncp;
     const unsigned char* pk = ta.packets + d.pk_off;
@@ -153,11 +158,25 @@ __device__ __forceinline__ void step_tile(const TileArrays& ta, const TileDesc d
         if (pf_self) bulk_prefetch_l2(pk, L.pk_bytes);
         if ((VAR & 1) && pf_tile >= 0) {
             const TileDesc dn = ta.desc[pf_tile];
-            const TileLayout Ln = tile_layout(D, ORDER, nslot, dn.n_own, dn.n_r1, dn.n_r2, dn.nFB, (LIM ? 1 : 0) | (VISC ? 2 : 0));
+            const TileLayout Ln = tile_layout(D, ORDER, nslot, dn.n_own, dn.n_r1, dn.n_r2, dn.nFB, EXT);
             bulk_prefetch_l2(ta.packets + dn.pk_off, Ln.pk_bytes);
             bulk_prefetch_l2(Qold + (size_t)dn.cb * U, (uint32_t)((dn.n_own + 1) & ~1) * U * 8u);
         }
     }
+    // Staged packet stream (VAR & 128): the weights and stencil ids of a thread's NEXT face are copied into
+    // its own shared-memory slots by cp.async while it works on the current one -- the bytes in flight live in
+    // shared memory instead of registers, and the first use of a packet word never waits for L2 / HBM.
+    // Slots are private to the thread (no barrier); [word][thread] layout, conflict-free.
+    double* stg_w = reinterpret_cast<double*>(smem + L.stage);
+    uint32_t* stg_i = reinterpret_cast<uint32_t*>(smem + L.stage + 2u * (NS - 1) * NT * 8u);
+    auto stage_issue = [&](int f) {
+#pragma unroll
+        for (int m = 0; m < 2 * (NS - 1); m++) cp_async8(smem_u32(stg_w + m * NT + tid), w_g + (size_t)m * nFBp + f);
+#pragma unroll
+        for (int m = 0; m < NS - 1; m++) cp_async4(smem_u32(stg_i + m * NT + tid), idx_g + (size_t)m * nFBp + f);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (STG && tid < nFB) stage_issue(tid);
     // ring cells: one thread per cell, U independent loads of a contiguous 8*U-byte row.
     // (Batching several cells per thread -- ids first, then rows -- was measured: it helps the
     // 128-thread variant but costs registers and was 1 % slower for the default 256-thread one.)
@@ -288,12 +307,29 @@ __device__ __forceinline__ void step_tile(const TileArrays& ta, const TileDesc d
         if (ORDER == 2) {
             uint32_t id[NS - 1];
             double wa[NS], wb[NS];
+            if (STG) {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
-            for (int m = 0; m < NS; m++) {
-                if (m < NS - 1) id[m] = idx_g[m * nFBp + f];
-                wa[m] = w_g[m * nFBp + f];
-                wb[m] = w_g[(NS + m) * nFBp + f];
+                for (int m = 0; m < NS - 1; m++) {
+                    id[m] = stg_i[m * NT + tid];
+                    wa[m + 1] = stg_w[m * NT + tid];
+                    wb[m + 1] = stg_w[(NS - 1 + m) * NT + tid];
+                }
+                if (f + NT < nFB) stage_issue(f + NT);  // the slots were just read by their only reader
+            } else {
+#pragma unroll
+                for (int m = 0; m < NS - 1; m++) {
+                    id[m] = idx_g[m * nFBp + f];
+                    wa[m + 1] = w_g[m * nFBp + f];
+                    wb[m + 1] = w_g[(NS - 1 + m) * nFBp + f];
+                }
             }
+            // own-cell weight: a closed cell reproduces constants (checked when the packets were built)
+            double sa = wa[1], sb = wb[1];
+#pragma unroll
+            for (int m = 2; m < NS; m++) { sa += wa[m]; sb += wb[m]; }
+            wa[0] = 1.0 - sa;
+            wb[0] = 1.0 - sb;
             const int la = id[0] & 0xFFFFu, lb = id[0] >> 16;
             const bool interior = lb != 0xFFFF;
             // the two cells of the face serve both sides: own cell of one, first neighbour of the other

@@ -2,6 +2,7 @@
 #include "tiles.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 
 #include "tile_layout.h"
@@ -273,6 +274,17 @@ std::string build_tiles(const Plan& p, int n_update, int T, int order, TilePack&
                         }
                     }
                 }
+                // The own-cell weight is not stored: the kernel forms it as 1 - (sum of the others), which equals
+                // beta[0] when the cell is closed (sum_j Sout_j = 0: a constant field has no gradient).  A mesh
+                // whose cells are not closed to round-off cannot use the fused kernel (NaN geometry passes:
+                // it is NaN either way).
+                auto closed = [&](const double* beta) {
+                    double sum = beta[1];
+                    for (int m = 2; m < NS; m++) sum += beta[m];
+                    const double defect = std::fabs((1.0 - sum) - beta[0]);
+                    return !(defect > 1e-12 * (1.0 + std::fabs(beta[0])));
+                };
+                int nopen = 0;
                 for (int lf = 0; lf < nFB; lf++) {
                     const int f = s.flist[lf];
                     const int a = p.fc0[f], b = p.fc1[f];
@@ -287,18 +299,24 @@ std::string build_tiles(const Plan& p, int n_update, int T, int order, TilePack&
                     int cells[9];
                     // idx rows: [0] = own cells (A | B << 16), [m-1] = stencil entry m >= 2; entry 1 is implicit
                     stencil(a, f, &p.dx0[(size_t)f * D], beta, cells);
-                    for (int m = 0; m < NS; m++) w[(size_t)m * nFBp + lf] = beta[m];
+                    if (!closed(beta)) nopen++;
+                    for (int m = 1; m < NS; m++) w[(size_t)(m - 1) * nFBp + lf] = beta[m];
                     idx[lf] = (uint32_t)cells[0];
                     for (int m = 2; m < NS; m++) idx[(size_t)(m - 1) * nFBp + lf] = (uint32_t)cells[m];
                     if (b >= 0) {
                         stencil(b, f, &p.dx1[(size_t)f * D], beta, cells);
-                        for (int m = 0; m < NS; m++) w[(size_t)(NS + m) * nFBp + lf] = beta[m];
+                        if (!closed(beta)) nopen++;
+                        for (int m = 1; m < NS; m++) w[(size_t)(NS - 1 + m - 1) * nFBp + lf] = beta[m];
                         idx[lf] |= (uint32_t)cells[0] << 16;
                         for (int m = 2; m < NS; m++) idx[(size_t)(m - 1) * nFBp + lf] |= (uint32_t)cells[m] << 16;
                     } else {
-                        for (int m = 0; m < NS; m++) w[(size_t)(NS + m) * nFBp + lf] = 0.0;
+                        for (int m = 1; m < NS; m++) w[(size_t)(NS - 1 + m - 1) * nFBp + lf] = 0.0;
                         idx[lf] |= 0xFFFFu << 16;  // boundary marker
                     }
+                }
+                if (nopen) {
+#pragma omp atomic
+                    tp.open_stencils += nopen;
                 }
             }
         }

@@ -44,6 +44,7 @@ struct TilePack {
     std::vector<unsigned char> packets;  // concatenated packets, layout = tile_layout()
     size_t max_smem = 0;                 // dynamic shared memory the largest tile needs
     int64_t sum_r1 = 0, sum_r2 = 0, sum_FB = 0, sum_FA = 0;
+    int64_t open_stencils = 0;           // face sides whose cell is not closed (own-cell weight != 1 - sum of the others)
 };
 
 // n_update: cells [0, n_update) are advanced (the rest are ghosts, read only)

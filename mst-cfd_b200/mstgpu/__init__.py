@@ -55,7 +55,7 @@ class MstConfig(C.Structure):
         ("mu", C.c_double), ("kappa", C.c_double), ("cv", C.c_double),
         ("inletQ", C.c_double * 5),
         ("kernel", C.c_int32), ("tile_cells", C.c_int32), ("block_threads", C.c_int32),
-        ("reserved_", C.c_int32),
+        ("tile_flags", C.c_int32),
         # extension (absent from the reference): gradient / limiter choice, include/mstgpu.h
         ("gradient", C.c_int32), ("limiter", C.c_int32), ("limiter_k", C.c_double),
     ]

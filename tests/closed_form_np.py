@@ -36,11 +36,18 @@ def roe_contract(A, B, flags, Sd, gamma=1.4, delta=0.125, eor=1e-10):
     ud = (uh * dq[..., 1:1 + D]).sum(-1)
     theta = (0.5 * q2 * dq[..., 0] - ud + dq[..., -1]) / g
     sh = dq[..., 1:1 + D] - uh * dq[..., :1]
-    rea = 1 / (A[..., 0] + eor)
-    reb = 1 / (B[..., 0] + eor)
+    # central part 1/2 (F_A + F_B) . S through the mass fluxes m.S (physics.cuh: contracted first)
+    mna = (Sd * A[..., 1:1 + D]).sum(-1)
+    mnb = (Sd * B[..., 1:1 + D]).sum(-1)
+    fa = mna / (A[..., 0] + eor)
+    fb = mnb / (B[..., 0] + eor)
     phi = np.zeros_like(A)
+    phi[..., 0] = 0.5 * (mna + mnb)
+    for i in range(D):
+        phi[..., i + 1] = 0.5 * (A[..., i + 1] * fa + B[..., i + 1] * fb) + 0.5 * (pa + pb) * Sd[..., i]
+    phi[..., -1] = 0.5 * (hta * mna + htb * mnb)
     for d in range(D):
-        sgn = np.where(flags[..., d] != 0, 0.5, -0.5)
+        ss = np.where(flags[..., d] != 0, 0.5, -0.5) * Sd[..., d]
         beta = sh[..., d] / ah
         lm = _efix(np.abs(uh[..., d] - ah), delta)
         le = _efix(np.abs(uh[..., d]), delta)
@@ -50,25 +57,18 @@ def roe_contract(A, B, flags, Sd, gamma=1.4, delta=0.125, eor=1e-10):
         wp = lp * 0.5 * (theta + beta)
         s = wm + we + wp
         dif = ah * (wp - wm)
-        ma, mb = A[..., d + 1], B[..., d + 1]
-        F = np.zeros_like(A)
-        F[..., 0] = 0.5 * (ma + mb) - sgn * s
         en = H * (wm + wp) + uh[..., d] * dif + 0.5 * q2 * we
+        phi[..., 0] -= ss * s
         for i in range(D):
-            fa = A[..., i + 1] * ma * rea
-            fb = B[..., i + 1] * mb * reb
             dis = uh[..., i] * s
             if i == d:
-                fa = fa + pa
-                fb = fb + pb
                 dis = dis + dif
             else:
                 ws = le * sh[..., i]
                 dis = dis + ws
                 en = en + uh[..., i] * ws
-            F[..., i + 1] = 0.5 * (fa + fb) - sgn * dis
-        F[..., -1] = 0.5 * (hta * ma + htb * mb) - sgn * en
-        phi += Sd[..., d:d + 1] * F
+            phi[..., i + 1] -= ss * dis
+        phi[..., -1] -= ss * en
     return phi
 
 

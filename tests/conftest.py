@@ -78,13 +78,28 @@ def char_scales(Q, gamma=1.4):
 
 
 def rel_linf(Qa, Qb, gamma=1.4):
-    """max_k max_c |Qa - Qb| / scale_k(Qb)"""
+    """max over cells and variables of |Qa - Qb| / scale, where scale is
+      * for every variable the per-variable characteristic scale of `char_scales` (momentum components
+        against max(|m| + rho a), so a physically zero component does not turn round-off into O(1)), and
+      * for rho and E ALSO the cell's own value (pointwise relative, the north star's "relative L-inf"),
+        floored at 1e-3 of the variable's scale so that a near-vacuum cell of an unlimited step from a
+        random state does not divide by ~0."""
     fin = np.isfinite(Qb).all(axis=1)
     assert np.array_equal(np.isfinite(Qa).all(axis=1), fin), "finite masks differ"
     if not fin.any():
         return 0.0  # everything NaN on both sides (unlimited scheme on a random state)
-    s = char_scales(Qb[fin], gamma)
-    return float((np.abs(Qa[fin] - Qb[fin]) / s).max())
+    a, b = Qa[fin], Qb[fin]
+    s = char_scales(b, gamma)
+    d = np.abs(a - b)
+    err = float((d / s).max())
+    for k in (0, -1):
+        err = max(err, float((d[:, k] / np.maximum(np.abs(b[:, k]), 1e-3 * s[k])).max()))
+    return err
+
+
+def rel_linf_pointwise(Qa, Qb, cols=(0, -1)):
+    """max_c |Qa - Qb| / |Qb| on rho and E (no floor): for states that stay away from vacuum"""
+    return max(float((np.abs(Qa[:, k] - Qb[:, k]) / np.abs(Qb[:, k])).max()) for k in cols)
 
 
 def hex_box_flat(nx, ny, nz, bc=(3, 3, 3, 3, 3, 3)):

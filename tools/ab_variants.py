@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--flux", default="", help="default: the workload's own (box roe, step ausm)")
     ap.add_argument("--block-threads", type=int, default=0, help="CTA size of the fused kernel (128|256), 0 = default")
     ap.add_argument("--tiles", default="0", help="comma list of tile sizes (cells per tile), 0 = default; one context each")
+    ap.add_argument("--configs", default="", help="comma list of NT:T:variant[:tile_flags] tuples (one context each); overrides --tiles/--variants/--block-threads")
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     import mstgpu
@@ -49,33 +50,44 @@ def main():
         kw["order"] = a.order
     if a.flux:
         kw["flux"] = a.flux
+    import hashlib
     ref, rows = None, []
-    for T in [int(s) for s in a.tiles.split(",")]:
-        t = time.time()
-        ctx = mstgpu.Context(f, tile_cells=T, block_threads=a.block_threads, **kw)
-        print(f"[ab] {f['ncells']} cells, T={T}: context in {time.time() - t:.1f}s", file=sys.stderr, flush=True)
-        for v in [int(s) for s in a.variants.split(",")]:
-            ctx.set_tile_variant(v)
-            ctx.set_state(Q0)
-            ctx.step(dt, 3)
-            Q3 = ctx.get_state()
-            r3 = ctx.residual()
-            if ref is None:
-                ref = (Q3.copy(), r3.copy())
-            same = bool(np.array_equal(Q3, ref[0], equal_nan=True) and np.array_equal(r3, ref[1], equal_nan=True))
-            ctx.step(dt, 5)
-            ctx.sync()
-            ctx.enable_kernel_timing(True)
-            ms = ctx.step_timed(dt, a.steps)
-            kms, kn = ctx.kernel_time("step_tiles")
-            ctx.enable_kernel_timing(False)
-            ctx.step(dt, 4)
-            ctx.sync()
-            gms = ctx.step_timed(dt, a.steps)   # no per-kernel events: pairs of steps from the CUDA graph
-            row = dict(tile_cells=T, variant=v, identical_to_v0=same, ms_per_step=ms / a.steps, kernel_ms=kms / max(kn, 1),
-                       graph_ms_per_step=gms / a.steps, gcells_per_s=f["ncells"] * a.steps / (ms * 1e-3) / 1e9)
-            rows.append(row)
-            print(json.dumps(row), flush=True)
+    if a.configs:
+        cfgs = [tuple(int(x) for x in (c.split(":") + ["0"])[:4]) for c in a.configs.split(",")]
+    else:
+        cfgs = [(a.block_threads, int(T), int(v), 0) for T in a.tiles.split(",") for v in a.variants.split(",")]
+    ctx, key = None, None
+    for NT, T, v, fl in cfgs:
+        if key != (NT, T, fl):
+            if ctx is not None:
+                ctx.close()
+            t = time.time()
+            ctx = mstgpu.Context(f, tile_cells=T, block_threads=NT, tile_flags=fl, **kw)
+            key = (NT, T, fl)
+            print(f"[ab] {f['ncells']} cells, NT={NT} T={T}: context in {time.time() - t:.1f}s", file=sys.stderr, flush=True)
+        ctx.set_tile_variant(v)
+        ctx.set_state(Q0)
+        ctx.step(dt, 3)
+        Q3 = ctx.get_state()
+        r3 = ctx.residual()
+        if ref is None:
+            ref = (Q3.copy(), r3.copy())
+        same = bool(np.array_equal(Q3, ref[0], equal_nan=True) and np.array_equal(r3, ref[1], equal_nan=True))
+        ctx.step(dt, 5)
+        ctx.sync()
+        ctx.enable_kernel_timing(True)
+        ms = ctx.step_timed(dt, a.steps)
+        kms, kn = ctx.kernel_time("step_tiles")
+        ctx.enable_kernel_timing(False)
+        ctx.step(dt, 4)
+        ctx.sync()
+        gms = ctx.step_timed(dt, a.steps)   # no per-kernel events: pairs of steps from the CUDA graph
+        row = dict(block_threads=NT, tile_cells=T, variant=v, tile_flags=fl, identical_to_first=same, sha=hashlib.sha256(Q3.tobytes()).hexdigest()[:12],
+                   ms_per_step=ms / a.steps, kernel_ms=kms / max(kn, 1),
+                   graph_ms_per_step=gms / a.steps, gcells_per_s=f["ncells"] * a.steps / (ms * 1e-3) / 1e9)
+        rows.append(row)
+        print(json.dumps(row), flush=True)
+    if ctx is not None:
         ctx.close()
     if a.out:
         json.dump(dict(cells=int(f["ncells"]), steps=a.steps, rows=rows), open(a.out, "w"), indent=1)
