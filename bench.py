@@ -486,18 +486,11 @@ def lusgs_cpu(args, budget_s=12.0):
                        "(oracle/lusgs_oracle.cpp, sequential like the reference)")
 
 
-def run_ours(args, rank, world):
+def measure(args, rank, world, dist, local, want_cpu=True):
+    """One workload through the CUDA path: K timed steps with the state resident in HBM, digest, every-step-residual
+    leg, roofline of the dominant kernel, e2e leg with host buffers.  Returns the JSON line as a dict."""
     import torch
     import mstgpu
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
-    local = int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
     f, Q0, desc = build_workload(args)
     nc_total, U, D = f["ncells"], f["dim"] + 2, f["dim"]
     dt_run, inlet = run_params(args, Q0)  # the inlet of the step / sphere cases is their free stream
@@ -679,7 +672,7 @@ def run_ours(args, rank, world):
     e2e = dict(value=nc_total / e2e_s, unit="cell-updates/s", h2d_bytes_per_step=nc * U * 8,
                d2h_bytes_per_step=nc * U * 8 + U * 8, ms_per_step=e2e_s * 1e3, steps=ne)
 
-    cpu = cpu_baseline(args) if (world == 1 and not args.no_cpu) else None
+    cpu = cpu_baseline(args) if (world == 1 and not args.no_cpu and want_cpu) else None
 
     out = dict(metric="cell_updates_per_sec", value=value, unit="cell-updates/s", n_gpus=world,
                steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True,
@@ -692,11 +685,64 @@ def run_ours(args, rank, world):
                clocks=clk, e2e=e2e, gpu_launches=launches, roofline=roof, cpu_baseline=cpu,
                state_digest=digest, every_step_residual=every,
                wall_ms_per_step=wall * 1e3 / args.steps, device_gib=ctx.device_bytes / 2 ** 30)
+    if dist is not None:
+        dist.barrier()
+    ctx.close()
+    return out
+
+
+# BASELINE.json configs 1, 2, 3, 5 next to the headline (config 4): short runs of the same code path, each with its
+# own roofline; the bound is named for what it is (configs 1 and 2 fit the 126 MB L2: launch / latency, not HBM)
+SECONDARY = [
+    ("config1_sod", dict(workload="sod", n=203, order=2, flux="roe", graph=1), 200,
+     "launch/latency: 18 282 cells, state + tables live in L2; the HBM fraction is not the binding bound"),
+    ("config2_step445_ausm", dict(workload="step", n=445, order=1, flux="ausm", graph=1), 200,
+     "L2/latency: 998 046 triangles, state + packets (~0.3 GB) mostly L2-resident, ~60 us per step"),
+    ("config3_sphere_roe_viscous", dict(workload="sphere", n=42, order=2, flux="roe", viscous=1), 20, "hbm"),
+    ("config5_implicit_lusgs", dict(workload="box", n=203, order=2, flux="roe", implicit=1), 3, "hbm"),
+]
+
+
+def run_ours(args, rank, world):
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    out = measure(args, rank, world, dist, local)
+    headline = (args.workload == "box" and args.n == 203 and not args.implicit and not args.viscous and args.limiter == "none"
+                and args.cfl <= 0 and args.order == 2 and args.flux == "roe")
+    if args.secondary == 1 or (args.secondary < 0 and headline):
+        sec = {}
+        for name, over, steps, bound in SECONDARY:
+            a = argparse.Namespace(**vars(args))
+            for k, v in over.items():
+                setattr(a, k, v)
+            a.steps, a.warmup, a.no_cpu = steps, 3, True
+            if name == "config5_implicit_lusgs" and world == 1:
+                a.n = 160  # the 50 M-row block system needs ~116 GiB: one B200 runs 24.6 M rows, >= 2 GPUs the full mesh
+            if (name in ("config1_sod", "config2_step445_ausm") and world > 1) or (name == "config3_sphere_roe_viscous" and world > 2):
+                continue   # BASELINE.json: configs 1 and 2 on one B200, config 3 on 1 and 2
+            t0 = time.time()
+            try:
+                o = measure(a, rank, world, dist, local, want_cpu=False)
+                o["roofline"]["bound_named"] = bound
+                sec[name] = {k: o[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "config", "gpu_config", "roofline",
+                                               "e2e", "gpu_launches", "state_digest", "device_gib", "n_gpus")}
+            except BaseException as e:  # a secondary line must never cost the headline
+                sec[name] = dict(error=f"{type(e).__name__}: {e}"[:300])
+                if dist is not None:
+                    raise
+            log(f"[bench] secondary {name}: {time.time() - t0:.1f}s")
+        out["secondary"] = sec
     if rank == 0:
         print(json.dumps(out), flush=True)
     if dist is not None:
         dist.barrier()
-        ctx.close()
         dist.destroy_process_group()
 
 
@@ -732,6 +778,8 @@ def main():
                     help="config 5: implicit steps (block assembly + 5 colour-ordered LU-SGS sweeps)")
     ap.add_argument("--implicit-dt", type=float, default=1e-3)
     ap.add_argument("--graph", type=int, default=0, choices=[0, 1], help="also time the K steps issued from the CUDA graph")
+    ap.add_argument("--secondary", type=int, default=-1, help="BASELINE configs 1, 2, 3, 5 as short runs under the `secondary` key: "
+                    "1 = always, 0 = never, -1 = with the headline workload only (default)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -139,7 +139,12 @@ typedef struct mstgpu_config {
     double limiter_k;     /* Venkatakrishnan K: eps^2 = (K h)^3, h = V^(1/D)            */
 } mstgpu_config;
 
-/* Fill `cfg` with the reference's shipped constants (CONST.h) for `dim`. */
+/* Fill `cfg` for `dim`: gas and flux constants are the reference's shipped ones (CONST.h:38-48,
+ * SolverRoe.cpp:115).  The SCHEME is not: the reference chooses it with macros at compile time and
+ * ships ACCURACY 1 / RHOSOLVER SolverAusm (CONST.h:6,10); this library defaults to order = 2,
+ * flux = MSTGPU_FLUX_ROE (the configuration the project's metric is quoted on).  A host that replaces
+ * the reference's solver sets cfg.order / cfg.flux / cfg.viscous from its own macros -- host/GpuRhoSolver.h
+ * does exactly that when it is compiled with the reference's CONST.h. */
 void mstgpu_default_config(mstgpu_config* cfg, int32_t dim);
 
 /* Build a solver context: renumber (Morton), lay the tables out in HBM,

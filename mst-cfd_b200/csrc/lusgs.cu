@@ -41,7 +41,9 @@ struct mstgpu_lusgs {
     double *val = nullptr, *D = nullptr, *Dinv = nullptr, *LD = nullptr, *UD = nullptr;
     double *b = nullptr, *x = nullptr, *rhs = nullptr, *rhs1 = nullptr, *ux = nullptr;
     double* s = nullptr;  // mode 1: U x of the next iteration, a by-product of the backward sweep
-    int mode = 0;         // 0 = the reference's four passes per iteration, 1 = fused (see solve_core)
+    int mode = 0;         // 0 = the reference's four passes per iteration, 1 = fused, 2 = lean (see solve_core)
+    bool s_valid = false; // h->s holds U x of the CURRENT x (left behind by the last backward sweep of modes 1 / 2)
+    bool x0_zero = false; // hint of the caller for the next solve: the start vector is zero (U x = 0, no pass over U)
     unsigned long long* res = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t launches = 0;
@@ -283,6 +285,35 @@ __global__ void k_bwd_fused(int nrows, const int* rows, const int* ptr, const in
     s[(size_t)r * B + i] = ss;
 }
 
+// ---- lean iteration (mode 2) ----------------------------------------------------------------------------
+// Mode 1 without the two whole-vector passes around the backward sweep: the reference's X1 = D^-1 rhs; rhs1 = D X1
+// (SparseSolver.cpp:86-90) is the identity up to rounding (cond(D) eps), so the backward sweep starts from v
+// itself, and x = D^-1 w is formed by the row's lane group the moment w[r] is final.  Per row and iteration this
+// drops D and D^-1 of k_mid and a second read of w: ~2.0 -> ~1.5 kB.  Level 0 runs too (x = D^-1 v there).
+template <int B>
+__global__ void k_bwd_lean(int nrows, const int* rows, const int* ptr, const int* col, const double* UD, const double* Dinv,
+                           const double* v, double* w, double* s, double* x) {
+    const Grp<B> g(nrows);
+    const int r = g.on ? rows[g.row] : 0, i = g.i;
+    double acc = 0.0;
+    if (g.on) {
+        double ss = 0.0;
+        acc = v[(size_t)r * B + i];
+        const int k0 = ptr[r], k1 = ptr[r + 1];
+        for (int kk = 0; kk < k1 - k0; kk++) {
+            const int k = k1 - 1 - kk;
+            const double d = row_dot<B>(UD + (size_t)k * B * B + i * B, w + (size_t)col[k] * B);
+            acc -= d;
+            ss += d;
+        }
+        w[(size_t)r * B + i] = acc;
+        s[(size_t)r * B + i] = ss;
+    }
+    if (B == 1) { if (g.on) x[r] = Dinv[r] * acc; return; }
+    const double xi = g.matvec_lanes(g.on ? Dinv + (size_t)r * B * B + i * B : nullptr, acc);
+    if (g.on) x[(size_t)r * B + i] = xi;
+}
+
 // X1 = D^-1 rhs; rhs1 = D X1   (SparseSolverNUM.cpp:184-187)
 template <int B>
 __global__ void k_mid(int n, const double* D, const double* Dinv, const double* rhs, double* rhs1) {
@@ -336,12 +367,20 @@ int solve_core(mstgpu_lusgs* h, const double* val, const double* b, double* x, i
         if (h->nU) k_scale<B><<<(unsigned)(((size_t)h->nU * B + T - 1) / T), T, 0, s>>>((size_t)h->nU, h->Ucol, h->Upos, val, h->D, h->Dinv, h->UD);
         h->launches += 3;
     }
-    const bool fused = h->mode == 1;
+    // the lean mode has no k_fin, which is where the scalar solver's residual (early exit) is formed
+    const bool lean = h->mode == 2 && !(B == 1 && (res_hist || early_exit));
+    const bool fused = h->mode == 1 || h->mode == 2;
     if (fused) {
         if (!h->s) LCK(cudaMalloc((void**)&h->s, (size_t)n * B * 8));
-        // the only read of the unscaled off-diagonal blocks in this mode: U x of the start vector
-        k_ux_raw<B><<<G::grid(n, T), T, 0, s>>>(n, h->Uptr, h->Ucol, h->Upos, val, x, h->s);
-        h->launches++;
+        if (setup) h->s_valid = false;
+        if (h->x0_zero) {
+            LCK(cudaMemsetAsync(h->s, 0, (size_t)n * B * 8, s));  // U 0 = 0
+        } else if (!h->s_valid) {
+            // the only read of the unscaled off-diagonal blocks in these modes: U x of the start vector
+            k_ux_raw<B><<<G::grid(n, T), T, 0, s>>>(n, h->Uptr, h->Ucol, h->Upos, val, x, h->s);
+            h->launches++;
+        }
+        h->x0_zero = false;
     }
     int it = 0;
     for (; it < max_iter; it++) {
@@ -360,6 +399,14 @@ int solve_core(mstgpu_lusgs* h, const double* val, const double* b, double* x, i
                 if (cnt > 0)
                     k_fwd_fused<B><<<G::grid(cnt, T), T, 0, s>>>(cnt, h->frows + h->fptr[l], h->Lptr, h->Lcol, h->LD, bb, h->s, h->rhs, h->ux);
             }
+            if (lean) {
+                for (size_t l = 0; l + 1 < h->bptr.size(); l++) {
+                    const int cnt = h->bptr[l + 1] - h->bptr[l];
+                    if (cnt > 0)
+                        k_bwd_lean<B><<<G::grid(cnt, T), T, 0, s>>>(cnt, h->brows + h->bptr[l], h->Uptr, h->Ucol, h->UD, h->Dinv, h->rhs, h->rhs1, h->s, x);
+                }
+                h->launches += (int64_t)(h->fptr.size() > 1 ? h->fptr.size() - 1 : 0) + (int64_t)(h->bptr.size() > 1 ? h->bptr.size() - 1 : 0);
+            } else {
             k_mid<B><<<G::grid(n, T), T, 0, s>>>(n, h->D, h->Dinv, h->rhs, h->rhs1);
             LCK(cudaMemsetAsync(h->s, 0, (size_t)n * B * 8, s));  // rows without upper entries (level 0): U x = 0
             for (size_t l = 1; l + 1 < h->bptr.size(); l++) {
@@ -369,6 +416,8 @@ int solve_core(mstgpu_lusgs* h, const double* val, const double* b, double* x, i
             }
             k_fin<B><<<G::grid(n, T), T, 0, s>>>(n, h->D, h->Dinv, h->rhs1, x, h->res);
             h->launches += 2 + (int64_t)(h->fptr.size() > 1 ? h->fptr.size() - 1 : 0) + (int64_t)(h->bptr.size() > 2 ? h->bptr.size() - 2 : 0);
+            }
+            h->s_valid = true;  // s = U x of the x just written (owned columns; ghost columns live in G)
         } else {
         k_ux<B><<<G::grid(n, T), T, 0, s>>>(n, h->Uptr, h->Ucol, h->Upos, val, h->D, h->Dinv, x, h->ux);
         k_rhs<B><<<G::grid(n, T), T, 0, s>>>(n, h->Lptr, h->Lcol, h->Lpos, val, bb, h->ux, h->rhs);
@@ -424,6 +473,8 @@ int solve_impl(mstgpu_lusgs* h, const double* val, const double* b, double* x, i
 
 // in-library entry for the implicit step of mstgpu.cu: the sweeps on the caller's stream, no sync
 namespace mst {
+// the next solve starts from x = 0 (the implicit step's dQ): U x = 0 needs no pass over the U blocks
+void lusgs_hint_zero_start(mstgpu_lusgs* h) { if (h) h->x0_zero = true; }
 int lusgs_solve_async(mstgpu_lusgs* h, cudaStream_t st, const double* val, const double* b, double* x, int iters, bool setup) {
     cudaStream_t own = h->stream;
     h->stream = st;
@@ -605,7 +656,7 @@ int mstgpu_lusgs_create_partitioned(mstgpu_lusgs** out, int32_t n, int32_t ncols
         return 0;
     }();
     if (rc) { mstgpu_lusgs_destroy(h); return rc; }
-    if (const char* v = getenv("MSTGPU_LUSGS_MODE")) h->mode = atoi(v) == 1 ? 1 : 0;
+    if (const char* v = getenv("MSTGPU_LUSGS_MODE")) { const int m = atoi(v); h->mode = (m >= 0 && m <= 2) ? m : 0; }
     *out = h;
     return MSTGPU_OK;
 }
@@ -676,8 +727,9 @@ int64_t mstgpu_lusgs_device_bytes(mstgpu_lusgs* h) {
 }
 
 int mstgpu_lusgs_set_mode(mstgpu_lusgs* h, int32_t mode) {
-    if (!h || (mode != 0 && mode != 1)) { g_lusgs_error = "mode must be 0 (reference passes) or 1 (fused)"; return MSTGPU_ERR_ARG; }
+    if (!h || mode < 0 || mode > 2) { g_lusgs_error = "mode must be 0 (reference passes), 1 (fused) or 2 (lean)"; return MSTGPU_ERR_ARG; }
     h->mode = mode;
+    h->s_valid = false;
     return MSTGPU_OK;
 }
 

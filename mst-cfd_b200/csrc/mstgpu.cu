@@ -30,6 +30,7 @@ using namespace mst;
 namespace mst {
 // csrc/lusgs.cu: the sweeps on the caller's stream, device arrays, no synchronisation
 int lusgs_solve_async(mstgpu_lusgs* h, cudaStream_t st, const double* val, const double* b, double* x, int iters, bool setup);
+void lusgs_hint_zero_start(mstgpu_lusgs* h);
 }
 
 #define CK(call)                                                                       \
@@ -110,6 +111,7 @@ struct mstgpu_ctx {
     std::map<const void*, size_t> smem_configured;  // dynamic shared memory opted in per kernel instantiation, on this context's device
     bool tile_staged = false;  // packet stream staged through shared memory (step_tiles.cuh, VAR & 128)
     int tile_ext = 0;          // tile_layout() ext argument of this context's tiles
+    int ring_stride = 0;       // ring ids per tile in the device array (fixed stride)
     int sm_count = 148;
     size_t tile_smem = 0;
     struct TileClass { int first, count; size_t smem; bool halo; };  // halo: a ring of the tile holds ghost cells
@@ -937,8 +939,9 @@ int launch_tiles(mstgpu_ctx* ctx, double dt, const double* dtd, const double* Qo
             default: break;
         }
     }
-    if (D == 3 && ORDER == 2 && NT == 128 && NS == 5 && (ctx->tile_var & 72)) {
-        // experimental: small tiles, 128 threads, registers sized for 4 (8) / 5 (64) resident CTAs per SM
+    if (D == 3 && ORDER == 2 && NT == 128 && NS == 5 && !(ctx->tile_var & 32)) {
+        // 128-thread CTAs (the default for tets at second order): registers sized for 4 resident CTAs per SM
+        // (MSTGPU_TILE_VAR 64: for 5, experimental; 32: the plain 3-CTA allocation)
         return (ctx->tile_var & 64) ? launch_tiles_var<3, 2, 128, 5, false, false, 64>(ctx, dt, dtd, Qo, Qn, wr, which, st)
                                     : launch_tiles_var<3, 2, 128, 5, false, false, 8>(ctx, dt, dtd, Qo, Qn, wr, which, st);
     }
@@ -1239,6 +1242,7 @@ static int step_implicit_impl(mstgpu_ctx* ctx, double dt, int nsteps, int iters)
             KTimer t(ctx, "lusgs");
             const int64_t l0 = mstgpu_lusgs_launch_count(ctx->imp_solver);
             int r = MSTGPU_OK;
+            lusgs_hint_zero_start(ctx->imp_solver);  // dQ starts from 0 (memset above)
             if (!dist) {
                 r = lusgs_solve_async(ctx->imp_solver, ctx->stream, ctx->imp_val, ctx->imp_b, ctx->imp_x, iters, true);
             } else {
@@ -1279,15 +1283,25 @@ static bool tile_staged_for(const mstgpu_config& cfg, int D, int nslot) {
     return env ? atoi(env) != 0 : false;
 }
 
+// tets at second order without extensions (the scheme the metric is quoted on): 4 CTAs of 128 threads per SM on
+// tiles of 240 cells instead of 2 x 256 threads on 512 -- the same 16 warps and registers, but four CTAs in
+// different phases overlap the memory-bound phase 0 of one with the FP64-bound phase 2 of the others
+// (measured at 50.2 M tets: 5.72-5.78 ms against 5.84-5.87 ms per step, profiles/r2_ab_variants.json)
+static bool small_ctas_default(const mstgpu_config& cfg, int D, int nslot) {
+    return D == 3 && nslot == 4 && cfg.order == 2 && !cfg.limiter && !cfg.viscous && cfg.block_threads == 0 && cfg.tile_cells == 0;
+}
+
 static int tile_threads_for(const mstgpu_config& cfg, int T, int D, int nslot) {
+    if (small_ctas_default(cfg, D, nslot)) return 128;
     int NT = cfg.block_threads == 128 ? 128 : (cfg.block_threads == 256 ? 256 : (T <= 96 ? 128 : 256));
     if ((cfg.block_threads == 320 || cfg.block_threads == 384) && D == 3 && nslot == 4 && cfg.order == 2 && !cfg.limiter && !cfg.viscous)
         NT = cfg.block_threads;
     return NT;
 }
 
-static int default_tile_cells(const mstgpu_config& cfg, bool staged = false) {
+static int default_tile_cells(const mstgpu_config& cfg, bool staged = false, int D = 0, int nslot = 0) {
     if (staged) return cfg.block_threads == 128 ? 208 : 416;  // + 80 B of landing slots per thread
+    if (small_ctas_default(cfg, D, nslot)) return 240;
     if (cfg.order != 2) return 512;
     if (cfg.viscous != 0) return cfg.limiter != 0 ? 192 : 256;  // + [(D+1) D][own + ring 1] primitive gradients
     return cfg.limiter != 0 ? 384 : 512;
@@ -1302,7 +1316,7 @@ int mstgpu_tile_stats(const mstgpu_mesh* mesh, const mstgpu_config* cfg, int64_t
     if (!perr.empty()) { set_error(nullptr, perr); return MSTGPU_ERR_ARG; }
     TilePack tp;
     const bool staged = tile_staged_for(*cfg, p.D, p.nslot);
-    int T = cfg->tile_cells > 0 ? cfg->tile_cells : default_tile_cells(*cfg, staged);
+    int T = cfg->tile_cells > 0 ? cfg->tile_cells : default_tile_cells(*cfg, staged, p.D, p.nslot);
     const int NTs = tile_threads_for(*cfg, T, p.D, p.nslot);
     int ext = tile_ext(cfg->order, cfg->limiter, cfg->viscous);
     if (staged) ext = tile_ext_staged(ext, NTs);
@@ -1424,7 +1438,7 @@ static int create_impl(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_c
         if (ctx->use_tiles) {
             TilePack tp;
             ctx->tile_staged = tile_staged_for(*cfg, p.D, p.nslot);
-            int T = cfg->tile_cells > 0 ? cfg->tile_cells : default_tile_cells(*cfg, ctx->tile_staged);
+            int T = cfg->tile_cells > 0 ? cfg->tile_cells : default_tile_cells(*cfg, ctx->tile_staged, p.D, p.nslot);
             ctx->tile_NT = tile_threads_for(*cfg, T, p.D, p.nslot);
             ctx->tile_ext = tile_ext(cfg->order, cfg->limiter, cfg->viscous);
             if (ctx->tile_staged) ctx->tile_ext = tile_ext_staged(ctx->tile_ext, ctx->tile_NT);
@@ -1477,6 +1491,19 @@ static int create_impl(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_c
                     for (int t = 0; t < tp.ntiles; t++) if (cls[t] == c) sorted.push_back(tp.desc[t]);
                 }
                 tp.desc.swap(sorted);
+                // ring ids at a fixed stride per tile, in the order of the sorted descriptors: the kernel loads them
+                // together with the descriptor (step_tiles.cuh, phase 0)
+                int stride = 4;
+                for (const TileDesc& d : tp.desc) stride = std::max(stride, (d.n_r1 + d.n_r2 + 3) & ~3);
+                std::vector<int32_t> ring((size_t)tp.ntiles * stride, 0);
+#pragma omp parallel for schedule(static)
+                for (int t = 0; t < tp.ntiles; t++) {
+                    TileDesc& d = tp.desc[t];
+                    std::copy(tp.ring.begin() + d.ring_off, tp.ring.begin() + d.ring_off + d.n_r1 + d.n_r2, ring.begin() + (size_t)t * stride);
+                    d.ring_off = (int64_t)t * stride;
+                }
+                tp.ring.swap(ring);
+                ctx->ring_stride = stride;
                 if (getenv("MSTGPU_VERBOSE"))
                     for (const auto& tc : ctx->tile_classes)
                         fprintf(stderr, "[mstgpu] tile class: %d tiles, %zu B smem, %s\n", tc.count, tc.smem, tc.halo ? "halo" : "interior");
@@ -1488,7 +1515,7 @@ static int create_impl(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_c
             ctx->tile_allocs.push_back(dring);
             if ((r = upload(ctx, &dpk, tp.packets))) return r;
             ctx->tile_allocs.push_back(dpk);
-            ctx->ta = TileArrays{ddesc, dring, dpk};
+            ctx->ta = TileArrays{ddesc, dring, dpk, ctx->ring_stride};
             CK(cudaStreamSynchronize(ctx->stream));  // tp goes out of scope
         }
         size_t nstage = std::max(nq * p.D, (size_t)p.nf * p.U);
@@ -1730,17 +1757,35 @@ int mstgpu_implicit_setup(mstgpu_ctx* ctx, int32_t colour_sweeps) {
     int rc = mstgpu_lusgs_create_partitioned(&ctx->imp_solver, nrow, nc, U, rowptr.data(), col.data(),
                                              colour_sweeps ? order.data() : nullptr, ctx->device);
     if (rc != MSTGPU_OK) { set_error(ctx, std::string("lusgs: ") + mstgpu_lusgs_last_error()); return rc; }
+    const int64_t bytes_before = ctx->dev_bytes;
     ctx->dev_bytes += mstgpu_lusgs_device_bytes(ctx->imp_solver);
     ctx->imp_sweep = order;
-    int r;
-    if ((r = upload(ctx, &ctx->imp_dpos, dpos))) return r;
-    if ((r = upload(ctx, &ctx->imp_pos, pos))) return r;
-    if ((r = dalloc(ctx, &ctx->imp_val, nnz * U * U))) return r;
-    if ((r = dalloc(ctx, &ctx->imp_b, (size_t)nc * U + 2 * U))) return r;  // + 2 rows: bulk stores of the fused kernel
-    CK(cudaMemsetAsync(ctx->imp_b, 0, ((size_t)nc * U + 2 * U) * sizeof(double), ctx->stream));
-    if ((r = dalloc(ctx, &ctx->imp_x, (size_t)nc * U))) return r;
-    CK(cudaStreamSynchronize(ctx->stream));
-    return MSTGPU_OK;
+    // imp_solver != nullptr means "fully set up" to mstgpu_step_implicit: on any failure from here on (out of
+    // memory on the block array at tens of millions of rows is plausible) everything is undone
+    rc = [&]() -> int {
+        int r;
+        if ((r = upload(ctx, &ctx->imp_dpos, dpos))) return r;
+        if ((r = upload(ctx, &ctx->imp_pos, pos))) return r;
+        if ((r = dalloc(ctx, &ctx->imp_val, nnz * U * U))) return r;
+        if ((r = dalloc(ctx, &ctx->imp_b, (size_t)nc * U + 2 * U))) return r;  // + 2 rows: bulk stores of the fused kernel
+        CK(cudaMemsetAsync(ctx->imp_b, 0, ((size_t)nc * U + 2 * U) * sizeof(double), ctx->stream));
+        if ((r = dalloc(ctx, &ctx->imp_x, (size_t)nc * U))) return r;
+        CK(cudaStreamSynchronize(ctx->stream));
+        return MSTGPU_OK;
+    }();
+    if (rc != MSTGPU_OK) {
+        cudaGetLastError();  // clear the sticky allocation error: the context itself stays usable
+        mstgpu_lusgs_destroy(ctx->imp_solver);
+        ctx->imp_solver = nullptr;
+        if (ctx->imp_dpos) { cudaFree(ctx->imp_dpos); ctx->imp_dpos = nullptr; }
+        if (ctx->imp_pos) { cudaFree(ctx->imp_pos); ctx->imp_pos = nullptr; }
+        if (ctx->imp_val) { cudaFree(ctx->imp_val); ctx->imp_val = nullptr; }
+        if (ctx->imp_b) { cudaFree(ctx->imp_b); ctx->imp_b = nullptr; }
+        if (ctx->imp_x) { cudaFree(ctx->imp_x); ctx->imp_x = nullptr; }
+        ctx->imp_sweep.clear();
+        ctx->dev_bytes = bytes_before;
+    }
+    return rc;
 }
 
 int mstgpu_implicit_sweep_order(mstgpu_ctx* ctx, int32_t* order_ref_ids) {

@@ -20,6 +20,10 @@ std::string default_cell_part(const mstgpu_mesh& g, int nparts, std::vector<int3
 
 std::string build_partition(const mstgpu_mesh& g, const mstgpu_config& cfg, int nparts, int rank,
                             const int32_t* cell_part, Partition& P) {
+    {
+        std::string verr = validate_mesh(g);
+        if (!verr.empty()) return verr;
+    }
     const int D = g.dim, nc = g.ncells, nf = g.nfaces;
     if (nparts < 1 || rank < 0 || rank >= nparts) return "bad nparts / rank";
     std::vector<int32_t> own_part;

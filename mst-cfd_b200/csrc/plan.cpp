@@ -86,20 +86,59 @@ void curve_order(const mstgpu_mesh& m, int renumber, int n, std::vector<int32_t>
     for (int i = 0; i < n; i++) new2old[i] = key[i].second;
 }
 
-std::string build_plan(const mstgpu_mesh& m, const mstgpu_config& cfg, Plan& p, int n_owned) {
+// One O(nf + nc) pass over a host mesh before anything indexes with its entries: every entry point that
+// takes an mstgpu_mesh (create, partition, tile statistics, adjacency, permutation) goes through it, so a bad
+// table is MSTGPU_ERR_ARG with a message instead of an out-of-bounds read.
+std::string validate_mesh(const mstgpu_mesh& m) {
     const int D = m.dim;
     if (D != 2 && D != 3) return "dim must be 2 or 3";
     if (m.ncells <= 0 || m.nfaces <= 0) return "empty mesh";
     if (m.nint < 0 || m.nint > m.nfaces) return "nint out of range";
+    if (!m.c0 || !m.c1 || !m.S || !m.fc || !m.eta || !m.flag || !m.ftype || !m.cc || !m.vol || !m.cf_ptr || !m.cf_idx)
+        return "null mesh table";
+    const int nc = m.ncells, nf = m.nfaces;
+    int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+    for (int f = 0; f < nf; f++) {
+        if (m.c0[f] < 0 || m.c0[f] >= nc) bad |= 1;
+        if (m.c1[f] >= nc || m.c1[f] < -1) bad |= 2;
+        if (m.ftype[f] == MSTGPU_BC_INTERIOR && m.c1[f] < 0) bad |= 4;
+    }
+    if (bad & 1) return "c0 out of range";
+    if (bad & 2) return "c1 out of range";
+    if (bad & 4) return "interior face without c1";
+    if (m.cf_ptr[0] != 0) return "cf_ptr[0] must be 0";
+#pragma omp parallel for schedule(static) reduction(| : bad)
+    for (int c = 0; c < nc; c++) {
+        const int64_t a = m.cf_ptr[c], b = m.cf_ptr[c + 1];
+        if (b < a) { bad |= 8; continue; }
+        if (b - a > 8) { bad |= 16; continue; }
+    }
+    if (bad & 8) return "cf_ptr must be non-decreasing";
+    if (bad & 16) return "cells must have 1..8 faces";
+    const int64_t ncf = m.cf_ptr[nc];
+    if (ncf < 0 || ncf > 2 * (int64_t)nf) return "cf_ptr total inconsistent with the face count";
+#pragma omp parallel for schedule(static) reduction(| : bad)
+    for (int c = 0; c < nc; c++)
+        for (int j = m.cf_ptr[c]; j < m.cf_ptr[c + 1]; j++) {
+            const int f = m.cf_idx[j];
+            if (f < 0 || f >= nf) { bad |= 32; continue; }
+            if (m.c0[f] != c && m.c1[f] != c) bad |= 64;
+        }
+    if (bad & 32) return "cf_idx entry out of range";
+    if (bad & 64) return "cf_idx lists a face that does not touch the cell";
+    return "";
+}
+
+std::string build_plan(const mstgpu_mesh& m, const mstgpu_config& cfg, Plan& p, int n_owned) {
+    {
+        std::string verr = validate_mesh(m);
+        if (!verr.empty()) return verr;
+    }
+    const int D = m.dim;
     const int nc = m.ncells, nf = m.nfaces;
     p.D = D; p.U = D + 2; p.nc = nc; p.nf = nf; p.nint = m.nint;
 
-    // ---- validate connectivity ------------------------------------------------
-    for (int f = 0; f < nf; f++) {
-        if (m.c0[f] < 0 || m.c0[f] >= nc) return "c0 out of range";
-        if (m.c1[f] >= nc) return "c1 out of range";
-        if (m.ftype[f] == MSTGPU_BC_INTERIOR && m.c1[f] < 0) return "interior face without c1";
-    }
     int nslot = 0;
     for (int c = 0; c < nc; c++) nslot = std::max(nslot, m.cf_ptr[c + 1] - m.cf_ptr[c]);
     if (nslot <= 0 || nslot > 8) return "cells must have 1..8 faces";

@@ -49,6 +49,8 @@ struct Plan {
 // returns empty string on success, error text otherwise.
 // n_owned >= 0: only cells [0, n_owned) are renumbered (among themselves); the
 // rest (ghost cells of a partition) keep their position behind them.
+// connectivity checks every host-mesh entry point runs first ("" = fine)
+std::string validate_mesh(const mstgpu_mesh& m);
 std::string build_plan(const mstgpu_mesh& m, const mstgpu_config& cfg, Plan& p, int n_owned = -1);
 
 // space-filling-curve order of the first n cells (renumber: 1 Morton, 2 Hilbert)

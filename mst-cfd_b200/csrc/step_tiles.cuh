@@ -39,8 +39,9 @@ namespace mst {
 
 struct TileArrays {
     const TileDesc* desc;
-    const int32_t* ring;
+    const int32_t* ring;           // ring-cell ids, ring_stride entries per tile in desc[] order (tile t: ring + t * ring_stride)
     const unsigned char* packets;
+    int32_t ring_stride;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -115,7 +116,7 @@ __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
 }
 
 template <int D, int ORDER, int NT, int NS, bool LIM, bool VISC, int VAR>
-__device__ __forceinline__ void step_tile(const TileArrays& ta, const TileDesc d, const int pf_tile, const bool first, const bool pf_self,
+__device__ __forceinline__ void step_tile(const TileArrays& ta, const int tile, const int pf_tile, const bool first, const bool pf_self,
                                           const uint32_t parity, int want_resid, const DevCfg& cfg, double dt_val,
                                           const double* __restrict__ dt_dev, const double* __restrict__ Qold,
                                           double* __restrict__ Qnew, unsigned long long* __restrict__ resid,
@@ -124,6 +125,16 @@ __device__ __forceinline__ void step_tile(const TileArrays& ta, const TileDesc d
     constexpr int nslot = NS - 1;
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x;
+    // Phase 0 is a chain of dependent global-memory latencies (descriptor -> ring ids -> ring rows, ~0.7 us
+    // each under load).  The ring ids sit at a FIXED stride per tile, so their loads are issued together with
+    // the descriptor's, before anything is known about the tile, and all rows of a thread are in flight at
+    // once afterwards: two latencies instead of 1 + 2 per loop trip.
+    constexpr int RB = NT >= 256 ? 1024 / NT : 4;  // ring rows per thread covered by the batch (the rest loop)
+    const int32_t* __restrict__ ring_t = ta.ring + (size_t)tile * ta.ring_stride;
+    int rid[RB];
+#pragma unroll
+    for (int j = 0; j < RB; j++) rid[j] = (tid + j * NT < ta.ring_stride) ? ring_t[tid + j * NT] : 0;
+    const TileDesc d = ta.desc[tile];
     const int n_own = d.n_own, n_ring = d.n_r1 + d.n_r2;
     const int nFB = d.nFB;
     constexpr bool STG = ORDER == 2 && (VAR & 128) != 0;
@@ -182,7 +193,7 @@ __device__ __forceinline__ void step_tile(const TileArrays& ta, const TileDesc d
     // 128-thread variant but costs registers and was 1 % slower for the default 256-thread one.)
     if (VAR & 4) {
         for (int r = tid; r < n_ring; r += NT) {
-            const int g = ta.ring[d.ring_off + r];
+            const int g = ring_t[r];
             const double* src = Qold + (size_t)g * U;
             const uint32_t dst = smem_u32(Qs + (n_own + r) * U);
 #pragma unroll
@@ -191,13 +202,26 @@ __device__ __forceinline__ void step_tile(const TileArrays& ta, const TileDesc d
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     } else {
-        for (int r = tid; r < n_ring; r += NT) {
-            const int g = ta.ring[d.ring_off + r];
-            double q[U];
+        double q[RB][U];
 #pragma unroll
-            for (int k = 0; k < U; k++) q[k] = Qold[(size_t)g * U + k];
+        for (int j = 0; j < RB; j++)
+            if (tid + j * NT < n_ring) {
 #pragma unroll
-            for (int k = 0; k < U; k++) Qs[(n_own + r) * U + k] = q[k];
+                for (int k = 0; k < U; k++) q[j][k] = Qold[(size_t)rid[j] * U + k];
+            }
+#pragma unroll
+        for (int j = 0; j < RB; j++)
+            if (tid + j * NT < n_ring) {
+#pragma unroll
+                for (int k = 0; k < U; k++) Qs[(n_own + tid + j * NT) * U + k] = q[j][k];
+            }
+        for (int r = tid + RB * NT; r < n_ring; r += NT) {  // tiles with more than 1024 ring cells
+            const int g = ring_t[r];
+            double q1[U];
+#pragma unroll
+            for (int k = 0; k < U; k++) q1[k] = Qold[(size_t)g * U + k];
+#pragma unroll
+            for (int k = 0; k < U; k++) Qs[(n_own + r) * U + k] = q1[k];
         }
     }
     mbar_wait(bar, parity);
@@ -521,13 +545,13 @@ __global__ void __launch_bounds__(NT, (VAR & 64) ? 5 : (VAR & 8) ? 4 : (VAR & 16
         uint32_t it = 0;
         for (int t = blockIdx.x; t < n_class; t += gridDim.x, it++) {
             const int tn = t + (int)gridDim.x;
-            step_tile<D, ORDER, NT, NS, LIM, VISC, VAR>(ta, ta.desc[tile_base + t], ((VAR & 1) && tn < n_class) ? tile_base + tn : -1, it == 0, !(VAR & 1) || it == 0, it & 1u,
+            step_tile<D, ORDER, NT, NS, LIM, VISC, VAR>(ta, tile_base + t, ((VAR & 1) && tn < n_class) ? tile_base + tn : -1, it == 0, !(VAR & 1) || it == 0, it & 1u,
                                                         want_resid, cfg, dt_val, dt_dev, Qold, Qnew, resid, nanflag);
             __syncthreads();  // the bulk store has read Qs (thread 0 waited for it): the next tile may overwrite it
         }
     } else {
         const int tn = (int)blockIdx.x + var_arg;
-        step_tile<D, ORDER, NT, NS, LIM, VISC, VAR>(ta, ta.desc[tile_base + blockIdx.x], ((VAR & 1) && tn < n_class) ? tile_base + tn : -1,
+        step_tile<D, ORDER, NT, NS, LIM, VISC, VAR>(ta, tile_base + (int)blockIdx.x, ((VAR & 1) && tn < n_class) ? tile_base + tn : -1,
                                                     true, !(VAR & 1) || (int)blockIdx.x < var_arg, 0u, want_resid, cfg, dt_val, dt_dev, Qold,
                                                     Qnew, resid, nanflag);
     }

@@ -40,10 +40,35 @@
 
 namespace mstgpu_host {
 
+// The reference picks its scheme with macros at compile time (CONST.h:6 ACCURACY, :10 RHOSOLVER, :14 FLAGVISCID;
+// shipped: first order, SolverAusm, inviscid).  A host that is compiled with the reference's CONST.h -- the drop-in
+// case -- inherits exactly those; without the macros the defaults are the library's (second-order Roe, the
+// configuration BASELINE.json quotes its metric on).
+#define MSTGPU_HOST_STR_(x) #x
+#define MSTGPU_HOST_STR(x) MSTGPU_HOST_STR_(x)
+inline int flux_of_rhosolver_macro(const char* name) {
+    for (const char* p = name; *p; p++)
+        if ((p[0] == 'A' || p[0] == 'a') && (p[1] == 'u' || p[1] == 'U') && (p[2] == 's' || p[2] == 'S') && (p[3] == 'm' || p[3] == 'M'))
+            return MSTGPU_FLUX_AUSM;
+    return MSTGPU_FLUX_ROE;
+}
+
 struct Options {
-    int order = 2;                 // ACCURACY      (R/include/CONST.h:6)
-    int flux = MSTGPU_FLUX_ROE;    // RHOSOLVER     (CONST.h:10)
-    int viscous = 0;               // FLAGVISCID    (CONST.h:14)
+#ifdef ACCURACY
+    int order = (ACCURACY);        // ACCURACY      (R/include/CONST.h:6)
+#else
+    int order = 2;
+#endif
+#ifdef RHOSOLVER
+    int flux = flux_of_rhosolver_macro(MSTGPU_HOST_STR(RHOSOLVER));  // RHOSOLVER (CONST.h:10)
+#else
+    int flux = MSTGPU_FLUX_ROE;
+#endif
+#ifdef FLAGVISCID
+    int viscous = (FLAGVISCID);    // FLAGVISCID    (CONST.h:14)
+#else
+    int viscous = 0;
+#endif
     int device = -1;
     double inletQ[5] = {0, 0, 0, 0, 0};
     bool have_inlet = false;

@@ -76,6 +76,7 @@ inline const char* parse_hex(const char* p, const char* e, int64_t& v) {
         else if (c >= 'a' && c <= 'f') d = c - 'a' + 10;
         else if (c >= 'A' && c <= 'F') d = c - 'A' + 10;
         else break;
+        if (p - s >= 15) return nullptr;  // more than 15 hex digits cannot be an id or a count
         x = x * 16 + d;
     }
     if (p == s) return nullptr;
@@ -220,7 +221,7 @@ bool parse(const char* buf, int64_t n, Msh& m) {
     for (int64_t h : hdr) {
         const char* b = L.b(h);
         const char* e = L.e(h);
-        if (e - b < 3 || *b != '(') continue;
+        if (e - b < 4 || *b != '(') continue;  // every header read below looks at b[0..3]
         if (b[1] == '0' && (b[2] == ' ' || b[2] == '"')) {  // (0 "comment")
             const char* q0 = (const char*)memchr(b, '"', (size_t)(e - b));
             const char* q1 = q0 ? (const char*)memchr(q0 + 1, '"', (size_t)(e - q0 - 1)) : nullptr;
@@ -286,6 +287,8 @@ bool parse(const char* buf, int64_t n, Msh& m) {
         } else if (sec == '3') {
             if (ntok < 5) return fail("face zone header needs (id first last type nodes-per-face): " + std::string(b, e));
             if (m.nfaces < 0 || m.ncells < 0 || m.nnodes < 0) return fail("face zone before the node / cell / face declarations");
+            for (int i = 0; i < 5; i++)
+                if (tok[i] < 0 || tok[i] >= (int64_t)1 << 31) return fail("face zone header field does not fit a 32-bit id: " + std::string(b, e));
             Zone z;
             z.id = (int32_t)tok[0];
             z.start = (int32_t)face_done;

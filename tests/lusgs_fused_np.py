@@ -15,7 +15,8 @@ The unscaled blocks are then read once per solve (for the first s) instead of tw
 import numpy as np
 
 
-def solve(rowptr, col, val, b, x0, B, iters):
+def solve(rowptr, col, val, b, x0, B, iters, lean=False):
+    """lean = mode 2: no D (D^-1 v) round trip before the backward sweep (identity up to cond(D) eps)"""
     n = rowptr.size - 1
     val = val.reshape(-1, B, B)
     x = x0.reshape(n, B).copy()
@@ -41,7 +42,7 @@ def solve(rowptr, col, val, b, x0, B, iters):
                     acc += XD[k] @ t[col[k]]
             v[r] = acc
             t[r] = s[r] - acc
-        w = np.einsum("nij,nj->ni", D, np.einsum("nij,nj->ni", Dinv, v))   # k_mid
+        w = v.copy() if lean else np.einsum("nij,nj->ni", D, np.einsum("nij,nj->ni", Dinv, v))   # k_mid
         s = np.zeros((n, B))
         for r in range(n - 1, -1, -1):                         # backward
             acc = w[r].copy(); ss = np.zeros(B)

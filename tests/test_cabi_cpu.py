@@ -91,6 +91,27 @@ def test_bad_arguments_are_rejected_before_touching_the_gpu():
         mstgpu.plan_permutation(bad)
     with pytest.raises(mstgpu.MstGpuError):
         mstgpu.Context(f, order=3)
+    # the connectivity is validated before anything indexes with it (plan, tile statistics, adjacency, partition)
+    cases = []
+    c1 = f["c1"].copy(); c1[5] = -7
+    cases.append(("c1", c1, "c1 out of range"))
+    ptr = f["cf_ptr"].copy(); ptr[4] = ptr[3] - 1
+    cases.append(("cf_ptr", ptr, "non-decreasing"))
+    ptr = f["cf_ptr"].copy(); ptr[0] = 1
+    cases.append(("cf_ptr", ptr, r"cf_ptr\[0\]"))
+    idx = f["cf_idx"].copy(); idx[7] = f["nfaces"] + 3
+    cases.append(("cf_idx", idx, "cf_idx entry out of range"))
+    idx = f["cf_idx"].copy(); idx[7] = -1
+    cases.append(("cf_idx", idx, "cf_idx entry out of range"))
+    idx = f["cf_idx"].copy()
+    other = next(g for g in range(f["nfaces"]) if f["c0"][g] != 0 and f["c1"][g] != 0)
+    idx[f["cf_ptr"][0]] = other
+    cases.append(("cf_idx", idx, "does not touch the cell"))
+    for key, arr, msg in cases:
+        bad = dict(f); bad[key] = arr
+        for call in (mstgpu.plan_permutation, mstgpu.tile_stats, mstgpu.mesh_adjacency, lambda m: mstgpu.Partition(m, 2, 0)):
+            with pytest.raises(mstgpu.MstGpuError, match=msg):
+                call(bad)
 
 
 def _mean_neighbour_distance(f, perm):

@@ -75,3 +75,7 @@ def test_fused_iteration_is_the_reference_iteration_reassociated(block, mesh):
     xo, _, _ = oracle.lusgs(rowptr, col, val, b, z, block, 3, early_exit=False)
     xf = lusgs_fused_np.solve(rowptr, col, val, b, z, block, 3)
     assert np.abs(xf - xo.reshape(xf.shape)).max() <= 1e-13 * np.abs(xo).max()
+    # mode 2 (lean): additionally drops the reference's w0 = D (D^-1 v) round trip (identity up to cond(D) eps)
+    xo, _, _ = oracle.lusgs(rowptr, col, val, b, x0, block, 5, early_exit=False)
+    xl = lusgs_fused_np.solve(rowptr, col, val, b, x0, block, 5, lean=True)
+    assert np.abs(xl - xo.reshape(xl.shape)).max() <= 1e-13 * np.abs(xo).max()

@@ -144,5 +144,16 @@ def test_fused_mode_matches_the_reference_passes(block):
     so.set_mode(1)
     xb, _, _ = so.solve(val, b, x0, 5)
     assert _rel(xb, xa) <= 1e-13
+    # mode 2 (lean): mode 1 without the D (D^-1 v) round trip and with x = D^-1 w formed inside the backward sweep
+    so.set_mode(2)
+    xc, _, _ = so.solve(val, b, x0, 5)
+    assert _rel(xc, xa) <= 1e-12
+    s.set_mode(2)
+    x2, h2, _ = s.solve(val, b, x0, 5)
+    assert _rel(x2, xo) <= 1e-12
+    xz2, _, _ = s.solve(val, b, np.zeros_like(x0), 3)
+    assert _rel(xz2, xoz) <= 1e-12
+    if block == 1:
+        assert np.allclose(h2, ho, rtol=1e-9)  # residual history / early exit: the scalar solver keeps k_fin
     with pytest.raises(mstgpu.MstGpuError):
-        so.set_mode(2)
+        so.set_mode(3)

@@ -123,10 +123,22 @@ _HEAD = b"(2 2)\n(10 (0 1 2 0 2))\n(10 (1 1 2 1 2)\n(\n"
     (_HEAD + b"0 0\n1 0\n))\n(12 (0 1 1 0 0))\n(13 (0 1 1 0 0))\n(13 (3 1 1 3 2)(\n1 9 1 0\n))\n", "out-of-range id"),
     (_HEAD + b"0 0\n1 0\n))\n(12 (0 1 1 0 0))\n(13 (0 1 2 0 0))\n(13 (3 1 1 3 2)(\n1 2 1 0\n))\n", "face zones cover 1 of 2"),
     (b"(10 (0 1 2 0 2))\n", "before the"),
+    # zone header fields must fit 32-bit ids (100000005 hex used to wrap to 5)
+    (_HEAD + b"0 0\n1 0\n))\n(12 (0 1 1 0 0))\n(13 (0 1 1 0 0))\n(13 (3 1 100000001 3 2)(\n1 2 1 0\n))\n", "32-bit"),
 ])
 def test_malformed_files_fail_loudly(text, msg):
     with pytest.raises(RuntimeError, match=msg):
         host.parse_msh(text)
+
+
+@pytest.mark.parametrize("tail", [b"(2 ", b"(13", b"(1", b"("])
+def test_truncated_header_at_the_end_of_the_input_is_not_read_past(tail):
+    """a header line shorter than 4 bytes at the very end of the buffer (exact-size copy: no slack behind it)"""
+    text = bytes(_HEAD + b"0 0\n1 0\n))\n(12 (0 1 1 0 0))\n(13 (0 1 1 0 0))\n(13 (3 1 1 3 2)(\n1 2 1 0\n))\n" + tail)
+    try:
+        host.parse_msh(text)
+    except RuntimeError:
+        pass  # an error is fine; reading b[3] of a 3-byte line is not
 
 
 def test_missing_file_is_an_error():
