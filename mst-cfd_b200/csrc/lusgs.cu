@@ -13,6 +13,12 @@
 // reordering is imposed.  The number of levels is what the ordering makes it:
 // a colour-ordered matrix (mstgpu_lusgs_color_order) has one level per colour,
 // a lexicographic one a level per wavefront.
+//
+// Internal numbering = SWEEP POSITION.  Everything the solver owns (the L / U / D index lists, the scaled blocks
+// LD / UD, D, D^-1 and the work vectors) is indexed by the position p of a row in the sweep, so the rows of one
+// level -- one colour -- are a contiguous range and a level's launch streams its blocks and vectors front to
+// back.  Only the caller's arrays keep the caller's numbering: val is reached through the entry positions,
+// b and x through rmap[p] = row of sweep position p (ghost columns >= n keep their index).
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -35,6 +41,7 @@ struct mstgpu_lusgs {
     int *Lptr = nullptr, *Lcol = nullptr, *Lpos = nullptr, *Uptr = nullptr, *Ucol = nullptr, *Upos = nullptr;
     int *Dptr = nullptr, *Dpos = nullptr;  // diagonal entries per row (summed)
     int *Gptr = nullptr, *Gcol = nullptr, *Gpos = nullptr;  // entries in ghost columns (>= n): lagged, moved to the right-hand side
+    int* rmap = nullptr;  // [n] sweep position -> row of the caller's b / x
     double* beff = nullptr;
     std::vector<int> fptr, bptr;           // level pointers (host)
     int *frows = nullptr, *brows = nullptr;
@@ -176,14 +183,14 @@ __global__ void k_scale(size_t ne, const int* col, const int* pos, const double*
 
 // ux[r] = D^-1 (sum_{c after r} U[r,c] x[c])     (SparseSolverNUM.cpp:158-166)
 template <int B>
-__global__ void k_ux(int n, const int* Uptr, const int* Ucol, const int* Upos, const double* val, const double* D,
+__global__ void k_ux(int n, const int* Uptr, const int* Ucol, const int* Upos, const int* rmap, const double* val, const double* D,
                      const double* Dinv, const double* x, double* ux) {
     const Grp<B> g(n);
     const int r = g.row, i = g.i;
     double acc = 0.0;
     if (g.on)
         for (int k = Uptr[r]; k < Uptr[r + 1]; k++)
-            acc += row_dot<B>(val + (size_t)Upos[k] * B * B + i * B, x + (size_t)Ucol[k] * B);
+            acc += row_dot<B>(val + (size_t)Upos[k] * B * B + i * B, x + (size_t)rmap[Ucol[k]] * B);
     if (B == 1) { if (g.on) ux[r] = acc / D[r]; return; }
     const double t = g.matvec_lanes(g.on ? Dinv + (size_t)r * B * B + i * B : nullptr, acc);
     if (g.on) ux[(size_t)r * B + i] = t;
@@ -192,12 +199,12 @@ __global__ void k_ux(int n, const int* Uptr, const int* Ucol, const int* Upos, c
 // beff[r] = b[r] - sum_{ghost columns c} A[r,c] x[c]: couplings to rows another partition owns, with the
 // x the caller supplied for them (the previous iteration's values: block Jacobi across partitions)
 template <int B>
-__global__ void k_ghost_rhs(int n, const int* Gptr, const int* Gcol, const int* Gpos, const double* val, const double* b,
+__global__ void k_ghost_rhs(int n, const int* Gptr, const int* Gcol, const int* Gpos, const int* rmap, const double* val, const double* b,
                             const double* x, double* beff) {
     const Grp<B> g(n);
     if (!g.on) return;
     const int r = g.row, i = g.i;
-    double acc = b[(size_t)r * B + i];
+    double acc = b[(size_t)rmap[r] * B + i];
     for (int k = Gptr[r]; k < Gptr[r + 1]; k++)
         acc -= row_dot<B>(val + (size_t)Gpos[k] * B * B + i * B, x + (size_t)Gcol[k] * B);
     beff[(size_t)r * B + i] = acc;
@@ -205,7 +212,7 @@ __global__ void k_ghost_rhs(int n, const int* Gptr, const int* Gcol, const int* 
 
 // rhs[r] = b[r] + sum_{c before r} L[r,c] ux[c]   (SparseSolverNUM.cpp:167-175)
 template <int B>
-__global__ void k_rhs(int n, const int* Lptr, const int* Lcol, const int* Lpos, const double* val, const double* b,
+__global__ void k_rhs(int n, const int* Lptr, const int* Lcol, const int* Lpos, const int* rmap, const double* val, const double* b,
                       const double* ux, double* rhs) {
     const Grp<B> g(n);
     if (!g.on) return;
@@ -213,7 +220,7 @@ __global__ void k_rhs(int n, const int* Lptr, const int* Lcol, const int* Lpos, 
     double acc = 0.0;
     for (int k = Lptr[r]; k < Lptr[r + 1]; k++)
         acc += row_dot<B>(val + (size_t)Lpos[k] * B * B + i * B, ux + (size_t)Lcol[k] * B);
-    rhs[(size_t)r * B + i] = b[(size_t)r * B + i] + acc;
+    rhs[(size_t)r * B + i] = b[(size_t)(rmap ? rmap[r] : r) * B + i] + acc;
 }
 
 // one level of a triangular sweep: v[r] -= sum_k XD[k] v[col[k]], k in sweep order (forward) or reversed (backward)
@@ -243,24 +250,24 @@ __global__ void k_sweep_level(int nrows, const int* rows, const int* ptr, const 
 
 // s[r] = sum_{c after r} U[r,c] x[c]   (RHSUx of SparseSolver.cpp:64-69, before the D^-1)
 template <int B>
-__global__ void k_ux_raw(int n, const int* Uptr, const int* Ucol, const int* Upos, const double* val, const double* x, double* s) {
+__global__ void k_ux_raw(int n, const int* Uptr, const int* Ucol, const int* Upos, const int* rmap, const double* val, const double* x, double* s) {
     const Grp<B> g(n);
     if (!g.on) return;
     const int r = g.row, i = g.i;
     double acc = 0.0;
     for (int k = Uptr[r]; k < Uptr[r + 1]; k++)
-        acc += row_dot<B>(val + (size_t)Upos[k] * B * B + i * B, x + (size_t)Ucol[k] * B);
+        acc += row_dot<B>(val + (size_t)Upos[k] * B * B + i * B, x + (size_t)rmap[Ucol[k]] * B);
     s[(size_t)r * B + i] = acc;
 }
 
 // one level of the fused forward sweep: v[r] = b[r] + sum_k LD[k] t[col[k]],  t[r] = s[r] - v[r]
 template <int B>
-__global__ void k_fwd_fused(int nrows, const int* rows, const int* ptr, const int* col, const double* LD, const double* b,
+__global__ void k_fwd_fused(int nrows, const int* rows, const int* ptr, const int* col, const int* rmap, const double* LD, const double* b,
                             const double* s, double* v, double* t) {
     const Grp<B> g(nrows);
     if (!g.on) return;
     const int r = rows[g.row], i = g.i;
-    double acc = b[(size_t)r * B + i];
+    double acc = b[(size_t)(rmap ? rmap[r] : r) * B + i];  // rmap == nullptr: b is the solver's own beff (sweep numbering)
     for (int k = ptr[r]; k < ptr[r + 1]; k++) acc += row_dot<B>(LD + (size_t)k * B * B + i * B, t + (size_t)col[k] * B);
     v[(size_t)r * B + i] = acc;
     t[(size_t)r * B + i] = s[(size_t)r * B + i] - acc;
@@ -291,7 +298,7 @@ __global__ void k_bwd_fused(int nrows, const int* rows, const int* ptr, const in
 // itself, and x = D^-1 w is formed by the row's lane group the moment w[r] is final.  Per row and iteration this
 // drops D and D^-1 of k_mid and a second read of w: ~2.0 -> ~1.5 kB.  Level 0 runs too (x = D^-1 v there).
 template <int B>
-__global__ void k_bwd_lean(int nrows, const int* rows, const int* ptr, const int* col, const double* UD, const double* Dinv,
+__global__ void k_bwd_lean(int nrows, const int* rows, const int* ptr, const int* col, const int* rmap, const double* UD, const double* Dinv,
                            const double* v, double* w, double* s, double* x) {
     const Grp<B> g(nrows);
     const int r = g.on ? rows[g.row] : 0, i = g.i;
@@ -309,9 +316,9 @@ __global__ void k_bwd_lean(int nrows, const int* rows, const int* ptr, const int
         w[(size_t)r * B + i] = acc;
         s[(size_t)r * B + i] = ss;
     }
-    if (B == 1) { if (g.on) x[r] = Dinv[r] * acc; return; }
+    if (B == 1) { if (g.on) x[rmap[r]] = Dinv[r] * acc; return; }
     const double xi = g.matvec_lanes(g.on ? Dinv + (size_t)r * B * B + i * B : nullptr, acc);
-    if (g.on) x[(size_t)r * B + i] = xi;
+    if (g.on) x[(size_t)rmap[r] * B + i] = xi;
 }
 
 // X1 = D^-1 rhs; rhs1 = D X1   (SparseSolverNUM.cpp:184-187)
@@ -327,18 +334,19 @@ __global__ void k_mid(int n, const double* D, const double* Dinv, const double* 
 
 // xnew = D^-1 rhs1; residual (scalar only); x = xnew   (SparseSolverNUM.cpp:194-203)
 template <int B>
-__global__ void k_fin(int n, const double* D, const double* Dinv, const double* rhs1, double* x, unsigned long long* res) {
+__global__ void k_fin(int n, const int* rmap, const double* D, const double* Dinv, const double* rhs1, double* x, unsigned long long* res) {
     const Grp<B> g(n);
     const int r = g.row, i = g.i;
     double rr = 0.0;
     if (g.on) {
+        const size_t rx = (size_t)rmap[r];
         if (B == 1) {
             const double xn = (1. / D[r]) * rhs1[r];
-            const double q = fabs(x[r] - xn) / x[r];
+            const double q = fabs(x[rx] - xn) / x[rx];
             rr = (q > 0.0) ? q : 0.0;
-            x[r] = xn;
+            x[rx] = xn;
         } else {
-            x[(size_t)r * B + i] = row_dot<B>(Dinv + (size_t)r * B * B + i * B, rhs1 + (size_t)r * B);
+            x[rx * B + i] = row_dot<B>(Dinv + (size_t)r * B * B + i * B, rhs1 + (size_t)r * B);
         }
     }
     if (B == 1) {
@@ -377,7 +385,7 @@ int solve_core(mstgpu_lusgs* h, const double* val, const double* b, double* x, i
             LCK(cudaMemsetAsync(h->s, 0, (size_t)n * B * 8, s));  // U 0 = 0
         } else if (!h->s_valid) {
             // the only read of the unscaled off-diagonal blocks in these modes: U x of the start vector
-            k_ux_raw<B><<<G::grid(n, T), T, 0, s>>>(n, h->Uptr, h->Ucol, h->Upos, val, x, h->s);
+            k_ux_raw<B><<<G::grid(n, T), T, 0, s>>>(n, h->Uptr, h->Ucol, h->Upos, h->rmap, val, x, h->s);
             h->launches++;
         }
         h->x0_zero = false;
@@ -386,10 +394,12 @@ int solve_core(mstgpu_lusgs* h, const double* val, const double* b, double* x, i
     for (; it < max_iter; it++) {
         LCK(cudaMemsetAsync(h->res, 0, 8, s));
         const double* bb = b;
+        const int* bmap = h->rmap;  // b is the caller's (row numbering); beff is the solver's own (sweep numbering)
         if (h->nG) {
-            k_ghost_rhs<B><<<G::grid(n, T), T, 0, s>>>(n, h->Gptr, h->Gcol, h->Gpos, val, b, x, h->beff);
+            k_ghost_rhs<B><<<G::grid(n, T), T, 0, s>>>(n, h->Gptr, h->Gcol, h->Gpos, h->rmap, val, b, x, h->beff);
             h->launches++;
             bb = h->beff;
+            bmap = nullptr;
         }
         if (fused) {
             // forward: every level, level 0 included (v = b there, but t = s - v is needed by the later levels);
@@ -397,13 +407,13 @@ int solve_core(mstgpu_lusgs* h, const double* val, const double* b, double* x, i
             for (size_t l = 0; l + 1 < h->fptr.size(); l++) {
                 const int cnt = h->fptr[l + 1] - h->fptr[l];
                 if (cnt > 0)
-                    k_fwd_fused<B><<<G::grid(cnt, T), T, 0, s>>>(cnt, h->frows + h->fptr[l], h->Lptr, h->Lcol, h->LD, bb, h->s, h->rhs, h->ux);
+                    k_fwd_fused<B><<<G::grid(cnt, T), T, 0, s>>>(cnt, h->frows + h->fptr[l], h->Lptr, h->Lcol, bmap, h->LD, bb, h->s, h->rhs, h->ux);
             }
             if (lean) {
                 for (size_t l = 0; l + 1 < h->bptr.size(); l++) {
                     const int cnt = h->bptr[l + 1] - h->bptr[l];
                     if (cnt > 0)
-                        k_bwd_lean<B><<<G::grid(cnt, T), T, 0, s>>>(cnt, h->brows + h->bptr[l], h->Uptr, h->Ucol, h->UD, h->Dinv, h->rhs, h->rhs1, h->s, x);
+                        k_bwd_lean<B><<<G::grid(cnt, T), T, 0, s>>>(cnt, h->brows + h->bptr[l], h->Uptr, h->Ucol, h->rmap, h->UD, h->Dinv, h->rhs, h->rhs1, h->s, x);
                 }
                 h->launches += (int64_t)(h->fptr.size() > 1 ? h->fptr.size() - 1 : 0) + (int64_t)(h->bptr.size() > 1 ? h->bptr.size() - 1 : 0);
             } else {
@@ -414,13 +424,13 @@ int solve_core(mstgpu_lusgs* h, const double* val, const double* b, double* x, i
                 if (cnt > 0)
                     k_bwd_fused<B><<<G::grid(cnt, T), T, 0, s>>>(cnt, h->brows + h->bptr[l], h->Uptr, h->Ucol, h->UD, h->rhs1, h->s);
             }
-            k_fin<B><<<G::grid(n, T), T, 0, s>>>(n, h->D, h->Dinv, h->rhs1, x, h->res);
+            k_fin<B><<<G::grid(n, T), T, 0, s>>>(n, h->rmap, h->D, h->Dinv, h->rhs1, x, h->res);
             h->launches += 2 + (int64_t)(h->fptr.size() > 1 ? h->fptr.size() - 1 : 0) + (int64_t)(h->bptr.size() > 2 ? h->bptr.size() - 2 : 0);
             }
             h->s_valid = true;  // s = U x of the x just written (owned columns; ghost columns live in G)
         } else {
-        k_ux<B><<<G::grid(n, T), T, 0, s>>>(n, h->Uptr, h->Ucol, h->Upos, val, h->D, h->Dinv, x, h->ux);
-        k_rhs<B><<<G::grid(n, T), T, 0, s>>>(n, h->Lptr, h->Lcol, h->Lpos, val, bb, h->ux, h->rhs);
+        k_ux<B><<<G::grid(n, T), T, 0, s>>>(n, h->Uptr, h->Ucol, h->Upos, h->rmap, val, h->D, h->Dinv, x, h->ux);
+        k_rhs<B><<<G::grid(n, T), T, 0, s>>>(n, h->Lptr, h->Lcol, h->Lpos, bmap, val, bb, h->ux, h->rhs);
         for (size_t l = 1; l + 1 < h->fptr.size(); l++) {  // level 0 has no dependencies: nothing to subtract
             const int cnt = h->fptr[l + 1] - h->fptr[l];
             k_sweep_level<B, true><<<G::grid(cnt, T), T, 0, s>>>(cnt, h->frows + h->fptr[l], h->Lptr, h->Lcol, h->LD, h->rhs);
@@ -430,7 +440,7 @@ int solve_core(mstgpu_lusgs* h, const double* val, const double* b, double* x, i
             const int cnt = h->bptr[l + 1] - h->bptr[l];
             k_sweep_level<B, false><<<G::grid(cnt, T), T, 0, s>>>(cnt, h->brows + h->bptr[l], h->Uptr, h->Ucol, h->UD, h->rhs1);
         }
-        k_fin<B><<<G::grid(n, T), T, 0, s>>>(n, h->D, h->Dinv, h->rhs1, x, h->res);
+        k_fin<B><<<G::grid(n, T), T, 0, s>>>(n, h->rmap, h->D, h->Dinv, h->rhs1, x, h->res);
         h->launches += 4 + (int64_t)(h->fptr.size() > 2 ? h->fptr.size() - 2 : 0) + (int64_t)(h->bptr.size() > 2 ? h->bptr.size() - 2 : 0);
         }
         if (B == 1 && (res_hist || early_exit)) {
@@ -580,41 +590,47 @@ int mstgpu_lusgs_create_partitioned(mstgpu_lusgs** out, int32_t n, int32_t ncols
         }
     }
     auto rk = [&](int r) { return sweep_new2old ? rank[r] : r; };
-    std::vector<int> Lptr(n + 1, 0), Uptr(n + 1, 0), Dptr(n + 1, 0), Gptr(n + 1, 0), Lcol, Lpos, Ucol, Upos, Dpos, Gcol, Gpos;
-    std::vector<std::pair<int, int>> lo, hi;  // (rank of column, index into the row)
-    for (int r = 0; r < n; r++) {
-        lo.clear(); hi.clear();
+    // index lists in SWEEP numbering: row p = sweep position, columns = sweep positions of the coupled rows
+    // (ghost columns >= n keep their index), entries of a row by ascending sweep position as the reference
+    // subtracts them
+    std::vector<int> Lptr(n + 1, 0), Uptr(n + 1, 0), Dptr(n + 1, 0), Gptr(n + 1, 0), Lcol, Lpos, Ucol, Upos, Dpos, Gcol, Gpos, rmap(n);
+    std::vector<std::pair<int, int>> lo, hi;  // (sweep position of the column, index into the row)
+    for (int r = 0; r < n; r++)
         for (int k = rowptr[r]; k < rowptr[r + 1]; k++) {
             const int c = col[k];
             if (c < 0 || c >= ncols) { g_lusgs_error = "column out of range"; return MSTGPU_ERR_ARG; }
             if (k > rowptr[r] && col[k - 1] > c) { g_lusgs_error = "columns must be ascending within a row"; return MSTGPU_ERR_ARG; }
+        }
+    for (int p = 0; p < n; p++) {
+        const int r = sweep_new2old ? sweep_new2old[p] : p;
+        rmap[p] = r;
+        lo.clear(); hi.clear();
+        for (int k = rowptr[r]; k < rowptr[r + 1]; k++) {
+            const int c = col[k];
             if (c >= n) { Gcol.push_back(c); Gpos.push_back(k); }
             else if (c == r) Dpos.push_back(k);
-            else if (rk(c) < rk(r)) lo.push_back({rk(c), k});
+            else if (rk(c) < p) lo.push_back({rk(c), k});
             else hi.push_back({rk(c), k});
         }
-        // the reference subtracts a row's terms by ascending (permuted) column index
         if (sweep_new2old) { std::sort(lo.begin(), lo.end()); std::sort(hi.begin(), hi.end()); }
-        for (auto& e : lo) { Lcol.push_back(col[e.second]); Lpos.push_back(e.second); }
-        for (auto& e : hi) { Ucol.push_back(col[e.second]); Upos.push_back(e.second); }
-        Lptr[r + 1] = (int)Lcol.size(); Uptr[r + 1] = (int)Ucol.size(); Dptr[r + 1] = (int)Dpos.size();
-        Gptr[r + 1] = (int)Gcol.size();
-        if (Dptr[r + 1] == Dptr[r]) { g_lusgs_error = "row without a diagonal entry"; return MSTGPU_ERR_ARG; }
+        for (auto& e : lo) { Lcol.push_back(e.first); Lpos.push_back(e.second); }
+        for (auto& e : hi) { Ucol.push_back(e.first); Upos.push_back(e.second); }
+        Lptr[p + 1] = (int)Lcol.size(); Uptr[p + 1] = (int)Ucol.size(); Dptr[p + 1] = (int)Dpos.size();
+        Gptr[p + 1] = (int)Gcol.size();
+        if (Dptr[p + 1] == Dptr[p]) { g_lusgs_error = "row without a diagonal entry"; return MSTGPU_ERR_ARG; }
     }
-    // dependency levels, rows visited in sweep order
+    // dependency levels, rows visited in sweep order (= ascending internal index)
     std::vector<int> lf(n, 0), lb(n, 0);
     int nlf = 0, nlb = 0;
-    for (int i = 0; i < n; i++) {
-        const int r = sweep_new2old ? sweep_new2old[i] : i;
+    for (int p = 0; p < n; p++) {
         int l = 0;
-        for (int k = Lptr[r]; k < Lptr[r + 1]; k++) l = std::max(l, lf[Lcol[k]] + 1);
-        lf[r] = l; nlf = std::max(nlf, l + 1);
+        for (int k = Lptr[p]; k < Lptr[p + 1]; k++) l = std::max(l, lf[Lcol[k]] + 1);
+        lf[p] = l; nlf = std::max(nlf, l + 1);
     }
-    for (int i = n - 1; i >= 0; i--) {
-        const int r = sweep_new2old ? sweep_new2old[i] : i;
+    for (int p = n - 1; p >= 0; p--) {
         int l = 0;
-        for (int k = Uptr[r]; k < Uptr[r + 1]; k++) l = std::max(l, lb[Ucol[k]] + 1);
-        lb[r] = l; nlb = std::max(nlb, l + 1);
+        for (int k = Uptr[p]; k < Uptr[p + 1]; k++) l = std::max(l, lb[Ucol[k]] + 1);
+        lb[p] = l; nlb = std::max(nlb, l + 1);
     }
     auto bucket = [&](const std::vector<int>& lev, int nl, std::vector<int>& ptr, std::vector<int>& rows) {
         ptr.assign(nl + 1, 0);
@@ -644,7 +660,7 @@ int mstgpu_lusgs_create_partitioned(mstgpu_lusgs** out, int32_t n, int32_t ncols
             if ((r = up(h, &h->Gptr, Gptr)) || (r = up(h, &h->Gcol, Gcol)) || (r = up(h, &h->Gpos, Gpos))) return r;
             LCK(cudaMalloc((void**)&h->beff, (size_t)n * block * 8));
         }
-        if ((r = up(h, &h->frows, frows)) || (r = up(h, &h->brows, brows))) return r;
+        if ((r = up(h, &h->frows, frows)) || (r = up(h, &h->brows, brows)) || (r = up(h, &h->rmap, rmap))) return r;
         const size_t BB = (size_t)block * block;
         // val / b / x buffers of the host-array entry point are allocated at its first use
         LCK(cudaMalloc((void**)&h->D, n * BB * 8));
@@ -668,7 +684,7 @@ void mstgpu_lusgs_destroy(mstgpu_lusgs* h) {
     for (void* p : {(void*)h->Lptr, (void*)h->Lcol, (void*)h->Lpos, (void*)h->Uptr, (void*)h->Ucol, (void*)h->Upos,
                     (void*)h->Dptr, (void*)h->Dpos, (void*)h->frows, (void*)h->brows, (void*)h->val, (void*)h->D,
                     (void*)h->Dinv, (void*)h->LD, (void*)h->UD, (void*)h->b, (void*)h->x, (void*)h->rhs, (void*)h->rhs1,
-                    (void*)h->ux, (void*)h->s, (void*)h->res, (void*)h->Gptr, (void*)h->Gcol, (void*)h->Gpos, (void*)h->beff})
+                    (void*)h->ux, (void*)h->s, (void*)h->res, (void*)h->Gptr, (void*)h->Gcol, (void*)h->Gpos, (void*)h->beff, (void*)h->rmap})
         if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);

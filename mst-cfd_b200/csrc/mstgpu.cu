@@ -893,7 +893,11 @@ int launch_tiles_var(mstgpu_ctx* ctx, double dt, const double* dtd, const double
     // context (a context lives on one device), not per thread -- one host thread may drive several devices
     size_t& configured_smem = ctx->smem_configured[(const void*)kern];
     if (configured_smem < ctx->tile_smem) {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->tile_smem));
+        // never lower it: another context on this device may have opted in to more for the same instantiation
+        cudaFuncAttributes fa;
+        CK(cudaFuncGetAttributes(&fa, kern));
+        if ((size_t)fa.maxDynamicSharedSizeBytes < ctx->tile_smem)
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->tile_smem));
         configured_smem = ctx->tile_smem;
     }
     // which: 0 = tiles without ghost cells, 1 = tiles whose rings hold ghost cells, 2 = all

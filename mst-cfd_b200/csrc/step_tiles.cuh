@@ -157,12 +157,15 @@ __device__ __forceinline__ void step_tile(const TileArrays& ta, const int tile, 
         __syncthreads();
     }
     if (tid == 0) {
-        const uint32_t qbytes = (uint32_t)((n_own + 1) & ~1) * U * 8u;
+        // bulk copies move multiples of 16 bytes = an even number of 8*U-byte rows.  An odd last row is copied by
+        // hand below: rounding the bulk copy UP would write row n_own of Qs, which is the first ring row, and
+        // race with the ring gather (asynchronous proxy against generic stores, no order between them).
+        const uint32_t qbytes = (uint32_t)(n_own & ~1) * U * 8u;
         // slots + cvol are adjacent in the packet: one more bulk copy brings the phase-3
         // operands into shared memory without holding registers across phase 2
         const uint32_t cbytes = L.pk_bytes - L.slots;
         mbar_expect_tx(bar, qbytes + cbytes);
-        bulk_g2s(smem_u32(Qs), Qold + (size_t)d.cb * U, qbytes, bar);
+        if (qbytes) bulk_g2s(smem_u32(Qs), Qold + (size_t)d.cb * U, qbytes, bar);
         bulk_g2s(smem_u32(smem + L.cells_s), pk + L.slots, cbytes, bar);
         // the packet is streamed from HBM by phase 2 / 3: start moving it into L2 now,
         // while the states are being staged
@@ -188,6 +191,10 @@ __device__ __forceinline__ void step_tile(const TileArrays& ta, const int tile, 
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     if (STG && tid < nFB) stage_issue(tid);
+    if ((n_own & 1) && tid >= NT - U) {  // the odd last owned row
+        const int k = tid - (NT - U);
+        Qs[(n_own - 1) * U + k] = Qold[(size_t)(d.cb + n_own - 1) * U + k];
+    }
     // ring cells: one thread per cell, U independent loads of a contiguous 8*U-byte row.
     // (Batching several cells per thread -- ids first, then rows -- was measured: it helps the
     // 128-thread variant but costs registers and was 1 % slower for the default 256-thread one.)

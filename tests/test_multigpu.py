@@ -185,3 +185,27 @@ def test_two_gpus_implicit_step_with_lagged_ghosts(kernel):
     one = oracle.Oracle(f, **kw)
     Qs1 = one.step_implicit(dt, one.step_implicit(dt, Q0, 5), 5)
     assert rel_linf(got, Qs1) < 0.05
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs two GPUs")
+def test_one_host_thread_drives_contexts_on_two_devices():
+    """The opt-in to > 48 KB of dynamic shared memory is a per-device attribute of a kernel: a host thread that
+    creates contexts on two devices must configure it on both (it used to be cached per thread, so the second
+    device's launches failed with cudaErrorInvalidValue).  Same mesh, same state, one thread: equal bits."""
+    f = box_flat(20, 20, 20)
+    Q0 = mesh_np.random_state(f, seed=3)
+    a = mstgpu.Context(f, order=2, flux="roe", device=0)
+    b = mstgpu.Context(f, order=2, flux="roe", device=1)
+    a.set_state(Q0); b.set_state(Q0)
+    for ctx in (a, b, a, b):  # interleaved: every entry point switches the device itself
+        ctx.step(1e-4, 3)
+    Qa, Qb = a.get_state(), b.get_state()
+    assert np.array_equal(Qa, Qb)
+    assert rel_linf(Qa, oracle.Oracle(f, order=2, flux="roe").run(1e-4, 6, Q0)) <= 1e-11
+    # a smaller context created afterwards must not shrink what the first ones configured
+    c = mstgpu.Context(box_flat(4, 4, 4), order=2, flux="roe", device=1)
+    c.set_state(mesh_np.random_state(box_flat(4, 4, 4), seed=1)); c.step(1e-4, 1)
+    b.step(1e-4, 1); a.step(1e-4, 1)
+    assert np.array_equal(a.get_state(), b.get_state())
+    for ctx in (a, b, c):
+        ctx.close()
