@@ -289,7 +289,7 @@ def run_reference(args, rank):
                    config=dict(workload=f"lusgs box{args.n}: block-5 LU-SGS, {LUSGS_ITERS} iterations per solve (bounded sample)"),
                    cpu_baseline=c, e2e=dict(value=c["value"], unit="cell-updates/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                    gpu_launches=0)
-        print(json.dumps(out), flush=True)
+        emit(json.dumps(out))
         return
     ref_io = os.path.join(ROOT, "oracle", "_ref", "ref_io")
     if args.workload == "sod" and args.order == 2 and args.flux == "roe" and os.path.exists(ref_io):
@@ -314,7 +314,7 @@ def run_reference(args, rank):
                                             f"(oracle/_ref/ref_io, {thr} OpenMP threads as hard-coded, host has {os.cpu_count()} cpus)"),
                    e2e=dict(value=val, unit="cell-updates/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                    gpu_launches=0)
-        print(json.dumps(out), flush=True)
+        emit(json.dumps(out))
         return
     from oracle import oracle
     # the SAME workload at the SAME size as the GPU arm (50.2 M tets by default: ~3-5 s per step on the box's
@@ -352,7 +352,7 @@ def run_reference(args, rank):
                cpu_baseline=dict(value=val, unit="cell-updates/s", cores=o.nthreads, kind="port", sample=sample),
                e2e=dict(value=val, unit="cell-updates/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                gpu_launches=0)
-    print(json.dumps(out), flush=True)
+    emit(json.dumps(out))
 
 
 def lusgs_system(args, n):
@@ -460,7 +460,7 @@ def run_lusgs(args, rank, world):
                            l2="inputs larger than L2" if nnz * 200 > 2 ** 28 else "inputs smaller than L2: flush not applied"),
                clocks=clk, e2e=e2e, gpu_launches=launches, roofline=roof, cpu_baseline=cpu,
                wall_ms_per_step=wall * 1e3 / args.steps, device_gib=dev_bytes / 2 ** 30)
-    print(json.dumps(out), flush=True)
+    emit(json.dumps(out))
 
 
 def lusgs_cpu(args, budget_s=12.0):
@@ -508,6 +508,11 @@ def measure(args, rank, world, dist, local, want_cpu=True):
             idt = torch.frombuffer(bytearray(mstgpu.comm_unique_id()), dtype=torch.uint8).cuda()
         dist.broadcast(idt, 0)
         ctx.comm_init(world, rank, idt.cpu().numpy().tobytes())
+        # halo through peer memory (stores into the neighbours' ghost blocks over NVLink + epoch flags) when every
+        # rank can open its neighbours' buffers; ncclSend/ncclRecv otherwise (the reductions stay on NCCL)
+        halo_mode = "nccl send/recv (pack kernel + grouped ncclSend/ncclRecv)"
+        if args.halo == "peer" and ctx.peer_connect_torch(dist, world, rank, device="cuda"):
+            halo_mode = "peer-memory push (one kernel stores boundary rows into the neighbours' ghost blocks over NVLink, epoch flags; CUDA IPC)"
         Q0 = np.ascontiguousarray(Q0[part.cell_ids[:part.n_owned]])
         nc = part.n_owned
         del f["cf_idx"]
@@ -516,6 +521,7 @@ def measure(args, rank, world, dist, local, want_cpu=True):
                              viscous=args.viscous, tile_cells=args.tile_cells, block_threads=args.block_threads, renumber=args.renumber,
                              **scheme_kwargs(args))
         nc = nc_total
+        halo_mode = None
     log(f"[bench] context built in {time.time() - t:.1f}s, {ctx.device_bytes / 2**30:.2f} GiB on device")
     ctx.set_state(Q0)
     if args.implicit:
@@ -558,7 +564,7 @@ def measure(args, rank, world, dist, local, want_cpu=True):
         ms = float(tms.item())
     launches = ctx.launch_count - l0
     kt = {k: ctx.kernel_time(k) for k in ("gradient", "gradient_lsq", "limiter", "flux", "update", "step_tiles", "halo_pack",
-                                           "assemble", "lusgs", "increment")}
+                                           "assemble", "lusgs", "increment", "halo_exchange", "halo_tiles", "interior_tiles")}
     kt = {k: v for k, v in kt.items() if v[1] > 0}
     ctx.enable_kernel_timing(False)
     res = ctx.residual()
@@ -592,7 +598,7 @@ def measure(args, rank, world, dist, local, want_cpu=True):
         every = dict(value=nc_total * args.steps / (ms1 * 1e-3), unit="cell-updates/s", ms_per_step=ms1 / args.steps,
                      what=f"{args.steps} calls of mstgpu_step(dt, 1): residual reduced on every step, one host call per step")
     graph_ms = None
-    if args.graph and args.cfl <= 0 and not args.implicit:
+    if (args.graph or world > 1) and args.cfl <= 0 and not args.implicit:
         # the same K steps issued as pairs from a CUDA graph (no per-kernel events): launch-bound meshes
         ctx.step(dt_run, 4)
         ctx.sync()
@@ -610,6 +616,8 @@ def measure(args, rank, world, dist, local, want_cpu=True):
         fpc = 2.0 if D == 3 else 1.5
         ab["step"] += 8 * U + 2 * 8 * U * D + 2 * fpc * 8 * D + 8
     per_kernel = {k: (v[0] / max(v[1], 1)) for k, v in kt.items()}
+    # spans of the partitioned step on its two streams (rank 0's own): exchange + wait, halo tiles, interior tiles
+    breakdown = {k: round(per_kernel.pop(k), 4) for k in ("halo_exchange", "halo_tiles", "interior_tiles") if k in per_kernel}
     dom = max(per_kernel, key=per_kernel.get)
     if args.viscous:
         ab = dict(ab, step=616, flux_update=368) if (D, args.order) == (3, 2) else ab  # + eta per face
@@ -679,6 +687,7 @@ def measure(args, rank, world, dist, local, want_cpu=True):
                scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
                config=workload_config(args, world, nc_total, f["nfaces"], U, desc, dt_run),
                gpu_config=dict(kernel=args.kernel, tile_cells=args.tile_cells, renumber=args.renumber, block_threads=args.block_threads,
+                               halo=halo_mode, step_breakdown_ms=breakdown or None,
                                graph_ms_per_step=None if graph_ms is None else graph_ms / args.steps,
                                residual="reduced on the last step of the timed mstgpu_step(dt, K) call (SURVEY 8f.1: residual every k); "
                                         "see every_step_residual for one call per step"),
@@ -740,16 +749,28 @@ def run_ours(args, rank, world):
             log(f"[bench] secondary {name}: {time.time() - t0:.1f}s")
         out["secondary"] = sec
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        emit(json.dumps(out))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: str):
+    """the ONE JSON line, on the process's real stdout"""
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (line + "\n").encode())
+
+
 def main():
-    # stdout carries exactly one JSON line: keep NCCL's version banner off it
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # stdout carries exactly one JSON line.  Native libraries write banners to fd 1 behind Python's back (NCCL's
+    # version line at any NCCL_DEBUG level >= VERSION): fd 1 is pointed at stderr for the whole run and the JSON
+    # line goes to a saved duplicate of the real stdout.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -778,6 +799,7 @@ def main():
                     help="config 5: implicit steps (block assembly + 5 colour-ordered LU-SGS sweeps)")
     ap.add_argument("--implicit-dt", type=float, default=1e-3)
     ap.add_argument("--graph", type=int, default=0, choices=[0, 1], help="also time the K steps issued from the CUDA graph")
+    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"], help="N > 1: halo exchange through peer memory (default) or NCCL send/recv")
     ap.add_argument("--secondary", type=int, default=-1, help="BASELINE configs 1, 2, 3, 5 as short runs under the `secondary` key: "
                     "1 = always, 0 = never, -1 = with the headline workload only (default)")
     args = ap.parse_args()

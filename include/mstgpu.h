@@ -254,6 +254,18 @@ int mstgpu_create_partitioned(mstgpu_ctx** out, const mstgpu_part* part, const m
  * own means (MPI, torch.distributed, a file), every rank calls comm_init. */
 int mstgpu_comm_unique_id(char* out128);
 int mstgpu_comm_init(mstgpu_ctx* ctx, int32_t nranks, int32_t rank, const char* id128);
+
+/* Peer-memory halo (one process per GPU on one NVLink / NVSwitch node): instead of pack + ncclSend/ncclRecv,
+ * each rank's own kernel STORES its boundary rows into the neighbours' ghost blocks through peer pointers and
+ * publishes an epoch flag; receivers wait (bounded, ~10 s -> MSTGPU_ERR_NCCL) on their flags.  Set-up is an
+ * exchange of fixed-size blobs (CUDA IPC handles + row offsets) that the host all-gathers by whatever means it
+ * has: export on every rank, gather, connect on every rank (collective; after mstgpu_comm_init, which stays in
+ * charge of the residual / time-step reductions).  If connect fails (no peer access between two devices) the
+ * context keeps exchanging through NCCL.  Results are bit-identical either way. */
+int64_t mstgpu_peer_blob_bytes(void);
+int mstgpu_peer_export(mstgpu_ctx* ctx, int32_t rank, void* blob);
+int mstgpu_peer_connect(mstgpu_ctx* ctx, int32_t nranks, int32_t rank, const void* blobs /* nranks blobs, by rank */);
+int mstgpu_peer_disable(mstgpu_ctx* ctx); /* back to the NCCL exchange (collective, like connect) */
 /* With a communicator, mstgpu_step exchanges ghost states before every step and
  * mstgpu_residual_linf is COLLECTIVE (max over ranks, ncclAllReduce). */
 

@@ -85,6 +85,13 @@ struct NcclApi {
 NcclApi g_nccl;
 }
 
+#define MSTGPU_MAX_NB 32
+struct PeerTable {
+    double* q[2][MSTGPU_MAX_NB];
+    unsigned long long* flag[MSTGPU_MAX_NB];
+    int nnb;
+};
+
 struct KernelStat {
     double ms = 0.0;
     int64_t launches = 0;
@@ -130,6 +137,16 @@ struct mstgpu_ctx {
     cudaEvent_t ev_halo = nullptr, ev_done = nullptr;
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
+    // peer-memory halo (mstgpu_peer_connect): boundary rows are STORED into the neighbours' ghost blocks over
+    // NVLink by this rank's own kernel, followed by a release flag; no pack buffer, no NCCL kernel on the data path
+    bool peer_ok = false;
+    PeerTable peer{};                        // neighbours' Q[0] / Q[1] and the address of MY slot in their flag arrays
+    unsigned long long* peer_flags = nullptr;  // [MSTGPU_MAX_NB] epochs written by the neighbours (slot = index in halo[])
+    int32_t* push_dst = nullptr;             // [send_total] row in the receiver's local numbering
+    uint8_t* push_slot = nullptr;            // [send_total] neighbour index
+    unsigned int* push_ticket = nullptr;     // last-CTA-done counter of k_peer_push
+    unsigned long long* peer_epochs = nullptr;  // device: [0] exchanges pushed, [1] exchanges received (every rank runs the same sequence)
+    std::vector<void*> peer_opened;          // cudaIpcOpenMemHandle results (closed in destroy)
     // multi-step CUDA graph: two ping-pong steps, the tile classes of a step as parallel
     // branches; one executable per starting buffer, rebuilt when dt changes
     cudaGraphExec_t step_graph[2] = {nullptr, nullptr};
@@ -755,6 +772,62 @@ __global__ void __launch_bounds__(256) k_update(int nc, int n_upd, int nslot, in
     if (anybad && threadIdx.x == 0) atomicOr(nanflag, 1);
 }
 
+// ---- peer-memory halo --------------------------------------------------------------------------------
+// One kernel moves this rank's boundary rows straight into the ghost blocks of its neighbours (stores through
+// peer pointers, NVLink), every thread fences at system scope, and the LAST CTA to finish publishes the epoch
+// in each neighbour's flag array with a release store.  The receiver spins (bounded) on its own flags before
+// the tiles that read ghost rows.  Why no "ready" handshake is needed for the ping-pong state: the rows of
+// exchange e go into buffer Q[cur]; a neighbour last READ the ghost rows of that buffer two steps ago, and it
+// cannot be more than one step behind (its step e-1 needed my exchange e-1).
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void k_peer_push(int n, int U, const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
+                            const uint8_t* __restrict__ slot, const double* __restrict__ Q, PeerTable pt, int buf,
+                            unsigned int* ticket, unsigned long long* epoch_dev) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n * U) {
+        const int r = i / U, k = i - r * U;
+        pt.q[buf][slot[r]][(size_t)dst[r] * U + k] = Q[(size_t)src[r] * U + k];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(ticket, 1u);
+        if (t == gridDim.x - 1) {  // every other CTA has fenced its stores before its ticket
+            *ticket = 0;
+            // the epoch lives on the device, so the exchange can sit in a CUDA graph that is launched many times
+            const unsigned long long e = *epoch_dev + 1ULL;
+            *epoch_dev = e;
+            __threadfence_system();
+            for (int j = 0; j < pt.nnb; j++) st_release_sys(pt.flag[j], e);
+        }
+    }
+}
+
+// bounded wait for the neighbours' next epoch: a lost peer must become an error, never a hung GPU
+__global__ void k_peer_wait(const unsigned long long* flags, int nnb, unsigned long long* wait_dev, int* errflag) {
+    const int j = threadIdx.x;
+    const unsigned long long epoch = *wait_dev + 1ULL;
+    // sticky: once a neighbour was lost, later exchanges return at once (the run ends with MSTGPU_ERR_NCCL at the
+    // next residual / sync instead of spending the bound on every step)
+    if (j < nnb && !(*(volatile int*)errflag & 4)) {
+        const long long t0 = clock64();
+        while (ld_acquire_sys(flags + j) < epoch) {
+            if (clock64() - t0 > 20000000000LL) { atomicOr(errflag, 4); break; }  // ~10 s
+            __nanosleep(200);
+        }
+    }
+    __syncwarp();
+    if (j == 0) *wait_dev = epoch;
+}
+
 // halo: gather the rows a neighbour needs into a contiguous send buffer
 __global__ void k_pack_rows(int n, int U, const int32_t* __restrict__ idx, const double* __restrict__ Q,
                             double* __restrict__ buf) {
@@ -805,9 +878,12 @@ int dalloc(mstgpu_ctx* ctx, T** dptr, size_t n) {
 struct KTimer {
     mstgpu_ctx* ctx;
     const char* name;
+    cudaStream_t st;
     cudaEvent_t a = nullptr, b = nullptr;
-    KTimer(mstgpu_ctx* c, const char* n) : ctx(c), name(n) {
-        ctx->launches++;
+    // st: the stream the timed work is issued on (default: the compute stream); count = false: a span over
+    // launches that are counted elsewhere
+    KTimer(mstgpu_ctx* c, const char* n, cudaStream_t stream = nullptr, bool count = true) : ctx(c), name(n), st(stream ? stream : c->stream) {
+        if (count) ctx->launches++;
         if (!ctx->ktiming) return;
         auto get = [&]() {
             cudaEvent_t e;
@@ -816,11 +892,11 @@ struct KTimer {
             return e;
         };
         a = get(); b = get();
-        cudaEventRecord(a, ctx->stream);
+        cudaEventRecord(a, st);
     }
     ~KTimer() {
         if (!ctx->ktiming) { ctx->kstat[name].launches++; return; }
-        cudaEventRecord(b, ctx->stream);
+        cudaEventRecord(b, st);
         ctx->pending.push_back({name, {a, b}});
     }
 };
@@ -873,6 +949,16 @@ int halo_exchange(mstgpu_ctx* ctx, double* Q, cudaStream_t st) {
     if (!ctx->partitioned || ctx->halo.empty()) return MSTGPU_OK;
     if (!ctx->comm) { set_error(ctx, "partitioned context without a communicator: call mstgpu_comm_init"); return MSTGPU_ERR_STATE; }
     const int U = ctx->U;
+    if (ctx->peer_ok && (Q == ctx->Q[0] || Q == ctx->Q[1])) {
+        // boundary rows -> the neighbours' ghost blocks of the same buffer, then the epoch; wait for theirs
+        const int buf = Q == ctx->Q[0] ? 0 : 1;
+        const int n = std::max(1, ctx->send_total * U);
+        k_peer_push<<<(n + 255) / 256, 256, 0, st>>>(ctx->send_total, U, ctx->send_idx, ctx->push_dst, ctx->push_slot, Q, ctx->peer, buf,
+                                                     ctx->push_ticket, ctx->peer_epochs);
+        k_peer_wait<<<1, 32, 0, st>>>(ctx->peer_flags, ctx->peer.nnb, ctx->peer_epochs + 1, ctx->nanflag);
+        ctx->launches += 2;
+        return MSTGPU_OK;
+    }
     if (ctx->send_total > 0) {
         ctx->launches++;
         k_pack_rows<<<(ctx->send_total * U + 255) / 256, 256, 0, st>>>(ctx->send_total, U, ctx->send_idx, Q, ctx->sendbuf);
@@ -1003,33 +1089,66 @@ int cfl_on_device(mstgpu_ctx* ctx, double cfl, const double* Q) {
     return MSTGPU_OK;
 }
 
+// One step of the fused path: Qc -> Qn.  Without neighbours: every tile class on the compute stream (under graph
+// capture the classes fork onto the second stream).  With neighbours: the exchange and the tiles whose rings
+// hold ghost cells on the high-priority second stream, the interior tiles on the compute stream meanwhile.
+template <int D>
+int issue_tile_step(mstgpu_ctx* ctx, double dt, const double* dtd, double* Qc, double* Qn, int wr, bool overlap, bool capturing) {
+    int r;
+    if (overlap) {
+        // comm stream: ghost rows <- owners, as soon as the previous step is complete;
+        // compute stream: tiles that touch no ghost cell meanwhile, the others after
+        // (the halo tiles follow the exchange on the comm stream, so they fill the SMs
+        // the interior launch leaves idle in its tail instead of waiting behind it)
+        CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_done, 0));
+        {   // per-step breakdown when kernel timing is on (bench.py): exchange, halo tiles, interior tiles
+            KTimer t(ctx, "halo_exchange", ctx->stream2, false);
+            if ((r = halo_exchange(ctx, Qc, ctx->stream2))) return r;
+        }
+        {
+            KTimer t(ctx, "halo_tiles", ctx->stream2, false);
+            if ((r = launch_tiles_any<D>(ctx, dt, dtd, Qc, Qn, wr, 1, ctx->stream2))) return r;
+        }
+        CK(cudaEventRecord(ctx->ev_halo, ctx->stream2));
+        {
+            KTimer t(ctx, "interior_tiles", ctx->stream, false);
+            if ((r = launch_tiles_any<D>(ctx, dt, dtd, Qc, Qn, wr, 0, ctx->stream))) return r;
+        }
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_halo, 0));
+        CK(cudaEventRecord(ctx->ev_done, ctx->stream));
+        return MSTGPU_OK;
+    }
+    const bool fork = capturing && ctx->tile_classes.size() > 1;
+    if (fork) {
+        CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+        ctx->fork_stream = ctx->stream2;
+    }
+    r = launch_tiles_any<D>(ctx, dt, dtd, Qc, Qn, wr, 2, ctx->stream);
+    ctx->fork_stream = nullptr;
+    if (fork) {
+        CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    }
+    return r;
+}
+
 // Two fixed-dt steps (Q[cur] -> Q[cur^1] -> Q[cur]) captured once as a CUDA graph: the host issues
 // one launch per pair of steps, and the tile classes of a step (separate launches because their
 // shared-memory sizes differ) run as parallel branches instead of one behind the other's tail.
+// A partitioned step is captured too when its halo goes through peer memory (kernels only: the push, the
+// bounded flag wait, the two tile classes on their two streams; the epochs live on the device).
 template <int D>
-int build_step_graph(mstgpu_ctx* ctx, double dt, int start_cur) {
-    const bool fork = ctx->tile_classes.size() > 1;
+int build_step_graph(mstgpu_ctx* ctx, double dt, int start_cur, bool overlap) {
     cudaGraph_t g = nullptr;
     // which = 3 selects no tile class: only the kernel's shared-memory attribute is set, outside the capture
     int r = launch_tiles_any<D>(ctx, dt, nullptr, ctx->Q[0], ctx->Q[1], 0, 3, ctx->stream);
     if (r) return r;
     CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
     const int64_t before = ctx->launches;
-    for (int s = 0; s < 2 && r == MSTGPU_OK; s++) {
-        const double* Qc = ctx->Q[start_cur ^ s];
-        double* Qn = ctx->Q[start_cur ^ s ^ 1];
-        if (fork) {
-            cudaEventRecord(ctx->ev_fork, ctx->stream);
-            cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0);
-            ctx->fork_stream = ctx->stream2;
-        }
-        r = launch_tiles_any<D>(ctx, dt, nullptr, Qc, Qn, 0, 2, ctx->stream);
-        ctx->fork_stream = nullptr;
-        if (fork) {
-            cudaEventRecord(ctx->ev_join, ctx->stream2);
-            cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
-        }
-    }
+    if (overlap) cudaEventRecord(ctx->ev_done, ctx->stream);
+    for (int s = 0; s < 2 && r == MSTGPU_OK; s++)
+        r = issue_tile_step<D>(ctx, dt, nullptr, ctx->Q[start_cur ^ s], ctx->Q[start_cur ^ s ^ 1], 0, overlap, true);
     ctx->graph_launches = ctx->launches - before;
     ctx->launches = before;
     cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
@@ -1045,16 +1164,18 @@ template <int D>
 int step_tiles_impl(mstgpu_ctx* ctx, double dt, int nsteps, double cfl) {
     const double* dtd = cfl > 0.0 ? ctx->dt_dev : nullptr;
     const bool overlap = ctx->partitioned && !ctx->halo.empty();
-    // long fixed-dt runs on one GPU: pairs of steps from the graph, the last one or two steps (the
-    // observable residual belongs to the last) launched directly
+    if (overlap && !ctx->comm) { set_error(ctx, "partitioned context without a communicator: call mstgpu_comm_init"); return MSTGPU_ERR_STATE; }
+    // long fixed-dt runs: pairs of steps from the graph, the last one or two steps (the observable residual
+    // belongs to the last) launched directly.  With neighbours only when the halo is peer memory (no NCCL call
+    // inside the capture).
     static const bool no_graph = getenv("MSTGPU_NO_GRAPH") != nullptr;
-    if (!overlap && !ctx->comm && cfl <= 0.0 && !ctx->ktiming && !no_graph && nsteps >= 4) {
+    if ((!overlap || ctx->peer_ok) && cfl <= 0.0 && !ctx->ktiming && !no_graph && nsteps >= 4) {
         if (ctx->step_graph_dt != dt) {
             for (auto& ge : ctx->step_graph) if (ge) { cudaGraphExecDestroy(ge); ge = nullptr; }
             ctx->step_graph_dt = dt;
         }
         if (!ctx->step_graph[ctx->cur]) {
-            int r = build_step_graph<D>(ctx, dt, ctx->cur);
+            int r = build_step_graph<D>(ctx, dt, ctx->cur, overlap);
             if (r) return r;
         }
         const int pairs = (nsteps - 1) / 2;
@@ -1064,7 +1185,6 @@ int step_tiles_impl(mstgpu_ctx* ctx, double dt, int nsteps, double cfl) {
         ctx->stepped = true;
         ctx->probes_valid = false;
     }
-    if (overlap && !ctx->comm) { set_error(ctx, "partitioned context without a communicator: call mstgpu_comm_init"); return MSTGPU_ERR_STATE; }
     if (overlap && nsteps > 0) CK(cudaEventRecord(ctx->ev_done, ctx->stream));
     for (int s = 0; s < nsteps; s++) {
         double* Qc = ctx->Q[ctx->cur];
@@ -1079,21 +1199,7 @@ int step_tiles_impl(mstgpu_ctx* ctx, double dt, int nsteps, double cfl) {
         }
         KTimer t(ctx, "step_tiles");
         ctx->launches--;  // the launches are counted one by one in launch_tiles
-        if (overlap) {
-            // comm stream: ghost rows <- owners, as soon as the previous step is complete;
-            // compute stream: tiles that touch no ghost cell meanwhile, the others after
-            // (the halo tiles follow the exchange on the comm stream, so they fill the SMs
-            // the interior launch leaves idle in its tail instead of waiting behind it)
-            CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_done, 0));
-            if ((r = halo_exchange(ctx, Qc, ctx->stream2))) return r;
-            if ((r = launch_tiles_any<D>(ctx, dt, dtd, Qc, Qn, wr, 1, ctx->stream2))) return r;
-            CK(cudaEventRecord(ctx->ev_halo, ctx->stream2));
-            if ((r = launch_tiles_any<D>(ctx, dt, dtd, Qc, Qn, wr, 0, ctx->stream))) return r;
-            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_halo, 0));
-            CK(cudaEventRecord(ctx->ev_done, ctx->stream));
-        } else {
-            if ((r = launch_tiles_any<D>(ctx, dt, dtd, Qc, Qn, wr, 2, ctx->stream))) return r;
-        }
+        if ((r = issue_tile_step<D>(ctx, dt, dtd, Qc, Qn, wr, overlap, false))) return r;
         ctx->cur ^= 1;
     }
     CK(cudaGetLastError());
@@ -1577,6 +1683,9 @@ void mstgpu_destroy(mstgpu_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (void* q : ctx->peer_opened) cudaIpcCloseMemHandle(q);
+    for (void* q : {(void*)ctx->peer_flags, (void*)ctx->push_dst, (void*)ctx->push_slot, (void*)ctx->push_ticket, (void*)ctx->peer_epochs})
+        if (q) cudaFree(q);
     if (ctx->comm && g_nccl.h) g_nccl.CommDestroy(ctx->comm);
     if (ctx->send_idx) cudaFree(ctx->send_idx);
     if (ctx->sendbuf) cudaFree(ctx->sendbuf);
@@ -1846,6 +1955,7 @@ int mstgpu_residual_linf(mstgpu_ctx* ctx, double* out) {
     CK(cudaMemcpyAsync(&nan, ctx->nanflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     for (int k = 0; k < ctx->U; k++) std::memcpy(&out[k], &bits[k], 8);
+    if (nan & 4) { set_error(ctx, "peer halo: a neighbour's rows did not arrive within the wait bound (lost rank?)"); return MSTGPU_ERR_NCCL; }
     if (nan) { set_error(ctx, "NaN in the state"); return MSTGPU_ERR_NAN; }
     return MSTGPU_OK;
 }
@@ -1965,6 +2075,113 @@ int mstgpu_comm_init(mstgpu_ctx* ctx, int32_t nranks, int32_t rank, const char* 
     std::memcpy(&id, id128, 128);
     NK(g_nccl.CommInitRank(&ctx->comm, nranks, id, rank));
     ctx->nranks = nranks; ctx->rank = rank;
+    return MSTGPU_OK;
+}
+
+// ---- peer-memory halo: handle exchange ------------------------------------------------------------------
+// Every rank exports one fixed-size blob (IPC handles of its two state buffers and of its flag array, plus
+// where each neighbour's rows go in ITS local numbering); the host all-gathers the blobs by whatever means it
+// has (torch.distributed, MPI, a file) and every rank opens its neighbours' buffers.
+struct PeerBlob {
+    cudaIpcMemHandle_t q[2], flags;
+    int32_t rank, nnb;
+    int32_t nb_rank[MSTGPU_MAX_NB], nb_recv_first[MSTGPU_MAX_NB], nb_recv_count[MSTGPU_MAX_NB];
+};
+
+int64_t mstgpu_peer_blob_bytes(void) { return (int64_t)sizeof(PeerBlob); }
+
+int mstgpu_peer_export(mstgpu_ctx* ctx, int32_t rank, void* blob) {
+    if (!ctx || !blob || rank < 0) return MSTGPU_ERR_ARG;
+    if (!ctx->partitioned) { set_error(ctx, "peer_export: not a partitioned context"); return MSTGPU_ERR_STATE; }
+    if ((int)ctx->halo.size() > MSTGPU_MAX_NB) { set_error(ctx, "peer halo supports up to 32 neighbours per rank"); return MSTGPU_ERR_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->peer_flags) {
+        int r;
+        if ((r = dalloc(ctx, &ctx->peer_flags, (size_t)MSTGPU_MAX_NB))) return r;
+        if ((r = dalloc(ctx, &ctx->push_ticket, (size_t)1))) return r;
+        if ((r = dalloc(ctx, &ctx->peer_epochs, (size_t)2))) return r;
+        CK(cudaMemset(ctx->peer_epochs, 0, 2 * sizeof(unsigned long long)));
+        CK(cudaMemset(ctx->peer_flags, 0, MSTGPU_MAX_NB * sizeof(unsigned long long)));
+        CK(cudaMemset(ctx->push_ticket, 0, sizeof(unsigned int)));
+    }
+    PeerBlob b;
+    std::memset(&b, 0, sizeof(b));
+    CK(cudaIpcGetMemHandle(&b.q[0], ctx->Q[0]));
+    CK(cudaIpcGetMemHandle(&b.q[1], ctx->Q[1]));
+    CK(cudaIpcGetMemHandle(&b.flags, ctx->peer_flags));
+    b.rank = rank; b.nnb = (int32_t)ctx->halo.size();
+    for (size_t i = 0; i < ctx->halo.size(); i++) {
+        b.nb_rank[i] = ctx->halo[i].rank; b.nb_recv_first[i] = ctx->halo[i].recv_first; b.nb_recv_count[i] = ctx->halo[i].recv_count;
+    }
+    std::memcpy(blob, &b, sizeof(b));
+    return MSTGPU_OK;
+}
+
+int mstgpu_peer_connect(mstgpu_ctx* ctx, int32_t nranks, int32_t rank, const void* blobs) {
+    if (!ctx || !blobs || nranks < 1 || rank < 0 || rank >= nranks) return MSTGPU_ERR_ARG;
+    if (!ctx->partitioned || !ctx->peer_flags) { set_error(ctx, "peer_connect before peer_export"); return MSTGPU_ERR_STATE; }
+    if (ctx->peer_ok) return MSTGPU_OK;
+    CK(cudaSetDevice(ctx->device));
+    const PeerBlob* all = static_cast<const PeerBlob*>(blobs);
+    PeerTable pt;
+    std::memset(&pt, 0, sizeof(pt));
+    pt.nnb = (int)ctx->halo.size();
+    std::vector<int32_t> dst((size_t)std::max(1, ctx->send_total));
+    std::vector<uint8_t> slot((size_t)std::max(1, ctx->send_total));
+    auto fail = [&](const std::string& m) {
+        for (void* q : ctx->peer_opened) cudaIpcCloseMemHandle(q);
+        ctx->peer_opened.clear();
+        cudaGetLastError();
+        set_error(ctx, m);
+        return MSTGPU_ERR_CUDA;
+    };
+    for (size_t i = 0; i < ctx->halo.size(); i++) {
+        const auto& h = ctx->halo[i];
+        if (h.rank < 0 || h.rank >= nranks) return fail("peer_connect: neighbour rank out of range");
+        const PeerBlob& nb = all[h.rank];
+        if (nb.rank != h.rank) return fail("peer_connect: blob " + std::to_string(h.rank) + " was exported by rank " + std::to_string(nb.rank));
+        int mine = -1;
+        for (int j = 0; j < nb.nnb; j++) if (nb.nb_rank[j] == rank) mine = j;
+        if (mine < 0 && (h.send_count || h.recv_count)) return fail("peer_connect: neighbour does not list this rank");
+        if (mine >= 0 && nb.nb_recv_count[mine] != h.send_count) return fail("peer_connect: send / receive counts of a neighbour pair differ");
+        void *q0 = nullptr, *q1 = nullptr, *fl = nullptr;
+        cudaError_t e;
+        if ((e = cudaIpcOpenMemHandle(&q0, nb.q[0], cudaIpcMemLazyEnablePeerAccess)) != cudaSuccess)
+            return fail(std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+        ctx->peer_opened.push_back(q0);
+        if ((e = cudaIpcOpenMemHandle(&q1, nb.q[1], cudaIpcMemLazyEnablePeerAccess)) != cudaSuccess)
+            return fail(std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+        ctx->peer_opened.push_back(q1);
+        if ((e = cudaIpcOpenMemHandle(&fl, nb.flags, cudaIpcMemLazyEnablePeerAccess)) != cudaSuccess)
+            return fail(std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+        ctx->peer_opened.push_back(fl);
+        pt.q[0][i] = static_cast<double*>(q0);
+        pt.q[1][i] = static_cast<double*>(q1);
+        pt.flag[i] = static_cast<unsigned long long*>(fl) + (mine >= 0 ? mine : 0);
+        for (int k = 0; k < h.send_count; k++) {
+            dst[(size_t)h.send_off + k] = nb.nb_recv_first[mine] + k;  // ghosts and send lists share the order (ascending global id)
+            slot[(size_t)h.send_off + k] = (uint8_t)i;
+        }
+    }
+    int r;
+    if ((r = upload(ctx, &ctx->push_dst, dst))) return r;
+    if ((r = upload(ctx, &ctx->push_slot, slot))) return r;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->peer = pt;
+    ctx->peer_ok = true;
+    // graphs captured before the switch hold the NCCL exchange
+    for (auto& ge : ctx->step_graph) if (ge) { cudaGraphExecDestroy(ge); ge = nullptr; }
+    return MSTGPU_OK;
+}
+
+// back to the NCCL exchange (a rank that could not connect makes every rank call this: the choice is collective)
+int mstgpu_peer_disable(mstgpu_ctx* ctx) {
+    if (!ctx) return MSTGPU_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream2));
+    ctx->peer_ok = false;
+    for (auto& ge : ctx->step_graph) if (ge) { cudaGraphExecDestroy(ge); ge = nullptr; }
     return MSTGPU_OK;
 }
 

@@ -363,12 +363,13 @@ __device__ __forceinline__ void step_tile(const TileArrays& ta, const int tile, 
             wb[0] = 1.0 - sb;
             const int la = id[0] & 0xFFFFu, lb = id[0] >> 16;
             const bool interior = lb != 0xFFFF;
+            const int lbx = interior ? lb : la;  // boundary face: the same row twice (one address select, no predicated loads)
             // the two cells of the face serve both sides: own cell of one, first neighbour of the other
             double qa[U], qb[U];
 #pragma unroll
             for (int k = 0; k < U; k++) {
                 qa[k] = Qs[la * U + k];
-                qb[k] = interior ? Qs[lb * U + k] : qa[k];
+                qb[k] = Qs[lbx * U + k];
                 A[k] = wa[0] * qa[k] + wa[1] * qb[k];
                 B[k] = wb[0] * qb[k] + wb[1] * qa[k];
             }

@@ -29,7 +29,7 @@ EXPORTS = [
     "mstgpu_device_bytes", "mstgpu_plan_permutation", "mstgpu_tile_stats",
     "mstgpu_partition_create", "mstgpu_partition_destroy", "mstgpu_partition_mesh", "mstgpu_partition_sizes",
     "mstgpu_partition_cell_ids", "mstgpu_partition_neighbor", "mstgpu_create_partitioned",
-    "mstgpu_comm_unique_id", "mstgpu_comm_init", "mstgpu_lusgs_create", "mstgpu_lusgs_destroy",
+    "mstgpu_comm_unique_id", "mstgpu_comm_init", "mstgpu_peer_blob_bytes", "mstgpu_peer_export", "mstgpu_peer_connect", "mstgpu_peer_disable", "mstgpu_lusgs_create", "mstgpu_lusgs_destroy",
     "mstgpu_lusgs_solve", "mstgpu_lusgs_levels", "mstgpu_lusgs_create_ordered", "mstgpu_lusgs_solve_device",
     "mstgpu_lusgs_create_partitioned", "mstgpu_lusgs_color_order_partitioned",
     "mstgpu_lusgs_launch_count", "mstgpu_lusgs_device_bytes", "mstgpu_mesh_adjacency", "mstgpu_lusgs_color_order", "mstgpu_lusgs_last_error",
@@ -127,6 +127,11 @@ def lib():
         L.mstgpu_create_partitioned.argtypes = [C.POINTER(vp), vp, C.POINTER(MstConfig)]
         L.mstgpu_comm_unique_id.argtypes = [vp]
         L.mstgpu_comm_init.argtypes = [vp, i32, i32, vp]
+        L.mstgpu_peer_blob_bytes.argtypes = []
+        L.mstgpu_peer_blob_bytes.restype = i64
+        L.mstgpu_peer_export.argtypes = [vp, i32, vp]
+        L.mstgpu_peer_connect.argtypes = [vp, i32, i32, vp]
+        L.mstgpu_peer_disable.argtypes = [vp]
         L.mstgpu_lusgs_create.argtypes = [C.POINTER(vp), i32, i32, vp, vp, i32]
         L.mstgpu_lusgs_create_ordered.argtypes = [C.POINTER(vp), i32, i32, vp, vp, vp, i32]
         L.mstgpu_lusgs_solve_device.argtypes = [vp, vp, vp, vp, i32, C.POINTER(C.c_float)]
@@ -377,6 +382,42 @@ class Context:
 
     def comm_init(self, nranks: int, rank: int, unique_id: bytes):
         self._check(lib().mstgpu_comm_init(self.h, nranks, rank, unique_id), "comm_init")
+
+    def peer_export(self, rank: int) -> bytes:
+        """this rank's blob for the peer-memory halo (CUDA IPC handles + row offsets)"""
+        n = int(lib().mstgpu_peer_blob_bytes())
+        buf = C.create_string_buffer(n)
+        self._check(lib().mstgpu_peer_export(self.h, rank, buf), "peer_export")
+        return buf.raw
+
+    def peer_connect(self, nranks: int, rank: int, blobs: bytes):
+        """blobs = the nranks blobs of peer_export, concatenated by rank (collective)"""
+        assert len(blobs) == nranks * int(lib().mstgpu_peer_blob_bytes())
+        self._check(lib().mstgpu_peer_connect(self.h, nranks, rank, blobs), "peer_connect")
+
+    def peer_connect_torch(self, dist, nranks: int, rank: int, device=None) -> bool:
+        """all-gather the blobs with torch.distributed and connect; False (and the NCCL exchange stays) if any
+        rank cannot open a neighbour's memory.  The decision is collective: all ranks switch or none does."""
+        import torch
+        mine = torch.frombuffer(bytearray(self.peer_export(rank)), dtype=torch.uint8)
+        if device is not None:
+            mine = mine.to(device)
+        parts = [torch.empty_like(mine) for _ in range(nranks)]
+        dist.all_gather(parts, mine)
+        blobs = b"".join(bytes(p.cpu().numpy().tobytes()) for p in parts)
+        ok = torch.ones(1, dtype=torch.int32, device=mine.device)
+        try:
+            self.peer_connect(nranks, rank, blobs)
+        except MstGpuError:
+            ok[0] = 0
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            self.peer_disable()
+            return False
+        return True
+
+    def peer_disable(self):
+        self._check(lib().mstgpu_peer_disable(self.h), "peer_disable")
 
     def set_state(self, Q):
         Q = np.ascontiguousarray(Q, dtype=np.float64)

@@ -25,7 +25,7 @@ def _ngpu():
 EXT = dict(limiter="bj", gradient="lsq")  # extension scheme for the CFL variant
 
 
-def _worker(rank, world, port, case, kernel, q, cfl=0.0):
+def _worker(rank, world, port, case, kernel, q, cfl=0.0, halo="nccl", nsteps=5):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -42,12 +42,15 @@ def _worker(rank, world, port, case, kernel, q, cfl=0.0):
         idt = torch.frombuffer(bytearray(mstgpu.comm_unique_id()), dtype=torch.uint8).clone()
     dist.broadcast(idt, 0)
     ctx.comm_init(world, rank, bytes(idt.numpy().tobytes()))
+    if halo == "peer":
+        # boundary rows stored straight into the neighbour's ghost block (CUDA IPC + NVLink), epoch flags
+        assert ctx.peer_connect_torch(dist, world, rank), "peer memory not available between the two GPUs"
     ctx.set_state(Q0[P.cell_ids[:P.n_owned]])
     if cfl > 0:
-        t = ctx.step_cfl(cfl, 5)  # global time step: min over ranks on the device (ncclAllReduce(min))
+        t = ctx.step_cfl(cfl, nsteps)  # global time step: min over ranks on the device (ncclAllReduce(min))
         assert t > 0
     else:
-        ctx.step(1e-4, 5)
+        ctx.step(1e-4, nsteps)
     res = ctx.residual()  # collective
     full = torch.zeros((f["ncells"], f["dim"] + 2), dtype=torch.float64)
     full[torch.from_numpy(P.cell_ids[:P.n_owned].astype(np.int64))] = torch.from_numpy(ctx.get_state())
@@ -209,3 +212,31 @@ def test_one_host_thread_drives_contexts_on_two_devices():
     assert np.array_equal(a.get_state(), b.get_state())
     for ctx in (a, b, c):
         ctx.close()
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("kernel,nsteps", [("tiles", 5), ("tiles", 12), ("split", 5)])
+def test_two_gpus_peer_memory_halo_matches_one(kernel, nsteps):
+    """The halo through peer memory (mstgpu_peer_connect: one kernel stores the boundary rows into the
+    neighbour's ghost block and publishes an epoch flag; no pack buffer, no ncclSend/ncclRecv) gives the bits of
+    the single-GPU run.  12 steps go through the CUDA graph of the partitioned step (pairs of steps, epochs on
+    the device), 5 are issued directly."""
+    import torch.multiprocessing as mp
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    port = 29750 + (os.getpid() % 2000)
+    procs = [mpc.Process(target=_worker, args=(r, 2, port, "box", kernel, q, 0.0, "peer", nsteps)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got, res = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    f = box_flat(12, 10, 8, bc=(10, 5, 3, 7, 3, 3))
+    inlet = np.array([1.0, 0.4, 0.0, 0.0, 2.58])
+    Q0 = mesh_np.random_state(f, seed=4)
+    one = mstgpu.Context(f, order=2, flux="roe", inletQ=inlet, kernel=kernel)
+    one.set_state(Q0)
+    one.step(1e-4, nsteps)
+    assert np.array_equal(got, one.get_state(), equal_nan=True)
+    assert np.array_equal(res, one.residual(), equal_nan=True)
