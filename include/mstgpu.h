@@ -309,12 +309,15 @@ int mstgpu_lusgs_solve(mstgpu_lusgs* h, const double* val, const double* b, doub
  * *ms (optional) = CUDA-event time of the whole solve on the solver's stream. */
 int mstgpu_lusgs_solve_device(mstgpu_lusgs* h, const double* d_val, const double* d_b, double* d_x, int32_t max_iter,
                               float* ms);
-/* Experimental: mode 1 = fused iteration (csrc/lusgs.cu): the backward sweep leaves U x of the next
- * iteration as a by-product and the right-hand side update is folded into the forward sweep, so the unscaled
- * off-diagonal blocks are read once per solve instead of twice per iteration.  Same mathematics as
- * SparseSolver.cpp:54-104, re-associated (6e-16 against the reference-pinned oracle on the CPU restatement,
- * tests/lusgs_fused_np.py).  Mode 0 (default) runs the reference's passes one by one.  MSTGPU_LUSGS_MODE sets
- * it at creation. */
+/* Iteration variants (csrc/lusgs.cu), all the mathematics of SparseSolver.cpp:54-104:
+ *   0  the reference's passes one by one (U x, right-hand side, forward sweep, D D^-1, backward sweep, D^-1);
+ *   1  fused: the backward sweep leaves U x of the next iteration as a by-product and the right-hand side update is
+ *      folded into the forward sweep -- the unscaled off-diagonal blocks are read once per solve instead of twice
+ *      per iteration (re-associated: 6e-16 against the reference-pinned oracle, tests/lusgs_fused_np.py);
+ *   2  lean (default): mode 1 without the reference's w0 = D (D^-1 v) round trip (the identity up to cond(D) eps)
+ *      and with x = D^-1 w formed inside the backward sweep (<= 1e-13 against the oracle on the test systems).
+ * The scalar solver's residual history / early exit needs the last pass of modes 0 / 1 and gets it in mode 2 too.
+ * MSTGPU_LUSGS_MODE sets the mode at creation. */
 int mstgpu_lusgs_set_mode(mstgpu_lusgs* h, int32_t mode);
 int64_t mstgpu_lusgs_launch_count(mstgpu_lusgs* h);
 int64_t mstgpu_lusgs_device_bytes(mstgpu_lusgs* h);

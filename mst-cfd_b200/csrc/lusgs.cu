@@ -42,13 +42,15 @@ struct mstgpu_lusgs {
     int *Dptr = nullptr, *Dpos = nullptr;  // diagonal entries per row (summed)
     int *Gptr = nullptr, *Gcol = nullptr, *Gpos = nullptr;  // entries in ghost columns (>= n): lagged, moved to the right-hand side
     int* rmap = nullptr;  // [n] sweep position -> row of the caller's b / x
+    int* rinv = nullptr;  // [n] row of the caller -> sweep position
+    int setup_mode = 1;   // 1 = k_diag_grp + k_scale_rows (default), 0 = the round-1 kernels (MSTGPU_LUSGS_SETUP=0)
     double* beff = nullptr;
     std::vector<int> fptr, bptr;           // level pointers (host)
     int *frows = nullptr, *brows = nullptr;
     double *val = nullptr, *D = nullptr, *Dinv = nullptr, *LD = nullptr, *UD = nullptr;
     double *b = nullptr, *x = nullptr, *rhs = nullptr, *rhs1 = nullptr, *ux = nullptr;
     double* s = nullptr;  // mode 1: U x of the next iteration, a by-product of the backward sweep
-    int mode = 0;         // 0 = the reference's four passes per iteration, 1 = fused, 2 = lean (see solve_core)
+    int mode = 2;         // 0 = the reference's four passes per iteration, 1 = fused, 2 = lean (default; see solve_core)
     bool s_valid = false; // h->s holds U x of the CURRENT x (left behind by the last backward sweep of modes 1 / 2)
     bool x0_zero = false; // hint of the caller for the next solve: the start vector is zero (U x = 0, no pass over U)
     unsigned long long* res = nullptr;
@@ -159,6 +161,102 @@ __global__ void k_diag(int n, const int* Dptr, const int* Dpos, const double* va
     double di[B * B];
     d_inverse<B>(d, di);
     for (int q = 0; q < B * B; q++) { D[(size_t)r * B * B + q] = d[q]; Dinv[(size_t)r * B * B + q] = di[q]; }
+}
+
+// D, D^-1 with a lane group per block row (lane i owns row i of [D | I]); the Gauss-Jordan elimination with partial
+// pivoting of d_inverse, same operations in the same order, rows exchanged and broadcast by shuffles -- no local
+// memory.  Rows are taken in the CALLER's order r (val streams front to back), results stored at p = rinv[r].
+template <int B>
+__global__ void k_diag_grp(int n, const int* __restrict__ rinv, const int* __restrict__ Dptr, const int* __restrict__ Dpos,
+                           const double* __restrict__ val, double* __restrict__ D, double* __restrict__ Dinv) {
+    const Grp<B> g(n);
+    const int i = g.i, base = g.base;
+    const int p = g.on ? rinv[g.row] : 0;
+    double w[2 * B];
+#pragma unroll
+    for (int j = 0; j < B; j++) { w[j] = 0.0; w[B + j] = (i == j) ? 1.0 : 0.0; }
+    if (g.on)
+        for (int k = Dptr[p]; k < Dptr[p + 1]; k++) {
+#pragma unroll
+            for (int j = 0; j < B; j++) w[j] += val[(size_t)Dpos[k] * B * B + i * B + j];
+        }
+    if (g.on) {
+#pragma unroll
+        for (int j = 0; j < B; j++) D[(size_t)p * B * B + i * B + j] = w[j];
+    } else {
+        w[i < B ? i : 0] = 1.0;  // idle lanes run the elimination on the identity: no 0/0 in the shuffles
+    }
+    if (B == 1) { if (g.on) Dinv[p] = 1.0 / w[0]; return; }
+#pragma unroll
+    for (int c = 0; c < B; c++) {
+        // pivot row: the first largest |w[r][c]| over r >= c (d_inverse)
+        const double mine = (i >= c) ? fabs(w[c]) : -1.0;
+        double best = __shfl_sync(0xffffffffu, mine, base + c);
+        int piv = c;
+#pragma unroll
+        for (int r = c + 1; r < B; r++) {
+            const double v = __shfl_sync(0xffffffffu, mine, base + r);
+            if (v > best) { best = v; piv = r; }
+        }
+        // exchange rows c and piv (a no-op when piv == c), then scale row c and eliminate column c elsewhere
+        double rowc[2 * B];
+#pragma unroll
+        for (int j = 0; j < 2 * B; j++) {
+            const double a = __shfl_sync(0xffffffffu, w[j], base + c), b = __shfl_sync(0xffffffffu, w[j], base + piv);
+            if (i == piv) w[j] = a;
+            if (i == c) w[j] = b;   // after the line above: piv == c leaves the row as it is
+            rowc[j] = b;            // the new row c, before scaling
+        }
+        const double ip = 1.0 / rowc[c];
+#pragma unroll
+        for (int j = 0; j < 2 * B; j++) rowc[j] *= ip;
+        if (i == c) {
+#pragma unroll
+            for (int j = 0; j < 2 * B; j++) w[j] = rowc[j];
+        } else {
+            const double f = w[c];
+            if (f != 0.0) {
+#pragma unroll
+                for (int j = 0; j < 2 * B; j++) w[j] -= f * rowc[j];
+            }
+        }
+    }
+    if (g.on) {
+#pragma unroll
+        for (int j = 0; j < B; j++) Dinv[(size_t)p * B * B + i * B + j] = w[B + j];
+    }
+}
+
+// LD / UD of one block row per lane group, rows in the caller's order: val streams front to back and the D^-1 blocks
+// of a row's neighbours -- close in the caller's (Hilbert) order, so used again within a few rows -- stay in L2,
+// instead of being fetched once per colour pass.  Same arithmetic as k_scale.
+template <int B>
+__global__ void k_scale_rows(int n, const int* __restrict__ rinv, const int* __restrict__ Lptr, const int* __restrict__ Lcol,
+                             const int* __restrict__ Lpos, const int* __restrict__ Uptr, const int* __restrict__ Ucol,
+                             const int* __restrict__ Upos, const double* __restrict__ val, const double* __restrict__ D,
+                             const double* __restrict__ Dinv, double* __restrict__ LD, double* __restrict__ UD) {
+    const Grp<B> g(n);
+    if (!g.on) return;
+    const int i = g.i, p = rinv[g.row];
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        const int* ptr = half ? Uptr : Lptr;
+        const int* col = half ? Ucol : Lcol;
+        const int* pos = half ? Upos : Lpos;
+        double* XD = half ? UD : LD;
+        for (int e = ptr[p]; e < ptr[p + 1]; e++) {
+            const double* a = val + (size_t)pos[e] * B * B + i * B;
+            if (B == 1) { XD[e] = a[0] * (1. / D[col[e]]); continue; }  // SparseSolverNUM.cpp:181: L * (1./D)
+            const double* di = Dinv + (size_t)col[e] * B * B;
+#pragma unroll
+            for (int j = 0; j < B; j++) {
+                double s = a[0] * di[j];
+#pragma unroll
+                for (int k = 1; k < B; k++) s += a[k] * di[k * B + j];
+                XD[(size_t)e * B * B + i * B + j] = s;
+            }
+        }
+    }
 }
 
 // XD[e] = X[e] * Dinv[col[e]]   (the reference's (L * D^-1) factor, SparseSolver.cpp:86,96); thread per (entry, row)
@@ -370,10 +468,16 @@ int solve_core(mstgpu_lusgs* h, const double* val, const double* b, double* x, i
     cudaStream_t s = h->stream;
     using G = Grp<B>;
     if (setup) {  // D, D^-1 and the scaled copies depend on the matrix only
-        k_diag<B><<<(n + T - 1) / T, T, 0, s>>>(n, h->Dptr, h->Dpos, val, h->D, h->Dinv);
-        if (h->nL) k_scale<B><<<(unsigned)(((size_t)h->nL * B + T - 1) / T), T, 0, s>>>((size_t)h->nL, h->Lcol, h->Lpos, val, h->D, h->Dinv, h->LD);
-        if (h->nU) k_scale<B><<<(unsigned)(((size_t)h->nU * B + T - 1) / T), T, 0, s>>>((size_t)h->nU, h->Ucol, h->Upos, val, h->D, h->Dinv, h->UD);
-        h->launches += 3;
+        if (h->setup_mode == 0) {  // round-1 kernels: thread per row / per (entry, row), sweep order
+            k_diag<B><<<(n + T - 1) / T, T, 0, s>>>(n, h->Dptr, h->Dpos, val, h->D, h->Dinv);
+            if (h->nL) k_scale<B><<<(unsigned)(((size_t)h->nL * B + T - 1) / T), T, 0, s>>>((size_t)h->nL, h->Lcol, h->Lpos, val, h->D, h->Dinv, h->LD);
+            if (h->nU) k_scale<B><<<(unsigned)(((size_t)h->nU * B + T - 1) / T), T, 0, s>>>((size_t)h->nU, h->Ucol, h->Upos, val, h->D, h->Dinv, h->UD);
+            h->launches += 3;
+        } else {  // lane group per block row, rows in the caller's order
+            k_diag_grp<B><<<G::grid(n, T), T, 0, s>>>(n, h->rinv, h->Dptr, h->Dpos, val, h->D, h->Dinv);
+            k_scale_rows<B><<<G::grid(n, T), T, 0, s>>>(n, h->rinv, h->Lptr, h->Lcol, h->Lpos, h->Uptr, h->Ucol, h->Upos, val, h->D, h->Dinv, h->LD, h->UD);
+            h->launches += 2;
+        }
     }
     // the lean mode has no k_fin, which is where the scalar solver's residual (early exit) is formed
     const bool lean = h->mode == 2 && !(B == 1 && (res_hist || early_exit));
@@ -661,6 +765,11 @@ int mstgpu_lusgs_create_partitioned(mstgpu_lusgs** out, int32_t n, int32_t ncols
             LCK(cudaMalloc((void**)&h->beff, (size_t)n * block * 8));
         }
         if ((r = up(h, &h->frows, frows)) || (r = up(h, &h->brows, brows)) || (r = up(h, &h->rmap, rmap))) return r;
+        {
+            std::vector<int> rinv(n);
+            for (int q = 0; q < n; q++) rinv[rmap[q]] = q;
+            if ((r = up(h, &h->rinv, rinv))) return r;
+        }
         const size_t BB = (size_t)block * block;
         // val / b / x buffers of the host-array entry point are allocated at its first use
         LCK(cudaMalloc((void**)&h->D, n * BB * 8));
@@ -673,6 +782,7 @@ int mstgpu_lusgs_create_partitioned(mstgpu_lusgs** out, int32_t n, int32_t ncols
     }();
     if (rc) { mstgpu_lusgs_destroy(h); return rc; }
     if (const char* v = getenv("MSTGPU_LUSGS_MODE")) { const int m = atoi(v); h->mode = (m >= 0 && m <= 2) ? m : 0; }
+    if (const char* v = getenv("MSTGPU_LUSGS_SETUP")) h->setup_mode = atoi(v) != 0;
     *out = h;
     return MSTGPU_OK;
 }
@@ -684,7 +794,7 @@ void mstgpu_lusgs_destroy(mstgpu_lusgs* h) {
     for (void* p : {(void*)h->Lptr, (void*)h->Lcol, (void*)h->Lpos, (void*)h->Uptr, (void*)h->Ucol, (void*)h->Upos,
                     (void*)h->Dptr, (void*)h->Dpos, (void*)h->frows, (void*)h->brows, (void*)h->val, (void*)h->D,
                     (void*)h->Dinv, (void*)h->LD, (void*)h->UD, (void*)h->b, (void*)h->x, (void*)h->rhs, (void*)h->rhs1,
-                    (void*)h->ux, (void*)h->s, (void*)h->res, (void*)h->Gptr, (void*)h->Gcol, (void*)h->Gpos, (void*)h->beff, (void*)h->rmap})
+                    (void*)h->ux, (void*)h->s, (void*)h->res, (void*)h->Gptr, (void*)h->Gcol, (void*)h->Gpos, (void*)h->beff, (void*)h->rmap, (void*)h->rinv})
         if (p) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);

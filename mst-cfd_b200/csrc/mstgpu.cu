@@ -124,6 +124,9 @@ struct mstgpu_ctx {
     struct TileClass { int first, count; size_t smem; bool halo; };  // halo: a ring of the tile holds ghost cells
     std::vector<TileClass> tile_classes;  // tiles grouped by shared-memory need (CTAs per SM)
     bool use_tiles = false;
+    bool split_ready = false;   // the per-face / per-cell tables of the split kernels are on the device (uploaded on first use
+                                // when the fused kernel is the step path: it never reads them)
+    size_t stage_cap = 0;       // doubles in `stage`
     bool probes_valid = false;  // G / Phi hold the stages of the last step
     // multi-GPU (partitioned context)
     int n_owned = 0;  // cells advanced by this context (== nc when not partitioned)
@@ -875,6 +878,46 @@ int dalloc(mstgpu_ctx* ctx, T** dptr, size_t n) {
     return MSTGPU_OK;
 }
 
+// per-face / per-cell tables of the split kernels (also read by the CFL reduction, the implicit assembly and the
+// stage probes): uploaded from the plan's host copies on first use, which are dropped afterwards
+int ensure_split_tables(mstgpu_ctx* ctx) {
+    if (ctx->split_ready) return MSTGPU_OK;
+    Plan& p = ctx->plan;
+    int r;
+    if ((r = upload(ctx, &ctx->fc0, p.fc0))) return r;
+    if ((r = upload(ctx, &ctx->fc1, p.fc1))) return r;
+    if ((r = upload(ctx, &ctx->Sd, p.Sd))) return r;
+    if ((r = upload(ctx, &ctx->dx0, p.dx0))) return r;
+    if ((r = upload(ctx, &ctx->dx1, p.dx1))) return r;
+    if ((r = upload(ctx, &ctx->eta, p.eta))) return r;
+    if ((r = upload(ctx, &ctx->meta, p.meta))) return r;
+    if ((r = upload(ctx, &ctx->vol, p.vol))) return r;
+    if ((r = upload(ctx, &ctx->cf, p.cf))) return r;
+    if ((r = upload(ctx, &ctx->face_new2old, p.face_new2old))) return r;
+    if (!p.lsq.empty() && (r = upload(ctx, &ctx->lsq, p.lsq))) return r;
+    if (!p.eps2.empty() && (r = upload(ctx, &ctx->eps2, p.eps2))) return r;
+    CK(cudaStreamSynchronize(ctx->stream));  // the uploads read pageable host vectors that are freed next
+    p.fc0 = {}; p.fc1 = {}; p.Sd = {}; p.dx0 = {}; p.dx1 = {}; p.eta = {}; p.meta = {}; p.vol = {}; p.cf = {};
+    p.lsq = {}; p.eps2 = {};
+    ctx->split_ready = true;
+    return MSTGPU_OK;
+}
+
+// the staging buffer holds at least n doubles
+int ensure_stage(mstgpu_ctx* ctx, size_t n) {
+    if (ctx->stage_cap >= n) return MSTGPU_OK;
+    if (ctx->stage) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaFree(ctx->stage));
+        ctx->dev_bytes -= (int64_t)(ctx->stage_cap * sizeof(double));
+        ctx->stage = nullptr; ctx->stage_cap = 0;
+    }
+    int r = dalloc(ctx, &ctx->stage, n);
+    if (r) return r;
+    ctx->stage_cap = n;
+    return MSTGPU_OK;
+}
+
 struct KTimer {
     mstgpu_ctx* ctx;
     const char* name;
@@ -1081,6 +1124,7 @@ int launch_tiles_any(mstgpu_ctx* ctx, double dt, const double* dtd, const double
 // cell minimum -> [min over ranks] -> dt_dev[0] = cfl * min, dt_dev[1] += dt
 template <int D>
 int cfl_on_device(mstgpu_ctx* ctx, double cfl, const double* Q) {
+    { int r0 = ensure_split_tables(ctx); if (r0) return r0; }
     k_cfl<D><<<(ctx->n_owned + 255) / 256, 256, 0, ctx->stream>>>(ctx->n_owned, ctx->nc, ctx->nslot, ctx->dcfg.gamma, Q, ctx->cf,
                                                                  ctx->Sd, ctx->vol, ctx->dtmin);
     if (ctx->comm) NK(g_nccl.AllReduce(ctx->dtmin, ctx->dtmin, 1, ncclUint64, ncclMin, ctx->comm, ctx->stream));
@@ -1232,6 +1276,7 @@ void launch_gradient_stage(mstgpu_ctx* ctx, const double* Qo) {
 template <int D>
 int step_impl(mstgpu_ctx* ctx, double dt, int nsteps, double cfl = 0.0) {
     if (ctx->use_tiles) return step_tiles_impl<D>(ctx, dt, nsteps, cfl);
+    { int r0 = ensure_split_tables(ctx); if (r0) return r0; }
     const double* dtd = cfl > 0.0 ? ctx->dt_dev : nullptr;
     const int nc = ctx->nc, nf = ctx->nf;
     {
@@ -1277,8 +1322,9 @@ int step_impl(mstgpu_ctx* ctx, double dt, int nsteps, double cfl = 0.0) {
 // state the last step started from (Q[cur^1]) with the split kernels.
 template <int D>
 int recompute_stages(mstgpu_ctx* ctx) {
-    int r = ensure_stage_buffers(ctx);
+    int r = ensure_split_tables(ctx);
     if (r) return r;
+    if ((r = ensure_stage_buffers(ctx))) return r;
     const int nc = ctx->nc, nf = ctx->nf;
     const double* Qo = ctx->Q[ctx->cur ^ 1];
     launch_gradient_stage<D>(ctx, Qo);
@@ -1296,6 +1342,7 @@ int recompute_stages(mstgpu_ctx* ctx) {
 
 int fetch_permuted(mstgpu_ctx* ctx, const double* dsrc, const int32_t* new2old, int n, int W, double* host) {
     const size_t tot = (size_t)n * W;
+    { int r0 = ensure_stage(ctx, tot); if (r0) return r0; }
     k_permute_out<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(n, W, dsrc, new2old, ctx->stage);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -1312,6 +1359,7 @@ static int step_implicit_impl(mstgpu_ctx* ctx, double dt, int nsteps, int iters)
     const int nc = ctx->nc, nrow = ctx->n_owned;
     const bool dist = ctx->partitioned && !ctx->halo.empty();
     if (dist && !ctx->comm) { set_error(ctx, "partitioned context without a communicator: call mstgpu_comm_init"); return MSTGPU_ERR_STATE; }
+    { int r0 = ensure_split_tables(ctx); if (r0) return r0; }  // the block assembly reads the per-face tables
     for (int s = 0; s < nsteps; s++) {
         double* Qc = ctx->Q[ctx->cur];
         double* Qn = ctx->Q[ctx->cur ^ 1];
@@ -1526,19 +1574,10 @@ static int create_impl(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_c
         CK(cudaEventCreate(&ctx->ev0));
         CK(cudaEventCreate(&ctx->ev1));
         int r;
-        if ((r = upload(ctx, &ctx->fc0, p.fc0))) return r;
-        if ((r = upload(ctx, &ctx->fc1, p.fc1))) return r;
-        if ((r = upload(ctx, &ctx->Sd, p.Sd))) return r;
-        if ((r = upload(ctx, &ctx->dx0, p.dx0))) return r;
-        if ((r = upload(ctx, &ctx->dx1, p.dx1))) return r;
-        if ((r = upload(ctx, &ctx->eta, p.eta))) return r;
-        if ((r = upload(ctx, &ctx->meta, p.meta))) return r;
-        if ((r = upload(ctx, &ctx->vol, p.vol))) return r;
-        if ((r = upload(ctx, &ctx->cf, p.cf))) return r;
+        // the split kernels' tables (~230 B per cell on tets) go up now only if the split kernels are the step
+        // path; under the fused kernel they wait for their first user (stage probes, CFL step, implicit step)
+        if (!ctx->use_tiles && (r = ensure_split_tables(ctx))) return r;
         if ((r = upload(ctx, &ctx->cell_new2old, p.cell_new2old))) return r;
-        if ((r = upload(ctx, &ctx->face_new2old, p.face_new2old))) return r;
-        if (!p.lsq.empty() && (r = upload(ctx, &ctx->lsq, p.lsq))) return r;
-        if (!p.eps2.empty() && (r = upload(ctx, &ctx->eps2, p.eps2))) return r;
         const size_t nq = (size_t)p.nc * p.U;
         // + 2 rows: the fused kernel's bulk copies move an even number of rows
         if ((r = dalloc(ctx, &ctx->Q[0], nq + 2 * p.U))) return r;
@@ -1628,8 +1667,8 @@ static int create_impl(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_c
             ctx->ta = TileArrays{ddesc, dring, dpk, ctx->ring_stride};
             CK(cudaStreamSynchronize(ctx->stream));  // tp goes out of scope
         }
-        size_t nstage = std::max(nq * p.D, (size_t)p.nf * p.U);
-        if ((r = dalloc(ctx, &ctx->stage, nstage))) return r;
+        // staging buffer of the state permutation; the stage probes (gradient, face flux) grow it on first use
+        if ((r = ensure_stage(ctx, nq))) return r;
         if (part) {
             std::vector<int32_t> sidx;
             for (const Neighbor& nb : part->nbrs) {
@@ -1668,9 +1707,7 @@ static int create_impl(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_c
     d.mu = cfg->mu; d.lambda = -0.666667 * cfg->mu; d.kappa = cfg->kappa; d.cv = cfg->cv; d.inv_cv = 1.0 / cfg->cv;
     for (int k = 0; k < 5; k++) d.inletQ[k] = cfg->inletQ[k];
     d.order = cfg->order; d.flux = cfg->flux; d.viscous = cfg->viscous; d.limiter = cfg->order == 2 ? cfg->limiter : 0;
-    // the big host tables are no longer needed
-    p.fc0 = {}; p.fc1 = {}; p.Sd = {}; p.dx0 = {}; p.dx1 = {}; p.eta = {}; p.meta = {}; p.vol = {}; p.cf = {};
-    p.lsq = {}; p.eps2 = {};
+    // the big host tables are no longer needed once they are on the device (ensure_split_tables drops them)
     *out = ctx;
     return MSTGPU_OK;
 }
@@ -1822,6 +1859,7 @@ int mstgpu_implicit_setup(mstgpu_ctx* ctx, int32_t colour_sweeps) {
     if (!ctx) return MSTGPU_ERR_ARG;
     if (ctx->imp_solver) return MSTGPU_OK;
     CK(cudaSetDevice(ctx->device));
+    { int r0 = ensure_split_tables(ctx); if (r0) return r0; }
     // rows = the cells this context advances; on a partition the ghost cells (ids >= n_owned) are
     // columns only, their couplings lagged by one sweep (block Jacobi across partitions)
     const int nc = ctx->nc, nrow = ctx->n_owned, nslot = ctx->nslot, U = ctx->U;
