@@ -654,31 +654,51 @@ def measure(args, rank, world, dist, local, want_cpu=True):
                 kernels_ms={k: round(v, 4) for k, v in per_kernel.items()}, dominant=dom,
                 step_frac=ab["step"] * value / 1e9 / peak)
 
-    # ---- e2e: reference-facing call sequence with HOST buffers -----------------
+    # ---- e2e: reference-facing call with HOST buffers -----------------------------
+    # Time.cpp:63-76 runs solve() and then reads old and new state on the host: one mstgpu_step_host call per
+    # step (H2D of the input rows, the step, D2H of the output rows, pipelined over chunks of host rows) and the
+    # residual.  The same sequence as three separate calls (set_state, step, get_state) is timed beside it.
     hin = torch.empty((nc, U), dtype=torch.float64, pin_memory=True)
     hout = torch.empty((nc, U), dtype=torch.float64, pin_memory=True)
-    hin.numpy()[:] = Q0
-    r = np.zeros(U)
     ne = max(2, min(args.steps, 5))
-    for it in range(1 + ne):
-        if it == 1:
-            torch.cuda.synchronize()
-            e0 = time.perf_counter()
-        ctx.set_state_ptr(hin.data_ptr())      # H2D of the step's input state
-        ctx.step(dt_run, 1)
-        ctx.get_state_ptr(hout.data_ptr())     # D2H of the new state (Time.cpp:66-67)
-        r = ctx.residual()                     # D2H of the residual (Time.cpp:69-76)
-        hin, hout = hout, hin                  # updateNewToOld on the host side
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    e2e_s = (time.perf_counter() - e0) / ne
-    if dist is not None:
-        te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e_s = float(te.item())
+
+    def e2e_leg(streamed):
+        nonlocal hin, hout
+        hin.numpy()[:] = Q0
+        for it in range(1 + ne):
+            if it == 1:
+                torch.cuda.synchronize()
+                if dist is not None:
+                    dist.barrier()
+                e0 = time.perf_counter()
+            if streamed:
+                ctx.step_host(hin.data_ptr(), hout.data_ptr(), dt_run, args.host_chunks)
+            else:
+                ctx.set_state_ptr(hin.data_ptr())      # H2D of the step's input state
+                ctx.step(dt_run, 1)
+                ctx.get_state_ptr(hout.data_ptr())     # D2H of the new state (Time.cpp:66-67)
+            ctx.residual()                         # D2H of the residual (Time.cpp:69-76)
+            hin, hout = hout, hin                  # updateNewToOld on the host side
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        s_ = (time.perf_counter() - e0) / ne
+        if dist is not None:
+            te = torch.tensor([s_], dtype=torch.float64, device="cuda")
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            s_ = float(te.item())
+        return s_, int(hin.numpy().view(np.uint64).sum(dtype=np.uint64))  # checksum of the final state's bit patterns
+
+    streamed_ok = args.kernel == "tiles" and not args.cfl and not args.implicit
+    e2e_3, sha3 = e2e_leg(False)
+    e2e_s, sha_s = e2e_leg(True) if streamed_ok else (e2e_3, sha3)
+    assert sha3 == sha_s, "streamed step differs from set_state + step + get_state"
     e2e = dict(value=nc_total / e2e_s, unit="cell-updates/s", h2d_bytes_per_step=nc * U * 8,
-               d2h_bytes_per_step=nc * U * 8 + U * 8, ms_per_step=e2e_s * 1e3, steps=ne)
+               d2h_bytes_per_step=nc * U * 8 + U * 8, ms_per_step=e2e_s * 1e3, steps=ne,
+               call="mstgpu_step_host (H2D, step, D2H pipelined over %d chunks of host rows) + mstgpu_residual_linf" % (args.host_chunks or 64)
+                    if streamed_ok else "mstgpu_set_state + mstgpu_step + mstgpu_get_state + mstgpu_residual_linf",
+               three_calls=dict(value=nc_total / e2e_3, ms_per_step=e2e_3 * 1e3,
+                                what="mstgpu_set_state + mstgpu_step(dt, 1) + mstgpu_get_state + mstgpu_residual_linf, one after the other"))
 
     cpu = cpu_baseline(args) if (world == 1 and not args.no_cpu and want_cpu) else None
 
@@ -799,6 +819,7 @@ def main():
                     help="config 5: implicit steps (block assembly + 5 colour-ordered LU-SGS sweeps)")
     ap.add_argument("--implicit-dt", type=float, default=1e-3)
     ap.add_argument("--graph", type=int, default=0, choices=[0, 1], help="also time the K steps issued from the CUDA graph")
+    ap.add_argument("--host-chunks", type=int, default=0, help="chunks of host rows of the streamed e2e step (0 = library default, 64)")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"], help="N > 1: halo exchange through peer memory (default) or NCCL send/recv")
     ap.add_argument("--secondary", type=int, default=-1, help="BASELINE configs 1, 2, 3, 5 as short runs under the `secondary` key: "
                     "1 = always, 0 = never, -1 = with the headline workload only (default)")

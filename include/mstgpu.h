@@ -52,6 +52,7 @@
 #ifndef MSTGPU_H
 #define MSTGPU_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -161,6 +162,27 @@ int mstgpu_get_prev_state(mstgpu_ctx* ctx, double* q_aos);
 int mstgpu_step(mstgpu_ctx* ctx, double dt, int32_t nsteps);
 /* Same, bracketed by CUDA events on the solver's own stream; *ms = elapsed. */
 int mstgpu_step_timed(mstgpu_ctx* ctx, double dt, int32_t nsteps, float* ms);
+/* One step with the state on the HOST on both sides: what Time::goNextTimeStep does with a solver
+ * whose fields live in AllData (R/time/Time.cpp:63-76: solve(), then getOldValue() / getNewValue() are
+ * read on the host), i.e. mstgpu_set_state + mstgpu_step(dt, 1) + mstgpu_get_state in one call.
+ * q_in / q_out: [ncells][DIMU] in reference order (q_in == q_out is allowed).  The three stages are
+ * PIPELINED over `nchunks` chunks of host rows (<= 0: default 64, MSTGPU_HOST_CHUNKS overrides):
+ * chunk j goes host -> device while the tiles whose input chunk j-1 completed run and the rows they
+ * finished go device -> host, both PCIe directions busy at once.  The schedule (which tiles can run
+ * after which chunk, which rows are final after which launch) is derived from the mesh numbering on
+ * first use; it is valid for any numbering and hides the copies to the extent the host cell order
+ * follows the mesh.  Results are bit-identical to the three separate calls.  Page-locked host buffers
+ * (cudaHostRegister / cudaMallocHost) are needed for the overlap; pageable ones work, serialised.
+ * Afterwards the context holds q_out as current and q_in as previous state, and
+ * mstgpu_residual_linf returns the residual of this step.  On a partitioned context (COLLECTIVE) the
+ * tiles next to ghost cells run after the halo exchange, which follows the last chunk.
+ * Fused kernel only (kernel = 1). */
+int mstgpu_step_host(mstgpu_ctx* ctx, const double* q_in, double* q_out, double dt, int32_t nchunks);
+/* Page-lock / release a host array (cudaHostRegister / cudaHostUnregister) for hosts that are not built
+ * against the CUDA headers: AllData's new[]-allocated field arrays (R/data/AllData.cpp:3-27) become
+ * eligible for the overlapped copies of mstgpu_step_host.  unregister(NULL) is a no-op. */
+int mstgpu_host_register(void* p, size_t bytes);
+int mstgpu_host_unregister(void* p);
 /* Extension (the reference's DT is the macro 1/STEP_TIME, R/time/Time.cpp:62):
  * global CFL time step  dt = cfl * min_c V_c / sum_{f in c} (|u_c.S_f| + a_c |S_f|)
  * of the current state.  With a communicator the minimum is taken over all ranks

@@ -43,7 +43,7 @@ struct mstgpu_lusgs {
     int *Gptr = nullptr, *Gcol = nullptr, *Gpos = nullptr;  // entries in ghost columns (>= n): lagged, moved to the right-hand side
     int* rmap = nullptr;  // [n] sweep position -> row of the caller's b / x
     int* rinv = nullptr;  // [n] row of the caller -> sweep position
-    int setup_mode = 1;   // 1 = k_diag_grp + k_scale_rows (default), 0 = the round-1 kernels (MSTGPU_LUSGS_SETUP=0)
+    int setup_mode = 2;   // MSTGPU_LUSGS_SETUP: 2 = k_diag_reg + k_scale_rows (default), 1 = k_diag_grp + k_scale_rows, 0 = k_diag + k_scale (round 1)
     double* beff = nullptr;
     std::vector<int> fptr, bptr;           // level pointers (host)
     int *frows = nullptr, *brows = nullptr;
@@ -225,6 +225,94 @@ __global__ void k_diag_grp(int n, const int* __restrict__ rinv, const int* __res
 #pragma unroll
         for (int j = 0; j < B; j++) Dinv[(size_t)p * B * B + i * B + j] = w[B + j];
     }
+}
+
+// D, D^-1 with a thread per block row and the augmented matrix in REGISTERS: d_inverse's Gauss-Jordan elimination
+// (same pivot rule, same operations in the same order) fully unrolled, rows exchanged by predicated swaps -- no
+// local memory (k_diag keeps [D | I] in a dynamically indexed local array) and no shuffles (k_diag_grp spends
+// ~250 of them per row).  Memory side: a warp fetches its 32 diagonal blocks one 8*B*B-byte row per request
+// (lanes < B*B) into shared memory and writes D and D^-1 as two contiguous 32-row runs.
+template <int B, int C>
+__device__ __forceinline__ void d_inverse_col(double (&w)[B][2 * B]) {
+    if constexpr (C < B) {
+        int p = C;
+        double best = fabs(w[C][C]);
+#pragma unroll
+        for (int r = C + 1; r < B; r++) {
+            const double v = fabs(w[r][C]);
+            if (v > best) { best = v; p = r; }
+        }
+#pragma unroll
+        for (int r = C + 1; r < B; r++) {
+            const bool sw = p == r;
+#pragma unroll
+            for (int j = 0; j < 2 * B; j++) {
+                const double a = w[C][j], b = w[r][j];
+                w[C][j] = sw ? b : a;
+                w[r][j] = sw ? a : b;
+            }
+        }
+        const double ip = 1.0 / w[C][C];
+#pragma unroll
+        for (int j = 0; j < 2 * B; j++) w[C][j] *= ip;
+#pragma unroll
+        for (int r = 0; r < B; r++) {
+            if (r != C) {
+                const double f = w[r][C];
+                if (f != 0.0) {
+#pragma unroll
+                    for (int j = 0; j < 2 * B; j++) w[r][j] -= f * w[C][j];
+                }
+            }
+        }
+        d_inverse_col<B, C + 1>(w);
+    }
+}
+template <int B>
+__device__ __forceinline__ void d_inverse_reg(double (&w)[B][2 * B]) { d_inverse_col<B, 0>(w); }
+
+template <int B>
+__global__ void __launch_bounds__(128) k_diag_reg(int n, const int* __restrict__ Dptr, const int* __restrict__ Dpos,
+                                                  const double* __restrict__ val, double* __restrict__ D, double* __restrict__ Dinv) {
+    constexpr int BB = B * B;
+    __shared__ double sh[4][32 * BB];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int r0 = (blockIdx.x * 4 + wib) * 32;
+    if (r0 >= n) return;  // whole warp
+    const int nr = min(32, n - r0);
+    double* sw = sh[wib];
+    // diagonal entries of "my" row; the common case is exactly one (its position is fetched ahead of the loop)
+    const int k0 = lane < nr ? Dptr[r0 + lane] : 0, k1 = lane < nr ? Dptr[r0 + lane + 1] : 0;
+    const int pos0 = k1 > k0 ? Dpos[k0] : -1;
+#pragma unroll 8
+    for (int i = 0; i < nr; i++) {
+        const int a0 = __shfl_sync(0xffffffffu, k0, i), a1 = __shfl_sync(0xffffffffu, k1, i), ps = __shfl_sync(0xffffffffu, pos0, i);
+        if (lane < BB) {
+            double a = ps >= 0 ? val[(size_t)ps * BB + lane] : 0.0;
+            for (int k = a0 + 1; k < a1; k++) a += val[(size_t)Dpos[k] * BB + lane];  // addD: several entries on the diagonal
+            sw[i * BB + lane] = a;
+        }
+    }
+    __syncwarp();
+    for (int t = lane; t < nr * BB; t += 32) D[(size_t)r0 * BB + t] = sw[t];
+    double w[B][2 * B];
+    if (lane < nr) {
+#pragma unroll
+        for (int i = 0; i < B; i++)
+#pragma unroll
+            for (int j = 0; j < B; j++) { w[i][j] = sw[lane * BB + i * B + j]; w[i][B + j] = (i == j) ? 1.0 : 0.0; }
+        if (B == 1) w[0][1] = 1.0 / w[0][0];
+        else d_inverse_reg<B>(w);
+    }
+    __syncwarp();
+    if (lane < nr) {
+#pragma unroll
+        for (int i = 0; i < B; i++)
+#pragma unroll
+            for (int j = 0; j < B; j++) sw[lane * BB + i * B + j] = w[i][B + j];
+    }
+    __syncwarp();
+    for (int t = lane; t < nr * BB; t += 32) Dinv[(size_t)r0 * BB + t] = sw[t];
 }
 
 // LD / UD of one block row per lane group, rows in the caller's order: val streams front to back and the D^-1 blocks
@@ -473,8 +561,9 @@ int solve_core(mstgpu_lusgs* h, const double* val, const double* b, double* x, i
             if (h->nL) k_scale<B><<<(unsigned)(((size_t)h->nL * B + T - 1) / T), T, 0, s>>>((size_t)h->nL, h->Lcol, h->Lpos, val, h->D, h->Dinv, h->LD);
             if (h->nU) k_scale<B><<<(unsigned)(((size_t)h->nU * B + T - 1) / T), T, 0, s>>>((size_t)h->nU, h->Ucol, h->Upos, val, h->D, h->Dinv, h->UD);
             h->launches += 3;
-        } else {  // lane group per block row, rows in the caller's order
-            k_diag_grp<B><<<G::grid(n, T), T, 0, s>>>(n, h->rinv, h->Dptr, h->Dpos, val, h->D, h->Dinv);
+        } else {  // LD / UD: lane group per block row, rows in the caller's order; D, D^-1: registers (2) or lane groups (1)
+            if (h->setup_mode == 2) k_diag_reg<B><<<(n + 127) / 128, 128, 0, s>>>(n, h->Dptr, h->Dpos, val, h->D, h->Dinv);
+            else k_diag_grp<B><<<G::grid(n, T), T, 0, s>>>(n, h->rinv, h->Dptr, h->Dpos, val, h->D, h->Dinv);
             k_scale_rows<B><<<G::grid(n, T), T, 0, s>>>(n, h->rinv, h->Lptr, h->Lcol, h->Lpos, h->Uptr, h->Ucol, h->Upos, val, h->D, h->Dinv, h->LD, h->UD);
             h->launches += 2;
         }
@@ -782,7 +871,7 @@ int mstgpu_lusgs_create_partitioned(mstgpu_lusgs** out, int32_t n, int32_t ncols
     }();
     if (rc) { mstgpu_lusgs_destroy(h); return rc; }
     if (const char* v = getenv("MSTGPU_LUSGS_MODE")) { const int m = atoi(v); h->mode = (m >= 0 && m <= 2) ? m : 0; }
-    if (const char* v = getenv("MSTGPU_LUSGS_SETUP")) h->setup_mode = atoi(v) != 0;
+    if (const char* v = getenv("MSTGPU_LUSGS_SETUP")) { const int m = atoi(v); h->setup_mode = (m >= 0 && m <= 2) ? m : 2; }
     *out = h;
     return MSTGPU_OK;
 }

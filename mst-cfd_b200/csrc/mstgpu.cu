@@ -172,6 +172,20 @@ struct mstgpu_ctx {
     int32_t *out_nf_ptr = nullptr, *out_nf_idx = nullptr, *out_c0 = nullptr, *out_c1 = nullptr;
     double *out_eta = nullptr, *out_w = nullptr, *out_fields = nullptr;
     int out_nn = 0;
+    // streamed step (mstgpu_step_host): host rows in, host rows out, pipelined over chunks of host rows
+    std::vector<int32_t> tile_ready_row;          // per tile (desc[] order): largest host row among its owned + owned-range ring cells
+    std::vector<int32_t> tile_cb_h, tile_nown_h;  // host copy of the descriptors' owned ranges
+    struct HostStream {
+        int nchunks = 0;
+        int64_t chunk_rows = 0;
+        int32_t *d_order = nullptr, *d_old2new = nullptr;
+        std::vector<std::vector<int>> off;         // [class][group 0 .. nchunks + 1]: first entry of the group in d_order
+        std::vector<std::vector<int>> out_chunks;  // [group 0 .. nchunks]: host chunks complete once that group has run
+        cudaStream_t s_in = nullptr, s_out = nullptr;
+        std::vector<cudaEvent_t> ev_in, ev_out;
+        cudaEvent_t ev_start = nullptr;
+    } hs;
+    int sub_group = -1;  // >= 0 while mstgpu_step_host launches the tiles of one group
     int cur = 0;          // Q[cur] = current ("old") state
     bool has_state = false, stepped = false;
     int64_t launches = 0, dev_bytes = 0;
@@ -1030,9 +1044,21 @@ int launch_tiles_var(mstgpu_ctx* ctx, double dt, const double* dtd, const double
         configured_smem = ctx->tile_smem;
     }
     // which: 0 = tiles without ghost cells, 1 = tiles whose rings hold ghost cells, 2 = all
-    int ci = 0;
+    int ci = 0, cidx = -1;
     for (const auto& tc : ctx->tile_classes) {
+        cidx++;
         if (which != 2 && (int)tc.halo != which) continue;
+        if (ctx->sub_group >= 0) {
+            // streamed step: the tiles of this class whose input is complete with host chunk sub_group
+            const std::vector<int>& off = ctx->hs.off[cidx];
+            const int first = off[ctx->sub_group], cnt = off[ctx->sub_group + 1] - first;
+            if (cnt <= 0) continue;
+            TileArrays ta = ctx->ta;
+            ta.order = ctx->hs.d_order;
+            kern<<<cnt, NT, tc.smem, st>>>(ta, first, cnt, 0, want_resid, ctx->dcfg, dt, dtd, Qo, Qn, ctx->resid, ctx->nanflag);
+            ctx->launches++;
+            continue;
+        }
         cudaStream_t s = (ctx->fork_stream && (ci++ & 1)) ? ctx->fork_stream : st;
         int grid = tc.count, wave = 0;
         if (VAR & 3) {  // experimental variants: CTAs resident at once for this class's shared-memory size
@@ -1351,6 +1377,168 @@ int fetch_permuted(mstgpu_ctx* ctx, const double* dsrc, const int32_t* new2old, 
     return MSTGPU_OK;
 }
 
+// ---- streamed step (mstgpu_step_host) ------------------------------------------------------------
+// rows [r0, r0 + n) of the staging buffer (reference order) -> their device-order rows of Q, and back
+__global__ void k_rows_in(int64_t r0, int64_t n, int U, const double* __restrict__ stage,
+                          const int32_t* __restrict__ old2new, double* __restrict__ Q) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * U) return;
+    const int64_t r = r0 + i / U;
+    const int k = (int)(i % U);
+    Q[(size_t)old2new[r] * U + k] = stage[(size_t)r * U + k];
+}
+__global__ void k_rows_out(int64_t r0, int64_t n, int U, const double* __restrict__ Q,
+                           const int32_t* __restrict__ old2new, double* __restrict__ stage) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * U) return;
+    const int64_t r = r0 + i / U;
+    const int k = (int)(i % U);
+    stage[(size_t)r * U + k] = Q[(size_t)old2new[r] * U + k];
+}
+
+void host_stream_free(mstgpu_ctx* ctx) {
+    auto& h = ctx->hs;
+    for (auto e : h.ev_in) cudaEventDestroy(e);
+    for (auto e : h.ev_out) cudaEventDestroy(e);
+    if (h.ev_start) cudaEventDestroy(h.ev_start);
+    if (h.s_in) cudaStreamDestroy(h.s_in);
+    if (h.s_out) cudaStreamDestroy(h.s_out);
+    if (h.d_order) { cudaFree(h.d_order); ctx->dev_bytes -= (int64_t)ctx->ntiles * 4; }
+    if (h.d_old2new) { cudaFree(h.d_old2new); ctx->dev_bytes -= (int64_t)ctx->n_owned * 4; }
+    h = mstgpu_ctx::HostStream{};
+}
+
+// Schedule of the streamed step for `nchunks` chunks of host rows:
+//   group(tile)  = the chunk whose arrival completes the tile's input (tiles with ghost cells in a ring: after
+//                  the halo exchange, group nchunks); the launch list of every tile class is sorted by group
+//   done(chunk)  = the last group that writes one of the chunk's rows: the chunk can leave after it
+// Whatever the host numbering is, the schedule is valid; how much of the copies it hides depends on how well
+// the host order follows the mesh (a mesher's cell order usually does; a random one degenerates to copy in,
+// step, copy out).
+int host_stream_setup(mstgpu_ctx* ctx, int nchunks) {
+    auto& h = ctx->hs;
+    const int64_t n = ctx->n_owned;
+    nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(nchunks, std::max<int64_t>(1, n / 1024)));
+    if (h.nchunks == nchunks && h.d_order) return MSTGPU_OK;
+    CK(cudaStreamSynchronize(ctx->stream));
+    host_stream_free(ctx);
+    const int64_t rows = (n + nchunks - 1) / nchunks;
+    nchunks = (int)((n + rows - 1) / rows);
+    const int nt = ctx->ntiles, G = nchunks;
+    std::vector<int> grp(nt);
+    std::vector<int32_t> order(nt);
+    h.off.assign(ctx->tile_classes.size(), std::vector<int>(G + 2, 0));
+    for (size_t ci = 0; ci < ctx->tile_classes.size(); ci++) {
+        const auto& tc = ctx->tile_classes[ci];
+        std::vector<int> cnt(G + 2, 0);
+        for (int t = tc.first; t < tc.first + tc.count; t++) {
+            grp[t] = tc.halo ? G : (int)(ctx->tile_ready_row[t] / rows);
+            cnt[grp[t] + 1]++;
+        }
+        auto& off = h.off[ci];
+        off[0] = tc.first;
+        for (int g = 0; g <= G; g++) off[g + 1] = off[g] + cnt[g + 1];
+        std::vector<int> pos(off.begin(), off.end() - 1);
+        for (int t = tc.first; t < tc.first + tc.count; t++) order[pos[grp[t]]++] = t;
+    }
+    // the group after which every row of a host chunk has been written
+    std::vector<int> done(G, 0);
+    const std::vector<int32_t>& n2o = ctx->plan.cell_new2old;
+#pragma omp parallel
+    {
+        std::vector<int> mine(G, 0);
+#pragma omp for schedule(static) nowait
+        for (int t = 0; t < nt; t++)
+            for (int c = ctx->tile_cb_h[t]; c < ctx->tile_cb_h[t] + ctx->tile_nown_h[t]; c++) {
+                const int j = (int)(n2o[c] / rows);
+                mine[j] = std::max(mine[j], grp[t]);
+            }
+#pragma omp critical
+        for (int j = 0; j < G; j++) done[j] = std::max(done[j], mine[j]);
+    }
+    h.out_chunks.assign(G + 1, {});
+    for (int j = 0; j < G; j++) h.out_chunks[done[j]].push_back(j);
+    int r;
+    if ((r = upload(ctx, &h.d_order, order))) return r;
+    std::vector<int32_t> o2n(ctx->plan.cell_old2new.begin(), ctx->plan.cell_old2new.begin() + n);
+    if ((r = upload(ctx, &h.d_old2new, o2n))) return r;
+    CK(cudaStreamSynchronize(ctx->stream));  // the uploads read the vectors above
+    CK(cudaStreamCreateWithFlags(&h.s_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h.s_out, cudaStreamNonBlocking));
+    h.ev_in.resize(G); h.ev_out.resize(G + 1);
+    for (auto& e : h.ev_in) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : h.ev_out) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h.ev_start, cudaEventDisableTiming));
+    h.nchunks = G;
+    h.chunk_rows = rows;
+    return MSTGPU_OK;
+}
+
+template <int D>
+int step_host_impl(mstgpu_ctx* ctx, const double* qin, double* qout, double dt) {
+    auto& h = ctx->hs;
+    const int U = ctx->U, G = h.nchunks;
+    const int64_t n = ctx->n_owned, rows = h.chunk_rows;
+    double* Qc = ctx->Q[ctx->cur];
+    double* Qn = ctx->Q[ctx->cur ^ 1];
+    const bool halo = ctx->partitioned && !ctx->halo.empty();
+    int r = launch_tiles_any<D>(ctx, dt, nullptr, Qc, Qn, 0, 3, ctx->stream);  // which = 3: shared-memory opt-in only
+    if (r) return r;
+    CK(cudaMemsetAsync(ctx->resid, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(ctx->nanflag, 0, sizeof(int), ctx->stream));
+    CK(cudaEventRecord(h.ev_start, ctx->stream));  // the staging buffer is free once earlier work has drained
+    CK(cudaStreamWaitEvent(h.s_in, h.ev_start, 0));
+    auto span = [&](int j, int64_t& r0, int64_t& cnt) { r0 = (int64_t)j * rows; cnt = std::min(rows, n - r0); };
+    // rows that are final after group g: device order -> staging buffer (the chunk's input was consumed long
+    // ago) on the compute stream, then device -> host on the output stream
+    auto emit = [&](int g) -> int {
+        const std::vector<int>& ch = h.out_chunks[g];
+        if (ch.empty()) return MSTGPU_OK;
+        for (int j : ch) {
+            int64_t r0, cnt; span(j, r0, cnt);
+            k_rows_out<<<(unsigned)((cnt * U + 255) / 256), 256, 0, ctx->stream>>>(r0, cnt, U, Qn, h.d_old2new, ctx->stage);
+            ctx->launches++;
+        }
+        CK(cudaEventRecord(h.ev_out[g], ctx->stream));
+        CK(cudaStreamWaitEvent(h.s_out, h.ev_out[g], 0));
+        for (int j : ch) {
+            int64_t r0, cnt; span(j, r0, cnt);
+            CK(cudaMemcpyAsync(qout + r0 * U, ctx->stage + r0 * U, (size_t)cnt * U * sizeof(double), cudaMemcpyDeviceToHost, h.s_out));
+        }
+        return MSTGPU_OK;
+    };
+    for (int g = 0; g < G; g++) {
+        int64_t r0, cnt; span(g, r0, cnt);
+        CK(cudaMemcpyAsync(ctx->stage + r0 * U, qin + r0 * U, (size_t)cnt * U * sizeof(double), cudaMemcpyHostToDevice, h.s_in));
+        CK(cudaEventRecord(h.ev_in[g], h.s_in));
+        CK(cudaStreamWaitEvent(ctx->stream, h.ev_in[g], 0));
+        k_rows_in<<<(unsigned)((cnt * U + 255) / 256), 256, 0, ctx->stream>>>(r0, cnt, U, ctx->stage, h.d_old2new, Qc);
+        ctx->launches++;
+        ctx->sub_group = g;
+        r = launch_tiles_any<D>(ctx, dt, nullptr, Qc, Qn, 1, 0, ctx->stream);
+        ctx->sub_group = -1;
+        if (r) return r;
+        if ((r = emit(g))) return r;
+    }
+    if (halo) {
+        // every owned row is in place: ghost rows <- owners, then the tiles whose rings hold ghost cells
+        if ((r = halo_exchange(ctx, Qc, ctx->stream))) return r;
+        ctx->sub_group = G;
+        r = launch_tiles_any<D>(ctx, dt, nullptr, Qc, Qn, 1, 1, ctx->stream);
+        ctx->sub_group = -1;
+        if (r) return r;
+    }
+    if ((r = emit(G))) return r;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(h.s_out));
+    ctx->cur ^= 1;
+    ctx->has_state = true;
+    ctx->stepped = true;
+    ctx->probes_valid = false;
+    return MSTGPU_OK;
+}
+
 }  // namespace
 
 template <int D>
@@ -1653,6 +1841,24 @@ static int create_impl(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_c
                 }
                 tp.ring.swap(ring);
                 ctx->ring_stride = stride;
+                // for the streamed step: the host row that completes a tile's input (largest reference-order row among
+                // its owned cells and the ring cells this context owns; ghost rows arrive with the halo exchange)
+                ctx->tile_ready_row.assign(tp.ntiles, 0);
+                ctx->tile_cb_h.resize(tp.ntiles);
+                ctx->tile_nown_h.resize(tp.ntiles);
+#pragma omp parallel for schedule(static)
+                for (int t = 0; t < tp.ntiles; t++) {
+                    const TileDesc& d = tp.desc[t];
+                    int32_t mx = 0;
+                    for (int c = d.cb; c < d.cb + d.n_own; c++) mx = std::max(mx, p.cell_new2old[c]);
+                    for (int i = 0; i < d.n_r1 + d.n_r2; i++) {
+                        const int32_t g = tp.ring[d.ring_off + i];
+                        if (g < ctx->n_owned) mx = std::max(mx, p.cell_new2old[g]);
+                    }
+                    ctx->tile_ready_row[t] = mx;
+                    ctx->tile_cb_h[t] = d.cb;
+                    ctx->tile_nown_h[t] = d.n_own;
+                }
                 if (getenv("MSTGPU_VERBOSE"))
                     for (const auto& tc : ctx->tile_classes)
                         fprintf(stderr, "[mstgpu] tile class: %d tiles, %zu B smem, %s\n", tc.count, tc.smem, tc.halo ? "halo" : "interior");
@@ -1664,7 +1870,7 @@ static int create_impl(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_c
             ctx->tile_allocs.push_back(dring);
             if ((r = upload(ctx, &dpk, tp.packets))) return r;
             ctx->tile_allocs.push_back(dpk);
-            ctx->ta = TileArrays{ddesc, dring, dpk, ctx->ring_stride};
+            ctx->ta = TileArrays{ddesc, dring, dpk, ctx->ring_stride, nullptr};
             CK(cudaStreamSynchronize(ctx->stream));  // tp goes out of scope
         }
         // staging buffer of the state permutation; the stage probes (gradient, face flux) grow it on first use
@@ -1744,6 +1950,7 @@ void mstgpu_destroy(mstgpu_ctx* ctx) {
     if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    host_stream_free(ctx);
     for (auto ge : ctx->step_graph) if (ge) cudaGraphExecDestroy(ge);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1790,6 +1997,36 @@ int mstgpu_step(mstgpu_ctx* ctx, double dt, int32_t nsteps) {
     int rc = (ctx->D == 2) ? step_impl<2>(ctx, dt, nsteps) : step_impl<3>(ctx, dt, nsteps);
     if (ctx->ktiming) drain_timers(ctx);
     return rc;
+}
+
+int mstgpu_step_host(mstgpu_ctx* ctx, const double* q_in, double* q_out, double dt, int32_t nchunks) {
+    if (!ctx || !q_in || !q_out) return MSTGPU_ERR_ARG;
+    if (!ctx->use_tiles) { set_error(ctx, "step_host needs the fused kernel (kernel = 1)"); return MSTGPU_ERR_STATE; }
+    if (ctx->tile_var & 3) { set_error(ctx, "step_host: not with the persistent / prefetch-ahead launch variants"); return MSTGPU_ERR_STATE; }
+    if (ctx->partitioned && !ctx->halo.empty() && !ctx->comm) { set_error(ctx, "partitioned context without a communicator: call mstgpu_comm_init"); return MSTGPU_ERR_STATE; }
+    CK(cudaSetDevice(ctx->device));
+    if (nchunks <= 0) {
+        nchunks = 64;
+        if (const char* v = getenv("MSTGPU_HOST_CHUNKS")) nchunks = std::max(1, atoi(v));
+    }
+    int r = ensure_stage(ctx, (size_t)ctx->n_owned * ctx->U);
+    if (r) return r;
+    if ((r = host_stream_setup(ctx, nchunks))) return r;
+    return (ctx->D == 2) ? step_host_impl<2>(ctx, q_in, q_out, dt) : step_host_impl<3>(ctx, q_in, q_out, dt);
+}
+
+int mstgpu_host_register(void* p, size_t bytes) {
+    if (!p || !bytes) return MSTGPU_ERR_ARG;
+    const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); g_create_error = std::string("cudaHostRegister: ") + cudaGetErrorString(e); return MSTGPU_ERR_CUDA; }
+    return MSTGPU_OK;
+}
+
+int mstgpu_host_unregister(void* p) {
+    if (!p) return MSTGPU_OK;
+    const cudaError_t e = cudaHostUnregister(p);
+    if (e != cudaSuccess) { cudaGetLastError(); return MSTGPU_ERR_CUDA; }
+    return MSTGPU_OK;
 }
 
 int mstgpu_step_timed(mstgpu_ctx* ctx, double dt, int32_t nsteps, float* ms) {

@@ -42,6 +42,10 @@ struct TileArrays {
     const int32_t* ring;           // ring-cell ids, ring_stride entries per tile in desc[] order (tile t: ring + t * ring_stride)
     const unsigned char* packets;
     int32_t ring_stride;
+    // streamed step (mstgpu_step_host): the launch covers entries [tile_base, tile_base + grid) of this list of
+    // tile indices instead of the tiles themselves (tiles sorted by the host chunk that completes their input);
+    // nullptr = the tiles in desc[] order
+    const int32_t* order;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -559,7 +563,8 @@ __global__ void __launch_bounds__(NT, (VAR & 64) ? 5 : (VAR & 8) ? 4 : (VAR & 16
         }
     } else {
         const int tn = (int)blockIdx.x + var_arg;
-        step_tile<D, ORDER, NT, NS, LIM, VISC, VAR>(ta, tile_base + (int)blockIdx.x, ((VAR & 1) && tn < n_class) ? tile_base + tn : -1,
+        const int tile = ta.order ? ta.order[tile_base + (int)blockIdx.x] : tile_base + (int)blockIdx.x;
+        step_tile<D, ORDER, NT, NS, LIM, VISC, VAR>(ta, tile, ((VAR & 1) && tn < n_class) ? tile_base + tn : -1,
                                                     true, !(VAR & 1) || (int)blockIdx.x < var_arg, 0u, want_resid, cfg, dt_val, dt_dev, Qold,
                                                     Qnew, resid, nanflag);
     }

@@ -76,6 +76,11 @@ struct Options {
     int gradient = MSTGPU_GRAD_GREEN_GAUSS;  // or MSTGPU_GRAD_LSQ
     int limiter = MSTGPU_LIMITER_NONE;       // or _BARTH_JESPERSEN / _VENKATAKRISHNAN
     double limiter_k = 5.0;
+    // host_mirror: the fields live in AllData like in the reference -- solve() reads AllData's old array and writes
+    // its new array (one mstgpu_step_host call: H2D, step and D2H pipelined over chunks of rows), the getters
+    // return AllData's arrays without a copy.  For hosts that touch the cell state between steps; the default
+    // keeps the state on the device and downloads lazily.
+    bool host_mirror = false;
     bool implicit = false;                   // solve() = residual + block assembly + LU-SGS sweeps of R/lusolver
     int lusgs_iterations = 5;                // LU_INTERVAL (CONST.h:58)
 };
@@ -133,7 +138,11 @@ struct SharedContext {
     bool state_on_device = false;  // device holds the current state
     bool new_on_host = false, old_on_host = false;
     bool output_ready = false;     // mstgpu_output_setup done (nodeFields)
-    ~SharedContext() { if (ctx) mstgpu_destroy(ctx); }
+    std::vector<void*> pinned;     // AllData arrays page-locked for the streamed step (host_mirror)
+    ~SharedContext() {
+        for (void* q : pinned) mstgpu_host_unregister(q);
+        if (ctx) mstgpu_destroy(ctx);
+    }
 };
 
 inline std::map<std::pair<const void*, const void*>, SharedContext>& registry() {
@@ -171,6 +180,21 @@ public:
     // RhoSolver::solve (RhoSolver.cpp:37-89).  The first call (or any call after the
     // host wrote AllData's old array, e.g. a restart) uploads the state.
     void solve() {
+        if (options().host_mirror && !options().implicit) {
+            // the reference's data flow: old array in, new array out, both on the host (RhoSolver.cpp:37-68)
+            double* qo = reinterpret_cast<double*>(pAllData->getP1OldCellQs());
+            double* qn = reinterpret_cast<double*>(pAllData->getP1NewCellQs());
+            if (sc->pinned.empty()) {
+                // page-locked buffers let the copies run beside the step; a failure only costs the overlap
+                const size_t bytes = sizeof(double) * (size_t)sc->ncells * sc->U;
+                for (double* q : {qo, qn})
+                    if (mstgpu_host_register(q, bytes) == MSTGPU_OK) sc->pinned.push_back(q);
+                if (sc->pinned.empty()) sc->pinned.push_back(nullptr);  // do not try again
+            }
+            check(mstgpu_step_host(sc->ctx, qo, qn, DT, 0), sc->ctx, "mstgpu_step_host");
+            sc->state_on_device = sc->new_on_host = sc->old_on_host = true;
+            return;
+        }
         if (!sc->state_on_device) upload_old();
         if (options().implicit)
             check(mstgpu_step_implicit(sc->ctx, DT, 1, options().lusgs_iterations, nullptr), sc->ctx, "mstgpu_step_implicit");

@@ -22,7 +22,7 @@ LIB_PATH = os.environ.get("MSTGPU_LIB", os.path.join(_ROOT, "libmstgpu.so"))  # 
 
 EXPORTS = [
     "mstgpu_default_config", "mstgpu_create", "mstgpu_destroy", "mstgpu_set_state",
-    "mstgpu_get_state", "mstgpu_get_prev_state", "mstgpu_step", "mstgpu_step_timed",
+    "mstgpu_get_state", "mstgpu_get_prev_state", "mstgpu_step", "mstgpu_step_timed", "mstgpu_step_host", "mstgpu_host_register", "mstgpu_host_unregister",
     "mstgpu_residual_linf", "mstgpu_sync", "mstgpu_cfl_dt", "mstgpu_step_cfl", "mstgpu_step_cfl_timed", "mstgpu_implicit_setup",
     "mstgpu_implicit_sweep_order", "mstgpu_step_implicit", "mstgpu_debug_gradient", "mstgpu_debug_face_flux",
     "mstgpu_launch_count", "mstgpu_enable_kernel_timing", "mstgpu_kernel_time",
@@ -93,6 +93,9 @@ def lib():
         L.mstgpu_get_prev_state.argtypes = [vp, vp]
         L.mstgpu_step.argtypes = [vp, dbl, i32]
         L.mstgpu_step_timed.argtypes = [vp, dbl, i32, C.POINTER(C.c_float)]
+        L.mstgpu_step_host.argtypes = [vp, vp, vp, dbl, i32]
+        L.mstgpu_host_register.argtypes = [vp, C.c_size_t]
+        L.mstgpu_host_unregister.argtypes = [vp]
         L.mstgpu_cfl_dt.argtypes = [vp, dbl, C.POINTER(dbl)]
         L.mstgpu_step_cfl.argtypes = [vp, dbl, i32, C.POINTER(dbl)]
         L.mstgpu_step_cfl_timed.argtypes = [vp, dbl, i32, C.POINTER(dbl), C.POINTER(C.c_float)]
@@ -469,6 +472,13 @@ class Context:
         ms = C.c_float()
         self._check(lib().mstgpu_step_timed(self.h, dt, nsteps, C.byref(ms)), "step_timed")
         return float(ms.value)
+
+    def step_host(self, q_in, q_out, dt: float, nchunks: int = 0):
+        """One step with HOST arrays on both sides (set_state + step + get_state, pipelined over chunks of host
+        rows; include/mstgpu.h).  q_in / q_out: numpy arrays [ncells][U] or raw pointers (page-locked for overlap)."""
+        pi = q_in if isinstance(q_in, int) else q_in.ctypes.data
+        po = q_out if isinstance(q_out, int) else q_out.ctypes.data
+        self._check(lib().mstgpu_step_host(self.h, pi, po, dt, nchunks), "step_host")
 
     def cfl_dt(self, cfl: float) -> float:
         """Global CFL time step of the current state (extension; collective with a communicator)."""

@@ -64,6 +64,9 @@ int main(int argc, char** argv) {
     }
     GpuRhoSolver::options().order = ACCURACY;
     GpuRhoSolver::options().flux = MST_FLUX;
+    // MST_HOST_MIRROR=1: the fields stay in AllData like in the reference, solve() = one streamed step
+    // (mstgpu_step_host: old array in, new array out)
+    if (const char* hm = getenv("MST_HOST_MIRROR")) GpuRhoSolver::options().host_mirror = atoi(hm) != 0;
     dump("Q0", "f8", allData.getP1OldCellQs(), (long long)nc * (DIMU), 8);
     std::vector<double> resid;
     int done = 0;

@@ -25,7 +25,7 @@ def _ngpu():
 EXT = dict(limiter="bj", gradient="lsq")  # extension scheme for the CFL variant
 
 
-def _worker(rank, world, port, case, kernel, q, cfl=0.0, halo="nccl", nsteps=5):
+def _worker(rank, world, port, case, kernel, q, cfl=0.0, halo="nccl", nsteps=5, host_chunks=0):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -46,7 +46,14 @@ def _worker(rank, world, port, case, kernel, q, cfl=0.0, halo="nccl", nsteps=5):
         # boundary rows stored straight into the neighbour's ghost block (CUDA IPC + NVLink), epoch flags
         assert ctx.peer_connect_torch(dist, world, rank), "peer memory not available between the two GPUs"
     ctx.set_state(Q0[P.cell_ids[:P.n_owned]])
-    if cfl > 0:
+    if host_chunks:
+        # streamed steps: the rank's rows live on the host, every step is host rows in -> host rows out
+        a, b = np.ascontiguousarray(Q0[P.cell_ids[:P.n_owned]]), np.empty((P.n_owned, f["dim"] + 2))
+        for _ in range(nsteps):
+            ctx.step_host(a, b, 1e-4, host_chunks)
+            a, b = b, a
+        assert np.array_equal(ctx.get_state(), a, equal_nan=True)
+    elif cfl > 0:
         t = ctx.step_cfl(cfl, nsteps)  # global time step: min over ranks on the device (ncclAllReduce(min))
         assert t > 0
     else:
@@ -238,5 +245,32 @@ def test_two_gpus_peer_memory_halo_matches_one(kernel, nsteps):
     one = mstgpu.Context(f, order=2, flux="roe", inletQ=inlet, kernel=kernel)
     one.set_state(Q0)
     one.step(1e-4, nsteps)
+    assert np.array_equal(got, one.get_state(), equal_nan=True)
+    assert np.array_equal(res, one.residual(), equal_nan=True)
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("halo", ["nccl", "peer"])
+def test_two_gpus_streamed_step_matches_one(halo):
+    """mstgpu_step_host on a partitioned context (collective): the tiles away from the cut stream with the host
+    chunks, the tiles next to ghost cells run after the halo exchange that follows the last chunk.  Same bits
+    as the single-GPU run with the state resident on the device."""
+    import torch.multiprocessing as mp
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    port = 29800 + (os.getpid() % 2000)
+    procs = [mpc.Process(target=_worker, args=(r, 2, port, "box", "tiles", q, 0.0, halo, 3, 6)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got, res = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    f = box_flat(12, 10, 8, bc=(10, 5, 3, 7, 3, 3))
+    inlet = np.array([1.0, 0.4, 0.0, 0.0, 2.58])
+    Q0 = mesh_np.random_state(f, seed=4)
+    one = mstgpu.Context(f, order=2, flux="roe", inletQ=inlet, kernel="tiles")
+    one.set_state(Q0)
+    one.step(1e-4, 3)
     assert np.array_equal(got, one.get_state(), equal_nan=True)
     assert np.array_equal(res, one.residual(), equal_nan=True)

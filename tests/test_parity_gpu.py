@@ -435,3 +435,73 @@ def test_config3_sphere_shell_roe_viscous(viscous, kernel):
         oi = oracle.Oracle(f, **dict(kw, viscous=0))
         assert rel_linf(o.solve(dt, Q0), oi.solve(dt, Q0)) > 1e-6
     ctx.close()
+
+
+# ---- streamed step: host rows in, host rows out (mstgpu_step_host) ----------------------------------
+def _three_calls(f, Q0, dt, **kw):
+    g = mstgpu.Context(f, **kw)
+    g.set_state(Q0)
+    g.step(dt, 1)
+    Q1 = g.get_state()
+    r = g.residual()
+    g.close()
+    return Q1, r
+
+
+@pytest.mark.parametrize("case", ["sod-roe2", "stair-ausm1", "box-roe2", "box-roe1"])
+@pytest.mark.parametrize("nchunks", [1, 5, 24])
+def test_step_host_equals_set_step_get(case, nchunks):
+    """mstgpu_step_host = mstgpu_set_state + mstgpu_step(dt, 1) + mstgpu_get_state, pipelined over chunks of host rows:
+    same bits whatever the chunk count, same residual, the context left with out = current and in = previous."""
+    if case == "sod-roe2":
+        f = load_flat("2d-shockwavepipe-2"); Q0 = mesh_np.sod_initial_state(f); kw = dict(order=2, flux="roe"); dt = DT_SOD
+    elif case == "stair-ausm1":
+        f = load_flat("2d-stair-un-3-tri"); Q0 = mesh_np.random_state(f, seed=3); kw = dict(order=1, flux="ausm"); dt = 1e-4
+    else:
+        f = box_flat(14, 11, 9); Q0 = mesh_np.random_state(f, seed=5); kw = dict(order=2 if case == "box-roe2" else 1, flux="roe"); dt = 1e-4
+    Qref, rref = _three_calls(f, Q0, dt, **kw)
+    g = mstgpu.Context(f, **kw)
+    out = np.full_like(Q0, -7.0)
+    g.step_host(Q0, out, dt, nchunks)
+    assert np.array_equal(out, Qref, equal_nan=True)
+    if np.isfinite(Qref).all():
+        assert np.array_equal(g.residual(), rref)
+    assert np.array_equal(g.get_state(), Qref, equal_nan=True)
+    assert np.array_equal(g.get_prev_state(), Q0)
+    # a second streamed step from the first one's output, in place (q_in == q_out), then plain steps on top
+    Qref2, _ = _three_calls(f, Qref, dt, **kw)
+    g.step_host(out, out, dt, nchunks)
+    assert np.array_equal(out, Qref2, equal_nan=True)
+    g.step(dt, 1)
+    Qref3, _ = _three_calls(f, Qref2, dt, **kw)
+    assert np.array_equal(g.get_state(), Qref3, equal_nan=True)
+    g.close()
+
+
+def test_step_host_with_a_shuffled_host_numbering():
+    """The schedule is derived from the numbering and must be valid for ANY numbering: cells renumbered at random
+    on the host side (every tile waits for the last chunk, every chunk leaves after the last group)."""
+    f = box_flat(10, 9, 8)
+    rng = np.random.default_rng(11)
+    perm = rng.permutation(f["ncells"])          # new host id -> old host id
+    inv = np.empty_like(perm); inv[perm] = np.arange(perm.size)
+    fp = dict(f)
+    for k in ("cc", "vol"):
+        fp[k] = np.ascontiguousarray(f[k][perm])
+    fp["c0"] = inv[f["c0"]].astype(np.int32)
+    fp["c1"] = np.where(f["c1"] >= 0, inv[np.maximum(f["c1"], 0)], -1).astype(np.int32)
+    # per-cell face lists follow their cells
+    ptr, idx = f["cf_ptr"], f["cf_idx"]
+    cnt = np.diff(ptr)[perm]
+    nptr = np.zeros(perm.size + 1, dtype=ptr.dtype); nptr[1:] = np.cumsum(cnt)
+    nidx = np.concatenate([idx[ptr[c]:ptr[c + 1]] for c in perm]).astype(idx.dtype)
+    fp["cf_ptr"], fp["cf_idx"] = nptr, nidx
+    if "Sout" in f:
+        fp["Sout"] = np.concatenate([f["Sout"][ptr[c]:ptr[c + 1]] for c in perm])
+    Q0 = mesh_np.random_state(f, seed=2)
+    Qref, _ = _three_calls(f, Q0, 1e-4, order=2, flux="roe")
+    g = mstgpu.Context(fp, order=2, flux="roe")
+    out = np.empty_like(Q0)
+    g.step_host(np.ascontiguousarray(Q0[perm]), out, 1e-4, 7)
+    g.close()
+    assert rel_linf(out[inv], Qref) <= TOL_1STEP

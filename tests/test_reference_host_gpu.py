@@ -21,8 +21,11 @@ CASES = ["sod_roe2_consistent", "sod_roe1_consistent", "stair5_roe1_random", "st
          "stair5_roe2_random_5to7", "stairW1_ausm1_random"]
 
 
+@pytest.mark.parametrize("host_mirror", [0, 1])
 @pytest.mark.parametrize("case", CASES)
-def test_reference_time_loop_on_the_gpu(case, tmp_path):
+def test_reference_time_loop_on_the_gpu(case, host_mirror, tmp_path):
+    """host_mirror = 1: GpuRhoSolver::options().host_mirror -- the fields stay in AllData and solve() is one streamed
+    step (mstgpu_step_host), the data flow of the reference's own RhoSolver::solve."""
     g = np.load(os.path.join(GOLDEN, f"ref_{case}.npz"))
     variant = str(g["variant"])
     exe = os.path.join(REF, f"ref_gpu_{variant}")
@@ -39,7 +42,7 @@ def test_reference_time_loop_on_the_gpu(case, tmp_path):
     out = str(tmp_path / "out.bin")
     steps = [int(s) for s in g["steps"] if int(s) <= 400]
     cmd = [exe, msh, out, str(int(g["flagmode"])), str(g["retag"]), init] + [str(s) for s in steps]
-    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, timeout=600)
+    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, timeout=600, env=dict(os.environ, MST_HOST_MIRROR=str(host_mirror)))
     d = refdump.read_dump(out)
     nc = int(d["hdr"][1])
     for s in steps:
