@@ -752,8 +752,6 @@ def run_ours(args, rank, world):
             for k, v in over.items():
                 setattr(a, k, v)
             a.steps, a.warmup, a.no_cpu = steps, 3, True
-            if name == "config5_implicit_lusgs" and world == 1:
-                a.n = 160  # the 50 M-row block system needs ~116 GiB: one B200 runs 24.6 M rows, >= 2 GPUs the full mesh
             if (name in ("config1_sod", "config2_step445_ausm") and world > 1) or (name == "config3_sphere_roe_viscous" and world > 2):
                 continue   # BASELINE.json: configs 1 and 2 on one B200, config 3 on 1 and 2
             t0 = time.time()

@@ -138,6 +138,12 @@ typedef struct mstgpu_config {
     int32_t limiter;      /* MSTGPU_LIMITER_*: 0 = none, 1 = Barth-Jespersen,
                              2 = Venkatakrishnan (on the conserved variables)          */
     double limiter_k;     /* Venkatakrishnan K: eps^2 = (K h)^3, h = V^(1/D)            */
+    int32_t tile_fit;     /* fused kernel: > 0 = tiles of VARIABLE size, each grown along the cell order until
+                             its flux faces would exceed tile_fit (or its cells tile_cells): with tile_fit a
+                             multiple of the CTA size every warp makes the same number of trips through the
+                             flux phase.  0 = library default (4 x block_threads for tets at second order
+                             when tile_cells is 0 too, fixed tile_cells otherwise), < 0 = fixed tile_cells   */
+    int32_t reserved_;    /* keeps the struct a multiple of 8 bytes; set to 0            */
 } mstgpu_config;
 
 /* Fill `cfg` for `dim`: gas and flux constants are the reference's shipped ones (CONST.h:38-48,

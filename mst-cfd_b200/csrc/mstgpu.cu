@@ -1645,9 +1645,25 @@ static int tile_threads_for(const mstgpu_config& cfg, int T, int D, int nslot) {
     return NT;
 }
 
+// Variable tile sizes (tiles.h): flux faces per tile <= the returned count, 0 = fixed tile_cells.  Default for the
+// 4 x 128-thread default on tets at second order: 512 faces = 4 trips of every warp through phase 2; fixed tiles of
+// 240 cells carry ~595 faces on the 203^3 box: 5 trips, the last one with a handful of live warps (measured
+// 5.83 -> 5.55 ms per step, profiles/r2_ab_variants.json).  MSTGPU_TILE_FIT overrides (experiments).
+static int tile_fit_faces(const mstgpu_config& cfg, int D, int nslot) {
+    if (const char* v = getenv("MSTGPU_TILE_FIT")) return std::max(0, atoi(v));
+    if (cfg.tile_fit) return std::max(0, cfg.tile_fit);
+    if (small_ctas_default(cfg, D, nslot)) return 512;
+    // 2-D first order on triangles (256-thread CTAs, tiles of <= 512 cells carry ~820 faces: 4 trips, the last one
+    // a fifth full): 768 faces = 3 full trips, 70.2 -> 64.8 us per step on 998 046 triangles (AUSM+)
+    if (D == 2 && nslot == 3 && cfg.order == 1 && cfg.tile_cells == 0 && cfg.block_threads == 0) return 768;
+    // limiter / viscous instantiations: measured neutral or slower (their per-cell phases grow with the rings of
+    // smaller tiles), fixed tile_cells
+    return 0;
+}
+
 static int default_tile_cells(const mstgpu_config& cfg, bool staged = false, int D = 0, int nslot = 0) {
     if (staged) return cfg.block_threads == 128 ? 208 : 416;  // + 80 B of landing slots per thread
-    if (small_ctas_default(cfg, D, nslot)) return 240;
+    if (small_ctas_default(cfg, D, nslot)) return 256;  // cap; the tiles are sized by their flux faces (tile_fit_faces)
     if (cfg.order != 2) return 512;
     if (cfg.viscous != 0) return cfg.limiter != 0 ? 192 : 256;  // + [(D+1) D][own + ring 1] primitive gradients
     return cfg.limiter != 0 ? 384 : 512;
@@ -1666,7 +1682,7 @@ int mstgpu_tile_stats(const mstgpu_mesh* mesh, const mstgpu_config* cfg, int64_t
     const int NTs = tile_threads_for(*cfg, T, p.D, p.nslot);
     int ext = tile_ext(cfg->order, cfg->limiter, cfg->viscous);
     if (staged) ext = tile_ext_staged(ext, NTs);
-    perr = build_tiles(p, p.nc, T, cfg->order, tp, ext);
+    perr = build_tiles(p, p.nc, T, cfg->order, tp, ext, tile_fit_faces(*cfg, p.D, p.nslot));
     if (!perr.empty()) { set_error(nullptr, perr); return MSTGPU_ERR_ARG; }
     for (int i = 0; i < 16; i++) out[i] = 0;
     out[0] = tp.ntiles; out[1] = (int64_t)tp.max_smem;
@@ -1710,6 +1726,8 @@ void mstgpu_default_config(mstgpu_config* cfg, int32_t dim) {
     cfg->gradient = MSTGPU_GRAD_GREEN_GAUSS;  // the reference's scheme: Green-Gauss, no limiter
     cfg->limiter = MSTGPU_LIMITER_NONE;
     cfg->limiter_k = 5.0;
+    cfg->tile_fit = 0;
+    cfg->reserved_ = 0;
     // CONST.h:70-83: rho = 1, u = v = w = 0, E = rho * (T*CV), T = 1/286.32
     cfg->inletQ[0] = 1.0;
     cfg->inletQ[dim + 1] = 1.0 * ((1 / 286.32) * 715.8 + 0.0);
@@ -1779,7 +1797,7 @@ static int create_impl(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_c
             ctx->tile_NT = tile_threads_for(*cfg, T, p.D, p.nslot);
             ctx->tile_ext = tile_ext(cfg->order, cfg->limiter, cfg->viscous);
             if (ctx->tile_staged) ctx->tile_ext = tile_ext_staged(ctx->tile_ext, ctx->tile_NT);
-            std::string terr = build_tiles(p, ctx->n_owned, T, cfg->order, tp, ctx->tile_ext);
+            std::string terr = build_tiles(p, ctx->n_owned, T, cfg->order, tp, ctx->tile_ext, tile_fit_faces(*cfg, p.D, p.nslot));
             if (!terr.empty()) { set_error(ctx, terr); return MSTGPU_ERR_ARG; }
             if (tp.open_stencils > 0) {
                 // the fused kernel derives the own-cell reconstruction weight from the closure of the cell

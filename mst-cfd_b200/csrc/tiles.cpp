@@ -40,7 +40,7 @@ inline int up(int x, int m) { return (x + m - 1) / m * m; }
 
 }  // namespace
 
-std::string build_tiles(const Plan& p, int n_update, int T, int order, TilePack& tp, int ext) {
+std::string build_tiles(const Plan& p, int n_update, int T, int order, TilePack& tp, int ext, int fit_faces) {
     if (order != 2) ext = 0;
     const int limiter = ext & 1, visc = ext & 2;
     const int D = p.D, nc = p.nc, nslot = p.nslot, NS = nslot + 1;
@@ -48,7 +48,52 @@ std::string build_tiles(const Plan& p, int n_update, int T, int order, TilePack&
     if (n_update <= 0 || n_update > nc) return "n_update out of range";
     tp.T = T; tp.order = order; tp.D = D; tp.nslot = nslot; tp.ext = ext;
     const bool lsq = !p.lsq.empty();
-    tp.ntiles = (n_update + T - 1) / T;
+    // tile t = cells [tb[t], tb[t+1]).  Fixed size T, or (fit_faces > 0) grown cell by cell while the tile's flux
+    // faces fit `fit_faces` (a multiple of the CTA size: every warp of the CTA then makes the same number of
+    // trips through phase 2 -- no trip with a handful of live lanes at the end) and its cells fit T.  Tiles
+    // start at even cells (the bulk copies of the state move 16-byte units = 2 rows of 40 bytes).
+    std::vector<int32_t> tb;
+    if (fit_faces > 0) {
+        tb.push_back(0);
+        int cb = 0, nfb = 0;
+        for (int c = 0; c < n_update; c++) {
+            int add = 0;
+            for (int j = 0; j < nslot; j++) {
+                const int v = p.cf[(size_t)j * nc + c];
+                if (v < 0) continue;
+                const int f = v >> 1, nb = (v & 1) ? p.fc0[f] : p.fc1[f];
+                if (!(nb >= cb && nb < c)) add++;  // not yet listed by an owned neighbour
+            }
+            if (c - cb >= 2 && (nfb + add > fit_faces || c - cb >= T) ) {
+                // close the tile at the last even size that fits
+                int end = c;
+                if ((end - cb) & 1) end--;
+                tb.push_back(end);
+                // faces of the cells [end, c] that were counted for the old tile start a new count
+                cb = end; nfb = 0;
+                for (int cc = cb; cc < c; cc++)
+                    for (int j = 0; j < nslot; j++) {
+                        const int v = p.cf[(size_t)j * nc + cc];
+                        if (v < 0) continue;
+                        const int f = v >> 1, nb = (v & 1) ? p.fc0[f] : p.fc1[f];
+                        if (!(nb >= cb && nb < cc)) nfb++;
+                    }
+                add = 0;
+                for (int j = 0; j < nslot; j++) {
+                    const int v = p.cf[(size_t)j * nc + c];
+                    if (v < 0) continue;
+                    const int f = v >> 1, nb = (v & 1) ? p.fc0[f] : p.fc1[f];
+                    if (!(nb >= cb && nb < c)) add++;
+                }
+            }
+            nfb += add;
+        }
+        tb.push_back(n_update);
+    } else {
+        for (int c = 0; c < n_update; c += T) tb.push_back(c);
+        tb.push_back(n_update);
+    }
+    tp.ntiles = (int)tb.size() - 1;
     tp.desc.assign(tp.ntiles, TileDesc{});
     const int nt = tp.ntiles;
 
@@ -82,7 +127,7 @@ std::string build_tiles(const Plan& p, int n_update, int T, int order, TilePack&
 #pragma omp for schedule(dynamic, 64)
             for (int t = 0; t < nt; t++) {
                 TileDesc& d = tp.desc[t];
-                const int cb = t * T, ce = std::min(cb + T, n_update), n_own = ce - cb;
+                const int cb = tb[t], ce = tb[t + 1], n_own = ce - cb;
                 s.cells.reset(); s.faces.reset(); s.ring.clear(); s.flist.clear();
                 auto owned = [&](int g) { return g >= cb && g < ce; };
                 auto local_of = [&](int g) -> int { return owned(g) ? g - cb : s.cells.find(g); };

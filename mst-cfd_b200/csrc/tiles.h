@@ -49,6 +49,7 @@ struct TilePack {
 
 // n_update: cells [0, n_update) are advanced (the rest are ghosts, read only)
 // ext (tile_ext()): the packets also carry the limiter / viscous tables of tile_layout.h
-std::string build_tiles(const Plan& p, int n_update, int T, int order, TilePack& tp, int ext = 0);
+// fit_faces > 0: variable tile sizes, each grown until its flux faces would exceed fit_faces (or its cells T)
+std::string build_tiles(const Plan& p, int n_update, int T, int order, TilePack& tp, int ext = 0, int fit_faces = 0);
 
 }  // namespace mst

@@ -58,6 +58,7 @@ class MstConfig(C.Structure):
         ("tile_flags", C.c_int32),
         # extension (absent from the reference): gradient / limiter choice, include/mstgpu.h
         ("gradient", C.c_int32), ("limiter", C.c_int32), ("limiter_k", C.c_double),
+        ("tile_fit", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 GRADIENTS = {"gg": 0, "lsq": 1}

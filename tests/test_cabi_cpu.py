@@ -71,7 +71,7 @@ def test_version_and_default_config():
 def test_struct_layout_matches_header():
     # 4 int32 + 12 pointers; 6 int32 + 6 doubles + 5 doubles
     assert C.sizeof(mstgpu.MstMesh) == 16 + 12 * 8
-    assert C.sizeof(mstgpu.MstConfig) == 24 + 11 * 8 + 16 + 8 + 8  # + gradient, limiter, limiter_k
+    assert C.sizeof(mstgpu.MstConfig) == 24 + 11 * 8 + 16 + 8 + 8 + 8  # + gradient, limiter, limiter_k, + tile_fit, reserved_
 
 
 @pytest.mark.skipif(have_gpu(), reason="checks the no-GPU failure mode")

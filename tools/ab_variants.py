@@ -53,18 +53,22 @@ def main():
     import hashlib
     ref, rows = None, []
     if a.configs:
-        cfgs = [tuple(int(x) for x in (c.split(":") + ["0"])[:4]) for c in a.configs.split(",")]
+        cfgs = [tuple(int(x) for x in (c.split(":") + ["0", "0"])[:5]) for c in a.configs.split(",")]
     else:
-        cfgs = [(a.block_threads, int(T), int(v), 0) for T in a.tiles.split(",") for v in a.variants.split(",")]
+        cfgs = [(a.block_threads, int(T), int(v), 0, 0) for T in a.tiles.split(",") for v in a.variants.split(",")]
     ctx, key = None, None
-    for NT, T, v, fl in cfgs:
-        if key != (NT, T, fl):
+    for NT, T, v, fl, fit in cfgs:
+        if key != (NT, T, fl, fit):
             if ctx is not None:
                 ctx.close()
             t = time.time()
+            # 5th field: MSTGPU_TILE_FIT -- variable tile sizes, flux faces per tile <= fit (tile_cells is the cap)
+            os.environ.pop("MSTGPU_TILE_FIT", None)
+            if fit:
+                os.environ["MSTGPU_TILE_FIT"] = str(fit)
             ctx = mstgpu.Context(f, tile_cells=T, block_threads=NT, tile_flags=fl, **kw)
-            key = (NT, T, fl)
-            print(f"[ab] {f['ncells']} cells, NT={NT} T={T}: context in {time.time() - t:.1f}s", file=sys.stderr, flush=True)
+            key = (NT, T, fl, fit)
+            print(f"[ab] {f['ncells']} cells, NT={NT} T={T} fit={fit}: context in {time.time() - t:.1f}s", file=sys.stderr, flush=True)
         ctx.set_tile_variant(v)
         ctx.set_state(Q0)
         ctx.step(dt, 3)
@@ -82,7 +86,7 @@ def main():
         ctx.step(dt, 4)
         ctx.sync()
         gms = ctx.step_timed(dt, a.steps)   # no per-kernel events: pairs of steps from the CUDA graph
-        row = dict(block_threads=NT, tile_cells=T, variant=v, tile_flags=fl, identical_to_first=same, sha=hashlib.sha256(Q3.tobytes()).hexdigest()[:12],
+        row = dict(block_threads=NT, tile_cells=T, variant=v, tile_flags=fl, fit_faces=fit, identical_to_first=same, sha=hashlib.sha256(Q3.tobytes()).hexdigest()[:12],
                    ms_per_step=ms / a.steps, kernel_ms=kms / max(kn, 1),
                    graph_ms_per_step=gms / a.steps, gcells_per_s=f["ncells"] * a.steps / (ms * 1e-3) / 1e9)
         rows.append(row)
