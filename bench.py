@@ -538,7 +538,14 @@ def measure(args, rank, world, dist, local, want_cpu=True):
     ctx.step(dt_run, args.warmup)
     ctx.sync()
     # ---- timed region: K steps, state resident in HBM -------------------------
-    ctx.enable_kernel_timing(True)
+    # Explicit fixed-dt steps: ONE mstgpu_step(dt, K) call as a user issues it (pairs of steps from the CUDA graph;
+    # with several GPUs the halo push, the flag wait and both tile classes are nodes of that graph), bracketed by
+    # CUDA events on the solver's stream.  The per-kernel durations of the roofline come from a second,
+    # instrumented pass of the same K steps right after it (events around every launch force the launches out of
+    # the graph and serialise the two streams of a partitioned step, so they are kept out of `value`).
+    # Implicit and CFL steps have no graph path: one pass, instrumented.
+    plain = not args.implicit and args.cfl <= 0
+    ctx.enable_kernel_timing(not plain)
     l0 = ctx.launch_count
     clocks = ClockSampler(local)
     clocks.start()
@@ -563,10 +570,6 @@ def measure(args, rank, world, dist, local, want_cpu=True):
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms = float(tms.item())
     launches = ctx.launch_count - l0
-    kt = {k: ctx.kernel_time(k) for k in ("gradient", "gradient_lsq", "limiter", "flux", "update", "step_tiles", "halo_pack",
-                                           "assemble", "lusgs", "increment", "halo_exchange", "halo_tiles", "interior_tiles")}
-    kt = {k: v for k, v in kt.items() if v[1] > 0}
-    ctx.enable_kernel_timing(False)
     res = ctx.residual()
     value = nc_total * args.steps / (ms * 1e-3)
     log(f"[bench] {args.steps} steps in {ms:.2f} ms (wall {wall * 1e3:.2f} ms), residual {res}")
@@ -584,10 +587,24 @@ def measure(args, rank, world, dist, local, want_cpu=True):
                   what="sum mod 2^64 over all cells and variables of splitmix64(bits(Q) ^ golden*(global_cell_id*U+k+1)), all-reduced over ranks")
     log(f"[bench] state digest after {args.warmup + args.steps} steps: {dg:016x}")
 
+    # ---- instrumented pass: the same K steps with CUDA events around every launch ----------------------------
+    inst_ms = None
+    if plain:
+        ctx.enable_kernel_timing(True)
+        inst_ms = ctx.step_timed(dt_run, args.steps)
+        if dist is not None:
+            ti = torch.tensor([inst_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(ti, op=dist.ReduceOp.MAX)
+            inst_ms = float(ti.item())
+    kt = {k: ctx.kernel_time(k) for k in ("gradient", "gradient_lsq", "limiter", "flux", "update", "step_tiles", "halo_pack",
+                                           "assemble", "lusgs", "increment", "halo_exchange", "halo_tiles", "interior_tiles")}
+    kt = {k: v for k, v in kt.items() if v[1] > 0}
+    ctx.enable_kernel_timing(False)
+
     # ---- the same K steps with the residual of EVERY step (Time.cpp:69-76 computes it each step; the timed
     # region above is one mstgpu_step(dt, K) call, which reduces the residual of its last step only) ----------
     every = None
-    if not args.implicit and args.cfl <= 0:
+    if plain:
         ms1 = 0.0
         for _ in range(args.steps):
             ms1 += ctx.step_timed(dt_run, 1)
@@ -597,16 +614,6 @@ def measure(args, rank, world, dist, local, want_cpu=True):
             ms1 = float(t1.item())
         every = dict(value=nc_total * args.steps / (ms1 * 1e-3), unit="cell-updates/s", ms_per_step=ms1 / args.steps,
                      what=f"{args.steps} calls of mstgpu_step(dt, 1): residual reduced on every step, one host call per step")
-    graph_ms = None
-    if (args.graph or world > 1) and args.cfl <= 0 and not args.implicit:
-        # the same K steps issued as pairs from a CUDA graph (no per-kernel events): launch-bound meshes
-        ctx.step(dt_run, 4)
-        ctx.sync()
-        graph_ms = ctx.step_timed(dt_run, args.steps)
-        if dist is not None:
-            tg = torch.tensor([graph_ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
-            graph_ms = float(tg.item())
 
     # ---- roofline of the dominant kernel --------------------------------------
     peak, peak_src = measured_peaks()
@@ -708,7 +715,9 @@ def measure(args, rank, world, dist, local, want_cpu=True):
                config=workload_config(args, world, nc_total, f["nfaces"], U, desc, dt_run),
                gpu_config=dict(kernel=args.kernel, tile_cells=args.tile_cells, renumber=args.renumber, block_threads=args.block_threads,
                                halo=halo_mode, step_breakdown_ms=breakdown or None,
-                               graph_ms_per_step=None if graph_ms is None else graph_ms / args.steps,
+                               timed_call="one mstgpu_step(dt, K) call: pairs of steps from the CUDA graph, the last step(s) launched directly"
+                                          if plain else "K steps, CUDA events around every launch",
+                               instrumented_ms_per_step=None if inst_ms is None else inst_ms / args.steps,
                                residual="reduced on the last step of the timed mstgpu_step(dt, K) call (SURVEY 8f.1: residual every k); "
                                         "see every_step_residual for one call per step"),
                clocks=clk, e2e=e2e, gpu_launches=launches, roofline=roof, cpu_baseline=cpu,
