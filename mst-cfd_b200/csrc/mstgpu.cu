@@ -1101,6 +1101,15 @@ int launch_tiles(mstgpu_ctx* ctx, double dt, const double* dtd, const double* Qo
     if (D == 3 && ORDER == 2 && NT == 128 && NS == 5 && !(ctx->tile_var & 32)) {
         // 128-thread CTAs (the default for tets at second order): registers sized for 4 resident CTAs per SM
         // (MSTGPU_TILE_VAR 64: for 5, experimental; 32: the plain 3-CTA allocation)
+        // experiments on the packet stream of phase 2 (step_tiles.cuh): 256 first face's words before the state wait,
+        // 512 next trip's lines into L1, 1024 next face's words requested after the reconstruction
+        switch (ctx->tile_var & (256 | 512 | 1024)) {
+            case 256: return launch_tiles_var<3, 2, 128, 5, false, false, 8 | 256>(ctx, dt, dtd, Qo, Qn, wr, which, st);
+            case 512: return launch_tiles_var<3, 2, 128, 5, false, false, 8 | 512>(ctx, dt, dtd, Qo, Qn, wr, which, st);
+            case 256 | 512: return launch_tiles_var<3, 2, 128, 5, false, false, 8 | 256 | 512>(ctx, dt, dtd, Qo, Qn, wr, which, st);
+            case 1024: return launch_tiles_var<3, 2, 128, 5, false, false, 8 | 1024>(ctx, dt, dtd, Qo, Qn, wr, which, st);
+            default: break;
+        }
         return (ctx->tile_var & 64) ? launch_tiles_var<3, 2, 128, 5, false, false, 64>(ctx, dt, dtd, Qo, Qn, wr, which, st)
                                     : launch_tiles_var<3, 2, 128, 5, false, false, 8>(ctx, dt, dtd, Qo, Qn, wr, which, st);
     }
@@ -2279,7 +2288,8 @@ int64_t mstgpu_launch_count(mstgpu_ctx* ctx) { return ctx ? ctx->launches : -1; 
 
 int mstgpu_set_tile_variant(mstgpu_ctx* ctx, int32_t variant) {
     if (!ctx) return MSTGPU_ERR_ARG;
-    if (!(variant == 8 || variant == 16 || variant == 32 || variant == 64 || (variant >= 0 && variant <= 7 && variant != 6))) { set_error(ctx, "tile variant must be 0-5, 7, 8, 16, 32 or 64"); return MSTGPU_ERR_ARG; }
+    const int base = variant & ~(256 | 512 | 1024);  // + packet-stream experiments of the 128-thread default (step_tiles.cuh)
+    if (variant < 0 || !(base == 8 || base == 16 || base == 32 || base == 64 || (base >= 0 && base <= 7 && base != 6))) { set_error(ctx, "tile variant must be 0-5, 7, 8, 16, 32 or 64 (+ 256 / 512 / 1024)"); return MSTGPU_ERR_ARG; }
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     for (auto& ge : ctx->step_graph) if (ge) { cudaGraphExecDestroy(ge); ge = nullptr; }  // the graph holds the old kernels

@@ -119,6 +119,25 @@ __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
 
+// the packet words of one flux face held in registers ahead of their use (experiments VAR & 256 / 1024)
+template <int D, int NS>
+struct FaceWords {
+    uint32_t mt, id[NS > 1 ? NS - 1 : 1];
+    double S[D], w[NS > 1 ? 2 * (NS - 1) : 1];
+    __device__ __forceinline__ void load(const uint32_t* __restrict__ fmeta_g, const double* __restrict__ fSd_g,
+                                         const uint32_t* __restrict__ idx_g, const double* __restrict__ w_g, int nFBp, int f) {
+        mt = fmeta_g[f];
+#pragma unroll
+        for (int dd = 0; dd < D; dd++) S[dd] = fSd_g[dd * nFBp + f];
+#pragma unroll
+        for (int m = 0; m < NS - 1; m++) {
+            id[m] = idx_g[m * nFBp + f];
+            w[m] = w_g[m * nFBp + f];
+            w[NS - 1 + m] = w_g[(NS - 1 + m) * nFBp + f];
+        }
+    }
+};
+
 template <int D, int ORDER, int NT, int NS, bool LIM, bool VISC, int VAR>
 __device__ __forceinline__ void step_tile(const TileArrays& ta, const int tile, const int pf_tile, const bool first, const bool pf_self,
                                           const uint32_t parity, int want_resid, const DevCfg& cfg, double dt_val,
@@ -235,6 +254,15 @@ __device__ __forceinline__ void step_tile(const TileArrays& ta, const int tile, 
             for (int k = 0; k < U; k++) Qs[(n_own + r) * U + k] = q1[k];
         }
     }
+    // VAR & 256 (experiment): the packet words of a thread's FIRST flux face are requested before the wait for the
+    // staged states -- they do not depend on them, and they are the ones most likely to miss L2 (the bulk
+    // prefetch of the packet was issued a moment ago): their HBM latency overlaps the ring rows' instead of
+    // following it.  VAR & 1024: the words of the NEXT face are requested as soon as the reconstruction of the
+    // current one is done (software pipeline through the registers the reconstruction just released).
+    constexpr bool PEEL = ORDER == 2 && (VAR & (256 | 1024)) != 0 && !STG;
+    constexpr bool ROT = ORDER == 2 && (VAR & 1024) != 0 && !STG;
+    FaceWords<D, NS> pw;
+    if constexpr (PEEL) { if (tid < nFB) pw.load(fmeta_g, fSd_g, idx_g, w_g, nFBp, tid); }
     mbar_wait(bar, parity);
     __syncthreads();
 
@@ -330,12 +358,33 @@ __device__ __forceinline__ void step_tile(const TileArrays& ta, const int tile, 
 
     // ---- phase 2: reconstruction (fixed stencil) + flux on every face with an owned cell ----
     for (int f = tid; f < nFB; f += NT) {
-        const uint32_t mt = fmeta_g[f];
+        if constexpr (PEEL && !ROT) { if (f != tid) pw.load(fmeta_g, fSd_g, idx_g, w_g, nFBp, f); }
+        if constexpr ((VAR & 512) != 0) if (f + NT < nFB && (tid & 15) == 0) {
+            // experiment: the next trip's packet lines into L1 (one request per 128-byte line)
+            const int fn = f + NT;
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(fmeta_g + fn));
+#pragma unroll
+            for (int dd = 0; dd < D; dd++) asm volatile("prefetch.global.L1 [%0];" ::"l"(fSd_g + dd * nFBp + fn));
+#pragma unroll
+            for (int m = 0; m < NS - 1; m++) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(idx_g + m * nFBp + fn));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(w_g + m * nFBp + fn));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(w_g + (NS - 1 + m) * nFBp + fn));
+            }
+        }
+        uint32_t mt;
+        double S[D];
+        if constexpr (PEEL) {
+            mt = pw.mt;
+#pragma unroll
+            for (int dd = 0; dd < D; dd++) S[dd] = pw.S[dd];
+        } else {
+            mt = fmeta_g[f];
+#pragma unroll
+            for (int dd = 0; dd < D; dd++) S[dd] = fSd_g[dd * nFBp + f];
+        }
         const int type = mt & 0xff;
         const uint32_t flags = mt >> 8;
-        double S[D];
-#pragma unroll
-        for (int dd = 0; dd < D; dd++) S[dd] = fSd_g[dd * nFBp + f];
         double A[U], B[U], phi[U];
         double visc[VISC ? U : 1];
         bool live = true;
@@ -351,6 +400,13 @@ __device__ __forceinline__ void step_tile(const TileArrays& ta, const int tile, 
                     wb[m + 1] = stg_w[(NS - 1 + m) * NT + tid];
                 }
                 if (f + NT < nFB) stage_issue(f + NT);  // the slots were just read by their only reader
+            } else if constexpr (PEEL) {
+#pragma unroll
+                for (int m = 0; m < NS - 1; m++) {
+                    id[m] = pw.id[m];
+                    wa[m + 1] = pw.w[m];
+                    wb[m + 1] = pw.w[NS - 1 + m];
+                }
             } else {
 #pragma unroll
                 for (int m = 0; m < NS - 1; m++) {
@@ -467,6 +523,7 @@ __device__ __forceinline__ void step_tile(const TileArrays& ta, const int tile, 
                 live = boundary_states<D>(type, qa, qa, S, cfg, A, B);
             }
         }
+        if constexpr (ROT) { if (f + NT < nFB) pw.load(fmeta_g, fSd_g, idx_g, w_g, nFBp, f + NT); }  // S of the current face was copied out above
         if (live) {
             riemann_contract<D>(cfg.flux, A, B, flags, S, cfg, phi);
         } else {
