@@ -150,7 +150,7 @@ class ClockSampler:
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,clocks.mem,temperature.gpu")
 
     def __init__(self, gpu_index=0):
         self.rows = []
@@ -177,7 +177,7 @@ class ClockSampler:
             self.proc.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons, pw = [], [], set(), []
+        sm, mx, reasons, pw, mem, temp = [], [], set(), [], [], []
         for ln in self.f.read().splitlines():
             c = [t.strip() for t in ln.split(",")]
             if len(c) < 9:
@@ -186,6 +186,10 @@ class ClockSampler:
                 sm.append(float(c[1])); mx.append(float(c[2])); pw.append(float(c[3]))
             except ValueError:
                 continue
+            try:
+                mem.append(float(c[9])); temp.append(float(c[10]))
+            except (ValueError, IndexError):
+                pass
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
@@ -193,6 +197,7 @@ class ClockSampler:
         if not sm:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
         return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), power_w_max=float(max(pw)),
+                    mem_mhz=float(np.median(mem)) if mem else None, temp_c_max=float(max(temp)) if temp else None,
                     samples=len(sm), reasons=sorted(reasons))
 
 
@@ -565,7 +570,14 @@ def measure(args, rank, world, dist, local, want_cpu=True):
         dist.barrier()
     wall = time.perf_counter() - w0
     clk = clocks.stop()
+    ranks_info = None
     if dist is not None:  # device time of the slowest rank
+        mine = torch.tensor([ms, clk.get("sm_mhz") or 0.0, clk.get("power_w_max") or 0.0, clk.get("mem_mhz") or 0.0, clk.get("temp_c_max") or 0.0,
+                             float(len(clk.get("reasons") or []))], dtype=torch.float64, device="cuda")
+        allm = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allm, mine)
+        ranks_info = [dict(rank=i, ms_per_step=round(float(m[0]) / args.steps, 4), sm_mhz=float(m[1]), power_w_max=float(m[2]), mem_mhz=float(m[3]),
+                           temp_c_max=float(m[4]), throttle_reasons=int(m[5])) for i, m in enumerate(allm)]
         tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms = float(tms.item())
@@ -625,6 +637,15 @@ def measure(args, rank, world, dist, local, want_cpu=True):
     per_kernel = {k: (v[0] / max(v[1], 1)) for k, v in kt.items()}
     # spans of the partitioned step on its two streams (rank 0's own): exchange + wait, halo tiles, interior tiles
     breakdown = {k: round(per_kernel.pop(k), 4) for k in ("halo_exchange", "halo_tiles", "interior_tiles") if k in per_kernel}
+    breakdown_ranks = None
+    if dist is not None and breakdown:
+        # every rank's spans (the step time is the slowest rank's; the exchange span of a fast rank is mostly waiting)
+        tb = torch.tensor([breakdown.get(k, 0.0) for k in ("halo_exchange", "halo_tiles", "interior_tiles")] + [float(part.n_local - part.n_owned), float(part.n_neighbors)],
+                          dtype=torch.float64, device="cuda")
+        allb = [torch.zeros_like(tb) for _ in range(world)]
+        dist.all_gather(allb, tb)
+        breakdown_ranks = [dict(rank=i, halo_exchange=round(float(b[0]), 4), halo_tiles=round(float(b[1]), 4), interior_tiles=round(float(b[2]), 4),
+                                ghost_cells=int(b[3]), neighbours=int(b[4])) for i, b in enumerate(allb)]
     dom = max(per_kernel, key=per_kernel.get)
     if args.viscous:
         ab = dict(ab, step=616, flux_update=368) if (D, args.order) == (3, 2) else ab  # + eta per face
@@ -714,7 +735,7 @@ def measure(args, rank, world, dist, local, want_cpu=True):
                scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
                config=workload_config(args, world, nc_total, f["nfaces"], U, desc, dt_run),
                gpu_config=dict(kernel=args.kernel, tile_cells=args.tile_cells, renumber=args.renumber, block_threads=args.block_threads,
-                               halo=halo_mode, step_breakdown_ms=breakdown or None,
+                               halo=halo_mode, per_rank=ranks_info, step_breakdown_ms=breakdown or None, step_breakdown_ms_per_rank=breakdown_ranks,
                                timed_call="one mstgpu_step(dt, K) call: pairs of steps from the CUDA graph, the last step(s) launched directly"
                                           if plain else "K steps, CUDA events around every launch",
                                instrumented_ms_per_step=None if inst_ms is None else inst_ms / args.steps,
@@ -760,7 +781,7 @@ def run_ours(args, rank, world):
             a = argparse.Namespace(**vars(args))
             for k, v in over.items():
                 setattr(a, k, v)
-            a.steps, a.warmup, a.no_cpu = steps, 3, True
+            a.steps, a.warmup, a.no_cpu = steps, 5, True  # >= 4 warm-up steps also run the CUDA graph of the launch-bound cases once
             if (name in ("config1_sod", "config2_step445_ausm") and world > 1) or (name == "config3_sphere_roe_viscous" and world > 2):
                 continue   # BASELINE.json: configs 1 and 2 on one B200, config 3 on 1 and 2
             t0 = time.time()

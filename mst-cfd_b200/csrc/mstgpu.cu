@@ -157,6 +157,7 @@ struct mstgpu_ctx {
     cudaStream_t fork_stream = nullptr;  // non-null while a step is captured: odd classes go here
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int64_t graph_launches = 0;
+    int graph_rc = 0;  // result of the last graph build
     // implicit step (extension): block system + the reference's LU-SGS sweeps (csrc/lusgs.cu)
     mstgpu_lusgs* imp_solver = nullptr;
     int32_t *imp_dpos = nullptr, *imp_pos = nullptr;
@@ -1004,6 +1005,10 @@ int ensure_stage_buffers(mstgpu_ctx* ctx) {
 // receives land directly in the ghost block of Q (ghosts are ordered by owner).
 int halo_exchange(mstgpu_ctx* ctx, double* Q, cudaStream_t st) {
     if (!ctx->partitioned || ctx->halo.empty()) return MSTGPU_OK;
+    // timing diagnosis only (WRONG results: the ghost rows keep their old values): every rank runs its tiles
+    // uncoupled from its neighbours, which separates a slow GPU / partition from waiting on the exchange
+    static const bool no_halo = getenv("MSTGPU_DEBUG_NO_HALO") != nullptr;
+    if (no_halo) return MSTGPU_OK;
     if (!ctx->comm) { set_error(ctx, "partitioned context without a communicator: call mstgpu_comm_init"); return MSTGPU_ERR_STATE; }
     const int U = ctx->U;
     if (ctx->peer_ok && (Q == ctx->Q[0] || Q == ctx->Q[1])) {
@@ -1239,24 +1244,39 @@ int build_step_graph(mstgpu_ctx* ctx, double dt, int start_cur, bool overlap) {
     return MSTGPU_OK;
 }
 
+// Will a call of nsteps fixed-dt steps go through the CUDA graph?  Builds the executable for the current buffer on
+// first use (and after a change of dt), so that callers that time a call can keep the one-time build out of it.
+// The graph pays where a step is launch-bound (SOD tube: 15.6 -> 9.3 us per step, 1 M triangles: 65 -> 60 us).  On
+// large meshes direct launches are the faster path -- measured at 50.2 M tets: 5.43 against 5.50 ms per step on one
+// GPU, 0.790 against 0.833 ms on eight (profiles/r2_scaling.md) -- so the graph is used up to 8192 tiles
+// (MSTGPU_GRAPH=1 forces it, MSTGPU_NO_GRAPH disables it).  With neighbours only when the halo is peer memory (no
+// NCCL call inside the capture).
+template <int D>
+bool step_graph_ready(mstgpu_ctx* ctx, double dt, int nsteps, double cfl) {
+    const bool overlap = ctx->partitioned && !ctx->halo.empty();
+    static const bool no_graph = getenv("MSTGPU_NO_GRAPH") != nullptr;
+    static const bool force_graph = getenv("MSTGPU_GRAPH") != nullptr;
+    if (!ctx->use_tiles || !((!overlap || ctx->peer_ok) && cfl <= 0.0 && !ctx->ktiming && !no_graph && nsteps >= 4 && (ctx->ntiles <= 8192 || force_graph)))
+        return false;
+    if (overlap && !ctx->comm) return false;
+    if (ctx->step_graph_dt != dt) {
+        for (auto& ge : ctx->step_graph) if (ge) { cudaGraphExecDestroy(ge); ge = nullptr; }
+        ctx->step_graph_dt = dt;
+    }
+    if (!ctx->step_graph[ctx->cur]) ctx->graph_rc = build_step_graph<D>(ctx, dt, ctx->cur, overlap);  // failure leaves it null
+    return true;
+}
+
 template <int D>
 int step_tiles_impl(mstgpu_ctx* ctx, double dt, int nsteps, double cfl) {
     const double* dtd = cfl > 0.0 ? ctx->dt_dev : nullptr;
     const bool overlap = ctx->partitioned && !ctx->halo.empty();
-    if (overlap && !ctx->comm) { set_error(ctx, "partitioned context without a communicator: call mstgpu_comm_init"); return MSTGPU_ERR_STATE; }
+    if (overlap && !ctx->comm && !getenv("MSTGPU_DEBUG_NO_HALO")) { set_error(ctx, "partitioned context without a communicator: call mstgpu_comm_init"); return MSTGPU_ERR_STATE; }
     // long fixed-dt runs: pairs of steps from the graph, the last one or two steps (the observable residual
     // belongs to the last) launched directly.  With neighbours only when the halo is peer memory (no NCCL call
     // inside the capture).
-    static const bool no_graph = getenv("MSTGPU_NO_GRAPH") != nullptr;
-    if ((!overlap || ctx->peer_ok) && cfl <= 0.0 && !ctx->ktiming && !no_graph && nsteps >= 4) {
-        if (ctx->step_graph_dt != dt) {
-            for (auto& ge : ctx->step_graph) if (ge) { cudaGraphExecDestroy(ge); ge = nullptr; }
-            ctx->step_graph_dt = dt;
-        }
-        if (!ctx->step_graph[ctx->cur]) {
-            int r = build_step_graph<D>(ctx, dt, ctx->cur, overlap);
-            if (r) return r;
-        }
+    if (step_graph_ready<D>(ctx, dt, nsteps, cfl)) {
+        if (!ctx->step_graph[ctx->cur]) return ctx->graph_rc ? ctx->graph_rc : MSTGPU_ERR_CUDA;  // the build failed; its message is in ctx->err
         const int pairs = (nsteps - 1) / 2;
         for (int i = 0; i < pairs; i++) CK(cudaGraphLaunch(ctx->step_graph[ctx->cur], ctx->stream));
         ctx->launches += pairs * ctx->graph_launches;
@@ -2060,6 +2080,8 @@ int mstgpu_step_timed(mstgpu_ctx* ctx, double dt, int32_t nsteps, float* ms) {
     if (!ctx || !ms) return MSTGPU_ERR_ARG;
     if (!ctx->has_state) { set_error(ctx, "step before set_state"); return MSTGPU_ERR_STATE; }
     CK(cudaSetDevice(ctx->device));
+    // one-time work (graph capture + instantiation on first use) stays outside the timed bracket
+    if (ctx->D == 2) step_graph_ready<2>(ctx, dt, nsteps, 0.0); else step_graph_ready<3>(ctx, dt, nsteps, 0.0);
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     int rc = (ctx->D == 2) ? step_impl<2>(ctx, dt, nsteps) : step_impl<3>(ctx, dt, nsteps);
