@@ -374,6 +374,13 @@ int mstgpu_mesh_adjacency(const mstgpu_mesh* mesh, const mstgpu_config* cfg, int
  * out[12..14]=sum over tiles of the loop trips of a CTA: ceil(flux faces / NT), ceil(owned cells / NT),
  * ceil(ring cells / NT); out[15]=NT.  (16 entries.) */
 int mstgpu_tile_stats(const mstgpu_mesh* mesh, const mstgpu_config* cfg, int64_t* out16);
+/* Same for a partition's local mesh (mstgpu_partition_mesh): cells [0, n_owned) are renumbered and tiled, the
+ * ghost cells behind them only lend their state -- the tiling mstgpu_create_partitioned builds.  n_owned < 0 = all. */
+int mstgpu_tile_stats_owned(const mstgpu_mesh* mesh, const mstgpu_config* cfg, int32_t n_owned, int64_t* out);
+/* Memory locality of the tiling (host only): out6 = tiles, ring rows, distinct 128-byte lines the ring rows of a tile
+ * touch (summed over tiles), runs of consecutive ring ids, 128-byte lines requested by the ring gather (per warp load
+ * instruction), flux faces.  Diagnostic for the cell order (profiles/r2_scaling.md). */
+int mstgpu_tile_locality(const mstgpu_mesh* mesh, const mstgpu_config* cfg, int32_t n_owned, int64_t* out6);
 
 const char* mstgpu_last_error(mstgpu_ctx* ctx); /* ctx may be NULL (create errors) */
 const char* mstgpu_version(void);

@@ -1698,12 +1698,112 @@ static int default_tile_cells(const mstgpu_config& cfg, bool staged = false, int
     return cfg.limiter != 0 ? 384 : 512;
 }
 
+// how scattered are the ring rows of the tiles in memory: distinct 128-byte lines, runs of consecutive ring ids, and
+// the 128-byte lines the gather of phase 0 requests (one thread per ring entry in list order, U loads of 8 bytes per
+// thread: per load instruction the distinct lines among the 32 addresses of a warp = its L1 wavefronts)
+static void tile_ring_runs(const TilePack& tp, int U, int64_t& rows_out, int64_t& lines_out, int64_t& runs_out, int64_t* gsec_out = nullptr) {
+    const int64_t rowb = 8 * U;
+    int64_t lines = 0, runs = 0, rows = 0, gsec = 0;
+#pragma omp parallel for schedule(static) reduction(+ : lines, runs, rows, gsec)
+    for (int t = 0; t < tp.ntiles; t++) {
+        const TileDesc& d = tp.desc[t];
+        const int n = d.n_r1 + d.n_r2;
+        const int32_t* lst = tp.ring.data() + d.ring_off;
+        for (int g = 0; g < n; g += 32)
+            for (int k = 0; k < U; k++) {
+                int64_t sec[32];
+                const int m = std::min(32, n - g);
+                for (int i = 0; i < m; i++) sec[i] = ((int64_t)lst[g + i] * rowb + 8 * k) / 128;
+                std::sort(sec, sec + m);
+                gsec += std::unique(sec, sec + m) - sec;
+            }
+        std::vector<int32_t> r(lst, lst + n);
+        std::sort(r.begin(), r.end());
+        int64_t last_line = -1;
+        for (size_t i = 0; i < r.size(); i++) {
+            if (i == 0 || r[i] != r[i - 1] + 1) runs++;
+            const int64_t l0 = (int64_t)r[i] * rowb / 128, l1 = ((int64_t)r[i] * rowb + rowb - 1) / 128;
+            for (int64_t l = std::max(l0, last_line + 1); l <= l1; l++) lines++;
+            last_line = l1;
+        }
+        rows += (int64_t)r.size();
+    }
+    rows_out = rows; lines_out = lines; runs_out = runs;
+    if (gsec_out) *gsec_out = gsec;
+}
+
+// The lattice of the Hilbert curve against the mesh.  The curve subdivides a cube; where its octree boxes fall on the
+// cells decides the shape of the tiles (contiguous curve ranges) and how the ring cells of a tile are spread over memory.
+// On lattice-like meshes this is not a small effect: on the 203^3 Kuhn box the runs of consecutive ring ids per tile
+// vary between 88 and 136 with the extent of the cube (two partitions of the same mesh, cut from the same curve, ran
+// 8 % apart for that reason alone: profiles/r2_scaling.md), and the flux faces per cell by 4 %.  The extent is therefore
+// chosen by a search: ten cubes between 1x and 1.9x the bounding box (2x is the same lattice one level up), each
+// evaluated by building the actual tiles on a sample -- a contiguous curve range of ~400 k cells from the middle of the
+// mesh, cut out with its ghost layers like a partition -- and scored with a two-factor model of the kernel's time
+// (flux faces per cell x ring lines per cell, below).  Unstructured meshes without a lattice score alike for every cube;
+// the default cube then stays.  MSTGPU_CURVE_SEARCH=0 switches it off.
+static CurveFrame choose_curve_frame(const mstgpu_mesh& m, const mstgpu_config& cfg) {
+    CurveFrame base = bbox_frame(m, m.ncells);
+    if (const char* v = getenv("MSTGPU_CURVE_SEARCH")) if (atoi(v) == 0) return base;
+    if (getenv("MSTGPU_CURVE_SCALE")) return base;  // the experiment knob of plan.cpp fixes the cube itself
+    if (cfg.renumber != 2 || cfg.kernel == 0 || !(base.ext > 0.0) || m.ncells < 4096) return base;
+    const int nc = m.ncells, M = 400000;
+    const mstgpu_mesh* sm = &m;
+    Partition P;
+    int n_own = -1;
+    if (nc > M + M / 2) {
+        std::vector<int32_t> ord;
+        curve_order(m, 2, nc, ord, &base);
+        std::vector<int32_t> cp(nc, 1);
+        for (int i = nc / 2 - M / 2; i < nc / 2 + M / 2; i++) cp[ord[i]] = 0;
+        if (!build_partition(m, cfg, 2, 0, cp.data(), P, &base).empty()) return base;
+        sm = &P.mesh;
+        n_own = P.n_owned;
+    }
+    mstgpu_config c2 = cfg;
+    if (n_own >= 0) c2.qf_copy_from = 0x7fffffff;
+    double best_cost = 0.0, cost0 = 0.0;
+    int best = 0;
+    for (int k = 0; k < 10; k++) {
+        Plan p;
+        p.frame = base;
+        p.frame.ext = base.ext * (1.0 + 0.1 * k);
+        if (!build_plan(*sm, c2, p, n_own).empty()) return base;
+        TilePack tp;
+        const bool staged = tile_staged_for(cfg, p.D, p.nslot);
+        const int T = cfg.tile_cells > 0 ? cfg.tile_cells : default_tile_cells(cfg, staged, p.D, p.nslot);
+        int ext = tile_ext(cfg.order, cfg.limiter, cfg.viscous);
+        if (staged) ext = tile_ext_staged(ext, tile_threads_for(cfg, T, p.D, p.nslot));
+        const int nu = n_own >= 0 ? n_own : p.nc;
+        if (!build_tiles(p, nu, T, cfg.order, tp, ext, tile_fit_faces(cfg, p.D, p.nslot)).empty()) return base;
+        int64_t rows, lines, runs;
+        tile_ring_runs(tp, p.U, rows, lines, runs);
+        const double F = (double)tp.sum_FB / nu, Ln = (double)lines / nu;
+        // Calibrated on the B200 (12 cubes on the 101^3 and 128^3 Kuhn boxes, profiles/r2_curve_calibration.md): the
+        // kernel's time follows (flux faces per cell) x (0.15 + distinct 128-byte lines of ring rows per cell) to 4 %.
+        const double cost = F * (0.15 + Ln);
+        if (k == 0) cost0 = cost;
+        if (getenv("MSTGPU_VERBOSE"))
+            fprintf(stderr, "[mstgpu] curve cube x%.1f: %.3f flux faces, %.3f ring rows, %.3f ring lines, %.3f runs per cell -> cost %.4f\n", 1.0 + 0.1 * k, F,
+                    (double)rows / nu, Ln, (double)runs / nu, cost / cost0);
+        if (k == 0 || cost < best_cost) { best_cost = cost; best = k; }
+    }
+    // the model is good to ~4 %: leave the bounding cube only for a predicted gain beyond that
+    if (best_cost > 0.96 * cost0) best = 0;
+    base.ext *= 1.0 + 0.1 * best;
+    return base;
+}
+
 extern "C" {
 
-int mstgpu_tile_stats(const mstgpu_mesh* mesh, const mstgpu_config* cfg, int64_t* out) {
+int mstgpu_tile_stats(const mstgpu_mesh* mesh, const mstgpu_config* cfg, int64_t* out) { return mstgpu_tile_stats_owned(mesh, cfg, -1, out); }
+
+int mstgpu_tile_stats_owned(const mstgpu_mesh* mesh, const mstgpu_config* cfg, int32_t n_owned, int64_t* out) {
     if (!mesh || !cfg || !out) { set_error(nullptr, "null argument"); return MSTGPU_ERR_ARG; }
+    if (n_owned > mesh->ncells) { set_error(nullptr, "n_owned > ncells"); return MSTGPU_ERR_ARG; }
     Plan p;
-    std::string perr = build_plan(*mesh, *cfg, p);
+    if (n_owned < 0) p.frame = choose_curve_frame(*mesh, *cfg);
+    std::string perr = build_plan(*mesh, *cfg, p, n_owned);
     if (!perr.empty()) { set_error(nullptr, perr); return MSTGPU_ERR_ARG; }
     TilePack tp;
     const bool staged = tile_staged_for(*cfg, p.D, p.nslot);
@@ -1711,7 +1811,7 @@ int mstgpu_tile_stats(const mstgpu_mesh* mesh, const mstgpu_config* cfg, int64_t
     const int NTs = tile_threads_for(*cfg, T, p.D, p.nslot);
     int ext = tile_ext(cfg->order, cfg->limiter, cfg->viscous);
     if (staged) ext = tile_ext_staged(ext, NTs);
-    perr = build_tiles(p, p.nc, T, cfg->order, tp, ext, tile_fit_faces(*cfg, p.D, p.nslot));
+    perr = build_tiles(p, n_owned >= 0 ? n_owned : p.nc, T, cfg->order, tp, ext, tile_fit_faces(*cfg, p.D, p.nslot));
     if (!perr.empty()) { set_error(nullptr, perr); return MSTGPU_ERR_ARG; }
     for (int i = 0; i < 16; i++) out[i] = 0;
     out[0] = tp.ntiles; out[1] = (int64_t)tp.max_smem;
@@ -1727,6 +1827,23 @@ int mstgpu_tile_stats(const mstgpu_mesh* mesh, const mstgpu_config* cfg, int64_t
         out[15] = NT;
     }
     out[2] = (int64_t)(sum / tp.ntiles);
+    return MSTGPU_OK;
+}
+
+int mstgpu_tile_locality(const mstgpu_mesh* mesh, const mstgpu_config* cfg, int32_t n_owned, int64_t* out4) {  // out4: 6 entries
+    if (!mesh || !cfg || !out4) { set_error(nullptr, "null argument"); return MSTGPU_ERR_ARG; }
+    if (n_owned > mesh->ncells) { set_error(nullptr, "n_owned > ncells"); return MSTGPU_ERR_ARG; }
+    Plan p;
+    if (n_owned < 0) p.frame = choose_curve_frame(*mesh, *cfg);
+    std::string perr = build_plan(*mesh, *cfg, p, n_owned);
+    if (!perr.empty()) { set_error(nullptr, perr); return MSTGPU_ERR_ARG; }
+    TilePack tp;
+    int T = cfg->tile_cells > 0 ? cfg->tile_cells : default_tile_cells(*cfg, false, p.D, p.nslot);
+    perr = build_tiles(p, n_owned >= 0 ? n_owned : p.nc, T, cfg->order, tp, tile_ext(cfg->order, cfg->limiter, cfg->viscous), tile_fit_faces(*cfg, p.D, p.nslot));
+    if (!perr.empty()) { set_error(nullptr, perr); return MSTGPU_ERR_ARG; }
+    int64_t lines = 0, runs = 0, rows = 0, gsec = 0;
+    tile_ring_runs(tp, p.U, rows, lines, runs, &gsec);
+    out4[0] = tp.ntiles; out4[1] = rows; out4[2] = lines; out4[3] = runs; out4[4] = gsec; out4[5] = tp.sum_FB;
     return MSTGPU_OK;
 }
 
@@ -1785,6 +1902,14 @@ static int create_impl(mstgpu_ctx** out, const mstgpu_mesh* mesh, const mstgpu_c
     ctx->use_tiles = cfg->kernel != 0 && (cfg->viscous == 0 || cfg->order == 2);
     mstgpu_config pcfg = *cfg;
     if (part) pcfg.qf_copy_from = 0x7fffffff;  // already folded into the partition's eta table
+    // curve lattice: a partition orders its cells on the global mesh's lattice (so its tiles are the tiles the single-GPU
+    // run has), a whole mesh on the cube the search picks
+    if (part) ctx->plan.frame = part->frame;
+    else {
+        std::string verr = validate_mesh(*mesh);
+        if (!verr.empty()) { set_error(nullptr, verr); delete ctx; return MSTGPU_ERR_ARG; }
+        ctx->plan.frame = choose_curve_frame(*mesh, pcfg);
+    }
     std::string perr = build_plan(*mesh, pcfg, ctx->plan, part ? part->n_owned : -1);
     if (!perr.empty()) { set_error(nullptr, perr); delete ctx; return MSTGPU_ERR_ARG; }
     Plan& p = ctx->plan;
@@ -2349,7 +2474,12 @@ int mstgpu_partition_create(mstgpu_part** out, const mstgpu_mesh* g, const mstgp
     if (!out || !g || !cfg) { set_error(nullptr, "null argument"); return MSTGPU_ERR_ARG; }
     *out = nullptr;
     mstgpu_part* h = new mstgpu_part;
-    std::string e = build_partition(*g, *cfg, nparts, rank, cell_part, h->p);
+    {
+        std::string verr = validate_mesh(*g);
+        if (!verr.empty()) { set_error(nullptr, verr); delete h; return MSTGPU_ERR_ARG; }
+    }
+    const CurveFrame fr = choose_curve_frame(*g, *cfg);
+    std::string e = build_partition(*g, *cfg, nparts, rank, cell_part, h->p, &fr);
     if (!e.empty()) { set_error(nullptr, e); delete h; return MSTGPU_ERR_ARG; }
     *out = h;
     return MSTGPU_OK;
@@ -2513,6 +2643,8 @@ int mstgpu_peer_disable(mstgpu_ctx* ctx) {
 int mstgpu_mesh_adjacency(const mstgpu_mesh* mesh, const mstgpu_config* cfg, int32_t* rowptr, int32_t* col, int64_t col_cap) {
     if (!mesh || !cfg || !rowptr) { set_error(nullptr, "null argument"); return MSTGPU_ERR_ARG; }
     Plan p;
+    { std::string verr = validate_mesh(*mesh); if (!verr.empty()) { set_error(nullptr, verr); return MSTGPU_ERR_ARG; } }
+    p.frame = choose_curve_frame(*mesh, *cfg);
     std::string perr = build_plan(*mesh, *cfg, p);
     if (!perr.empty()) { set_error(nullptr, perr); return MSTGPU_ERR_ARG; }
     const int nc = p.nc;
@@ -2549,6 +2681,8 @@ int mstgpu_plan_permutation(const mstgpu_mesh* mesh, const mstgpu_config* cfg, i
                             int32_t* face_new2old) {
     if (!mesh || !cfg) { set_error(nullptr, "null argument"); return MSTGPU_ERR_ARG; }
     Plan p;
+    { std::string verr = validate_mesh(*mesh); if (!verr.empty()) { set_error(nullptr, verr); return MSTGPU_ERR_ARG; } }
+    p.frame = choose_curve_frame(*mesh, *cfg);
     std::string perr = build_plan(*mesh, *cfg, p);
     if (!perr.empty()) { set_error(nullptr, perr); return MSTGPU_ERR_ARG; }
     if (cell_new2old) std::memcpy(cell_new2old, p.cell_new2old.data(), sizeof(int32_t) * p.nc);

@@ -8,10 +8,10 @@
 
 namespace mst {
 
-std::string default_cell_part(const mstgpu_mesh& g, int nparts, std::vector<int32_t>& part) {
+std::string default_cell_part(const mstgpu_mesh& g, int nparts, std::vector<int32_t>& part, const CurveFrame* frame) {
     if (nparts < 1) return "nparts < 1";
     std::vector<int32_t> ord;
-    curve_order(g, 2, g.ncells, ord);
+    curve_order(g, 2, g.ncells, ord, frame);
     part.resize(g.ncells);
     // equal ranges of the Hilbert curve: compact, balanced to +-1 cell
     for (int64_t i = 0; i < g.ncells; i++) part[ord[i]] = (int32_t)(i * nparts / g.ncells);
@@ -19,7 +19,7 @@ std::string default_cell_part(const mstgpu_mesh& g, int nparts, std::vector<int3
 }
 
 std::string build_partition(const mstgpu_mesh& g, const mstgpu_config& cfg, int nparts, int rank,
-                            const int32_t* cell_part, Partition& P) {
+                            const int32_t* cell_part, Partition& P, const CurveFrame* frame) {
     {
         std::string verr = validate_mesh(g);
         if (!verr.empty()) return verr;
@@ -28,11 +28,12 @@ std::string build_partition(const mstgpu_mesh& g, const mstgpu_config& cfg, int 
     if (nparts < 1 || rank < 0 || rank >= nparts) return "bad nparts / rank";
     std::vector<int32_t> own_part;
     if (!cell_part) {
-        std::string e = default_cell_part(g, nparts, own_part);
+        std::string e = default_cell_part(g, nparts, own_part, frame);
         if (!e.empty()) return e;
         cell_part = own_part.data();
     }
     P.nparts = nparts; P.rank = rank; P.D = D;
+    P.frame = (frame && frame->set) ? *frame : bbox_frame(g, nc);
     // the viscous term needs the primitive gradient of layer-1 cells as well
     P.layers = (cfg.order == 2 || cfg.viscous != 0) ? 2 : 1;
     const int L = P.layers;

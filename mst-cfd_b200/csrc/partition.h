@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../include/mstgpu.h"
+#include "plan.h"
 
 namespace mst {
 
@@ -39,14 +40,15 @@ struct Partition {
     std::vector<int8_t> dac;
     std::vector<uint8_t> flag;
     mstgpu_mesh mesh{};
+    CurveFrame frame;  // curve lattice of the GLOBAL mesh: the local plans order their cells on the same lattice
 };
 
 // cell_part: optional [ncells] partition id per global cell; nullptr = split the
 // Hilbert-ordered cell list into nparts equal ranges.
 std::string build_partition(const mstgpu_mesh& g, const mstgpu_config& cfg, int nparts, int rank,
-                            const int32_t* cell_part, Partition& out);
+                            const int32_t* cell_part, Partition& out, const CurveFrame* frame = nullptr);
 
 // the default assignment (Hilbert ranges), exposed for tests / other ranks
-std::string default_cell_part(const mstgpu_mesh& g, int nparts, std::vector<int32_t>& part);
+std::string default_cell_part(const mstgpu_mesh& g, int nparts, std::vector<int32_t>& part, const CurveFrame* frame = nullptr);
 
 }  // namespace mst

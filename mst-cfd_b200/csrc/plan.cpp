@@ -2,6 +2,7 @@
 #include "plan.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cmath>
 #include <numeric>
 #include <parallel/algorithm>  // libstdc++ parallel mode: multi-threaded sort of the 50-100 M keys
@@ -49,19 +50,29 @@ inline void axes_to_transpose(uint32_t* X, int b, int n) {
 
 }  // namespace
 
-void curve_order(const mstgpu_mesh& m, int renumber, int n, std::vector<int32_t>& new2old) {
+CurveFrame bbox_frame(const mstgpu_mesh& m, int n) {
     const int D = m.dim;
-    new2old.resize(n);
+    CurveFrame fr;
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
     for (int c = 0; c < n; c++)
         for (int d = 0; d < D; d++) {
             double x = m.cc[(size_t)c * D + d];
             if (x == x) { lo[d] = std::min(lo[d], x); hi[d] = std::max(hi[d], x); }
         }
-    const double bits = (D == 3) ? 2097151.0 : 2147483647.0;
     // one scale for all axes: the curve's cells stay cubes on a stretched domain
-    double ext = 0.0;
-    for (int d = 0; d < D; d++) ext = std::max(ext, hi[d] - lo[d]);
+    for (int d = 0; d < D; d++) { fr.lo[d] = lo[d]; fr.ext = std::max(fr.ext, hi[d] - lo[d]); }
+    fr.set = true;
+    return fr;
+}
+
+void curve_order(const mstgpu_mesh& m, int renumber, int n, std::vector<int32_t>& new2old, const CurveFrame* frame) {
+    const int D = m.dim;
+    new2old.resize(n);
+    const CurveFrame fr = (frame && frame->set) ? *frame : bbox_frame(m, n);
+    const double* lo = fr.lo;
+    const double bits = (D == 3) ? 2097151.0 : 2147483647.0;
+    double ext = fr.ext;
+    if (const char* v = getenv("MSTGPU_CURVE_SCALE")) ext *= std::max(1.0, atof(v));  // experiment: lattice of the curve against the mesh
     const double sc = ext > 0 ? bits / ext : 0.0;
     std::vector<std::pair<uint64_t, int32_t>> key(n);
 #pragma omp parallel for schedule(static)
@@ -149,7 +160,7 @@ std::string build_plan(const mstgpu_mesh& m, const mstgpu_config& cfg, Plan& p, 
     std::iota(p.cell_new2old.begin(), p.cell_new2old.end(), 0);
     if (cfg.renumber != 0) {
         std::vector<int32_t> ord;
-        curve_order(m, cfg.renumber, n_owned >= 0 ? n_owned : nc, ord);
+        curve_order(m, cfg.renumber, n_owned >= 0 ? n_owned : nc, ord, &p.frame);
         std::copy(ord.begin(), ord.end(), p.cell_new2old.begin());
     }
     p.cell_old2new.resize(nc);

@@ -25,7 +25,18 @@
 
 namespace mst {
 
+// Lattice of the space-filling curve: origin and extent of the cube its octree subdivides.  Unset = the bounding box of
+// the cells being ordered.  How the octree boxes fall on the mesh decides how contiguous a tile's ring cells are in
+// memory (on lattice-like meshes runs of consecutive ring ids vary by 40 % with the extent), so the
+// extent is chosen by a search (mstgpu.cu, choose_curve_frame) and a partition inherits the frame of the global mesh.
+struct CurveFrame {
+    bool set = false;
+    double lo[3] = {0, 0, 0};
+    double ext = 0.0;
+};
+
 struct Plan {
+    CurveFrame frame;  // INPUT of build_plan (optional)
     int D = 0, U = 0;
     int nc = 0, nf = 0, nint = 0, nslot = 0;
     std::vector<int32_t> cell_new2old, cell_old2new;
@@ -54,6 +65,8 @@ std::string validate_mesh(const mstgpu_mesh& m);
 std::string build_plan(const mstgpu_mesh& m, const mstgpu_config& cfg, Plan& p, int n_owned = -1);
 
 // space-filling-curve order of the first n cells (renumber: 1 Morton, 2 Hilbert)
-void curve_order(const mstgpu_mesh& m, int renumber, int n, std::vector<int32_t>& new2old);
+void curve_order(const mstgpu_mesh& m, int renumber, int n, std::vector<int32_t>& new2old, const CurveFrame* frame = nullptr);
+// bounding cube of the first n cell centres (the default frame)
+CurveFrame bbox_frame(const mstgpu_mesh& m, int n);
 
 }  // namespace mst

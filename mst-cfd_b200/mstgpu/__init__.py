@@ -26,7 +26,7 @@ EXPORTS = [
     "mstgpu_residual_linf", "mstgpu_sync", "mstgpu_cfl_dt", "mstgpu_step_cfl", "mstgpu_step_cfl_timed", "mstgpu_implicit_setup",
     "mstgpu_implicit_sweep_order", "mstgpu_step_implicit", "mstgpu_debug_gradient", "mstgpu_debug_face_flux",
     "mstgpu_launch_count", "mstgpu_enable_kernel_timing", "mstgpu_kernel_time",
-    "mstgpu_device_bytes", "mstgpu_plan_permutation", "mstgpu_tile_stats",
+    "mstgpu_device_bytes", "mstgpu_plan_permutation", "mstgpu_tile_stats", "mstgpu_tile_stats_owned", "mstgpu_tile_locality",
     "mstgpu_partition_create", "mstgpu_partition_destroy", "mstgpu_partition_mesh", "mstgpu_partition_sizes",
     "mstgpu_partition_cell_ids", "mstgpu_partition_neighbor", "mstgpu_create_partitioned",
     "mstgpu_comm_unique_id", "mstgpu_comm_init", "mstgpu_peer_blob_bytes", "mstgpu_peer_export", "mstgpu_peer_connect", "mstgpu_peer_disable", "mstgpu_lusgs_create", "mstgpu_lusgs_destroy",
@@ -209,18 +209,33 @@ def mesh_adjacency(flat: dict, renumber: int = 2):
     return rowptr, col
 
 
-def tile_stats(flat: dict, order: int = 2, tile_cells: int = 0, renumber: int = 2) -> dict:
-    """Statistics of the fused kernel's tiling (host only)."""
+def tile_stats(flat: dict, order: int = 2, tile_cells: int = 0, renumber: int = 2, n_owned: int = -1) -> dict:
+    """Statistics of the fused kernel's tiling (host only).  n_owned >= 0: `flat` is a partition's local mesh
+    (Partition.local_flat()), only its first n_owned cells are renumbered and tiled."""
     m, keep = _mesh_struct(flat)
     cfg = default_config(int(flat["dim"]))
     cfg.order, cfg.tile_cells, cfg.renumber = order, tile_cells, renumber
     out = np.zeros(16, dtype=np.int64)
-    rc = lib().mstgpu_tile_stats(C.byref(m), C.byref(cfg), out.ctypes.data)
+    lib().mstgpu_tile_stats_owned.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    rc = lib().mstgpu_tile_stats_owned(C.byref(m), C.byref(cfg), int(n_owned), out.ctypes.data)
     if rc != 0:
         raise MstGpuError(f"tile_stats failed ({rc}): {lib().mstgpu_last_error(None).decode()}")
     keys = ("tiles", "max_smem", "mean_smem", "sum_ring1", "sum_ring2", "sum_flux_faces", "sum_local_faces",
             "packet_bytes", "le56k", "le75k", "le113k", "more", "face_trips", "cell_trips", "ring_trips", "block_threads")
     return dict(zip(keys, (int(x) for x in out)))
+
+
+def tile_locality(flat: dict, order: int = 2, renumber: int = 2, n_owned: int = -1) -> dict:
+    """How scattered the ring rows of the tiles are in memory (host only; include/mstgpu.h)."""
+    m, keep = _mesh_struct(flat)
+    cfg = default_config(int(flat["dim"]))
+    cfg.order, cfg.renumber = order, renumber
+    out = np.zeros(6, dtype=np.int64)
+    lib().mstgpu_tile_locality.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    rc = lib().mstgpu_tile_locality(C.byref(m), C.byref(cfg), int(n_owned), out.ctypes.data)
+    if rc != 0:
+        raise MstGpuError(f"tile_locality failed ({rc}): {lib().mstgpu_last_error(None).decode()}")
+    return dict(tiles=int(out[0]), ring_rows=int(out[1]), lines=int(out[2]), runs=int(out[3]), gather_sectors=int(out[4]), flux_faces=int(out[5]))
 
 
 def _apply_consts(cfg, consts):

@@ -39,19 +39,6 @@ def main():
         print(json.dumps(dict(rank=r, owned=int(P.n_owned), ghosts=int(P.n_local - P.n_owned), ms_per_step=ms / a.steps,
                               spans={k: v[0] / max(v[1], 1) for k, v in kt.items()})), flush=True)
         ctx.close()
-        # the same local mesh (owned + ghost cells) as an ordinary, unpartitioned context: one launch, one stream
-        lf = P.local_flat()
-        ids = P.cell_ids
-        c2 = mstgpu.Context(lf, order=2, flux="roe", device=0)
-        c2.set_state(np.ascontiguousarray(Q0[ids]))
-        c2.step(1e-4, 3)
-        c2.sync()
-        c2.enable_kernel_timing(True)
-        ms2 = c2.step_timed(1e-4, a.steps)
-        c2.enable_kernel_timing(False)
-        print(json.dumps(dict(rank=r, standalone_cells=int(lf["ncells"]), ms_per_step=ms2 / a.steps,
-                              ns_per_cell=ms2 / a.steps * 1e6 / lf["ncells"], partitioned_ns_per_cell=ms / a.steps * 1e6 / P.n_owned)), flush=True)
-        c2.close()
         P.close()
 
 
