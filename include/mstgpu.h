@@ -83,6 +83,7 @@ extern "C" {
 #define MSTGPU_BC_INLET 10
 
 typedef struct mstgpu_ctx mstgpu_ctx;
+typedef struct mstgpu_part mstgpu_part;  /* one rank's piece of a mesh (mstgpu_partition_create, below) */
 
 /* Flattened mesh, reference order.  D = dim, all arrays host memory. */
 typedef struct mstgpu_mesh {
@@ -228,9 +229,20 @@ int mstgpu_sync(mstgpu_ctx* ctx);
  *                        state, bit-identical to the reference's numbers (the columns it prints
  *                        after the coordinates, Work.cpp:299-303).  Zone types its switch does not
  *                        list (symmetry) read an uninitialised array there; Q[c0] here.
- * Not available on a partitioned context (gather the state with mstgpu_get_state instead). */
+ * A partitioned context takes mstgpu_output_setup_partitioned instead: the GLOBAL mesh, node lists and weights
+ * (what every rank has read anyway) and the partition the context was created from.  Every node is computed by
+ * exactly one rank -- the owner of c0 of the first face in its list -- from fresh rows: the states of other ranks'
+ * cells around its nodes (they can lie beyond the ghost layers of the step) are fetched inside mstgpu_node_fields,
+ * which is then COLLECTIVE (one pack kernel + grouped ncclSend / ncclRecv; lists derived on every rank from the
+ * global tables, no negotiation).  mstgpu_output_node_count / _ids give the nodes of this rank's rows (global ids,
+ * ascending; all nodes in order on an unpartitioned context); out is [count][D+4].  Bit-identical to the
+ * single-GPU numbers (same faces, same order, same arithmetic per node). */
 int mstgpu_output_setup(mstgpu_ctx* ctx, const mstgpu_mesh* mesh, int32_t nnodes, const int32_t* nf_ptr,
                         const int32_t* nf_idx, const double* node_weight);
+int mstgpu_output_setup_partitioned(mstgpu_ctx* ctx, const mstgpu_part* part, const mstgpu_mesh* global_mesh, int32_t nnodes,
+                                    const int32_t* nf_ptr, const int32_t* nf_idx, const double* node_weight);
+int32_t mstgpu_output_node_count(mstgpu_ctx* ctx);
+int mstgpu_output_node_ids(mstgpu_ctx* ctx, int32_t* ids);
 int mstgpu_node_fields(mstgpu_ctx* ctx, double* out);
 
 /* Stage probes of the last step, reference order.
@@ -262,7 +274,6 @@ int64_t mstgpu_device_bytes(mstgpu_ctx* ctx);
  * context on it and joins a communicator.  State moves in the partition's own
  * cell order: owned cells by ascending global id (mstgpu_partition_cell_ids).
  * Results are bit-identical to the single-GPU run for any partition count. */
-typedef struct mstgpu_part mstgpu_part;
 
 /* cell_part: [ncells] partition of every global cell, or NULL for equal ranges of
  * the Hilbert curve.  Host only (no CUDA call). */

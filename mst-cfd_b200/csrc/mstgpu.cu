@@ -173,6 +173,15 @@ struct mstgpu_ctx {
     int32_t *out_nf_ptr = nullptr, *out_nf_idx = nullptr, *out_c0 = nullptr, *out_c1 = nullptr;
     double *out_eta = nullptr, *out_w = nullptr, *out_fields = nullptr;
     int out_nn = 0;
+    // partitioned output: the nodes this rank computes, the fresh rows it needs from other ranks and owes them
+    std::vector<int32_t> out_node_ids;        // global ids of the nodes of out_fields, ascending (empty = all nodes, in order)
+    double* out_Q = nullptr;                  // [nc + out_nextra][U]: copy of the local state + rows received for the output
+    int out_nextra = 0;
+    struct OutNb { int rank, send_off, send_count, recv_off, recv_count; };
+    std::vector<OutNb> out_nbrs;
+    int32_t* out_send_idx = nullptr;          // device-order local ids of the owned rows to send, all ranks back to back
+    double* out_sendbuf = nullptr;
+    int out_send_total = 0;
     // streamed step (mstgpu_step_host): host rows in, host rows out, pipelined over chunks of host rows
     std::vector<int32_t> tile_ready_row;          // per tile (desc[] order): largest host row among its owned + owned-range ring cells
     std::vector<int32_t> tile_cb_h, tile_nown_h;  // host copy of the descriptors' owned ranges
@@ -2108,7 +2117,7 @@ void mstgpu_destroy(mstgpu_ctx* ctx) {
                     ctx->vol, ctx->fc0, ctx->fc1, ctx->cf, ctx->cell_new2old, ctx->face_new2old, ctx->meta,
                     ctx->resid, ctx->nanflag, ctx->lsq, ctx->eps2, ctx->dtmin, ctx->dt_dev, ctx->imp_dpos, ctx->imp_pos,
                     ctx->imp_val, ctx->imp_b, ctx->imp_x, ctx->out_nf_ptr, ctx->out_nf_idx, ctx->out_c0, ctx->out_c1,
-                    ctx->out_eta, ctx->out_w, ctx->out_fields};
+                    ctx->out_eta, ctx->out_w, ctx->out_fields, ctx->out_Q, ctx->out_send_idx, ctx->out_sendbuf};
     if (ctx->imp_solver) mstgpu_lusgs_destroy(ctx->imp_solver);
     for (void* q : ptrs)
         if (q) cudaFree(q);

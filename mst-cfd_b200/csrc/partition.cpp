@@ -33,6 +33,7 @@ std::string build_partition(const mstgpu_mesh& g, const mstgpu_config& cfg, int 
         cell_part = own_part.data();
     }
     P.nparts = nparts; P.rank = rank; P.D = D;
+    P.cell_part.assign(cell_part, cell_part + nc);
     P.frame = (frame && frame->set) ? *frame : bbox_frame(g, nc);
     // the viscous term needs the primitive gradient of layer-1 cells as well
     P.layers = (cfg.order == 2 || cfg.viscous != 0) ? 2 : 1;

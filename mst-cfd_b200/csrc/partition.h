@@ -40,6 +40,7 @@ struct Partition {
     std::vector<int8_t> dac;
     std::vector<uint8_t> flag;
     mstgpu_mesh mesh{};
+    std::vector<int32_t> cell_part;  // [global cells] the assignment this partition was cut from (output path: who owns a node's cells)
     CurveFrame frame;  // curve lattice of the GLOBAL mesh: the local plans order their cells on the same lattice
 };
 

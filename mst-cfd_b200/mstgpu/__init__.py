@@ -33,7 +33,7 @@ EXPORTS = [
     "mstgpu_lusgs_solve", "mstgpu_lusgs_levels", "mstgpu_lusgs_create_ordered", "mstgpu_lusgs_solve_device",
     "mstgpu_lusgs_create_partitioned", "mstgpu_lusgs_color_order_partitioned",
     "mstgpu_lusgs_launch_count", "mstgpu_lusgs_device_bytes", "mstgpu_mesh_adjacency", "mstgpu_lusgs_color_order", "mstgpu_lusgs_last_error",
-    "mstgpu_output_setup", "mstgpu_node_fields", "mstgpu_set_tile_variant", "mstgpu_lusgs_set_mode",
+    "mstgpu_output_setup", "mstgpu_output_setup_partitioned", "mstgpu_output_node_count", "mstgpu_output_node_ids", "mstgpu_node_fields", "mstgpu_set_tile_variant", "mstgpu_lusgs_set_mode",
     "mstgpu_last_error", "mstgpu_version",
 ]
 
@@ -107,6 +107,10 @@ def lib():
         L.mstgpu_sync.argtypes = [vp]
         L.mstgpu_output_setup.argtypes = [vp, C.POINTER(MstMesh), i32, vp, vp, vp]
         L.mstgpu_node_fields.argtypes = [vp, vp]
+        L.mstgpu_output_setup_partitioned.argtypes = [vp, vp, C.POINTER(MstMesh), i32, vp, vp, vp]
+        L.mstgpu_output_node_count.argtypes = [vp]
+        L.mstgpu_output_node_count.restype = i32
+        L.mstgpu_output_node_ids.argtypes = [vp, vp]
         L.mstgpu_set_tile_variant.argtypes = [vp, i32]
         L.mstgpu_debug_gradient.argtypes = [vp, vp]
         L.mstgpu_debug_face_flux.argtypes = [vp, vp]
@@ -468,6 +472,19 @@ class Context:
         self.nnodes = nf_ptr.size - 1
         self._check(lib().mstgpu_output_setup(self.h, C.byref(m), self.nnodes, nf_ptr.ctypes.data, nf_idx.ctypes.data,
                                               None if w is None else w.ctypes.data), "output_setup")
+
+    def output_setup_partitioned(self, part, flat_global, nf_ptr, nf_idx, node_weight=None):
+        """Output path on a partitioned context: `part` is the Partition the context was created from, the other
+        arguments are GLOBAL (mesh, node -> faces lists, per-node weight).  Afterwards node_ids holds the global ids
+        of the nodes this rank computes and node_fields() (collective) returns their rows."""
+        m, keep = _mesh_struct(flat_global)
+        nf_ptr = np.ascontiguousarray(nf_ptr, dtype=np.int32); nf_idx = np.ascontiguousarray(nf_idx, dtype=np.int32)
+        w = None if node_weight is None else np.ascontiguousarray(node_weight, dtype=np.float64)
+        self._check(lib().mstgpu_output_setup_partitioned(self.h, part.h, C.byref(m), nf_ptr.size - 1, nf_ptr.ctypes.data, nf_idx.ctypes.data,
+                                                          None if w is None else w.ctypes.data), "output_setup_partitioned")
+        self.nnodes = int(lib().mstgpu_output_node_count(self.h))
+        self.node_ids = np.empty(self.nnodes, dtype=np.int32)
+        self._check(lib().mstgpu_output_node_ids(self.h, self.node_ids.ctypes.data), "output_node_ids")
 
     def node_fields(self, out=None):
         """[nnodes, dim+4] = rho, u_i, T, p, Ma per node of the current state (bit-identical to the

@@ -274,3 +274,82 @@ def test_two_gpus_streamed_step_matches_one(halo):
     one.step(1e-4, 3)
     assert np.array_equal(got, one.get_state(), equal_nan=True)
     assert np.array_equal(res, one.residual(), equal_nan=True)
+
+
+def _output_worker(rank, world, port, case, q):
+    import torch
+    import torch.distributed as dist
+    from mstgpu import host
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.cuda.set_device(rank)
+    raw, f, inlet = _output_case(case)
+    Q0 = mesh_np.random_state(f, seed=9)
+    ptr, idx = host.node_faces(raw)
+    w = host.node_weights(f, raw["nodes"].shape[0])
+    P = mstgpu.Partition(f, world, rank, order=2)
+    ctx = mstgpu.Context(P, order=2, flux="roe", inletQ=inlet, device=rank)
+    idt = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        idt = torch.frombuffer(bytearray(mstgpu.comm_unique_id()), dtype=torch.uint8).clone()
+    dist.broadcast(idt, 0)
+    ctx.comm_init(world, rank, bytes(idt.numpy().tobytes()))
+    ctx.output_setup_partitioned(P, f, ptr, idx, w)
+    ctx.set_state(Q0[P.cell_ids[:P.n_owned]])
+    ctx.step(1e-4, 3)
+    fld = ctx.node_fields()  # collective: fresh rows of the other rank's cells around this rank's nodes
+    got = [None] * world
+    dist.all_gather_object(got, (ctx.node_ids.copy(), fld))
+    if rank == 0:
+        q.put(got)
+    ctx.close()
+    dist.destroy_process_group()
+
+
+def _output_case(case):
+    from mstgpu import host
+    if case == "box":
+        raw = host.box_tets_raw(9, 8, 7, bc=(10, 5, 3, 7, 3, 3))
+        return raw, host.flatten_raw(raw), np.array([1.0, 0.4, 0.0, 0.0, 2.58])
+    from conftest import load_raw
+    raw = load_raw(case)
+    return raw, host.flatten_raw(raw, "consistent"), None
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("case", ["box", "2d-stairW-1"])
+def test_two_gpus_node_fields_match_one(case):
+    """Output path on partitioned contexts (mstgpu_output_setup_partitioned): every node is computed by one rank from
+    fresh rows of all cells around it -- also the other rank's, also beyond the ghost layers of the step.  The union of
+    the two ranks' rows is every node exactly once and equals the single-GPU node fields bit for bit."""
+    import torch.multiprocessing as mp
+    from mstgpu import host
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    port = 29850 + (os.getpid() % 2000)
+    procs = [mpc.Process(target=_output_worker, args=(r, 2, port, case, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    raw, f, inlet = _output_case(case)
+    Q0 = mesh_np.random_state(f, seed=9)
+    ptr, idx = host.node_faces(raw)
+    one = mstgpu.Context(f, order=2, flux="roe", inletQ=inlet)
+    one.output_setup(f, ptr, idx, host.node_weights(f, raw["nodes"].shape[0]))
+    one.set_state(Q0)
+    one.step(1e-4, 3)
+    want = one.node_fields()
+    nn = raw["nodes"].shape[0]
+    seen = np.zeros(nn, dtype=np.int32)
+    full = np.full_like(want, np.nan)
+    for ids, fld in got:
+        seen[ids] += 1
+        full[ids] = fld
+    has_faces = np.diff(ptr) > 0
+    assert np.array_equal(seen[has_faces], np.ones(int(has_faces.sum()), dtype=np.int32))  # every node exactly once
+    assert all(len(ids) > 0 for ids, _ in got)                                           # both ranks own nodes
+    assert np.array_equal(full[has_faces], want[has_faces], equal_nan=True)
