@@ -1771,37 +1771,76 @@ static CurveFrame choose_curve_frame(const mstgpu_mesh& m, const mstgpu_config& 
     }
     mstgpu_config c2 = cfg;
     if (n_own >= 0) c2.qf_copy_from = 0x7fffffff;
-    double best_cost = 0.0, cost0 = 0.0;
-    int best = 0;
-    for (int k = 0; k < 10; k++) {
+    const bool verbose = getenv("MSTGPU_VERBOSE") != nullptr;
+    double cost0 = 0.0;
+    auto evaluate = [&](const CurveFrame& fr, const char* what, double arg) -> double {
         Plan p;
-        p.frame = base;
-        p.frame.ext = base.ext * (1.0 + 0.1 * k);
-        if (!build_plan(*sm, c2, p, n_own).empty()) return base;
+        p.frame = fr;
+        if (!build_plan(*sm, c2, p, n_own).empty()) return -1.0;
         TilePack tp;
         const bool staged = tile_staged_for(cfg, p.D, p.nslot);
         const int T = cfg.tile_cells > 0 ? cfg.tile_cells : default_tile_cells(cfg, staged, p.D, p.nslot);
         int ext = tile_ext(cfg.order, cfg.limiter, cfg.viscous);
         if (staged) ext = tile_ext_staged(ext, tile_threads_for(cfg, T, p.D, p.nslot));
         const int nu = n_own >= 0 ? n_own : p.nc;
-        if (!build_tiles(p, nu, T, cfg.order, tp, ext, tile_fit_faces(cfg, p.D, p.nslot)).empty()) return base;
+        if (!build_tiles(p, nu, T, cfg.order, tp, ext, tile_fit_faces(cfg, p.D, p.nslot)).empty()) return -1.0;
         int64_t rows, lines, runs;
         tile_ring_runs(tp, p.U, rows, lines, runs);
         const double F = (double)tp.sum_FB / nu, Ln = (double)lines / nu;
         // Calibrated on the B200 (12 cubes on the 101^3 and 128^3 Kuhn boxes, profiles/r2_curve_calibration.md): the
         // kernel's time follows (flux faces per cell) x (0.15 + distinct 128-byte lines of ring rows per cell) to 4 %.
         const double cost = F * (0.15 + Ln);
-        if (k == 0) cost0 = cost;
-        if (getenv("MSTGPU_VERBOSE"))
-            fprintf(stderr, "[mstgpu] curve cube x%.1f: %.3f flux faces, %.3f ring rows, %.3f ring lines, %.3f runs per cell -> cost %.4f\n", 1.0 + 0.1 * k, F,
+        if (cost0 == 0.0) cost0 = cost;
+        if (verbose)
+            fprintf(stderr, "[mstgpu] curve cube %s %.4g: %.3f flux faces, %.3f ring rows, %.3f ring lines, %.3f runs per cell -> cost %.4f\n", what, arg, F,
                     (double)rows / nu, Ln, (double)runs / nu, cost / cost0);
-        if (k == 0 || cost < best_cost) { best_cost = cost; best = k; }
+        return cost;
+    };
+    CurveFrame best_fr = base;
+    double best_cost = evaluate(base, "x", 1.0);
+    if (best_cost < 0.0) return base;
+    // (a) ten extents of the bounding cube
+    for (int k = 1; k < 10; k++) {
+        CurveFrame fr = base;
+        fr.ext = base.ext * (1.0 + 0.1 * k);
+        const double c = evaluate(fr, "x", 1.0 + 0.1 * k);
+        if (c > 0.0 && c < best_cost) { best_cost = c; best_fr = fr; }
+    }
+    // (b) cubes whose finest boxes ARE the mesh's own lattice, if it has one: a mesh made of k cells per lattice cell (6
+    // Kuhn tets per hexahedron, 24 tets about a hexahedron's centroid, 2 triangles per quadrilateral ...) has the spacing
+    // (V k / N)^(1/D); the octree is anchored at the domain's lower corner (the smallest face-centre coordinates: boundary
+    // faces lie on it) and sized to a power of two of that spacing.  Boxes then hold whole lattice cells everywhere -- no
+    // drift of the boxes against the mesh, which an extent of the bounding cube only achieves by accident (128^3).
+    {
+        const int D = m.dim;
+        double V = 0.0;
+        for (int c = 0; c < nc; c++) if (m.vol[c] == m.vol[c]) V += std::fabs(m.vol[c]);
+        double flo[3] = {1e300, 1e300, 1e300}, fhi[3] = {-1e300, -1e300, -1e300};
+        for (int f = 0; f < m.nfaces; f++)
+            for (int d = 0; d < D; d++) {
+                const double x = m.fc[(size_t)f * D + d];
+                if (x == x) { flo[d] = std::min(flo[d], x); fhi[d] = std::max(fhi[d], x); }
+            }
+        double span = 0.0;
+        for (int d = 0; d < D; d++) span = std::max(span, fhi[d] - flo[d]);
+        if (V > 0.0 && span > 0.0)
+            for (int k : {1, 2, 4, 5, 6, 8, 12, 24}) {
+                const double h = std::pow(V * k / nc, 1.0 / D);
+                double ext = h;
+                while (ext < span * (1.0 + 1e-9)) ext *= 2.0;
+                CurveFrame fr;
+                fr.set = true;
+                for (int d = 0; d < D; d++) fr.lo[d] = flo[d];
+                fr.ext = ext;
+                const double c = evaluate(fr, "lattice k =", (double)k);
+                if (c > 0.0 && c < best_cost) { best_cost = c; best_fr = fr; }
+            }
     }
     // the model is good to ~4 %: leave the bounding cube only for a predicted gain beyond that
-    if (best_cost > 0.96 * cost0) best = 0;
-    base.ext *= 1.0 + 0.1 * best;
-    return base;
+    if (best_cost > 0.96 * cost0) return base;
+    return best_fr;
 }
+
 
 extern "C" {
 
