@@ -15,6 +15,13 @@ RhoSolver::solve() + residual + new->old over the whole mesh.
 Both arms print the same `config`; `--impl reference` runs the CPU restatement on
 ALL host cores (whatever WORLD_SIZE says), on the same mesh at the same size.
 
+What is timed: `value` = ONE un-instrumented mstgpu_step(dt, K) call (CUDA events on the
+solver's stream, max over ranks); the per-kernel durations of `roofline` come from an
+instrumented repeat of the same K steps; `e2e` = one mstgpu_step_host call per step with
+pinned HOST buffers on both sides (H2D, tiles and D2H pipelined) + the residual, with the
+same sequence as three separate calls beside it; `every_step_residual` = K calls of one
+step.  `secondary` holds short runs of BASELINE configs 1, 2, 3 and 5 through the same code.
+
 One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
 """
 import argparse
