@@ -125,7 +125,8 @@ typedef struct mstgpu_config {
     double cv;            /* CV (CONST.h:39)                                         */
     double inletQ[5];     /* inlet state (RhoSolver.cpp:123,266)                     */
     int32_t kernel;       /* 1 = fused tile kernel (default), 0 = three-kernel path;
-                             viscous = 1 always runs the three-kernel path            */
+                             viscous = 1 at FIRST order always runs the three-kernel path
+                             (the fused kernel carries the viscous term at second order) */
     int32_t tile_cells;   /* cells per tile of the fused kernel, 0 = default         */
     int32_t block_threads;/* CTA size of the fused kernel (128|256), 0 = default     */
     int32_t tile_flags;   /* fused kernel, tets at second order: MSTGPU_TILE_DIRECT or
@@ -142,8 +143,9 @@ typedef struct mstgpu_config {
     int32_t tile_fit;     /* fused kernel: > 0 = tiles of VARIABLE size, each grown along the cell order until
                              its flux faces would exceed tile_fit (or its cells tile_cells): with tile_fit a
                              multiple of the CTA size every warp makes the same number of trips through the
-                             flux phase.  0 = library default (4 x block_threads for tets at second order
-                             when tile_cells is 0 too, fixed tile_cells otherwise), < 0 = fixed tile_cells   */
+                             flux phase.  0 = library default (512 = 4 x 128 threads for tets at second order,
+                             768 = 3 x 256 for triangles at first order, when tile_cells and block_threads are 0
+                             too; fixed tile_cells otherwise), < 0 = fixed tile_cells                        */
     int32_t reserved_;    /* keeps the struct a multiple of 8 bytes; set to 0            */
 } mstgpu_config;
 
