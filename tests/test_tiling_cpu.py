@@ -78,3 +78,17 @@ def test_partition_tiling_statistics_take_the_owned_cells_only():
     assert st["sum_flux_faces"] >= 2 * P.n_owned                       # every owned cell's faces are evaluated here
     with pytest.raises(mstgpu.MstGpuError):
         mstgpu.tile_stats(lf, order=2, n_owned=lf["ncells"] + 1)
+
+
+def test_curve_cube_search_finds_the_lattice_of_a_kuhn_box(monkeypatch):
+    """37^3 hexahedra x 6 tets: with the octree anchored at the domain corner and its finest boxes = hexahedra (lattice
+    candidate k = 6 of choose_curve_frame) tiles are unions of whole hexahedra -- fewer cut faces, fewer tiles than on the
+    bounding cube, whose boxes (0.57 of a hexahedron) drift against the mesh"""
+    f = box_flat(37, 37, 37)
+    nc = f["ncells"]
+    st = mstgpu.tile_stats(f, order=2)
+    monkeypatch.setenv("MSTGPU_CURVE_SEARCH", "0")
+    st0 = mstgpu.tile_stats(f, order=2)
+    assert st["sum_flux_faces"] / nc < 2.40 < 2.45 < st0["sum_flux_faces"] / nc
+    assert st["tiles"] < st0["tiles"]
+    assert st["sum_ring1"] + st["sum_ring2"] < st0["sum_ring1"] + st0["sum_ring2"]
