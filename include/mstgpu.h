@@ -30,6 +30,10 @@
  *                                    nsteps times = Time::goNextTimeStep
  *                                    (R/time/Time.cpp:54-81) without the host
  *                                    round trip.
+ *   mstgpu_step_host                 one RhoSolver::solve with the fields where the
+ *                                    reference keeps them: AllData's old array in,
+ *                                    its new array out (Time.cpp:63-67), the copies
+ *                                    overlapped with the step.
  *   mstgpu_residual_linf             the residual loop of Time.cpp:69-76.
  *   mstgpu_get_state                 RhoSolver::getNewValue (== old after
  *                                    updateNewToOld), device -> host.
@@ -38,6 +42,10 @@
  *   mstgpu_debug_gradient            p1NewCellGradFlux   (RhoSolver.cpp:442-452)
  *   mstgpu_debug_face_flux           sum_d S[d] * p1OldFaceConvectFlux.col(d)
  *                                    per face (RhoSolver.cpp:53, 90-369)
+ *   mstgpu_output_setup[_partitioned],
+ *   mstgpu_node_fields               the arithmetic of
+ *                                    Work::writedataRhoBasedMshNodePlt
+ *                                    (R/work/Work.cpp:243-304) on the device.
  *   mstgpu_lusgs_*                   SparseSolverNUM::solveILUSGS
  *                                    (R/lusolver/SparseSolverNUM.cpp:144-212)
  *                                    and SparseSolver<MT,VCT>::solveILU
